@@ -1,0 +1,320 @@
+"""Generates tests/golden/*.npz by driving the LIVE reference through its public
+API on seeded inputs with injected proposal / threshold streams.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Run in the development container:
+
+    python -m oracle.gen_golden            # writes tests/golden/*.npz
+
+The reference's own tests hold no vectors for this path,
+so these fixtures -- outputs of the reference itself -- are what pins the oracle
+and, through it, the CUDA path.  Sizes are kept small (a few hundred steps, a
+few thousand grid cells) so the fixtures stay a few hundred KB.
+"""
+import os
+import sys
+import numpy as np
+import scipy.stats
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                   "tests", "golden")
+
+
+def _summary_arrays(sp, samples, keys):
+    summary = sp(samples)
+    x = np.stack([np.asarray(summary.v[k], dtype=float) for k in keys], axis=-1)
+    s = np.array([np.nan] + [float(v) for v in summary.s])  # s is None on step 1
+    t = np.array([float(v) for v in summary.t])
+    u = np.array([v is True for v in summary.u])
+    xp = np.stack([np.asarray(summary.p[k], dtype=float) for k in keys], axis=-1)
+    return dict(x=x, prob=np.asarray(summary.v.prob, dtype=float), s=s, t=t, u=u,
+                xprop=xp, pprop=np.asarray(summary.p.prob, dtype=float))
+
+
+# ---------------------------------------------------------------------------
+def mh_mvn(seed, T, init, log_pscale=False, cov_tran=None):
+    """examples/mcmc/mcmc_prob4a.py:38-51 with injected streams.
+    cov_tran: use ``set_tran(covariance ndarray)`` (probayes/rf.py:209-220)
+    instead of the explicit symmetric q, so the injected delta is coloured by
+    the Cholesky factor."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    Z = rng.standard_normal((T, 2))
+    U = rng.random(T)
+    zi, ui = iter(Z), iter(U)
+    mean, cov = [0., 0.], [[2.0, 1.2], [1.2, 2.0]]
+
+    def q(**kwds):
+        x, xprime = kwds['x'], kwds["x'"]
+        y, yprime = kwds['y'], kwds["y'"]
+        return scipy.stats.norm.pdf(yprime, loc=y, scale=1.) * \
+            scipy.stats.norm.pdf(xprime, loc=x, scale=1.)
+
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    sp = pb.SP(x & y)
+    if log_pscale:
+        sp.set_prob(scipy.stats.multivariate_normal, mean, cov, pscale='log')
+    else:
+        sp.set_prob(scipy.stats.multivariate_normal, mean, cov)
+    if cov_tran is None:
+        sp.set_tran(q)
+    else:
+        sp.set_tran(np.array(cov_tran))
+    sp.set_delta(lambda: (lambda z: sp.Delta(x=z[0], y=z[1]))(next(zi)))
+    sp.set_scores('hastings')
+    sp.set_update('metropolis')
+    sp.set_thresh(lambda: next(ui))        # after set_scores (sp.py:64-65)
+    sampler = sp.sampler({'x': init[0], 'y': init[1]}, stop=T)
+    samples = [s for s in sampler]
+    out = _summary_arrays(sp, samples, ['x', 'y'])
+    out.update(delta=Z, thresh=U, init=np.array(init, dtype=float),
+               mean=np.array(mean), cov=np.array(cov),
+               log_pscale=np.array(log_pscale),
+               cov_tran=np.array(cov_tran if cov_tran is not None else np.eye(2)),
+               has_cov_tran=np.array(cov_tran is not None))
+    return out
+
+
+# ---------------------------------------------------------------------------
+def mh_norm1d(seed, T, N, scores):
+    """examples/mcmc/metrohast_norm1d.py:23-42 ((mu, sigma) posterior, log
+    pscale, sigma with (np.log, np.exp) ufun, iid+joint), uniforms injected by
+    patching np.random.uniform.  scores='hastings' keeps the script's
+    asymmetric (tran, tran) pair -> the e-exponent score of SURVEY A.4;
+    scores='metropolis' is the plain ratio."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    x_obs = rng.normal(50., 10., size=N)
+    mu_lims, sigma_lims = (40, 60), (5, 20.)
+    step = 0.005
+    mu = pb.RV('mu', vtype=float, vset=mu_lims, pscale='log')
+    sigma = pb.RV('sigma', vtype=float, vset=sigma_lims, pscale='log')
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    sigma.set_ufun((np.log, np.exp))
+    paras = pb.RF(mu, sigma)
+    stats = pb.RF(x)
+    sp = pb.SP(stats, paras)
+    sp.set_prob(scipy.stats.norm.logpdf,
+                order={'x': 0, 'mu': 'loc', 'sigma': 'scale'})
+    tran = lambda **x: 1.
+    if scores == 'hastings':
+        paras.set_tran((tran, tran))
+    else:
+        paras.set_tran(tran)
+    paras.set_delta([step], scale=True)
+    sp.set_tran(paras)
+    sp.set_delta(paras)
+    sp.set_scores(scores)
+    if scores == 'hastings':
+        sp.set_update('metropolis')
+    R = rng.random((T, 3))               # per step: d_mu, d_sigma, threshold
+    init = {mu: 50., sigma: 12.5}
+    with ref_shim.injected_uniform(R.ravel()):
+        sampler = sp.sampler(init, {x: x_obs}, stop=T, iid=True, joint=True)
+        samples = [s for s in sampler]
+    out = _summary_arrays(sp, samples, ['mu', 'sigma'])
+    lengths = np.array([20., np.log(20.) - np.log(5.)])
+    dmax = step * lengths                # scale=True: probayes/field.py:299-303
+    delta = -dmax + (dmax - (-dmax)) * R[:, :2]
+    out.update(x_obs=x_obs, delta=delta, thresh=R[:, 2], runif=R,
+               init=np.array([50., 12.5]), dmax=dmax,
+               lims=np.array([[40., 60.], [5., 20.]]),
+               ex=np.array([[True, True], [True, True]]),
+               log_ufun=np.array([False, True]),
+               coef=np.array(np.e if scores == 'hastings' else 1.0))
+    return out
+
+
+# ---------------------------------------------------------------------------
+def mh_linreg(seed, T, N, dstep=0.02):
+    """Config C3's model at reference-feasible size: priors of
+    examples/mcmc/gibbs_linreg.py:28-32, likelihood 35-36, driven as an MH
+    sampler per SURVEY appendix B.5 ('metropolis' scores, [delta] proposal)."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    x_obs = rng.normal(0, 1, size=N)
+    y_obs = rng.normal(1.5 * x_obs - 1.0, 0.5)
+    x = pb.RV('x', vtype=float, vset=[-3, 3])
+    y = pb.RV('y', vtype=float, vset=[-np.inf, np.inf])
+    beta_0 = pb.RV('beta_0', vtype=float, vset=[-6., 6.], pscale='log')
+    beta_1 = pb.RV('beta_1', vtype=float, vset=[-6., 6.], pscale='log')
+    y_sigma = pb.RV('y_sigma', vtype=float, vset=[(0.001), 10.], pscale='log')
+
+    def norm_reg(x, y, beta_0, beta_1, y_sigma):
+        return scipy.stats.norm.logpdf(y, loc=beta_0 + beta_1 * x, scale=y_sigma)
+
+    stats = x & y
+    paras = beta_0 & beta_1 & y_sigma
+    sp = pb.SP(stats, paras)
+    sp.set_prob(norm_reg, pscale='log')
+    paras.set_tran(lambda **k: 0.)
+    paras.set_delta([dstep])
+    sp.set_tran(paras)
+    sp.set_delta(paras)
+    sp.set_scores('metropolis')
+    R = rng.random((T, 4))
+    init = np.array([-0.9, 1.4, 0.6])
+    with ref_shim.injected_uniform(R.ravel()):
+        sampler = sp.sampler({'beta_0': init[0], 'beta_1': init[1],
+                              'y_sigma': init[2]},
+                             {'x,y': [x_obs, y_obs]}, stop=T, iid=True,
+                             joint=True)
+        samples = [s for s in sampler]
+    out = _summary_arrays(sp, samples, ['beta_0', 'beta_1', 'y_sigma'])
+    delta = -dstep + (2 * dstep) * R[:, :3]
+    out.update(x_obs=x_obs, y_obs=y_obs, delta=delta, thresh=R[:, 3], runif=R,
+               init=init, dmax=np.full(3, dstep),
+               lims=np.array([[-6., 6.], [-6., 6.], [0.001, 10.]]),
+               ex=np.array([[False, False], [False, False], [False, False]]),
+               log_ufun=np.array([False, False, False]), coef=np.array(1.0))
+    return out
+
+
+# ---------------------------------------------------------------------------
+def dgei(seed, N, M, S):
+    """examples/dgei/dgei_norm1d_improved.py:20-46 with (N, M, S) arguments."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    data = rng.normal(50., 10., size=N)
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    paras = pb.RF(mu, sigma)
+    stats = pb.RF(x)
+    model = pb.SD(stats, paras)
+    model.set_prob(scipy.stats.norm.logpdf,
+                   order={'x': 0, 'mu': 'loc', 'sigma': 'scale'}, pscale='log')
+    joint = model({x: data, 'mu': {M}, 'sigma': {S}}, iid=True, joint=True)
+    posterior = joint.conditionalise('x')
+    post_mu = posterior.marginal('mu')
+    post_sigma = posterior.marginal('sigma')
+    expt = posterior.expectation()
+    q_mu = post_mu.quantile()
+    q_sigma = post_sigma.quantile()
+    q3_mu = post_mu.quantile([0.025, 0.5, 0.975])
+    return dict(data=data, mu=np.ravel(joint['mu']), sigma=np.ravel(joint['sigma']),
+                joint=np.asarray(joint.prob), posterior=np.asarray(posterior.prob),
+                marg_mu=np.asarray(post_mu.prob), marg_sigma=np.asarray(post_sigma.prob),
+                post_linear=np.asarray(posterior.rescaled().prob),
+                expt_mu=np.array(float(expt['mu'])),
+                expt_sigma=np.array(float(expt['sigma'])),
+                med_mu=np.array(float(q_mu['mu'])),
+                med_sigma=np.array(float(q_sigma['sigma'])),
+                q3_mu=np.array([float(q['mu']) for q in q3_mu]),
+                joint_name=np.array(joint.name), post_name=np.array(posterior.name),
+                marg_mu_name=np.array(post_mu.name))
+
+
+# ---------------------------------------------------------------------------
+def gibbs2d(seed, T):
+    """examples/mcmc/gibbs_norm2d.py:15-22 with the cdf uniforms injected."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    lims = (-10., 10.)
+    means = [0.5, -0.5]
+    covar = [[1.5, -1.0], [-1.0, 2.]]
+    x = pb.RV('x', vtype=float, vset=lims)
+    y = pb.RV('y', vtype=float, vset=lims)
+    sp = pb.SP(x & y)
+    sp.set_prob(scipy.stats.multivariate_normal, means, covar)
+    sp.set_tran(scipy.stats.multivariate_normal, means, covar, tsteps=1)
+    sp.set_scores('gibbs')
+    R = rng.random(T)
+    with ref_shim.injected_uniform(R):
+        sampler = sp.sampler({'x': 0., 'y': 1.}, stop=T)
+        samples = [s for s in sampler]
+    summary = sp(samples)
+    xs = np.stack([np.asarray(summary.v['x'], float),
+                   np.asarray(summary.v['y'], float)], axis=-1)
+    cc = sp._cond_cov
+    return dict(x=xs, prob=np.asarray(summary.v.prob, float), runif=R,
+                init=np.array([0., 1.]), mean=np.array(means), cov=np.array(covar),
+                lims=np.array([lims, lims]), stdv=np.asarray(cc._stdv),
+                cdfs=np.asarray(cc._cdfs),
+                coef=np.stack([np.ravel(c) for c in cc._coef]),
+                n_true=np.array(summary.u.count(True)))
+
+
+def condcov_bare(seed, d, T):
+    """Bare probayes/cond_cov.py CondCov at dimension d: construction constants
+    and T cyclic coordinate draws from injected uniforms."""
+    ref_shim.load()
+    from probayes.cond_cov import CondCov
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + np.eye(d)
+    mean = rng.standard_normal(d)
+    lims = np.tile(np.array([-10., 10.]), (d, 1))
+    cc = CondCov(mean, cov, lims)
+    R = rng.random(T)
+    x = mean.copy()
+    X = np.empty((T, d))
+    with ref_shim.injected_uniform(R):
+        for k in range(T):
+            i = k % d
+            args = [float(v) for v in x]
+            args[i] = {0}
+            x[i] = float(cc.interp(*args))
+            X[k] = x
+    coef = np.zeros((d, d))
+    for i in range(d):
+        idx = [j for j in range(d) if j != i]
+        coef[i, idx] = np.ravel(cc._coef[i])
+    return dict(x=X, runif=R, init=mean.copy(), mean=mean, cov=cov, lims=lims,
+                stdv=np.asarray(cc._stdv), cdfs=np.asarray(cc._cdfs), coef=coef)
+
+
+# ---------------------------------------------------------------------------
+def pscales_table():
+    """Edge-case table for the clamped log/exp/div of probayes/pscales.py."""
+    ref_shim.load()
+    from probayes import pscales as ps
+    p = np.array([0.0, 1e-320, 2.2250738585072014e-308, 2.3e-308, 1e-300, 0.5,
+                  1.0, 7.0, 1e300])
+    l = np.array([-1.7976931348623158e308, -1e4, -745.2, -744.0, -708.4, -1.0,
+                  0.0, 709.7, 709.79, 1e4])
+    num = np.array([0.0, 1e-310, 1e-300, 0.3, 2.0, 1e308])
+    den = np.array([0.0, 1e-310, 1e-300, 0.6, 1.0, 1e-308])
+    lnum = np.array([-800., -750., -700., -1.0, 0.0, 3.0])
+    lden = np.array([-800., -745., -710., -2.0, 0.0, -3.0])
+    return dict(p=p, log_prob=ps.log_prob(p), l=l, exp_logp=ps.exp_logp(l),
+                num=num, den=den, div_lin=ps.div_prob(num, den),
+                lnum=lnum, lden=lden,
+                div_log_to_lin=ps.div_prob(lnum, lden, 0j, 0j, pscale=1.),
+                resc_lin_to_log=ps.rescale(p, 1., 0j),
+                resc_log_to_lin=ps.rescale(l, 0j, 1.))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    cases = {
+        "mh_mvn_c1": lambda: mh_mvn(11, 512, (0., 1.)),
+        "mh_mvn_c1_b": lambda: mh_mvn(12, 256, (-2.5, 3.0)),
+        "mh_mvn_log": lambda: mh_mvn(13, 256, (0., 1.), log_pscale=True),
+        "mh_norm1d_hastings": lambda: mh_norm1d(21, 300, 60, 'hastings'),
+        "mh_norm1d_metropolis": lambda: mh_norm1d(22, 300, 60, 'metropolis'),
+        "mh_norm1d_underflow": lambda: mh_norm1d(23, 60, 1000, 'metropolis'),
+        "mh_linreg": lambda: mh_linreg(31, 300, 100),
+        "dgei_small": lambda: dgei(41, 60, 48, 40),
+        "dgei_peaked": lambda: dgei(42, 2000, 40, 36),
+        "gibbs2d": lambda: gibbs2d(51, 400),
+        "condcov_d8": lambda: condcov_bare(52, 8, 160),
+        "condcov_d64": lambda: condcov_bare(53, 64, 256),
+        "pscales": pscales_table,
+    }
+    only = sys.argv[1:]
+    for name, fn in cases.items():
+        if only and name not in only:
+            continue
+        out = fn()
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

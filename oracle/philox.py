@@ -1,0 +1,128 @@
+"""numpy Philox4x32-10 and the draw conventions shared with the CUDA kernels.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference has no
+counter-based RNG (it draws from the global ``np.random`` state:
+probayes/sp_utils.py:30-31, probayes/variable.py:631-633); this module defines
+the *new* stream the device path uses so that a native-RNG device run can be
+replayed bit-for-bit on the CPU via the injected-stream restatement.
+
+Stream layout (must match probayes_b200/csrc/pbx_philox.cuh):
+  key     = (seed & 0xffffffff, seed >> 32)
+  counter = (step & 0xffffffff, step >> 32, chain, slot)
+  slot 0..  : proposal draws, two doubles per slot (dims 2*slot, 2*slot+1)
+  slot 255  : the accept threshold t (first double of the block)
+  u01(a, b) = (2*k + 1) * 2**-53,  k = (a << 20) | (b >> 12)     in (0, 1)
+  normal pair from one block (w0..w3): u1 = u01(w0, w1), u2 = u01(w2, w3),
+      r = sqrt(-2 log u1), z0 = r cospi(2 u2), z1 = r sinpi(2 u2)
+  uniform pair from one block: u01(w0, w1), u01(w2, w3)
+"""
+import numpy as np
+
+M0 = np.uint64(0xD2511F53)
+M1 = np.uint64(0xCD9E8D57)
+W0 = 0x9E3779B9
+W1 = 0xBB67AE85
+MASK = np.uint64(0xFFFFFFFF)
+SLOT_THRESH = 255
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10. Inputs broadcastable integer arrays (< 2**32).
+    Returns four uint64 arrays holding 32-bit words."""
+    c0, c1, c2, c3 = np.broadcast_arrays(
+        *[np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3)])
+    c0, c1, c2, c3 = c0.copy(), c1.copy(), c2.copy(), c3.copy()
+    k0 = int(k0) & 0xFFFFFFFF
+    k1 = int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0), lo1,
+                          hi0 ^ c3 ^ np.uint64(k1), lo0)
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def u01(a, b):
+    """Two 32-bit words -> double in (0,1), exactly (2k+1)/2**53 with 52-bit k."""
+    k = (a << np.uint64(20)) | (b >> np.uint64(12))
+    return (2.0 * k.astype(np.float64) + 1.0) * 2.0 ** -53
+
+
+def block(seed, step, chain, slot):
+    seed = int(seed)
+    step = np.asarray(step, dtype=np.uint64)
+    return philox4x32_10(step & MASK, step >> np.uint64(32), chain, slot,
+                         seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+
+
+def uniform_pair(seed, step, chain, slot):
+    w0, w1, w2, w3 = block(seed, step, chain, slot)
+    return u01(w0, w1), u01(w2, w3)
+
+
+def normal_pair(seed, step, chain, slot):
+    u1, u2 = uniform_pair(seed, step, chain, slot)
+    r = np.sqrt(-2.0 * np.log(u1))
+    # cospi/sinpi(2 u2); computed via exact-argument reduction to keep parity
+    # with the device's sincospi to ~1 ulp
+    return r * _cospi(2.0 * u2), r * _sinpi(2.0 * u2)
+
+
+def _reduce_pi(x):
+    # x in (0, 2): reduce to multiples of 0.5 exactly
+    n = np.rint(2.0 * x)
+    r = x - 0.5 * n           # exact, |r| <= 0.25
+    return n.astype(np.int64) & 3, r * np.pi
+
+
+def _sinpi(x):
+    q, a = _reduce_pi(x)
+    s, c = np.sin(a), np.cos(a)
+    return np.choose(q, [s, c, -s, -c])
+
+
+def _cospi(x):
+    q, a = _reduce_pi(x)
+    s, c = np.sin(a), np.cos(a)
+    return np.choose(q, [c, -s, -c, s])
+
+
+def normals(seed, steps, chains, ndim, step0=0):
+    """Proposal normals Z[T, C, D] for steps step0..step0+T-1."""
+    t = (np.arange(steps, dtype=np.uint64) + np.uint64(step0))[:, None]
+    c = np.arange(chains, dtype=np.uint64)[None, :] if np.isscalar(chains) \
+        else np.asarray(chains, dtype=np.uint64)[None, :]
+    out = np.empty((steps, c.shape[1], ndim))
+    for slot in range((ndim + 1) // 2):
+        z0, z1 = normal_pair(seed, t, c, slot)
+        out[:, :, 2 * slot] = z0
+        if 2 * slot + 1 < ndim:
+            out[:, :, 2 * slot + 1] = z1
+    return out
+
+
+def uniforms(seed, steps, chains, ndim, step0=0):
+    """Proposal uniforms R[T, C, D] in (0,1) for steps step0..step0+T-1."""
+    t = (np.arange(steps, dtype=np.uint64) + np.uint64(step0))[:, None]
+    c = np.arange(chains, dtype=np.uint64)[None, :] if np.isscalar(chains) \
+        else np.asarray(chains, dtype=np.uint64)[None, :]
+    out = np.empty((steps, c.shape[1], ndim))
+    for slot in range((ndim + 1) // 2):
+        u0, u1 = uniform_pair(seed, t, c, slot)
+        out[:, :, 2 * slot] = u0
+        if 2 * slot + 1 < ndim:
+            out[:, :, 2 * slot + 1] = u1
+    return out
+
+
+def thresholds(seed, steps, chains, step0=0):
+    """Accept thresholds U[T, C]."""
+    t = (np.arange(steps, dtype=np.uint64) + np.uint64(step0))[:, None]
+    c = np.arange(chains, dtype=np.uint64)[None, :] if np.isscalar(chains) \
+        else np.asarray(chains, dtype=np.uint64)[None, :]
+    u0, _ = uniform_pair(seed, t, c, SLOT_THRESH)
+    return u0

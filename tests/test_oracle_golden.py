@@ -1,0 +1,125 @@
+"""Pins the numpy oracle against fixtures generated from the LIVE reference
+(oracle/gen_golden.py): identical accept decisions, trajectories and densities
+within 1e-12 relative (north_star tolerance for fp64)."""
+import numpy as np
+import pytest
+from conftest import load_golden, relerr
+from oracle import np_oracle as o
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_c1_b", "mh_mvn_log"])
+def test_mh_mvn(name):
+    g = load_golden(name)
+    r = o.mh_mvn_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                      g["mean"], g["cov"], log_pscale=bool(g["log_pscale"]))
+    assert np.array_equal(r["u"][:, 0], g["u"])
+    assert np.abs(r["x"][:, 0] - g["x"]).max() <= TOL
+    assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
+    assert relerr(r["s"][1:, 0], g["s"][1:]) <= TOL
+    assert relerr(r["xprop"][:, 0], g["xprop"]) <= TOL
+    assert relerr(r["pprop"][:, 0], g["pprop"]) <= TOL
+    assert np.isnan(g["s"][0]) and g["u"][0]          # step 1 accepts with s=None
+
+
+@pytest.mark.parametrize("name", ["mh_norm1d_hastings", "mh_norm1d_metropolis",
+                                  "mh_norm1d_underflow"])
+def test_mh_norm1d(name):
+    g = load_golden(name)
+    r = o.mh_normreg_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                          None, g["x_obs"], g["lims"], g["ex"], g["log_ufun"],
+                          has_slope=False, coef=float(g["coef"]))
+    assert np.array_equal(r["u"][:, 0], g["u"])
+    assert relerr(r["x"][:, 0], g["x"]) <= TOL
+    assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
+    assert np.nanmax(np.abs(r["s"][1:, 0] - g["s"][1:])) <= TOL
+
+
+def test_mh_norm1d_underflow_is_degenerate():
+    """at N=1000 the reference's linear-space ratio underflows and
+    only the first step is accepted; the log-space rule does accept."""
+    g = load_golden("mh_norm1d_underflow")
+    assert g["u"].sum() == 1
+    r = o.mh_normreg_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                          None, g["x_obs"], g["lims"], g["ex"], g["log_ufun"],
+                          has_slope=False, accept="log")
+    assert r["u"].sum() > 10
+
+
+def test_mh_linreg():
+    g = load_golden("mh_linreg")
+    r = o.mh_normreg_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                          g["x_obs"], g["y_obs"], g["lims"], g["ex"], g["log_ufun"],
+                          has_slope=True)
+    assert np.array_equal(r["u"][:, 0], g["u"])
+    assert relerr(r["x"][:, 0], g["x"]) <= TOL
+    assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
+    # where the linear ratio does not underflow the log rule decides identically
+    r2 = o.mh_normreg_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                           g["x_obs"], g["y_obs"], g["lims"], g["ex"], g["log_ufun"],
+                           has_slope=True, accept="log")
+    assert np.array_equal(r2["u"], r["u"])
+
+
+@pytest.mark.parametrize("name", ["dgei_small", "dgei_peaked"])
+def test_dgei(name):
+    g = load_golden(name)
+    M, S = len(g["mu"]), len(g["sigma"])
+    mu = o.uniform_grid(40, 60, M, True, True)
+    sg = np.exp(o.uniform_grid(np.log(5), np.log(20), S, True, True))
+    assert np.array_equal(mu, g["mu"]) and np.array_equal(sg, g["sigma"])
+    lj = o.grid_norm_logjoint(g["data"], mu, sg, np.full(M, -np.log(20.)),
+                              np.full(S, -np.log(np.log(20) - np.log(5))))
+    assert relerr(lj, g["joint"]) <= TOL
+    post = o.grid_conditionalise(lj)
+    assert relerr(post, g["posterior"]) <= TOL
+    assert relerr(o.grid_marginal(post, 1), g["marg_mu"]) <= TOL
+    assert relerr(o.grid_marginal(post, 0), g["marg_sigma"]) <= TOL
+    assert abs(o.grid_expectation(post, mu, 0) - g["expt_mu"]) <= 1e-12 * 60
+    assert abs(o.grid_expectation(post, sg, 1) - g["expt_sigma"]) <= 1e-12 * 20
+    if name == "dgei_peaked":       # clamped cells: log_prob(<tiny) = -1.797e308
+        assert (g["posterior"] == o.NEARLY_NEGATIVE_INF).sum() > 0
+        assert np.array_equal(post == o.NEARLY_NEGATIVE_INF,
+                              g["posterior"] == o.NEARLY_NEGATIVE_INF)
+
+
+def test_gibbs2d():
+    g = load_golden("gibbs2d")
+    r = o.gibbs_mvn_walk(g["init"][None], g["runif"][:, None], g["mean"], g["cov"],
+                         g["lims"])
+    assert np.abs(r["x"][:, 0] - g["x"]).max() <= TOL
+    assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
+    assert int(g["n_true"]) == len(g["runif"])          # gibbs always updates
+
+
+@pytest.mark.parametrize("name", ["condcov_d8", "condcov_d64"])
+def test_condcov(name):
+    g = load_golden(name)
+    cc = o.CondCovOracle(g["mean"], g["cov"], g["lims"])
+    assert relerr(cc.stdv, g["stdv"]) <= TOL
+    assert np.abs(cc.coef - g["coef"]).max() <= TOL
+    assert np.abs(cc.cdfs - g["cdfs"]).max() <= TOL
+    # precision-matrix identities the device path relies on
+    P = np.linalg.inv(g["cov"])
+    for i in range(cc.n):
+        idx = [j for j in range(cc.n) if j != i]
+        assert np.allclose(cc.coef[i, idx], -P[i, idx] / P[i, i], rtol=1e-9, atol=1e-12)
+        assert np.isclose(cc.stdv[i], P[i, i] ** -0.5, rtol=1e-10)
+    x = g["init"][None].copy()
+    for k in range(len(g["runif"])):
+        x = cc.step(x, k % cc.n, g["runif"][k:k + 1])
+        assert np.abs(x[0] - g["x"][k]).max() <= 1e-11
+
+
+def test_pscales_table():
+    g = load_golden("pscales")
+    assert np.array_equal(o.log_prob(g["p"]), g["log_prob"])
+    assert np.array_equal(o.exp_logp(g["l"]), g["exp_logp"])
+    with np.errstate(over="ignore"):
+        assert np.array_equal(o.div_prob_linear(g["num"], g["den"]), g["div_lin"])
+        assert np.array_equal(
+            o.div_prob_linear(o.exp_logp(g["lnum"]), o.exp_logp(g["lden"])),
+            g["div_log_to_lin"])
+    assert np.array_equal(o.from_linear(g["p"], True), g["resc_lin_to_log"])
+    assert np.array_equal(o.to_linear(g["l"], True), g["resc_log_to_lin"])
