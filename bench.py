@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the probayes hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c2] [--chains C] [--walk-steps T]
+
+Workload (BASELINE.json configs[1], "C2"): 4096 independent Metropolis-Hastings
+chains x 10^4 steps on the 2-D correlated normal of examples/mcmc/mcmc_prob4a.py,
+fp64, native Philox RNG, every step recorded (thin=1).  One bench "step" = one
+whole walk (C x T chain-steps).  Under torchrun each rank runs its own 4096
+chains (chains are independent: weak scaling, no data-path collective; the
+per-chain summaries are all-reduced once after the timed region).
+
+Prints ONE JSON line (rank 0):
+  value   chain-steps/s, device-resident (outputs written to HBM)
+  e2e     same metric through the host-buffer C-ABI call: H2D of the initial
+          state + D2H of every recorded sample and density inside the timed region
+  roofline / cpu_baseline / clocks / gpu_launches as the bench contract asks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+COV = np.array([[2.0, 1.2], [1.2, 2.0]])
+MEAN = np.array([0.0, 0.0])
+INIT = np.array([0.0, 1.0])
+METRIC = "mh_chain_steps_per_sec"
+UNIT = "chain-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
+    ap.add_argument("--walk-steps", type=int, default=10000, help="MH steps per walk")
+    ap.add_argument("--thin", type=int, default=1)
+    ap.add_argument("--accept", default="reference", choices=["reference", "log"])
+    ap.add_argument("--cpu-sample-steps", type=int, default=0,
+                    help="MH steps of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config(args, n_gpus):
+    return {"workload": "C2: %d MH chains/GPU x %d steps, 2-D correlated normal "
+                        "(mcmc_prob4a), thin=%d, Philox4x32-10" % (args.chains, args.walk_steps,
+                                                                  args.thin),
+            "chains_per_gpu": args.chains, "walk_steps": args.walk_steps, "thin": args.thin,
+            "accept": args.accept, "parallelism": "chains x%d" % n_gpus,
+            "l2": "outputs per walk (%.0f MB) exceed the 126 MB L2; no explicit flush"
+                  % (args.chains * (args.walk_steps // args.thin) * 24 / 1e6)}
+
+
+# ---------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(power)), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (cpu_baseline / --impl reference)
+# ---------------------------------------------------------------------------
+def cpu_walk_rate(chains, steps, accept, seed=1234):
+    """Times the oracle port of the C2 walk on a bounded sample.  Prefers the C
+    restatement (OpenMP, all host cores); falls back to the numpy restatement
+    (1 core).  Returns (chain_steps_per_s, cores, kind_detail, seconds)."""
+    try:
+        from oracle.c import liboracle
+        lib = liboracle.load()
+    except Exception:
+        lib = None
+    if lib is not None:
+        cores = liboracle.num_threads()
+        t0 = time.perf_counter()
+        liboracle.mh_mvn_walk(np.tile(INIT, (chains, 1)), MEAN, COV, steps, seed,
+                              accept=accept, record=True)
+        dt = time.perf_counter() - t0
+        return chains * steps / dt, cores, "C restatement (oracle/c, OpenMP)", dt
+    from oracle import np_oracle as o
+    from oracle import philox
+    t0 = time.perf_counter()
+    Z = philox.normals(seed, steps, chains, 2)
+    U = philox.thresholds(seed, steps, chains)
+    o.mh_mvn_walk(np.tile(INIT, (chains, 1)), Z, U, MEAN, COV, accept=accept)
+    dt = time.perf_counter() - t0
+    return chains * steps / dt, 1, "numpy restatement (oracle/np_oracle.py)", dt
+
+
+def auto_cpu_steps(chains, accept):
+    """Sizes the CPU sample for roughly 10-20 s of work from a short probe."""
+    rate, _, _, _ = cpu_walk_rate(chains, 20, accept)
+    return int(max(50, min(10000, rate * 12.0 / chains)))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = args.cpu_sample_steps or auto_cpu_steps(args.chains, args.accept)
+    rates = []
+    for _ in range(args.warmup):
+        cpu_walk_rate(args.chains, max(10, steps // 10), args.accept)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, detail, dt = cpu_walk_rate(args.chains, steps, args.accept)
+        rates.append(r)
+        if time.perf_counter() - t_all > 150:
+            break
+    value = float(np.mean(rates))
+    sample = "%d chains x %d steps per bench step (%s)" % (args.chains, steps, detail)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": len(rates), "warmup": args.warmup,
+            "ms_per_step": 1e3 * args.chains * steps / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from probayes_b200.engine import get_engine
+    eng = get_engine(local)
+    C, T, thin, D = args.chains, args.walk_steps, args.thin, 2
+    R = T // thin
+    chain0 = rank * C
+    init_host = np.tile(INIT[:, None], (1, C))
+    state = eng.to_device(init_host)
+    init_dev = eng.to_device(init_host)
+    out_bytes = R * (D + 1) * C * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def walk(seed):
+        state.copy_(init_dev)
+        return eng.mh_mvn(state, MEAN, COV, T, thin=thin, seed=seed, chain0=chain0,
+                          accept=args.accept)
+
+    # ---- device-resident timing ------------------------------------------------
+    for w in range(args.warmup):
+        walk(1000 + w)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    kms = []
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        out = walk(2000 + k)
+        kms.append(eng.last_kernel_ms())     # CUDA events around the kernel on its stream
+    t_end.record()
+    barrier()
+    launches = eng.launches - l0
+    total_ms = t_start.elapsed_time(t_end)
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+    ms_per_step = total_ms / args.steps
+    value = world * C * T / (ms_per_step * 1e-3)
+    kernel_ms = float(np.mean(kms))
+
+    # per-chain summaries -> R-hat inputs, all-reduced once (not in the timed region)
+    st = eng.chain_stats(out["stat_sum"], out["stat_sumsq"], T)
+    if world > 1:
+        dist.all_reduce(st)
+    st = st.cpu().numpy()
+    Cn = st[:, 3]
+    W = st[:, 2] / Cn
+    B = T * (st[:, 1] - st[:, 0] ** 2 / Cn) / (Cn - 1)
+    rhat = np.sqrt(((T - 1) / T * W + B / T) / W)
+    acc_rate = float(out["accept_count"].sum().item()) / (C * T)
+
+    # ---- end-to-end through the host-buffer C-ABI call -----------------------
+    pin_x = torch.empty((R, D, C), dtype=torch.float64, pin_memory=True)
+    pin_p = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    for w in range(2):
+        eng.mh_mvn_walk_host(init_host.copy(), MEAN, COV, T, thin=thin, seed=3000 + w,
+                             chain0=chain0, accept=args.accept, out_x=pin_x, out_prob=pin_p)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        eng.mh_mvn_walk_host(init_host.copy(), MEAN, COV, T, thin=thin, seed=4000 + k,
+                             chain0=chain0, accept=args.accept, out_x=pin_x, out_prob=pin_p)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * C * T * e2e_steps / float(te.item())
+    h2d = D * C * 8
+    d2h = out_bytes + (2 * D + 2) * C * 8 + D * C * 8
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        achieved = out_bytes / (kernel_ms * 1e-3) / 1e9
+        fp64_peak = eng.fp64_peak_tflops()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": which, "kernel": "mh_mvn_kernel<2,false>",
+                         "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": out_bytes,
+                         "note": "K1 writes (D+1)*8 B per recorded chain-step; it is "
+                                 "FP64-pipe/latency bound, not HBM bound (see fp64)"},
+            "fp64": {"peak_tflops_measured": fp64_peak},
+            "clocks": clocks,
+            "quality": {"accept_rate": acc_rate, "rhat": [float(v) for v in rhat]},
+        }
+        if not args.no_cpu_baseline:
+            steps = args.cpu_sample_steps or auto_cpu_steps(C, args.accept)
+            r, cores, detail, dt = cpu_walk_rate(C, steps, args.accept)
+            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d chains x %d steps, %.1f s (%s)"
+                                              % (C, steps, dt, detail),
+                                    "reference_python_survey": "1332 chain-steps/s, 1 core "
+                                                               "(BASELINE.md, config C1)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

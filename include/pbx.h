@@ -1,0 +1,284 @@
+/*
+ * pbx.h -- C ABI of libpbx, the B200 (sm_100a) drop-in for the probayes hot path.
+ *
+ * The reference (Bhumbra/probayes) is pure Python and has no FFI of its own; the
+ * seams this ABI sits behind are the reference's Python entry points for the
+ * path (cited per function below, paths relative to the reference checkout).
+ * The Python host mirror (probayes_b200/) binds these with ctypes; INTEGRATION.md
+ * shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no exceptions / Python objects / torch types cross the boundary;
+ *   - every function returns PBX_OK (0) or a negative pbx_status; the message of
+ *     the last failure on the calling thread is at pbx_last_error();
+ *   - the CALLER allocates every buffer.  Pointers documented "device" are CUDA
+ *     device pointers valid on the context's device (e.g. torch data_ptr()),
+ *     "host" are ordinary host pointers read before the call returns;
+ *   - calls are asynchronous on the context's stream unless named *_host or
+ *     *_sync; buffers must stay alive until the stream is synchronised;
+ *   - a context is bound to one GPU and is not thread-safe (the reference is
+ *     single-threaded with global RNG state); use one context per GPU/process;
+ *   - all arithmetic is fp64 (probayes/constants.py:7), chain-minor layouts
+ *     ([.., C]) so that warps read/write coalesced.
+ */
+#ifndef PBX_H
+#define PBX_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PBX_API __attribute__((visibility("default")))
+#else
+#define PBX_API
+#endif
+
+#define PBX_VERSION 100            /* 0.1.0 */
+#define PBX_MAX_DIMS 8             /* max state dimension of the small-target MH kernel */
+#define PBX_MAX_PARAMS 3           /* (b0, b1, sigma) */
+
+typedef enum {
+  PBX_OK = 0,
+  PBX_ERR_INVALID = -1,            /* bad argument */
+  PBX_ERR_CUDA = -2,               /* CUDA runtime error (message has the string) */
+  PBX_ERR_UNSUPPORTED = -3,        /* outside the catalogue (no CPU fallback by design) */
+  PBX_ERR_NOMEM = -4
+} pbx_status;
+
+/* accept rule ---------------------------------------------------------------
+ * REFERENCE: s = min(1, lin(p')/max(tiny, lin(p))), accept iff s >= t, with the
+ *   clamped exp of probayes/pscales.py:56-65,219-236 (sp_utils.py:19-37).
+ * LOG: accept iff coef*(logp' - logp) >= log(t); identical decisions wherever the
+ *   reference's linear ratio does not underflow, and the only usable rule for
+ *   N >~ 200 observations. */
+#define PBX_ACCEPT_REFERENCE 0
+#define PBX_ACCEPT_LOG 1
+/* proposal draw kind (probayes/field.py:469-531, variable.py:600-638) */
+#define PBX_PROP_NORMAL 0          /* delta_j = scale_j * z_j,  z ~ N(0,1) (then optional L) */
+#define PBX_PROP_UNIFORM 1         /* delta_j = -scale_j + 2 scale_j r_j, r ~ U(0,1)  ([delta] lists) */
+
+typedef struct pbx_ctx pbx_ctx;
+
+typedef struct {
+  int32_t device;
+  int32_t cc_major, cc_minor;
+  int32_t sm_count;
+  int32_t l2_bytes_mb;
+  int32_t smem_per_block_optin;
+  int64_t global_mem_bytes;
+  char name[64];
+} pbx_devinfo;
+
+PBX_API int pbx_version(void);
+PBX_API const char* pbx_last_error(void);
+PBX_API int pbx_device_count(int* n);
+PBX_API int pbx_device_info(int device, pbx_devinfo* out);
+
+/* stream: a cudaStream_t (as void*) to run on, or NULL to let the context own one. */
+PBX_API int pbx_ctx_create(int device, void* stream, pbx_ctx** out);
+PBX_API int pbx_ctx_destroy(pbx_ctx* ctx);
+PBX_API int pbx_ctx_sync(pbx_ctx* ctx);
+/* number of kernels this context has launched since creation (bench: gpu_launches) */
+PBX_API int64_t pbx_ctx_launch_count(pbx_ctx* ctx);
+/* device time in ms of the kernels launched by the most recent *_run call on this
+ * context, measured with CUDA events on the context's stream; syncs the stream. */
+PBX_API int pbx_ctx_last_kernel_ms(pbx_ctx* ctx, float* ms);
+
+/* pinned host memory for the *_host entry points */
+PBX_API int pbx_host_alloc(size_t bytes, void** out);
+PBX_API int pbx_host_free(void* p);
+
+/* ---------------------------------------------------------------------------
+ * K1  batched-chain Metropolis-Hastings on a multivariate-normal target.
+ * Replaces the SP.next loop (probayes/sp.py:221-258, sp_utils.py:8-37) when the
+ * target is scipy.stats.multivariate_normal (probayes/prob.py:347-360) and the
+ * proposal is an additive delta (field.py:534-552, rf.py:340-354), e.g.
+ * examples/mcmc/mcmc_prob4a.py:38-51.  One chain per reference sampler.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_chains;        /* C (local to this GPU) */
+  int32_t n_dims;          /* D, 1..PBX_MAX_DIMS */
+  int32_t n_steps;         /* T steps in this call */
+  int32_t thin;            /* record every thin-th step (step index % thin == thin-1) */
+  int64_t step0;           /* global index of this call's first step; step 0 accepts
+                              unconditionally (sp.py:253, sp_utils.py:24-25) */
+  int64_t chain0;          /* global id of local chain 0 (Philox stream is keyed on
+                              the global chain id => results invariant to sharding) */
+  uint64_t seed;
+  int32_t log_pscale;      /* recorded prob: 0 = pdf (linear pscale), 1 = logpdf */
+  int32_t accept_mode;     /* PBX_ACCEPT_* */
+  int32_t prop_kind;       /* PBX_PROP_* */
+  int32_t has_prop_mat;    /* delta = prop_mat @ (scaled draw)  (rf.py:346-348) */
+  double mean[PBX_MAX_DIMS];
+  /* whitening matrix U (row-major [D][D]) of scipy's _PSD with the value
+   * permutation of prob.py:349-358 folded into its rows: maha = |(x-mean') U'|^2 */
+  double whiten[PBX_MAX_DIMS * PBX_MAX_DIMS];
+  double norm_c;           /* D log 2pi + log_pdet;  logpdf = -0.5*(norm_c + maha), scipy's form */
+  double prop_scale[PBX_MAX_DIMS];
+  double prop_mat[PBX_MAX_DIMS * PBX_MAX_DIMS];   /* row-major lower-triangular L */
+  /* device buffers */
+  double* state;           /* [D][C] in/out: current state */
+  double* state_lp;        /* [C]    in/out: log-density of state (ignored on input when step0 == 0) */
+  const double* inj_delta; /* [T][D][C] injected raw proposal draws, or NULL = Philox */
+  const double* inj_thresh;/* [T][C] injected thresholds, or NULL = Philox */
+  double* out_x;           /* [T/thin][D][C] or NULL */
+  double* out_prob;        /* [T/thin][C] or NULL */
+  uint8_t* out_accept;     /* [T][C] or NULL (u: 1 = True, 0 = None) */
+  double* out_score;       /* [T][C] or NULL (s; NaN on the unconditional first step) */
+  int64_t* accept_count;   /* [C] accumulated, or NULL */
+  double* stat_sum;        /* [D][C] accumulated sum of the retained state, or NULL */
+  double* stat_sumsq;      /* [D][C] accumulated sum of squares, or NULL */
+} pbx_mh_mvn_params;
+
+PBX_API int pbx_mh_mvn_run(pbx_ctx* ctx, const pbx_mh_mvn_params* p);
+
+/* Whole-walk call with HOST output buffers: runs the walk in chunks of
+ * chunk_steps on the device and streams out_x/out_prob back to (pinned) host
+ * memory on a copy stream, overlapped with the next chunk.  state/state_lp are
+ * HOST [D][C]/[C] in/out; out_x/out_prob HOST; the inj_*, out_accept, out_score
+ * pointers must be NULL; accept_count/stat_* are HOST or NULL.  Synchronous. */
+PBX_API int pbx_mh_mvn_walk_host(pbx_ctx* ctx, const pbx_mh_mvn_params* p, int32_t chunk_steps);
+
+/* ---------------------------------------------------------------------------
+ * K2  streaming normal log-likelihood MH (iid=True, joint=True, log pscale).
+ *   y_i ~ N(b0 + b1 x_i, sigma)   params (b0, b1, sigma)   has_slope = 1
+ *   y_i ~ N(mu, sigma)            params (mu, sigma)       has_slope = 0
+ * Replaces RF.__call__(iid=True) + SD.__call__(joint=True) evaluated every step
+ * (probayes/rf.py:541-581, pd.py:332-370, sd.py:148-161) with scipy.stats.norm
+ * .logpdf as the likelihood (examples/mcmc/metrohast_norm1d.py:30-31,
+ * gibbs_linreg.py:35-36), box-uniform priors in ufun space (rv.py:153-166,
+ * rv_utils.py:8-47) and ufun-space proposals (variable.py:693-697).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_chains;
+  int32_t n_params;        /* 2 or 3 */
+  int32_t n_steps;
+  int32_t thin;
+  int64_t step0;
+  int64_t chain0;
+  uint64_t seed;
+  int32_t has_slope;
+  int32_t accept_mode;
+  double accept_coef;      /* linear proposal density multiplied into the log target by
+                              hastings_scores (sp_utils.py:62-64); 1.0 for metropolis */
+  int32_t prop_kind;
+  int32_t variant;         /* 0 auto; 1 chains-in-registers + TMA-staged obs tiles;
+                              2 obs-per-thread streaming + warp-shuffle reduction */
+  int64_t n_obs;
+  const double* x_obs;     /* device [N] (unused when !has_slope) */
+  const double* y_obs;     /* device [N] */
+  double lims[PBX_MAX_PARAMS][2];        /* vlims */
+  int32_t open_end[PBX_MAX_PARAMS][2];   /* 1 = exclusive end (tuple in vset) */
+  int32_t log_ufun[PBX_MAX_PARAMS];      /* 1 = (np.log, np.exp) ufun */
+  double prop_scale[PBX_MAX_PARAMS];
+  double* state;           /* [P][C] in/out */
+  double* state_lp;        /* [C] in/out */
+  const double* inj_delta; /* [T][P][C] or NULL */
+  const double* inj_thresh;/* [T][C] or NULL */
+  double* out_x;           /* [T/thin][P][C] or NULL */
+  double* out_prob;        /* [T/thin][C] (log-joint) or NULL */
+  uint8_t* out_accept;     /* [T][C] or NULL */
+  double* out_score;       /* [T][C] or NULL */
+  int64_t* accept_count;   /* [C] or NULL */
+  double* stat_sum;        /* [P][C] or NULL */
+  double* stat_sumsq;      /* [P][C] or NULL */
+} pbx_mh_normreg_params;
+
+PBX_API int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p);
+
+/* log-joint (likelihood + box priors) of theta[P][C] -> out[C]; the array density
+ * evaluation on its own ("log-likelihood evals"). Uses the same kernels as K2. */
+PBX_API int pbx_normreg_logjoint(pbx_ctx* ctx, const pbx_mh_normreg_params* model,
+                         const double* theta, double* out);
+
+/* ---------------------------------------------------------------------------
+ * K3/K4  discrete grid exact inference of a normal (mu, sigma) posterior.
+ * Replaces SD.__call__({x: data, mu: {M}, sigma: {S}}, iid=True, joint=True)
+ * (probayes/sd.py:148-161, rf.py:565-581, pd.py:332-370, pd_utils.py:85-328)
+ * and PD.conditionalise / PD.marginal (pd.py:136-165,168-211,214-295), as in
+ * examples/dgei/dgei_norm1d_improved.py:36-43.
+ * ------------------------------------------------------------------------- */
+/* out[m][s] = logprior_mu[m] + logprior_sigma[s] + sum_i norm.logpdf(x_i; mu_m, sigma_s) */
+PBX_API int pbx_grid_norm_logjoint(pbx_ctx* ctx, const double* x_obs, int64_t n_obs,
+                           const double* mu, int32_t n_mu,
+                           const double* sigma, int32_t n_sigma,
+                           const double* logprior_mu, const double* logprior_sigma,
+                           double* out);
+/* out[0] = max over n entries (device scalar) */
+PBX_API int pbx_grid_max(pbx_ctx* ctx, const double* logjoint, int64_t n, double* out);
+/* out[0] = sum exp_logp(logjoint - gmax[0]) (device scalars) */
+PBX_API int pbx_grid_sumexp(pbx_ctx* ctx, const double* logjoint, int64_t n,
+                    const double* gmax, double* out);
+/* post[m][s] = log_prob( exp_logp(lj - gmax) / max(tiny, gsum) )   (pd.py:285-295)
+ * marg_mu_lin[m]    = sum_s exp_logp(post[m][s])                    (pd.py:162-163)
+ * marg_sigma_lin[s] = sum_m exp_logp(post[m][s])  (partial over this slab's rows)
+ * post may be NULL (marginals only) or alias logjoint (in place). */
+PBX_API int pbx_grid_posterior(pbx_ctx* ctx, const double* logjoint, int32_t n_mu, int32_t n_sigma,
+                       const double* gmax, const double* gsum,
+                       double* post, double* marg_mu_lin, double* marg_sigma_lin);
+/* v[i] = log_prob(v[i]) in place (clamped log of pscales.py:44-53) */
+PBX_API int pbx_log_prob_inplace(pbx_ctx* ctx, double* v, int64_t n);
+/* v[i] = exp_logp(v[i]) in place (clamped exp of pscales.py:56-65; PD.rescaled) */
+PBX_API int pbx_exp_logp_inplace(pbx_ctx* ctx, double* v, int64_t n);
+
+/* ---------------------------------------------------------------------------
+ * K5  batched Gibbs sweep over the conditionals of a multivariate normal.
+ * Replaces RF.eval_tfun -> sample_cond_cov -> CondCov.interp
+ * (probayes/rf.py:413-462, rf_utils.py:50-65, cond_cov.py:22-65) with the
+ * per-step evaluation of the mvn target (sd.py:286), as in
+ * examples/mcmc/gibbs_norm2d.py:15-22.  One step = one coordinate update
+ * (tsteps=1); coordinate = (step0 + k) mod d.
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_chains;
+  int32_t n_dims;          /* d, 1..64 */
+  int32_t n_steps;         /* coordinate steps in this call */
+  int32_t thin;
+  int64_t step0;
+  int64_t chain0;
+  uint64_t seed;
+  int32_t log_pscale;
+  int32_t want_prob;       /* evaluate + record the target density */
+  const double* mean;      /* device [d] */
+  const double* coef;      /* device [d][d] CondCov regression rows (0 on the diagonal) */
+  const double* stdv;      /* device [d] conditional stdv */
+  const double* cdf_lo;    /* device [d] fixed cdf limits (cond_cov.py:38-39) */
+  const double* cdf_hi;    /* device [d] */
+  const double* whiten;    /* device [d][d] row-major, value permutation folded in */
+  double norm_c;           /* d log 2pi + log_pdet */
+  double* state;           /* [d][C] in/out */
+  const double* inj_runif; /* [T][C] injected U(0,1) draws or NULL = Philox */
+  double* out_x;           /* [T/thin][d][C] or NULL */
+  double* out_prob;        /* [T/thin][C] or NULL */
+  double* stat_sum;        /* [d][C] or NULL */
+  double* stat_sumsq;      /* [d][C] or NULL */
+} pbx_gibbs_mvn_params;
+
+PBX_API int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p);
+
+/* batched mvn log-density: x[d][C] -> out[C] (logpdf, or pdf when !log_pscale);
+ * d >= 64 routes the [C,d]x[d,d] whitening product through FP64 tensor-core MMA. */
+PBX_API int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int64_t n_chains,
+                   const double* mean, const double* whiten, double norm_c,
+                   int32_t log_pscale, double* out);
+
+/* ---------------------------------------------------------------------------
+ * Chain summaries for R-hat: from per-chain sums over n_steps retained states,
+ * out[j][0..3] = ( sum_c mean_cj, sum_c mean_cj^2, sum_c var_cj, C ) per dim j;
+ * these are what the ranks all-reduce.  out: device [D][4].
+ * ------------------------------------------------------------------------- */
+PBX_API int pbx_reduce_chain_stats(pbx_ctx* ctx, const double* stat_sum, const double* stat_sumsq,
+                           int32_t n_dims, int64_t n_chains, int64_t n_steps, double* out);
+
+/* FP64 FMA peak micro-benchmark (roofline denominator for the compute-bound
+ * kernels; MEASURED_PEAKS.json has no FP64 figure). Returns TFLOP/s. */
+PBX_API int pbx_fp64_peak(pbx_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBX_H */

@@ -1,0 +1,94 @@
+"""Builds probayes_b200/csrc/libpbx.so for sm_100a with nvcc (in-tree, so the
+``.so`` travels with a repo snapshot; it is git-ignored).
+
+    python -m probayes_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  Each ``.cu`` is compiled to an object in
+parallel and the objects are linked into one shared library that depends only
+on the (statically linked) CUDA runtime.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+LIB = os.path.join(CSRC, "libpbx.so")
+OBJDIR = os.path.join(CSRC, "_obj")
+
+NVCC_FLAGS = [
+    "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "--expt-relaxed-constexpr",
+    "-I", INCLUDE, "-I", CSRC,
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps():
+    out = [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
+    out += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    out.append(os.path.abspath(__file__))
+    return out
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compiles (if stale) and returns the path of libpbx.so."""
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = _nvcc()
+    hdrs = _deps()
+    jobs = []
+    objs = []
+    for src in sources():
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                  ["-c", src, "-o", obj]
+            jobs.append(cmd)
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return cmd, r
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for cmd, r in ex.map(run, jobs):
+                if verbose or r.returncode:
+                    sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+                if r.returncode:
+                    raise RuntimeError("nvcc failed for " + cmd[-3])
+    if jobs or force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + \
+              ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

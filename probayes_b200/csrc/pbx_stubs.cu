@@ -1,0 +1,31 @@
+// pbx_stubs.cu -- entry points declared in pbx.h whose kernels are not in yet.
+// They fail loudly (no CPU fallback); each is removed as its kernel lands.
+#include "pbx_common.cuh"
+
+#define PBX_STUB(name)                                            \
+  pbx_set_error(name ": kernel not implemented in this build");   \
+  return PBX_ERR_UNSUPPORTED
+
+extern "C" {
+int pbx_mh_normreg_run(pbx_ctx*, const pbx_mh_normreg_params*) { PBX_STUB("pbx_mh_normreg_run"); }
+int pbx_normreg_logjoint(pbx_ctx*, const pbx_mh_normreg_params*, const double*, double*) {
+  PBX_STUB("pbx_normreg_logjoint");
+}
+int pbx_grid_norm_logjoint(pbx_ctx*, const double*, int64_t, const double*, int32_t, const double*,
+                           int32_t, const double*, const double*, double*) {
+  PBX_STUB("pbx_grid_norm_logjoint");
+}
+int pbx_grid_max(pbx_ctx*, const double*, int64_t, double*) { PBX_STUB("pbx_grid_max"); }
+int pbx_grid_sumexp(pbx_ctx*, const double*, int64_t, const double*, double*) {
+  PBX_STUB("pbx_grid_sumexp");
+}
+int pbx_grid_posterior(pbx_ctx*, const double*, int32_t, int32_t, const double*, const double*,
+                       double*, double*, double*) {
+  PBX_STUB("pbx_grid_posterior");
+}
+int pbx_gibbs_mvn_run(pbx_ctx*, const pbx_gibbs_mvn_params*) { PBX_STUB("pbx_gibbs_mvn_run"); }
+int pbx_mvn_logpdf(pbx_ctx*, const double*, int32_t, int64_t, const double*, const double*, double,
+                   int32_t, double*) {
+  PBX_STUB("pbx_mvn_logpdf");
+}
+}

@@ -1,0 +1,271 @@
+"""Device engine: thin Python layer between the host mirror (SP/SD/PD objects) and
+the C ABI of libpbx.  PyTorch is used only for device memory, streams and
+``torch.distributed``; every computation on the path is a libpbx kernel.
+
+All device arrays are fp64 and chain-minor: state ``[D, C]``, samples
+``[R, D, C]``, per-step scalars ``[T, C]``.
+"""
+import ctypes as C
+import math
+import numpy as np
+
+from . import _lib
+from ._lib import (PbxError, MhMvnParams, MhNormregParams, GibbsMvnParams, DevInfo,
+                   ACCEPT_REFERENCE, ACCEPT_LOG, PROP_NORMAL, PROP_UNIFORM, PBX_MAX_DIMS)
+
+LOG_2PI = math.log(2.0 * math.pi)
+
+_ACCEPT = {"reference": ACCEPT_REFERENCE, "log": ACCEPT_LOG}
+_PROP = {"normal": PROP_NORMAL, "uniform": PROP_UNIFORM}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def mvn_value_order(d):
+    """Order in which the reference hands the variables of a scipy multivariate
+    target to scipy (probayes/prob.py:349-358): reversed, and rotated for d > 2."""
+    if d == 1:
+        return [0]
+    order = list(range(d))[::-1]
+    if d > 2:
+        order = order[1:] + [order[0]]
+    return order
+
+
+def mvn_setup(mean, cov, reorder=True):
+    """Host-side constants of the mvn target in natural variable order:
+    whitening matrix (scipy _PSD: U = u * sqrt(1/s) from eigh) with the value
+    permutation folded in, permuted mean, and norm_c = d log 2pi + log_pdet."""
+    mean = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+    cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    d = mean.shape[0]
+    if cov.shape != (d, d):
+        raise ValueError("Means and covariance matrix incommensurate")
+    s, u = np.linalg.eigh(cov)
+    if np.min(s) <= 0:
+        raise ValueError("covariance matrix must be positive definite")
+    U = u * np.sqrt(1.0 / s)
+    norm_c = d * LOG_2PI + float(np.sum(np.log(s)))
+    order = mvn_value_order(d) if reorder else list(range(d))
+    # scipy sees point y with y[j] = x[order[j]]; dev = y - mean; maha = |dev @ U|^2.
+    # In natural order: dev_nat[i] = x[i] - mean_nat[i] with mean_nat[order[j]] = mean[j],
+    # W[order[j], :] = U[j, :].
+    W = np.empty_like(U)
+    mean_nat = np.empty_like(mean)
+    for j, i in enumerate(order):
+        W[i, :] = U[j, :]
+        mean_nat[i] = mean[j]
+    return mean_nat, W, norm_c
+
+
+class Engine:
+    """One libpbx context on one GPU (one per process, as torch.distributed
+    launches them).  Not thread-safe, like the reference's global RNG state."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise PbxError("probayes_b200 needs a CUDA device (no CPU fallback)")
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        _lib.check(self.lib.pbx_ctx_create(self.device_index,
+                                           C.c_void_p(self.stream.cuda_stream), C.byref(h)),
+                   "pbx_ctx_create")
+        self.ctx = h
+        info = DevInfo()
+        _lib.check(self.lib.pbx_device_info(self.device_index, C.byref(info)), "pbx_device_info")
+        self.info = info
+        self._keep = []     # tensors that must outlive the async call
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.pbx_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ utils
+    def sync(self):
+        _lib.check(self.lib.pbx_ctx_sync(self.ctx), "pbx_ctx_sync")
+        self._keep.clear()
+
+    @property
+    def launches(self):
+        return int(self.lib.pbx_ctx_launch_count(self.ctx))
+
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        _lib.check(self.lib.pbx_ctx_last_kernel_ms(self.ctx, C.byref(ms)), "last_kernel_ms")
+        return float(ms.value)
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        _lib.check(self.lib.pbx_fp64_peak(self.ctx, C.byref(v)), "pbx_fp64_peak")
+        return float(v.value)
+
+    def empty(self, *shape, dtype=None):
+        torch = _torch()
+        return torch.empty(*shape, dtype=dtype or torch.float64, device=self.device)
+
+    def zeros(self, *shape, dtype=None):
+        torch = _torch()
+        return torch.zeros(*shape, dtype=dtype or torch.float64, device=self.device)
+
+    def to_device(self, a):
+        """numpy / tensor -> contiguous fp64 device tensor."""
+        torch = _torch()
+        if isinstance(a, torch.Tensor):
+            return a.to(self.device, torch.float64).contiguous()
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+        return torch.from_numpy(a).to(self.device)
+
+    @staticmethod
+    def _ptr(t):
+        return C.c_void_p(0 if t is None else t.data_ptr())
+
+    # ------------------------------------------------------------ K1: mh mvn
+    def _mvn_params(self, D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
+                    prop, prop_scale, prop_chol, mean, cov, reorder):
+        if not 1 <= D <= PBX_MAX_DIMS:
+            raise NotImplementedError(
+                "mh_mvn supports 1..%d dimensions (got %d)" % (PBX_MAX_DIMS, D))
+        p = MhMvnParams()
+        p.n_chains, p.n_dims, p.n_steps, p.thin = C_, D, T, thin
+        p.step0, p.chain0, p.seed = step0, chain0, seed & 0xFFFFFFFFFFFFFFFF
+        p.log_pscale = 1 if log_pscale else 0
+        p.accept_mode = _ACCEPT[accept]
+        p.prop_kind = _PROP[prop]
+        mean_nat, W, norm_c = mvn_setup(mean, cov, reorder)
+        for j in range(D):
+            p.mean[j] = mean_nat[j]
+        for i, v in enumerate(W.ravel()):
+            p.whiten[i] = v
+        p.norm_c = norm_c
+        scale = np.broadcast_to(np.asarray(prop_scale, dtype=np.float64), (D,))
+        for j in range(D):
+            p.prop_scale[j] = scale[j]
+        if prop_chol is not None:
+            L = np.asarray(prop_chol, dtype=np.float64)
+            if L.shape != (D, D):
+                raise ValueError("prop_chol must be [D, D]")
+            p.has_prop_mat = 1
+            for i, v in enumerate(L.ravel()):
+                p.prop_mat[i] = v
+        return p
+
+    def mh_mvn(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
+               log_pscale=False, accept="reference", prop="normal", prop_scale=1.0,
+               prop_chol=None, reorder=True, inj_delta=None, inj_thresh=None,
+               state_lp=None, record=True, per_step=False, stats=True):
+        """Runs ``steps`` MH steps for all chains of ``state`` ([D, C] device fp64,
+        updated in place).  Returns a dict of device tensors:
+        x [R, D, C], prob [R, C] (record), accept [T, C] uint8 + score [T, C]
+        (per_step), accept_count [C] int64, stat_sum/stat_sumsq [D, C] (stats),
+        state_lp [C]."""
+        torch = _torch()
+        D, C_ = state.shape
+        T = int(steps)
+        p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
+                             prop, prop_scale, prop_chol, mean, cov, reorder)
+        out = {}
+        if state_lp is None:
+            if step0 != 0:
+                raise ValueError("state_lp is required when resuming (step0 > 0)")
+            state_lp = self.zeros(C_)
+        R = T // thin
+        if record:
+            out["x"] = self.empty(R, D, C_)
+            out["prob"] = self.empty(R, C_)
+        if per_step:
+            out["accept"] = self.empty(T, C_, dtype=torch.uint8)
+            out["score"] = self.empty(T, C_)
+        out["accept_count"] = self.zeros(C_, dtype=torch.int64)
+        if stats:
+            out["stat_sum"] = self.zeros(D, C_)
+            out["stat_sumsq"] = self.zeros(D, C_)
+        out["state_lp"] = state_lp
+        if inj_delta is not None:
+            if tuple(inj_delta.shape) != (T, D, C_) or tuple(inj_thresh.shape) != (T, C_):
+                raise ValueError("injected streams must be delta[T, D, C], thresh[T, C]")
+        p.state, p.state_lp = state.data_ptr(), state_lp.data_ptr()
+        p.inj_delta = 0 if inj_delta is None else inj_delta.data_ptr()
+        p.inj_thresh = 0 if inj_thresh is None else inj_thresh.data_ptr()
+        p.out_x = out["x"].data_ptr() if record else 0
+        p.out_prob = out["prob"].data_ptr() if record else 0
+        p.out_accept = out["accept"].data_ptr() if per_step else 0
+        p.out_score = out["score"].data_ptr() if per_step else 0
+        p.accept_count = out["accept_count"].data_ptr()
+        p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
+        p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0
+        _lib.check(self.lib.pbx_mh_mvn_run(self.ctx, C.byref(p)), "pbx_mh_mvn_run")
+        self._keep.append((state, state_lp, inj_delta, inj_thresh, out))
+        return out
+
+    def mh_mvn_walk_host(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
+                         log_pscale=False, accept="reference", prop="normal",
+                         prop_scale=1.0, prop_chol=None, reorder=True, state_lp=None,
+                         chunk_steps=1000, out_x=None, out_prob=None):
+        """Whole walk through the host-buffer entry point: ``state`` is a HOST
+        ndarray [D, C] (updated in place); samples are streamed back into pinned
+        host buffers while the next chunk runs.  Returns dict of ndarrays."""
+        torch = _torch()
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        D, C_ = state.shape
+        T = int(steps)
+        R = T // thin
+        p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
+                             prop, prop_scale, prop_chol, mean, cov, reorder)
+        if out_x is None:
+            out_x = torch.empty((R, D, C_), dtype=torch.float64, pin_memory=True)
+        if out_prob is None:
+            out_prob = torch.empty((R, C_), dtype=torch.float64, pin_memory=True)
+        lp = np.zeros(C_) if state_lp is None else np.ascontiguousarray(state_lp, np.float64)
+        acc = np.zeros(C_, dtype=np.int64)
+        ssum = np.zeros((D, C_))
+        ssq = np.zeros((D, C_))
+        p.state, p.state_lp = state.ctypes.data, lp.ctypes.data
+        p.out_x, p.out_prob = out_x.data_ptr(), out_prob.data_ptr()
+        p.accept_count, p.stat_sum, p.stat_sumsq = acc.ctypes.data, ssum.ctypes.data, \
+            ssq.ctypes.data
+        _lib.check(self.lib.pbx_mh_mvn_walk_host(self.ctx, C.byref(p), int(chunk_steps)),
+                   "pbx_mh_mvn_walk_host")
+        return dict(x=out_x.numpy(), prob=out_prob.numpy(), state=state, state_lp=lp,
+                    accept_count=acc, stat_sum=ssum, stat_sumsq=ssq)
+
+    # ------------------------------------------------------- chain summaries
+    def chain_stats(self, stat_sum, stat_sumsq, n_steps):
+        """[D, 4] device tensor (sum_c mean, sum_c mean^2, sum_c var, C)."""
+        D, C_ = stat_sum.shape
+        out = self.empty(D, 4)
+        _lib.check(self.lib.pbx_reduce_chain_stats(self.ctx, self._ptr(stat_sum),
+                                                   self._ptr(stat_sumsq), D, C_, int(n_steps),
+                                                   self._ptr(out)), "pbx_reduce_chain_stats")
+        self._keep.append((stat_sum, stat_sumsq, out))
+        return out
+
+
+_engines = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine for ``device`` (default: the current CUDA device)."""
+    torch = _torch()
+    if device is None:
+        if not torch.cuda.is_available():
+            raise PbxError("probayes_b200 needs a CUDA device (no CPU fallback)")
+        device = torch.cuda.current_device()
+    device = int(device)
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

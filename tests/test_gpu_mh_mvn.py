@@ -1,0 +1,159 @@
+"""K1 parity (GPU, through the C ABI): batched-chain MH on a multivariate-normal
+target against the golden fixtures (live reference) and the numpy oracle.
+Tolerances: accept decisions identical; trajectories / densities within 1e-12
+(north_star, fp64)."""
+import numpy as np
+import pytest
+from conftest import load_golden, relerr
+from gpu_util import engine, dev, tcd_to_tdc, host
+from oracle import np_oracle as o
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+COV = np.array([[2.0, 1.2], [1.2, 2.0]])
+
+
+@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_c1_b", "mh_mvn_log"])
+def test_golden_injected(name):
+    eng = engine()
+    g = load_golden(name)
+    T = len(g["thresh"])
+    state = dev(eng, g["init"][:, None])
+    out = eng.mh_mvn(state, g["mean"], g["cov"], T, log_pscale=bool(g["log_pscale"]),
+                     inj_delta=dev(eng, tcd_to_tdc(g["delta"][:, None, :])),
+                     inj_thresh=dev(eng, g["thresh"][:, None]), per_step=True)
+    eng.sync()
+    assert np.array_equal(host(out["accept"])[:, 0].astype(bool), g["u"])
+    assert np.abs(host(out["x"])[:, :, 0] - g["x"]).max() <= TOL
+    assert relerr(host(out["prob"])[:, 0], g["prob"]) <= TOL
+    s = host(out["score"])[:, 0]
+    assert np.isnan(s[0]) and relerr(s[1:], g["s"][1:]) <= TOL
+    assert int(host(out["accept_count"])[0]) == int(g["u"].sum())
+
+
+@pytest.mark.parametrize("D,C,T,log_pscale,chol", [
+    (2, 257, 300, False, False), (2, 64, 200, True, False), (3, 33, 150, False, True),
+    (5, 100, 120, True, False), (8, 40, 100, False, True), (1, 31, 100, False, False)])
+def test_oracle_injected(D, C, T, log_pscale, chol):
+    eng = engine()
+    rng = np.random.default_rng(100 + D)
+    A = rng.standard_normal((D, D))
+    cov = A @ A.T / D + np.eye(D)
+    mean = rng.standard_normal(D)
+    init = rng.standard_normal((C, D)) * 2
+    delta = rng.standard_normal((T, C, D)) * 0.8
+    thresh = rng.random((T, C))
+    L = None
+    if chol:
+        B = rng.standard_normal((D, D))
+        L = np.linalg.cholesky(B @ B.T / D + 0.5 * np.eye(D))
+    ref = o.mh_mvn_walk(init, delta, thresh, mean, cov, tran_chol=L, log_pscale=log_pscale)
+    state = dev(eng, init.T)
+    out = eng.mh_mvn(state, mean, cov, T, log_pscale=log_pscale, prop_chol=L,
+                     inj_delta=dev(eng, tcd_to_tdc(delta)), inj_thresh=dev(eng, thresh),
+                     per_step=True)
+    eng.sync()
+    assert np.array_equal(host(out["accept"]).astype(bool), ref["u"])
+    assert np.abs(host(out["x"]) - tcd_to_tdc(ref["x"])).max() <= TOL
+    assert relerr(host(out["prob"]), ref["prob"]) <= TOL
+    assert relerr(host(out["score"])[1:], ref["s"][1:]) <= 1e-11
+    assert np.abs(host(state) - ref["x"][-1].T).max() <= TOL
+    assert np.array_equal(host(out["accept_count"]), ref["u"].sum(axis=0))
+    # running sums feed R-hat
+    assert relerr(host(out["stat_sum"]), ref["x"].sum(axis=0).T) <= 1e-11
+
+
+@pytest.mark.parametrize("accept", ["reference", "log"])
+def test_philox_replay(accept):
+    """Native-RNG run == injected-stream restatement fed with the same Philox
+    stream generated on the CPU (oracle/philox.py)."""
+    eng = engine()
+    C, T, seed = 96, 250, 20240607
+    init = np.tile(np.array([0., 1.]), (C, 1))
+    Z = philox.normals(seed, T, C, 2)
+    U = philox.thresholds(seed, T, C)
+    ref = o.mh_mvn_walk(init, Z, U, [0., 0.], COV, log_pscale=(accept == "log"),
+                        accept=accept)
+    state = dev(eng, init.T)
+    out = eng.mh_mvn(state, [0., 0.], COV, T, seed=seed, accept=accept,
+                     log_pscale=(accept == "log"), per_step=True)
+    eng.sync()
+    same = host(out["accept"]).astype(bool) == ref["u"]
+    assert same.all()
+    assert np.abs(host(out["x"]) - tcd_to_tdc(ref["x"])).max() <= 1e-11
+    assert relerr(host(out["prob"]), ref["prob"]) <= 1e-11
+
+
+def test_resume_thin_and_sharding():
+    eng = engine()
+    C, T, seed = 70, 120, 5
+    init = np.random.default_rng(1).standard_normal((2, C))
+    full = eng.mh_mvn(dev(eng, init), [0., 0.], COV, T, seed=seed)
+    eng.sync()
+    X = host(full["x"])
+    # resume: 2 calls of T/2 with step0
+    st = dev(eng, init)
+    a = eng.mh_mvn(st, [0., 0.], COV, T // 2, seed=seed)
+    b = eng.mh_mvn(st, [0., 0.], COV, T // 2, seed=seed, step0=T // 2,
+                   state_lp=a["state_lp"])
+    eng.sync()
+    assert np.array_equal(np.concatenate([host(a["x"]), host(b["x"])]), X)
+    # thinning keeps every 5th recorded state
+    th = eng.mh_mvn(dev(eng, init), [0., 0.], COV, T, seed=seed, thin=5)
+    eng.sync()
+    assert np.array_equal(host(th["x"]), X[4::5])
+    assert np.array_equal(host(th["prob"]), host(full["prob"])[4::5])
+    # sharding: chains 32.. as a separate call with chain0=32
+    lo = eng.mh_mvn(dev(eng, init[:, :32]), [0., 0.], COV, T, seed=seed)
+    hi = eng.mh_mvn(dev(eng, init[:, 32:]), [0., 0.], COV, T, seed=seed, chain0=32)
+    eng.sync()
+    assert np.array_equal(np.concatenate([host(lo["x"]), host(hi["x"])], axis=2), X)
+
+
+def test_walk_host_matches_device():
+    eng = engine()
+    C, T, seed = 130, 230, 9
+    init = np.random.default_rng(2).standard_normal((2, C))
+    d = eng.mh_mvn(dev(eng, init), [0., 0.], COV, T, seed=seed, thin=2)
+    eng.sync()
+    h = eng.mh_mvn_walk_host(init.copy(), [0., 0.], COV, T, seed=seed, thin=2,
+                             chunk_steps=64)
+    assert np.array_equal(h["x"], host(d["x"]))
+    assert np.array_equal(h["prob"], host(d["prob"]))
+    assert np.array_equal(h["accept_count"], host(d["accept_count"]))
+    assert relerr(h["stat_sum"], host(d["stat_sum"])) <= 1e-13
+
+
+def test_philox_posterior_moments():
+    """Native RNG: pooled moments of the 2-D target within Monte Carlo error and
+    R-hat ~ 1 (config C2 at reduced length)."""
+    eng = engine()
+    C, T = 4096, 2000
+    state = dev(eng, np.tile(np.array([[0.], [1.]]), (1, C)))
+    burn = eng.mh_mvn(state, [0., 0.], COV, 500, seed=77, record=False)   # burn-in
+    out = eng.mh_mvn(state, [0., 0.], COV, T, seed=77, step0=500, accept="log",
+                     state_lp=burn["state_lp"], thin=10)
+    eng.sync()
+    X = host(out["x"])                              # [R, 2, C]
+    flat = X.transpose(1, 0, 2).reshape(2, -1)
+    assert np.abs(flat.mean(axis=1)).max() < 0.02
+    assert np.abs(np.cov(flat) - COV).max() < 0.05
+    acc = host(out["accept_count"]).sum() / (C * T)
+    assert 0.55 < acc < 0.68                        # reference run: 0.614
+    st = host(eng.chain_stats(out["stat_sum"], out["stat_sumsq"], T))
+    eng.sync()
+    Cn = st[:, 3]
+    W = st[:, 2] / Cn
+    B = T * (st[:, 1] - st[:, 0] ** 2 / Cn) / (Cn - 1)
+    rhat = np.sqrt(((T - 1) / T * W + B / T) / W)
+    assert np.all(np.abs(rhat - 1) < 0.02)
+
+
+def test_errors_are_loud():
+    from probayes_b200._lib import PbxError
+    eng = engine()
+    with pytest.raises(NotImplementedError):
+        eng.mh_mvn(eng.zeros(9, 4), np.zeros(9), np.eye(9), 10)
+    with pytest.raises(PbxError):
+        eng.mh_mvn(eng.zeros(2, 4), np.zeros(2), np.eye(2), 10, thin=0)
