@@ -47,7 +47,8 @@ def parse():
     ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
     ap.add_argument("--walk-steps", type=int, default=10000, help="MH steps per walk")
     ap.add_argument("--thin", type=int, default=1)
-    ap.add_argument("--accept", default="reference", choices=["reference", "log"])
+    ap.add_argument("--accept", default="log", choices=["reference", "log"])
+    ap.add_argument("--variant", type=int, default=0, help="K1 kernel: 0 auto, 1 per-thread, 2 warp-specialised")
     ap.add_argument("--cpu-sample-steps", type=int, default=0,
                     help="MH steps of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -220,10 +221,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    bufs = {"x": eng.empty(R, D, C), "prob": eng.empty(R, C)}
+
     def walk(seed):
         state.copy_(init_dev)
         return eng.mh_mvn(state, MEAN, COV, T, thin=thin, seed=seed, chain0=chain0,
-                          accept=args.accept)
+                          accept=args.accept, variant=args.variant, out=bufs)
 
     # ---- device-resident timing ------------------------------------------------
     for w in range(args.warmup):
@@ -300,7 +303,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                         "peak_source": which, "kernel": "mh_mvn_kernel<2,false>",
+                         "peak_source": which, "kernel": "mh_mvn_kernel<2>" if args.variant == 1 else "mh_mvn_ws_kernel<2>",
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": out_bytes,
                          "note": "K1 writes (D+1)*8 B per recorded chain-step; it is "

@@ -20,7 +20,6 @@
 #define HUGE_P 1.7976931348623158e+308
 #define LOG_HUGE 709.782712893384
 #define LOG_SQRT_2PI 0.91893853320467274178
-#define SLOT_THRESH 255u
 
 /* probayes/pscales.py:44-65 */
 static inline double log_prob(double p) { return p >= TINY ? log(p) : -HUGE_P; }
@@ -39,9 +38,17 @@ static inline void block(uint64_t seed, uint64_t step, uint32_t chain, uint32_t 
   w[0] = (uint32_t)step; w[1] = (uint32_t)(step >> 32); w[2] = chain; w[3] = slot;
   philox(w, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
-static inline double u01(uint32_t a, uint32_t b) {
-  uint64_t k = ((uint64_t)a << 20) | (uint64_t)(b >> 12);
-  return (double)(2 * k + 1) * 1.1102230246251565e-16;
+/* stream layout of oracle/philox.py: u52 / u32 / t44 */
+static inline double u52(uint32_t w0, uint32_t w1) {
+  uint64_t k = ((uint64_t)w0 << 20) | (uint64_t)(w1 >> 12);
+  return (double)(2 * k + 1) * 1.1102230246251565e-16;          /* 2^-53 */
+}
+static inline double u32(uint32_t w2) {
+  return (double)(2 * (uint64_t)w2 + 1) * 1.1641532182693481e-10; /* 2^-33 */
+}
+static inline double t44(uint32_t w3, uint32_t w1) {
+  uint64_t k = ((uint64_t)w3 << 12) | (uint64_t)(w1 & 0xfffu);
+  return (double)(2 * k + 1) * 2.8421709430404007e-14;           /* 2^-45 */
 }
 static inline void sincospi_(double x, double* s, double* c) {   /* x in (0, 2) */
   double n = rint(2.0 * x);
@@ -55,7 +62,7 @@ static inline void sincospi_(double x, double* s, double* c) {   /* x in (0, 2) 
   }
 }
 static inline void normal_pair(const uint32_t w[4], double* z0, double* z1) {
-  double u1 = u01(w[0], w[1]), u2 = u01(w[2], w[3]);
+  double u1 = u52(w[0], w[1]), u2 = u32(w[2]);
   double r = sqrt(-2.0 * log(u1)), s, c;
   sincospi_(2.0 * u2, &s, &c);
   *z0 = r * c; *z1 = r * s;
@@ -104,15 +111,15 @@ void orc_mh_mvn_walk(int C, int D, int T, const double* init, const double* mean
     for (int k = 0; k < T; ++k) {
       uint64_t gstep = (uint64_t)(step0 + k);
       uint32_t w[4];
+      double t = 0.0;
       for (int s = 0; s < (D + 1) / 2; ++s) {
         double z0, z1;
         block(seed, gstep, gchain, (uint32_t)s, w);
         normal_pair(w, &z0, &z1);
+        if (s == 0) t = t44(w[3], w[1]);
         dl[2 * s] = z0 * scale[2 * s];
         if (2 * s + 1 < D) dl[2 * s + 1] = z1 * scale[2 * s + 1];
       }
-      block(seed, gstep, gchain, SLOT_THRESH, w);
-      double t = u01(w[0], w[1]);
       for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[j];
       double lpp = mvn_logpdf(xp, D, mean, W, norm_c);
       int acc;
@@ -268,7 +275,7 @@ void orc_gibbs_mvn_walk(int C, int d, int T, double* x, const double* mean, cons
       else {
         uint32_t w[4];
         block(seed, (uint64_t)(step0 + k), (uint32_t)(chain0 + c), 0u, w);
-        r = u01(w[0], w[1]);
+        r = u52(w[0], w[1]);
       }
       double u = cdf_lo[i] + (cdf_hi[i] - cdf_lo[i]) * r;
       double cm = mean[i];

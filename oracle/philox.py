@@ -9,12 +9,14 @@ replayed bit-for-bit on the CPU via the injected-stream restatement.
 Stream layout (must match probayes_b200/csrc/pbx_philox.cuh):
   key     = (seed & 0xffffffff, seed >> 32)
   counter = (step & 0xffffffff, step >> 32, chain, slot)
-  slot 0..  : proposal draws, two doubles per slot (dims 2*slot, 2*slot+1)
-  slot 255  : the accept threshold t (first double of the block)
-  u01(a, b) = (2*k + 1) * 2**-53,  k = (a << 20) | (b >> 12)     in (0, 1)
-  normal pair from one block (w0..w3): u1 = u01(w0, w1), u2 = u01(w2, w3),
-      r = sqrt(-2 log u1), z0 = r cospi(2 u2), z1 = r sinpi(2 u2)
-  uniform pair from one block: u01(w0, w1), u01(w2, w3)
+  slot s    : proposal draws for dims 2s, 2s+1 -- one block (w0..w3) per slot:
+      u52 = (2*k + 1) * 2**-53,  k = (w0 << 20) | (w1 >> 12)        in (0, 1)
+      u32 = (2*w2 + 1) * 2**-33                                     in (0, 1)
+      normal pair : r = sqrt(-2 log u52), z0 = r cospi(2 u32), z1 = r sinpi(2 u32)
+      uniform pair: (u52, u32)
+  threshold : the spare bits of slot 0 -- t44 = (2*k + 1) * 2**-45,
+      k = (w3 << 12) | (w1 & 0xfff)       => ONE Philox block per step for D <= 2
+  (all three are exact in fp64 and strictly inside (0, 1))
 """
 import numpy as np
 
@@ -23,7 +25,6 @@ M1 = np.uint64(0xCD9E8D57)
 W0 = 0x9E3779B9
 W1 = 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
-SLOT_THRESH = 255
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -46,10 +47,21 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def u01(a, b):
-    """Two 32-bit words -> double in (0,1), exactly (2k+1)/2**53 with 52-bit k."""
-    k = (a << np.uint64(20)) | (b >> np.uint64(12))
+def u52(w0, w1):
+    """(2k+1)/2**53 with the 52-bit k = (w0 << 20) | (w1 >> 12)."""
+    k = (w0 << np.uint64(20)) | (w1 >> np.uint64(12))
     return (2.0 * k.astype(np.float64) + 1.0) * 2.0 ** -53
+
+
+def u32(w2):
+    """(2 w2 + 1)/2**33."""
+    return (2.0 * w2.astype(np.float64) + 1.0) * 2.0 ** -33
+
+
+def t44(w3, w1):
+    """(2k+1)/2**45 with the 44-bit k = (w3 << 12) | (w1 & 0xfff)."""
+    k = (w3 << np.uint64(12)) | (w1 & np.uint64(0xFFF))
+    return (2.0 * k.astype(np.float64) + 1.0) * 2.0 ** -45
 
 
 def block(seed, step, chain, slot):
@@ -61,7 +73,7 @@ def block(seed, step, chain, slot):
 
 def uniform_pair(seed, step, chain, slot):
     w0, w1, w2, w3 = block(seed, step, chain, slot)
-    return u01(w0, w1), u01(w2, w3)
+    return u52(w0, w1), u32(w2)
 
 
 def normal_pair(seed, step, chain, slot):
@@ -124,5 +136,5 @@ def thresholds(seed, steps, chains, step0=0):
     t = (np.arange(steps, dtype=np.uint64) + np.uint64(step0))[:, None]
     c = np.arange(chains, dtype=np.uint64)[None, :] if np.isscalar(chains) \
         else np.asarray(chains, dtype=np.uint64)[None, :]
-    u0, _ = uniform_pair(seed, t, c, SLOT_THRESH)
-    return u0
+    w0, w1, w2, w3 = block(seed, t, c, 0)
+    return t44(w3, w1)

@@ -32,6 +32,7 @@ class MhMvnParams(C.Structure):
         ("thin", C.c_int32), ("step0", C.c_int64), ("chain0", C.c_int64),
         ("seed", C.c_uint64), ("log_pscale", C.c_int32), ("accept_mode", C.c_int32),
         ("prop_kind", C.c_int32), ("has_prop_mat", C.c_int32),
+        ("kernel_variant", C.c_int32), ("reserved0", C.c_int32),
         ("mean", C.c_double * PBX_MAX_DIMS),
         ("whiten", C.c_double * (PBX_MAX_DIMS * PBX_MAX_DIMS)),
         ("norm_c", C.c_double),

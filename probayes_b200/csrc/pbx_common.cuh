@@ -67,9 +67,9 @@ __device__ __forceinline__ double pbx_exp_logp(double l) {
 // ---------------------------------------------------------------------------
 // Philox4x32-10 counter RNG.  Stream layout documented in oracle/philox.py:
 //   key = (seed lo, seed hi); counter = (step lo, step hi, chain, slot)
+//   slot s -> draws for dims 2s, 2s+1:  u52(w0, w1), u32(w2)
+//   threshold = t44(w3, w1) of slot 0  => one Philox block per step for D <= 2
 // ---------------------------------------------------------------------------
-#define PBX_SLOT_THRESH 255u
-
 struct pbx_u4 { uint32_t x, y, z, w; };
 
 __host__ __device__ __forceinline__ pbx_u4 pbx_philox(uint32_t c0, uint32_t c1, uint32_t c2,
@@ -98,20 +98,80 @@ __host__ __device__ __forceinline__ pbx_u4 pbx_block(uint64_t seed, uint64_t ste
                     (uint32_t)(seed >> 32));
 }
 
-// (a, b) -> (2k+1) * 2^-53 with 52-bit k: exact in fp64, strictly inside (0,1)
-__host__ __device__ __forceinline__ double pbx_u01(uint32_t a, uint32_t b) {
-  uint64_t k = ((uint64_t)a << 20) | (uint64_t)(b >> 12);
-  return (double)(2 * k + 1) * 1.1102230246251565e-16;   // 2^-53
+#ifdef __CUDACC__
+// The three uniforms are built by dropping the random bits into the mantissa of a
+// double in [1, 2) and subtracting (1 - half ulp of the grid): exact, no I2F.
+//   u52 = (2k+1) 2^-53, k = (w0 << 20) | (w1 >> 12)
+__device__ __forceinline__ double pbx_u52(uint32_t w0, uint32_t w1) {
+  double v = __hiloint2double((int)(0x3FF00000u | (w0 >> 12)), (int)((w0 << 20) | (w1 >> 12)));
+  return v - 0.99999999999999988897769753748;       // 1 - 2^-53
+}
+//   u32 = (2 w2 + 1) 2^-33
+__device__ __forceinline__ double pbx_u32(uint32_t w2) {
+  double v = __hiloint2double((int)(0x3FF00000u | (w2 >> 12)), (int)(w2 << 20));
+  return v - 0.99999999988358467817306518555;       // 1 - 2^-33
+}
+//   t44 = (2k+1) 2^-45, k = (w3 << 12) | (w1 & 0xfff)
+__device__ __forceinline__ double pbx_t44(uint32_t w3, uint32_t w1) {
+  double v = __hiloint2double((int)(0x3FF00000u | (w3 >> 12)),
+                              (int)((w3 << 20) | ((w1 & 0xFFFu) << 8)));
+  return v - 0.99999999999997157829056959599;       // 1 - 2^-45
 }
 
-#ifdef __CUDACC__
 // Box-Muller pair from one Philox block
 __device__ __forceinline__ void pbx_normal_pair(pbx_u4 w, double& z0, double& z1) {
-  double u1 = pbx_u01(w.x, w.y), u2 = pbx_u01(w.z, w.w);
+  double u1 = pbx_u52(w.x, w.y), u2 = pbx_u32(w.z);
   double r = sqrt(-2.0 * log(u1));
   double s, c;
   sincospi(2.0 * u2, &s, &c);
   z0 = r * c;
   z1 = r * s;
+}
+
+// ---- mbarrier helpers (shared::cta, generic-proxy producers/consumers) --------
+__device__ __forceinline__ uint32_t pbx_smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void pbx_mbar_init(void* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pbx_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pbx_mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pbx_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pbx_mbar_expect_tx(void* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pbx_smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool pbx_mbar_try_wait(void* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(pbx_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void pbx_mbar_wait(void* bar, uint32_t parity) {
+  while (!pbx_mbar_try_wait(bar, parity)) {
+  }
+}
+// 1-D bulk copy global -> shared (TMA engine, no tensor map), completes on mbarrier
+__device__ __forceinline__ void pbx_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             void* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(pbx_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(pbx_smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void pbx_fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void pbx_fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 #endif

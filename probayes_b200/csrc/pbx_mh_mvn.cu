@@ -6,9 +6,19 @@
 // Layout: state[D][C], outputs [..][D][C] / [..][C] -- chain-minor so a warp of 32
 // chains reads/writes 256 contiguous bytes per dimension.
 //
-// v1 kernel (this file): one thread = one chain, state + running sums in registers,
-// Philox4x32-10 + Box-Muller in-thread (or injected streams for bit-parity runs),
-// accept test and thinned write-back fused.
+// Two kernels, identical arithmetic (bit-identical results for the same seed):
+//  * mh_mvn_kernel     one thread = one chain, state + running sums in registers,
+//                      Philox4x32-10 + Box-Muller in-thread or INJECTED streams (the
+//                      bit-parity path), per-step accept/score outputs.
+//  * mh_mvn_ws_kernel  warp-specialised native-RNG fast path.  A CTA owns 32 chains:
+//                      15 producer warps draw Philox blocks and turn them into
+//                      proposal deltas and log-thresholds for batches of steps (that
+//                      work does not depend on the chain state, so it parallelises
+//                      over steps), hand them through a shared-memory ring guarded
+//                      by mbarriers to ONE consumer warp that runs the inherently
+//                      sequential part (propose, 2-D quadratic form, accept, record)
+//                      for its 32 chains.  This takes a 4096-chain walk from one
+//                      latency-bound warp per SM to ~16 busy warps per SM.
 #include <math.h>
 #include "pbx_common.cuh"
 
@@ -56,6 +66,49 @@ __device__ __forceinline__ double mvn_logpdf(const double (&x)[D], const MhMvnCo
   return -0.5 * (m.norm_c + maha);
 }
 
+// Native draws of one step: proposal deltas (scaled) and the threshold.  Shared by
+// both kernels so their streams are identical (layout: oracle/philox.py).
+template <int D>
+__device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_t gchain,
+                                          int prop_kind, const MhMvnConst& m, double (&dl)[D],
+                                          double& t) {
+#pragma unroll
+  for (int s = 0; s < (D + 1) / 2; ++s) {
+    pbx_u4 w = pbx_block(seed, gstep, gchain, (uint32_t)s);
+    if (s == 0) t = pbx_t44(w.w, w.y);
+    double d0, d1;
+    if (prop_kind == PBX_PROP_NORMAL) {
+      pbx_normal_pair(w, d0, d1);
+      d0 *= m.scale[2 * s];
+      if (2 * s + 1 < D) d1 *= m.scale[2 * s + 1];
+    } else {
+      double r0 = pbx_u52(w.x, w.y), r1 = pbx_u32(w.z);
+      d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * r0;
+      d1 = (2 * s + 1 < D) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * r1 : 0.0;
+    }
+    dl[2 * s] = d0;
+    if (2 * s + 1 < D) dl[2 * s + 1] = d1;
+  }
+}
+
+// delta -> proposal displacement (optional Cholesky colouring: rf.py:346-348)
+template <int D>
+__device__ __forceinline__ void colour_delta(int has_L, const MhMvnConst& m, const double (&dl)[D],
+                                             double (&v)[D]) {
+  if (has_L) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc = fma(m.L[i * D + j], dl[j], acc);
+      v[i] = acc;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) v[j] = dl[j];
+  }
+}
+
 template <int D, bool kInjected>
 __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
                                                      const __grid_constant__ MhMvnConst m) {
@@ -87,39 +140,13 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
       for (int j = 0; j < D; ++j) dl[j] = a.inj_delta[((int64_t)k * D + j) * C + c];
       t = a.inj_thresh[(int64_t)k * C + c];
     } else {
-#pragma unroll
-      for (int s = 0; s < (D + 1) / 2; ++s) {
-        pbx_u4 w = pbx_block(a.seed, (uint64_t)gstep, gchain, (uint32_t)s);
-        double d0, d1;
-        if (a.prop_kind == PBX_PROP_NORMAL) {
-          pbx_normal_pair(w, d0, d1);
-          d0 *= m.scale[2 * s];
-          if (2 * s + 1 < D) d1 *= m.scale[2 * s + 1];
-        } else {
-          double r0 = pbx_u01(w.x, w.y), r1 = pbx_u01(w.z, w.w);
-          d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * r0;
-          d1 = (2 * s + 1 < D) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * r1 : 0.0;
-        }
-        dl[2 * s] = d0;
-        if (2 * s + 1 < D) dl[2 * s + 1] = d1;
-      }
-      pbx_u4 w = pbx_block(a.seed, (uint64_t)gstep, gchain, PBX_SLOT_THRESH);
-      t = pbx_u01(w.x, w.y);
+      draw_step<D>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, dl, t);
     }
     // ---- propose: x' = x + delta  (or + L delta: rf.py:346-348) -------------
-    double xp[D];
-    if (a.has_L) {
+    double xp[D], dv[D];
+    colour_delta<D>(a.has_L, m, dl, dv);
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        double v = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) v = fma(m.L[i * D + j], dl[j], v);
-        xp[i] = x[i] + v;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[j];
-    }
+    for (int j = 0; j < D; ++j) xp[j] = x[j] + dv[j];
     // ---- evaluate target ----------------------------------------------------
     const double lpp = mvn_logpdf<D>(xp, m);
     // ---- score / threshold / update (sp_utils.py:19-37) ---------------------
@@ -180,13 +207,204 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
   if (a.accept_count) a.accept_count[c] += nacc;
 }
 
+// ---------------------------------------------------------------------------
+// Warp-specialised native-RNG kernel.  One CTA = 32 chains (lane = chain).
+//   warp 0       consumer: the sequential chain only (propose, quadratic form,
+//                accept, select, running sums) -- ~30 instructions per step, no
+//                global traffic.  It overwrites the ring slot it just consumed
+//                with the retained states (x, logp) of that batch.
+//   warps 1..15  producer/writers: each owns one ring slot.  Per use: drain the
+//                consumer's results of the slot's previous batch (thinning, exp()
+//                for linear-pscale output, coalesced global stores), then refill
+//                it with Philox + Box-Muller deltas and log-thresholds for the next
+//                batch of G steps.  Both jobs are independent of the chain state
+//                and therefore parallel over steps.
+// One mbarrier pair per slot: in_full (producer -> consumer), out_full (consumer
+// -> owning producer).
+// ---------------------------------------------------------------------------
+#define WS_NPROD 15
+#define WS_THREADS ((WS_NPROD + 1) * 32)
+template <int D> struct WsCfg {
+  // steps per ring slot: G*(D+1) doubles per lane per slot, <= 6 KB per slot
+  static constexpr int G = (D <= 2) ? 8 : (D == 3 ? 6 : (D <= 5 ? 4 : (D <= 7 ? 3 : 2)));
+  static constexpr int SLOT_DOUBLES = G * (D + 1) * 32;
+  static constexpr size_t SMEM = (size_t)WS_NPROD * SLOT_DOUBLES * sizeof(double);
+};
+
+template <int D, bool kRefAccept>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+    mh_mvn_ws_kernel(const MhMvnArgs a, const __grid_constant__ MhMvnConst m) {
+  constexpr int G = WsCfg<D>::G;
+  constexpr int SD = WsCfg<D>::SLOT_DOUBLES;
+  extern __shared__ __align__(16) double ring[];          // [WS_NPROD][G][D+1][32]
+  __shared__ __align__(8) unsigned long long in_full[WS_NPROD], out_full[WS_NPROD];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t C = a.C;
+  const int c = blockIdx.x * 32 + lane;
+  const bool valid = c < a.C;
+  const uint32_t gchain = (uint32_t)(a.chain0 + (valid ? c : 0));
+  const int nb = (a.T + G - 1) / G;                       // batches of G steps
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WS_NPROD; ++i) {
+      pbx_mbar_init(&in_full[i], 1);
+      pbx_mbar_init(&out_full[i], 1);
+    }
+  }
+  __syncthreads();
+
+  if (warp >= 1) {
+    // ================= producer / writer for ring slot p ========================
+    const int p = warp - 1;
+    double* slot = ring + (size_t)p * SD + lane;
+    uint32_t use = 0;
+    for (int b = p;; b += WS_NPROD, ++use) {
+      if (use > 0) {
+        // ---- drain the results of batch (b - WS_NPROD) ------------------------
+        pbx_mbar_wait(&out_full[p], (use - 1) & 1);
+        const int k0 = (b - WS_NPROD) * G;
+        const int ng = min(G, a.T - k0);
+        int rem = (k0 + 1) % a.thin;                      // (k+1) % thin of step k0
+        int64_t rec = (k0 + 1) / a.thin - 1;              // record index if rem == 0
+        for (int g = 0; g < ng; ++g) {
+          if (rem == 0) {
+            if (valid) {
+              if (a.out_x) {
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                  a.out_x[(rec * D + j) * C + c] = slot[(g * (D + 1) + j) * 32];
+              }
+              if (a.out_prob) {
+                const double lpv = slot[(g * (D + 1) + D) * 32];
+                // linear pscale: pdf = exp(logpdf) as scipy does
+                a.out_prob[rec * C + c] = a.log_pscale ? lpv : exp(lpv);
+              }
+            }
+          }
+          if (++rem == a.thin) { rem = 0; ++rec; }
+        }
+      }
+      if (b >= nb) break;
+      // ---- refill with the draws of batch b -----------------------------------
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        const int k = b * G + g;
+        if (k >= a.T) break;
+        const int64_t gstep = a.step0 + k;
+        double dl[D], dv[D], t;
+        draw_step<D>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, dl, t);
+        colour_delta<D>(a.has_L, m, dl, dv);
+#pragma unroll
+        for (int j = 0; j < D; ++j) slot[(g * (D + 1) + j) * 32] = dv[j];
+        // global step 0 accepts unconditionally (sp.py:253): threshold that always passes
+        double th = kRefAccept ? t : log(t);
+        if (gstep == 0) th = kRefAccept ? 0.0 : -INFINITY;
+        slot[(g * (D + 1) + D) * 32] = th;
+      }
+      __syncwarp();
+      if (lane == 0) pbx_mbar_arrive(&in_full[p]);
+    }
+    return;
+  }
+
+  // ======================= consumer: the sequential chain =====================
+  double x[D], ssum[D], ssq[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    x[j] = valid ? a.state[j * C + c] : 0.0;
+    ssum[j] = ssq[j] = 0.0;
+  }
+  double lp = (a.step0 > 0 && valid) ? a.state_lp[c] : 0.0;
+  double lin = 0.0;
+  if (kRefAccept && a.step0 > 0) lin = a.log_pscale ? pbx_exp_logp(lp) : exp(lp);
+  int64_t nacc = 0;
+
+  for (int b = 0; b < nb; ++b) {
+    const int s = b % WS_NPROD;
+    double* slot = ring + (size_t)s * SD + lane;
+    pbx_mbar_wait(&in_full[s], (uint32_t)(b / WS_NPROD) & 1);
+    const int ng = min(G, a.T - b * G);
+    double dl[G][D], th[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) dl[g][j] = slot[(g * (D + 1) + j) * 32];
+      th[g] = slot[(g * (D + 1) + D) * 32];
+    }
+    // every lane only ever touches its own column of the slot, so the results can
+    // overwrite the inputs as soon as they are in registers
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (g < ng) {
+        double xp[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[g][j];
+        const double lpp = mvn_logpdf<D>(xp, m);
+        bool acc;
+        double linp = 0.0;
+        if (kRefAccept) {
+          linp = a.log_pscale ? pbx_exp_logp(lpp) : exp(lpp);
+          acc = fmin(1.0, linp / fmax(PBX_TINY, lin)) >= th[g];
+        } else {
+          acc = (lpp - lp) >= th[g];
+        }
+        if (acc) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) x[j] = xp[j];
+          lp = lpp;
+          lin = linp;
+          ++nacc;
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          ssum[j] += x[j];
+          ssq[j] = fma(x[j], x[j], ssq[j]);
+          slot[(g * (D + 1) + j) * 32] = x[j];
+        }
+        slot[(g * (D + 1) + D) * 32] = lp;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) pbx_mbar_arrive(&out_full[s]);
+  }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      a.state[j * C + c] = x[j];
+      if (a.stat_sum) a.stat_sum[j * C + c] += ssum[j];
+      if (a.stat_sumsq) a.stat_sumsq[j * C + c] += ssq[j];
+    }
+    a.state_lp[c] = lp;
+    if (a.accept_count) a.accept_count[c] += nacc;
+  }
+}
+
 template <int D>
-static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m) {
+static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, int kernel_variant) {
+  const bool injected = a.inj_delta != nullptr;
+  const bool per_step = a.out_accept != nullptr || a.out_score != nullptr;
+  const bool use_ws = !injected && !per_step && kernel_variant != 1;
+  if (use_ws) {
+    const int grid = (a.C + 31) / 32;
+    const size_t smem = WsCfg<D>::SMEM;
+    if (a.accept_mode == PBX_ACCEPT_REFERENCE) {
+      PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mh_mvn_ws_kernel<D, true><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);
+    } else {
+      PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mh_mvn_ws_kernel<D, false><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);
+    }
+    PBX_LAUNCH_CHECK(ctx);
+    return PBX_OK;
+  }
   const int warps = (a.C + 31) / 32;
   // few chains: one warp per CTA so the warps spread over all SMs
   const int block = (warps <= ctx->sm_count * 8) ? 32 : 128;
   const int grid = (a.C + block - 1) / block;
-  if (a.inj_delta)
+  if (injected)
     mh_mvn_kernel<D, true><<<grid, block, 0, ctx->stream>>>(a, m);
   else
     mh_mvn_kernel<D, false><<<grid, block, 0, ctx->stream>>>(a, m);
@@ -240,14 +458,14 @@ static int run_device(pbx_ctx* ctx, const pbx_mh_mvn_params* p) {
   a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
   if (a.T == 0) return PBX_OK;
   switch (p->n_dims) {
-    case 1: return launch_mh_mvn<1>(ctx, a, m);
-    case 2: return launch_mh_mvn<2>(ctx, a, m);
-    case 3: return launch_mh_mvn<3>(ctx, a, m);
-    case 4: return launch_mh_mvn<4>(ctx, a, m);
-    case 5: return launch_mh_mvn<5>(ctx, a, m);
-    case 6: return launch_mh_mvn<6>(ctx, a, m);
-    case 7: return launch_mh_mvn<7>(ctx, a, m);
-    case 8: return launch_mh_mvn<8>(ctx, a, m);
+    case 1: return launch_mh_mvn<1>(ctx, a, m, p->kernel_variant);
+    case 2: return launch_mh_mvn<2>(ctx, a, m, p->kernel_variant);
+    case 3: return launch_mh_mvn<3>(ctx, a, m, p->kernel_variant);
+    case 4: return launch_mh_mvn<4>(ctx, a, m, p->kernel_variant);
+    case 5: return launch_mh_mvn<5>(ctx, a, m, p->kernel_variant);
+    case 6: return launch_mh_mvn<6>(ctx, a, m, p->kernel_variant);
+    case 7: return launch_mh_mvn<7>(ctx, a, m, p->kernel_variant);
+    case 8: return launch_mh_mvn<8>(ctx, a, m, p->kernel_variant);
   }
   pbx_set_error("pbx_mh_mvn_run: unsupported n_dims %d", p->n_dims);
   return PBX_ERR_UNSUPPORTED;

@@ -82,7 +82,9 @@ class Engine:
         info = DevInfo()
         _lib.check(self.lib.pbx_device_info(self.device_index, C.byref(info)), "pbx_device_info")
         self.info = info
-        self._keep = []     # tensors that must outlive the async call
+        # The context runs on torch's current stream, so torch's stream-ordered
+        # caching allocator keeps every tensor handed to a kernel valid until
+        # that kernel has run; no extra keep-alive list is needed.
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -98,7 +100,6 @@ class Engine:
     # ------------------------------------------------------------------ utils
     def sync(self):
         _lib.check(self.lib.pbx_ctx_sync(self.ctx), "pbx_ctx_sync")
-        self._keep.clear()
 
     @property
     def launches(self):
@@ -136,11 +137,16 @@ class Engine:
 
     # ------------------------------------------------------------ K1: mh mvn
     def _mvn_params(self, D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
-                    prop, prop_scale, prop_chol, mean, cov, reorder):
+                    prop, prop_scale, prop_chol, mean, cov, reorder, variant=0):
         if not 1 <= D <= PBX_MAX_DIMS:
             raise NotImplementedError(
                 "mh_mvn supports 1..%d dimensions (got %d)" % (PBX_MAX_DIMS, D))
+        if int(thin) < 1:
+            raise ValueError("thin must be >= 1")
+        if accept not in _ACCEPT or prop not in _PROP:
+            raise ValueError("unknown accept/prop mode: %r / %r" % (accept, prop))
         p = MhMvnParams()
+        p.kernel_variant = int(variant)
         p.n_chains, p.n_dims, p.n_steps, p.thin = C_, D, T, thin
         p.step0, p.chain0, p.seed = step0, chain0, seed & 0xFFFFFFFFFFFFFFFF
         p.log_pscale = 1 if log_pscale else 0
@@ -167,26 +173,32 @@ class Engine:
     def mh_mvn(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
                log_pscale=False, accept="reference", prop="normal", prop_scale=1.0,
                prop_chol=None, reorder=True, inj_delta=None, inj_thresh=None,
-               state_lp=None, record=True, per_step=False, stats=True):
+               state_lp=None, record=True, per_step=False, stats=True, variant=0,
+               out=None):
         """Runs ``steps`` MH steps for all chains of ``state`` ([D, C] device fp64,
         updated in place).  Returns a dict of device tensors:
         x [R, D, C], prob [R, C] (record), accept [T, C] uint8 + score [T, C]
         (per_step), accept_count [C] int64, stat_sum/stat_sumsq [D, C] (stats),
-        state_lp [C]."""
+        state_lp [C].  ``out`` may carry preallocated "x"/"prob" buffers to
+        reuse; ``variant`` 1 forces the one-thread-per-chain kernel."""
         torch = _torch()
         D, C_ = state.shape
         T = int(steps)
         p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
-                             prop, prop_scale, prop_chol, mean, cov, reorder)
-        out = {}
+                             prop, prop_scale, prop_chol, mean, cov, reorder, variant)
+        out = dict(out) if out else {}
         if state_lp is None:
             if step0 != 0:
                 raise ValueError("state_lp is required when resuming (step0 > 0)")
             state_lp = self.zeros(C_)
         R = T // thin
         if record:
-            out["x"] = self.empty(R, D, C_)
-            out["prob"] = self.empty(R, C_)
+            if "x" not in out:
+                out["x"] = self.empty(R, D, C_)
+            if "prob" not in out:
+                out["prob"] = self.empty(R, C_)
+            if tuple(out["x"].shape) != (R, D, C_) or tuple(out["prob"].shape) != (R, C_):
+                raise ValueError("preallocated outputs must be x[R, D, C], prob[R, C]")
         if per_step:
             out["accept"] = self.empty(T, C_, dtype=torch.uint8)
             out["score"] = self.empty(T, C_)
@@ -209,7 +221,6 @@ class Engine:
         p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
         p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0
         _lib.check(self.lib.pbx_mh_mvn_run(self.ctx, C.byref(p)), "pbx_mh_mvn_run")
-        self._keep.append((state, state_lp, inj_delta, inj_thresh, out))
         return out
 
     def mh_mvn_walk_host(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
@@ -251,7 +262,6 @@ class Engine:
         _lib.check(self.lib.pbx_reduce_chain_stats(self.ctx, self._ptr(stat_sum),
                                                    self._ptr(stat_sumsq), D, C_, int(n_steps),
                                                    self._ptr(out)), "pbx_reduce_chain_stats")
-        self._keep.append((stat_sum, stat_sumsq, out))
         return out
 
 

@@ -26,9 +26,10 @@ def test_philox_known_answers():
 
 
 def test_u01_open_interval():
-    lo_, hi_ = philox.u01(np.uint64(0), np.uint64(0)), \
-        philox.u01(np.uint64(0xffffffff), np.uint64(0xffffffff))
-    assert 0.0 < lo_ < 1e-15 and 1.0 - 1e-15 < hi_ < 1.0
+    z, f = np.uint64(0), np.uint64(0xffffffff)
+    for lo_, hi_ in [(philox.u52(z, z), philox.u52(f, f)), (philox.u32(z), philox.u32(f)),
+                     (philox.t44(z, z), philox.t44(f, f))]:
+        assert 0.0 < lo_ < 1e-9 and 1.0 - 1e-9 < hi_ < 1.0
 
 
 def test_c_mh_mvn_matches_numpy(lo):
