@@ -1,0 +1,615 @@
+// pbx_mh_normreg.cu -- K2: streaming normal log-likelihood Metropolis-Hastings.
+//
+// Target (log pscale, iid=True, joint=True):
+//   log p(theta, data) = sum_j boxprior_j(theta_j) + sum_i norm.logpdf(y_i; loc_i, sigma)
+//   loc_i = b0 + b1 x_i (has_slope, theta = (b0, b1, sigma)) or mu (theta = (mu, sigma))
+// following probayes/rf.py:541-581, pd.py:332-370 (iid product = sum over the
+// observation axis), sd.py:154-161 + rf_utils.py:10-22 + rv_utils.py:8-47 (product
+// with the independent box priors, prior first), scipy.stats.norm.logpdf per term,
+// proposals in ufun space (variable.py:693-697) and the accept rule of
+// sp_utils.py:19-64 / pscales.py:219-236.
+//
+// One MH step = ONE kernel launch:
+//   phase A  every CTA accumulates S_c = sum_i (y_i - loc_i)^2 over its slice of the
+//            observations for its chains and writes a partial sum;
+//   phase B  the last CTA to finish (per chain group) reduces the partials in a
+//            fixed order, adds -N(log sqrt(2pi) + log sigma) and the priors, runs
+//            the accept test, records the sample and draws the NEXT proposal.
+// Two phase-A kernels:
+//   tiles  (many chains)  chains live in registers (KC per thread); observation
+//          tiles are staged into shared memory with 1-D TMA bulk copies behind a
+//          3-stage mbarrier pipeline and read back as 128-bit broadcast loads, so
+//          every observation byte is fetched once per CTA and used by 128*KC chains.
+//   stream (<= 8 chains)  one pass over HBM: every thread reads observations with
+//          128-bit coalesced loads, updates all chains' sums, warp-shuffle + block
+//          reduce.  This is the HBM-roofline regime (16 B per observation per step).
+#include <math.h>
+#include <string.h>
+#include "pbx_common.cuh"
+
+#define NR_TILE 2048          // observations per shared-memory tile
+#define NR_STAGES 3
+#define NR_THREADS 128
+#define NR_SMAX 8             // chains per pass of the streaming kernel
+
+struct NrModel {
+  int P, has_slope, accept_mode, prop_kind;
+  double coef;
+  double lims[PBX_MAX_PARAMS][2];
+  int open_end[PBX_MAX_PARAMS][2];
+  int log_ufun[PBX_MAX_PARAMS];
+  double scale[PBX_MAX_PARAMS];
+  double nlhv[PBX_MAX_PARAMS];      // -log(length in ufun space): rv.py:153-166
+};
+
+struct NrArgs {
+  int C;
+  int64_t N;
+  const double* x;
+  const double* y;
+  int n_slices;                // partial sums per chain
+  double* partial;             // [n_slices][C]
+  unsigned int* counters;      // one per chain group, zero between launches
+  const double* theta_in;      // [P][C] parameters to evaluate (the proposal)
+  // ---- phase B (MH) ----
+  int mode;                    // 0 = MH step, 1 = evaluate only (write logjoint to eval_out)
+  double* eval_out;            // [C]
+  double* prop;                // [P][C] next proposal (written by phase B)
+  double* state;               // [P][C]
+  double* state_lp;            // [C]
+  int64_t gstep;               // global index of THIS step
+  int64_t step0;
+  int k;                       // index of this step within the call
+  int T, thin;
+  int64_t chain0;
+  uint64_t seed;
+  const double* inj_delta;     // [T][P][C]
+  const double* inj_thresh;    // [T][C]
+  double* out_x;
+  double* out_prob;
+  uint8_t* out_accept;
+  double* out_score;
+  int64_t* accept_count;
+  double* stat_sum;
+  double* stat_sumsq;
+};
+
+// ----------------------------------------------------------------------------
+// proposal: theta' = ufun^-1(ufun(theta) + delta)  (variable.py:693-697)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void nr_draw_delta(const NrArgs& a, const NrModel& m, int64_t gstep,
+                                              int kk, int c, double (&dl)[PBX_MAX_PARAMS]) {
+  const int64_t C = a.C;
+  if (a.inj_delta) {
+    for (int j = 0; j < m.P; ++j) dl[j] = a.inj_delta[((int64_t)kk * m.P + j) * C + c];
+    return;
+  }
+  const uint32_t gchain = (uint32_t)(a.chain0 + c);
+  for (int s = 0; s < (m.P + 1) / 2; ++s) {
+    pbx_u4 w = pbx_block(a.seed, (uint64_t)gstep, gchain, (uint32_t)s);
+    double d0, d1;
+    if (m.prop_kind == PBX_PROP_NORMAL) {
+      pbx_normal_pair(w, d0, d1);
+      d0 *= m.scale[2 * s];
+      if (2 * s + 1 < m.P) d1 *= m.scale[2 * s + 1];
+    } else {
+      d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * pbx_u52(w.x, w.y);
+      d1 = (2 * s + 1 < m.P) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * pbx_u32(w.z)
+                             : 0.0;
+    }
+    dl[2 * s] = d0;
+    if (2 * s + 1 < m.P) dl[2 * s + 1] = d1;
+  }
+}
+
+__device__ __forceinline__ double nr_threshold(const NrArgs& a, int64_t gstep, int kk, int c) {
+  if (a.inj_thresh) return a.inj_thresh[(int64_t)kk * a.C + c];
+  pbx_u4 w = pbx_block(a.seed, (uint64_t)gstep, (uint32_t)(a.chain0 + c), 0u);
+  return pbx_t44(w.w, w.y);
+}
+
+__device__ __forceinline__ void nr_propose(const NrArgs& a, const NrModel& m, int64_t gstep,
+                                           int kk, int c, const double* th) {
+  double dl[PBX_MAX_PARAMS];
+  nr_draw_delta(a, m, gstep, kk, c, dl);
+  for (int j = 0; j < m.P; ++j) {
+    double v = m.log_ufun[j] ? exp(log(th[j]) + dl[j]) : th[j] + dl[j];
+    a.prop[(int64_t)j * a.C + c] = v;
+  }
+}
+
+// log-joint from the residual sum of squares S (see file header)
+__device__ __forceinline__ double nr_logjoint(const NrArgs& a, const NrModel& m, const double* th,
+                                              double S) {
+  const double sg = th[m.P - 1];
+  const double n = (double)a.N;
+  double ll = -(S / (sg * sg)) * 0.5 - n * (PBX_LOG_SQRT_2PI + log(sg));
+  double prior = 0.0;
+  for (int j = 0; j < m.P; ++j) {
+    const double v = th[j];
+    const bool in_lo = m.open_end[j][0] ? (v > m.lims[j][0]) : (v >= m.lims[j][0]);
+    const bool in_hi = m.open_end[j][1] ? (v < m.lims[j][1]) : (v <= m.lims[j][1]);
+    prior += (in_lo && in_hi) ? m.nlhv[j] : -PBX_HUGE;
+  }
+  return prior + ll;
+}
+
+// phase B for one chain: S is the complete residual sum of squares of the proposal
+__device__ void nr_phase_b(const NrArgs& a, const NrModel& m, int c, double S) {
+  const int64_t C = a.C;
+  double thp[PBX_MAX_PARAMS];
+  for (int j = 0; j < m.P; ++j) thp[j] = a.theta_in[(int64_t)j * C + c];
+  const double lpp = nr_logjoint(a, m, thp, S);
+  if (a.mode == 1) {
+    a.eval_out[c] = lpp;
+    return;
+  }
+  double th[PBX_MAX_PARAMS];
+  for (int j = 0; j < m.P; ++j) th[j] = a.state[(int64_t)j * C + c];
+  double lp = a.state_lp[c];
+  const double t = nr_threshold(a, a.gstep, a.k, c);
+  bool acc;
+  double s = nan("");
+  if (a.gstep == 0) {
+    acc = true;                                            // sp.py:253, sp_utils.py:24-25
+  } else if (m.accept_mode == PBX_ACCEPT_REFERENCE) {
+    // hastings_scores multiplies the linear proposal density into the LOG target
+    // (sp_utils.py:62-64); coef = 1 for metropolis
+    const double num = pbx_exp_logp(lpp * m.coef), den = pbx_exp_logp(lp * m.coef);
+    s = fmin(1.0, num / fmax(PBX_TINY, den));
+    acc = (s >= t);
+  } else {
+    const double d = m.coef * (lpp - lp);
+    acc = (d >= log(t));
+    if (a.out_score) s = fmin(1.0, exp(fmin(d, 0.0)));
+  }
+  if (acc) {
+    for (int j = 0; j < m.P; ++j) {
+      th[j] = thp[j];
+      a.state[(int64_t)j * C + c] = thp[j];
+    }
+    lp = lpp;
+    a.state_lp[c] = lpp;
+    if (a.accept_count) a.accept_count[c] += 1;
+  }
+  for (int j = 0; j < m.P; ++j) {
+    if (a.stat_sum) a.stat_sum[(int64_t)j * C + c] += th[j];
+    if (a.stat_sumsq) a.stat_sumsq[(int64_t)j * C + c] = fma(th[j], th[j], a.stat_sumsq[(int64_t)j * C + c]);
+  }
+  if (a.out_accept) a.out_accept[(int64_t)a.k * C + c] = acc ? 1 : 0;
+  if (a.out_score) a.out_score[(int64_t)a.k * C + c] = s;
+  if ((a.k + 1) % a.thin == 0) {
+    const int64_t r = (a.k + 1) / a.thin - 1;
+    if (a.out_x)
+      for (int j = 0; j < m.P; ++j) a.out_x[(r * m.P + j) * C + c] = th[j];
+    if (a.out_prob) a.out_prob[r * C + c] = lp;
+  }
+  // draw the proposal of the NEXT step (none after the last step of the call)
+  if (a.k + 1 < a.T) nr_propose(a, m, a.gstep + 1, a.k + 1, c, th);
+}
+
+// first proposal of a call, from the current state
+__global__ void __launch_bounds__(256) nr_init_kernel(const NrArgs a, const __grid_constant__ NrModel m) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  double th[PBX_MAX_PARAMS];
+  for (int j = 0; j < m.P; ++j) th[j] = a.state[(int64_t)j * a.C + c];
+  nr_propose(a, m, a.step0, 0, c, th);
+}
+
+// "last CTA of the group" election; returns true in the CTA that arrives last
+__device__ __forceinline__ bool nr_arrive_last(unsigned int* counter, unsigned int expected) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(counter, 1u);
+    s_last = (old == expected - 1);
+    if (s_last) *counter = 0;                              // ready for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// ----------------------------------------------------------------------------
+// phase A, "tiles": chains in registers, observation tiles via TMA bulk copies
+// grid = (n_slices, n_groups); group = NR_THREADS*KC chains
+// ----------------------------------------------------------------------------
+template <int KC, bool kSlope>
+__global__ void __launch_bounds__(NR_THREADS)
+    nr_tiles_kernel(const NrArgs a, const __grid_constant__ NrModel m, int use_tma) {
+  extern __shared__ __align__(128) double sm[];            // [NR_STAGES][2][NR_TILE]
+  __shared__ __align__(8) unsigned long long full_bar[NR_STAGES];
+  const int slice = blockIdx.x, group = blockIdx.y;
+  const int64_t C = a.C;
+  const int cbase = group * (NR_THREADS * KC) + threadIdx.x;
+
+  double b0[KC], b1[KC], acc[KC];
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = cbase + k * NR_THREADS;
+    const bool v = c < a.C;
+    b0[k] = v ? a.theta_in[c] : 0.0;
+    b1[k] = (v && kSlope) ? a.theta_in[C + c] : 0.0;
+    acc[k] = 0.0;
+  }
+
+  // this CTA's range of full tiles
+  const int64_t n_full = a.N / NR_TILE;
+  const int64_t per = (n_full + a.n_slices - 1) / a.n_slices;
+  const int64_t t_begin = (int64_t)slice * per;
+  const int64_t t_end = (t_begin + per < n_full) ? t_begin + per : n_full;
+  const int64_t nt = t_end > t_begin ? t_end - t_begin : 0;
+  constexpr uint32_t kTileBytes = NR_TILE * sizeof(double);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NR_STAGES; ++s) pbx_mbar_init(&full_bar[s], 1);
+    pbx_fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int64_t t) {                            // thread 0 only
+    const int s = (int)(t % NR_STAGES);
+    double* dx = sm + (size_t)s * 2 * NR_TILE;
+    double* dy = dx + NR_TILE;
+    const int64_t o = (t_begin + t) * NR_TILE;
+    pbx_mbar_expect_tx(&full_bar[s], kSlope ? 2 * kTileBytes : kTileBytes);
+    if (kSlope) pbx_bulk_g2s(dx, a.x + o, kTileBytes, &full_bar[s]);
+    pbx_bulk_g2s(dy, a.y + o, kTileBytes, &full_bar[s]);
+  };
+  auto tile_math = [&](const double* sx, const double* sy, int cnt) {
+#pragma unroll 2
+    for (int i = 0; i < cnt; i += 2) {
+      const double2 yv = *reinterpret_cast<const double2*>(sy + i);
+      double2 xv = make_double2(0.0, 0.0);
+      if (kSlope) xv = *reinterpret_cast<const double2*>(sx + i);
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const double r0 = yv.x - (kSlope ? fma(b1[k], xv.x, b0[k]) : b0[k]);
+        const double r1 = yv.y - (kSlope ? fma(b1[k], xv.y, b0[k]) : b0[k]);
+        acc[k] = fma(r0, r0, acc[k]);
+        acc[k] = fma(r1, r1, acc[k]);
+      }
+    }
+  };
+
+  if (use_tma) {
+    if (threadIdx.x == 0)
+      for (int64_t t = 0; t < nt && t < NR_STAGES; ++t) issue(t);
+    for (int64_t t = 0; t < nt; ++t) {
+      const int s = (int)(t % NR_STAGES);
+      pbx_mbar_wait(&full_bar[s], (uint32_t)(t / NR_STAGES) & 1);
+      const double* sx = sm + (size_t)s * 2 * NR_TILE;
+      tile_math(sx, sx + NR_TILE, NR_TILE);
+      __syncthreads();                                     // everyone is done with stage s
+      if (threadIdx.x == 0 && t + NR_STAGES < nt) issue(t + NR_STAGES);
+    }
+  } else {
+    // unaligned base pointers: cooperative copy instead of bulk copies
+    for (int64_t t = 0; t < nt; ++t) {
+      const int64_t o = (t_begin + t) * NR_TILE;
+      for (int i = threadIdx.x; i < NR_TILE; i += NR_THREADS) {
+        if (kSlope) sm[i] = a.x[o + i];
+        sm[NR_TILE + i] = a.y[o + i];
+      }
+      __syncthreads();
+      tile_math(sm, sm + NR_TILE, NR_TILE);
+      __syncthreads();
+    }
+  }
+  // ragged tail (< NR_TILE observations): handled by the last slice
+  if (slice == a.n_slices - 1) {
+    const int64_t o = n_full * NR_TILE;
+    const int rem = (int)(a.N - o);
+    if (rem > 0) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < NR_TILE; i += NR_THREADS) {
+        // pad with (x = 0, y = b0-independent) handled by counting: zero-pad and fix below
+        sm[i] = (kSlope && i < rem) ? a.x[o + i] : 0.0;
+        sm[NR_TILE + i] = (i < rem) ? a.y[o + i] : 0.0;
+      }
+      __syncthreads();
+      const int even = rem & ~1;
+      tile_math(sm, sm + NR_TILE, even);
+      if (rem & 1) {
+        const double yv = sm[NR_TILE + even], xv = sm[even];
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const double r0 = yv - (kSlope ? fma(b1[k], xv, b0[k]) : b0[k]);
+          acc[k] = fma(r0, r0, acc[k]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < KC; ++k) {
+    const int c = cbase + k * NR_THREADS;
+    if (c < a.C) a.partial[(int64_t)slice * C + c] = acc[k];
+  }
+  if (!nr_arrive_last(&a.counters[group], (unsigned int)a.n_slices)) return;
+  // ---- phase B: this CTA is the last of its chain group ----------------------
+#pragma unroll 1
+  for (int k = 0; k < KC; ++k) {
+    const int c = cbase + k * NR_THREADS;
+    if (c >= a.C) continue;
+    double S = 0.0;
+    for (int s = 0; s < a.n_slices; ++s) S += __ldcg(&a.partial[(int64_t)s * C + c]);
+    nr_phase_b(a, m, c, S);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// phase A, "stream": <= NR_SMAX chains, one coalesced 128-bit pass over HBM
+// grid = n_slices CTAs of 256 threads, grid-stride over pairs of observations
+// ----------------------------------------------------------------------------
+template <int KS, bool kSlope>
+__global__ void __launch_bounds__(256)
+    nr_stream_kernel(const NrArgs a, const __grid_constant__ NrModel m) {
+  __shared__ double s_b0[KS], s_b1[KS];
+  __shared__ double s_red[8][KS];
+  if (threadIdx.x < KS) {
+    const int c = threadIdx.x;
+    s_b0[c] = (c < a.C) ? a.theta_in[c] : 0.0;
+    s_b1[c] = (c < a.C && kSlope) ? a.theta_in[(int64_t)a.C + c] : 0.0;
+  }
+  __syncthreads();
+  double b0[KS], b1[KS], acc[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) { b0[k] = s_b0[k]; b1[k] = s_b1[k]; acc[k] = 0.0; }
+
+  const int64_t npair = a.N / 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const double2* __restrict__ y2 = reinterpret_cast<const double2*>(a.y);
+  const double2* __restrict__ x2 = reinterpret_cast<const double2*>(a.x);
+#pragma unroll 4
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
+    const double2 yv = __ldcs(y2 + i);                     // streaming: evict-first
+    double2 xv = make_double2(0.0, 0.0);
+    if (kSlope) xv = __ldcs(x2 + i);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const double r0 = yv.x - (kSlope ? fma(b1[k], xv.x, b0[k]) : b0[k]);
+      const double r1 = yv.y - (kSlope ? fma(b1[k], xv.y, b0[k]) : b0[k]);
+      acc[k] = fma(r0, r0, acc[k]);
+      acc[k] = fma(r1, r1, acc[k]);
+    }
+  }
+  if ((a.N & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail
+    const double yv = a.y[a.N - 1], xv = kSlope ? a.x[a.N - 1] : 0.0;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const double r0 = yv - (kSlope ? fma(b1[k], xv, b0[k]) : b0[k]);
+      acc[k] = fma(r0, r0, acc[k]);
+    }
+  }
+  // warp-shuffle reduction, then across the 8 warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KS; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < KS && threadIdx.x < a.C) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+    a.partial[(int64_t)blockIdx.x * a.C + threadIdx.x] = v;
+  }
+  if (!nr_arrive_last(&a.counters[0], gridDim.x)) return;
+  if (threadIdx.x < a.C && threadIdx.x < KS) {
+    const int c = threadIdx.x;
+    double S = 0.0;
+    for (int s = 0; s < (int)gridDim.x; ++s) S += __ldcg(&a.partial[(int64_t)s * a.C + c]);
+    nr_phase_b(a, m, c, S);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+struct NrPlan {
+  int variant;       // 1 tiles, 2 stream
+  int kc;            // chains per thread (tiles)
+  int n_groups, n_slices;
+  int use_tma;
+  size_t smem;
+};
+
+static NrPlan nr_plan(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
+  NrPlan pl;
+  const int C = p->n_chains;
+  int variant = p->variant;
+  if (variant == 0) variant = (C <= NR_SMAX) ? 2 : 1;
+  if (variant == 2 && C > NR_SMAX) variant = 1;
+  const bool aligned = (((uintptr_t)p->y_obs) % 16 == 0) &&
+                       (!p->has_slope || ((uintptr_t)p->x_obs) % 16 == 0);
+  if (variant == 2 && !aligned) variant = 1;               // 128-bit loads need alignment
+  pl.variant = variant;
+  pl.use_tma = aligned ? 1 : 0;
+  pl.smem = 0;
+  if (variant == 1) {
+    pl.kc = (C >= 4 * NR_THREADS * 8) ? 4 : ((C >= 2 * NR_THREADS * 8) ? 2 : 1);
+    pl.n_groups = (C + NR_THREADS * pl.kc - 1) / (NR_THREADS * pl.kc);
+    pl.smem = (size_t)NR_STAGES * 2 * NR_TILE * sizeof(double);     // 96 KB -> 2 CTAs / SM
+    const int64_t n_full = p->n_obs / NR_TILE;
+    const int concurrent = ctx->sm_count * 2;
+    int64_t slices = (2 * (int64_t)concurrent) / pl.n_groups;       // ~2 full waves
+    if (slices > n_full) slices = n_full;
+    if (slices < 1) slices = 1;
+    pl.n_slices = (int)slices;
+  } else {
+    pl.kc = 0;
+    pl.n_groups = 1;
+    int64_t want = (p->n_obs / 2 + 255) / 256;
+    int64_t cap = (int64_t)ctx->sm_count * 8;
+    pl.n_slices = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  }
+  return pl;
+}
+
+static int nr_validate(const pbx_mh_normreg_params* p, const char* who, bool need_state) {
+  PBX_REQUIRE(p != nullptr, "%s: null params", who);
+  PBX_REQUIRE(p->n_chains >= 1, "%s: n_chains must be >= 1", who);
+  PBX_REQUIRE(p->n_params == 2 || p->n_params == 3, "%s: n_params must be 2 or 3", who);
+  PBX_REQUIRE((p->has_slope != 0) == (p->n_params == 3),
+              "%s: has_slope needs 3 params (b0, b1, sigma), otherwise 2 (mu, sigma)", who);
+  PBX_REQUIRE(p->n_obs >= 1, "%s: n_obs must be >= 1", who);
+  PBX_REQUIRE(p->y_obs != nullptr && (!p->has_slope || p->x_obs != nullptr),
+              "%s: observation arrays missing", who);
+  PBX_REQUIRE(p->accept_mode == PBX_ACCEPT_REFERENCE || p->accept_mode == PBX_ACCEPT_LOG,
+              "%s: unknown accept_mode", who);
+  PBX_REQUIRE(p->prop_kind == PBX_PROP_NORMAL || p->prop_kind == PBX_PROP_UNIFORM,
+              "%s: unknown prop_kind", who);
+  for (int j = 0; j < p->n_params; ++j) {
+    PBX_REQUIRE(p->lims[j][1] > p->lims[j][0], "%s: empty prior box for parameter %d", who, j);
+    PBX_REQUIRE(!p->log_ufun[j] || p->lims[j][0] > 0.0,
+                "%s: log ufun needs positive limits (parameter %d)", who, j);
+  }
+  if (need_state) {
+    PBX_REQUIRE(p->n_steps >= 0 && p->thin >= 1, "%s: n_steps >= 0 and thin >= 1 required", who);
+    PBX_REQUIRE(p->step0 >= 0 && p->chain0 >= 0, "%s: step0/chain0 must be >= 0", who);
+    PBX_REQUIRE(p->state && p->state_lp, "%s: state/state_lp are mandatory", who);
+    PBX_REQUIRE((p->inj_delta == nullptr) == (p->inj_thresh == nullptr),
+                "%s: inj_delta and inj_thresh must be given together", who);
+  }
+  return PBX_OK;
+}
+
+static void nr_fill_model(const pbx_mh_normreg_params* p, NrModel& m) {
+  m.P = p->n_params;
+  m.has_slope = p->has_slope;
+  m.accept_mode = p->accept_mode;
+  m.prop_kind = p->prop_kind;
+  m.coef = p->accept_coef;
+  for (int j = 0; j < PBX_MAX_PARAMS; ++j) {
+    m.lims[j][0] = p->lims[j][0];
+    m.lims[j][1] = p->lims[j][1];
+    m.open_end[j][0] = p->open_end[j][0];
+    m.open_end[j][1] = p->open_end[j][1];
+    m.log_ufun[j] = p->log_ufun[j];
+    m.scale[j] = p->prop_scale[j];
+    double len = 1.0;
+    if (j < p->n_params)
+      len = p->log_ufun[j] ? log(p->lims[j][1]) - log(p->lims[j][0]) : p->lims[j][1] - p->lims[j][0];
+    m.nlhv[j] = -log(len);
+  }
+}
+
+template <int KC>
+static int nr_launch_tiles(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const NrModel& m) {
+  dim3 grid(pl.n_slices, pl.n_groups);
+  if (m.has_slope) {
+    PBX_CUDA(cudaFuncSetAttribute(nr_tiles_kernel<KC, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    nr_tiles_kernel<KC, true><<<grid, NR_THREADS, pl.smem, ctx->stream>>>(a, m, pl.use_tma);
+  } else {
+    PBX_CUDA(cudaFuncSetAttribute(nr_tiles_kernel<KC, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    nr_tiles_kernel<KC, false><<<grid, NR_THREADS, pl.smem, ctx->stream>>>(a, m, pl.use_tma);
+  }
+  PBX_LAUNCH_CHECK(ctx);
+  return PBX_OK;
+}
+
+static int nr_launch_step(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const NrModel& m) {
+  if (pl.variant == 1) {
+    switch (pl.kc) {
+      case 4: return nr_launch_tiles<4>(ctx, pl, a, m);
+      case 2: return nr_launch_tiles<2>(ctx, pl, a, m);
+      default: return nr_launch_tiles<1>(ctx, pl, a, m);
+    }
+  }
+  if (m.has_slope)
+    nr_stream_kernel<NR_SMAX, true><<<pl.n_slices, 256, 0, ctx->stream>>>(a, m);
+  else
+    nr_stream_kernel<NR_SMAX, false><<<pl.n_slices, 256, 0, ctx->stream>>>(a, m);
+  PBX_LAUNCH_CHECK(ctx);
+  return PBX_OK;
+}
+
+// workspace: partial [n_slices][C] | counters [n_groups] | prop [P][C]
+static int nr_workspace(pbx_ctx* ctx, const NrPlan& pl, int C, int P, double** partial,
+                        unsigned int** counters, double** prop) {
+  size_t off = 0;
+  auto take = [&](size_t b) { size_t o = off; off += (b + 255) / 256 * 256; return o; };
+  const size_t o_part = take((size_t)pl.n_slices * C * 8);
+  const size_t o_cnt = take((size_t)pl.n_groups * 4);
+  const size_t o_prop = take((size_t)P * C * 8);
+  int rc = pbx_ws_reserve(ctx, off);
+  if (rc) return rc;
+  char* ws = (char*)ctx->ws;
+  *partial = (double*)(ws + o_part);
+  *counters = (unsigned int*)(ws + o_cnt);
+  *prop = (double*)(ws + o_prop);
+  PBX_CUDA(cudaMemsetAsync(*counters, 0, (size_t)pl.n_groups * 4, ctx->stream));
+  return PBX_OK;
+}
+
+extern "C" int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
+  PBX_REQUIRE(ctx != nullptr, "pbx_mh_normreg_run: null ctx");
+  int rc = nr_validate(p, "pbx_mh_normreg_run", true);
+  if (rc) return rc;
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  NrModel m;
+  nr_fill_model(p, m);
+  const NrPlan pl = nr_plan(ctx, p);
+  NrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = p->n_chains; a.N = p->n_obs; a.x = p->x_obs; a.y = p->y_obs;
+  a.n_slices = pl.n_slices;
+  rc = nr_workspace(ctx, pl, a.C, m.P, &a.partial, &a.counters, &a.prop);
+  if (rc) return rc;
+  a.theta_in = a.prop;
+  a.mode = 0;
+  a.state = p->state; a.state_lp = p->state_lp;
+  a.step0 = p->step0; a.T = p->n_steps; a.thin = p->thin;
+  a.chain0 = p->chain0; a.seed = p->seed;
+  a.inj_delta = p->inj_delta; a.inj_thresh = p->inj_thresh;
+  a.out_x = p->out_x; a.out_prob = p->out_prob;
+  a.out_accept = p->out_accept; a.out_score = p->out_score;
+  a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
+  PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (a.T > 0) {
+    nr_init_kernel<<<(a.C + 255) / 256, 256, 0, ctx->stream>>>(a, m);
+    PBX_LAUNCH_CHECK(ctx);
+    for (int k = 0; k < a.T; ++k) {
+      a.k = k;
+      a.gstep = p->step0 + k;
+      rc = nr_launch_step(ctx, pl, a, m);
+      if (rc) return rc;
+    }
+  }
+  PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  return PBX_OK;
+}
+
+extern "C" int pbx_normreg_logjoint(pbx_ctx* ctx, const pbx_mh_normreg_params* p,
+                                    const double* theta, double* out) {
+  PBX_REQUIRE(ctx != nullptr && theta != nullptr && out != nullptr,
+              "pbx_normreg_logjoint: null argument");
+  int rc = nr_validate(p, "pbx_normreg_logjoint", false);
+  if (rc) return rc;
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  NrModel m;
+  nr_fill_model(p, m);
+  const NrPlan pl = nr_plan(ctx, p);
+  NrArgs a;
+  memset(&a, 0, sizeof(a));
+  a.C = p->n_chains; a.N = p->n_obs; a.x = p->x_obs; a.y = p->y_obs;
+  a.n_slices = pl.n_slices;
+  rc = nr_workspace(ctx, pl, a.C, m.P, &a.partial, &a.counters, &a.prop);
+  if (rc) return rc;
+  a.theta_in = theta;
+  a.mode = 1;
+  a.eval_out = out;
+  a.T = 1; a.thin = 1;
+  PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  rc = nr_launch_step(ctx, pl, a, m);
+  if (rc) return rc;
+  PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  return PBX_OK;
+}

@@ -7,10 +7,6 @@
   return PBX_ERR_UNSUPPORTED
 
 extern "C" {
-int pbx_mh_normreg_run(pbx_ctx*, const pbx_mh_normreg_params*) { PBX_STUB("pbx_mh_normreg_run"); }
-int pbx_normreg_logjoint(pbx_ctx*, const pbx_mh_normreg_params*, const double*, double*) {
-  PBX_STUB("pbx_normreg_logjoint");
-}
 int pbx_grid_norm_logjoint(pbx_ctx*, const double*, int64_t, const double*, int32_t, const double*,
                            int32_t, const double*, const double*, double*) {
   PBX_STUB("pbx_grid_norm_logjoint");

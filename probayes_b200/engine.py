@@ -254,6 +254,96 @@ class Engine:
         return dict(x=out_x.numpy(), prob=out_prob.numpy(), state=state, state_lp=lp,
                     accept_count=acc, stat_sum=ssum, stat_sumsq=ssq)
 
+    # ------------------------------------------------- K2: streaming normal MH
+    def _normreg_params(self, C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
+                        accept="log", accept_coef=1.0, prop="uniform", variant=0):
+        if P not in (2, 3):
+            raise NotImplementedError("normal-likelihood MH supports (mu, sigma) or "
+                                      "(b0, b1, sigma) parameters, got %d" % P)
+        if accept not in _ACCEPT or prop not in _PROP:
+            raise ValueError("unknown accept/prop mode: %r / %r" % (accept, prop))
+        has_slope = P == 3
+        if has_slope and x_obs is None:
+            raise ValueError("x_obs is required for the regression likelihood")
+        p = MhNormregParams()
+        p.n_chains, p.n_params = C_, P
+        p.has_slope = 1 if has_slope else 0
+        p.accept_mode, p.accept_coef = _ACCEPT[accept], float(accept_coef)
+        p.prop_kind, p.variant = _PROP[prop], int(variant)
+        p.n_obs = int(y_obs.numel())
+        if has_slope and int(x_obs.numel()) != p.n_obs:
+            raise ValueError("x_obs and y_obs differ in length")
+        p.x_obs = x_obs.data_ptr() if has_slope else 0
+        p.y_obs = y_obs.data_ptr()
+        lims = np.asarray(lims, dtype=np.float64).reshape(P, 2)
+        open_end = np.asarray(open_end).reshape(P, 2)
+        log_ufun = np.asarray(log_ufun).reshape(P)
+        scale = np.broadcast_to(np.asarray(prop_scale, dtype=np.float64), (P,))
+        for j in range(P):
+            p.lims[j][0], p.lims[j][1] = lims[j]
+            p.open_end[j][0], p.open_end[j][1] = int(open_end[j][0]), int(open_end[j][1])
+            p.log_ufun[j] = int(log_ufun[j])
+            p.prop_scale[j] = scale[j]
+        return p
+
+    def mh_normreg(self, state, y_obs, x_obs, steps, lims, open_end, log_ufun, prop_scale,
+                   thin=1, seed=0, step0=0, chain0=0, accept="log", accept_coef=1.0,
+                   prop="uniform", variant=0, inj_delta=None, inj_thresh=None, state_lp=None,
+                   record=True, per_step=False, stats=True):
+        """MH on the iid-normal posterior; ``state`` [P, C] device fp64 (in place),
+        ``y_obs``/``x_obs`` device fp64 [N].  Same outputs as :meth:`mh_mvn`; the
+        recorded ``prob`` is the log-joint (log pscale)."""
+        torch = _torch()
+        P, C_ = state.shape
+        T = int(steps)
+        if int(thin) < 1:
+            raise ValueError("thin must be >= 1")
+        p = self._normreg_params(C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
+                                 accept, accept_coef, prop, variant)
+        p.n_steps, p.thin, p.step0, p.chain0 = T, thin, step0, chain0
+        p.seed = seed & 0xFFFFFFFFFFFFFFFF
+        if state_lp is None:
+            if step0 != 0:
+                raise ValueError("state_lp is required when resuming (step0 > 0)")
+            state_lp = self.zeros(C_)
+        out = {"state_lp": state_lp}
+        R = T // thin
+        if record:
+            out["x"] = self.empty(R, P, C_)
+            out["prob"] = self.empty(R, C_)
+        if per_step:
+            out["accept"] = self.empty(T, C_, dtype=torch.uint8)
+            out["score"] = self.empty(T, C_)
+        out["accept_count"] = self.zeros(C_, dtype=torch.int64)
+        if stats:
+            out["stat_sum"] = self.zeros(P, C_)
+            out["stat_sumsq"] = self.zeros(P, C_)
+        if inj_delta is not None:
+            if tuple(inj_delta.shape) != (T, P, C_) or tuple(inj_thresh.shape) != (T, C_):
+                raise ValueError("injected streams must be delta[T, P, C], thresh[T, C]")
+        p.state, p.state_lp = state.data_ptr(), state_lp.data_ptr()
+        p.inj_delta = 0 if inj_delta is None else inj_delta.data_ptr()
+        p.inj_thresh = 0 if inj_thresh is None else inj_thresh.data_ptr()
+        p.out_x = out["x"].data_ptr() if record else 0
+        p.out_prob = out["prob"].data_ptr() if record else 0
+        p.out_accept = out["accept"].data_ptr() if per_step else 0
+        p.out_score = out["score"].data_ptr() if per_step else 0
+        p.accept_count = out["accept_count"].data_ptr()
+        p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
+        p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0
+        _lib.check(self.lib.pbx_mh_normreg_run(self.ctx, C.byref(p)), "pbx_mh_normreg_run")
+        return out
+
+    def normreg_logjoint(self, theta, y_obs, x_obs, lims, open_end, log_ufun, variant=0):
+        """log-joint (likelihood + box priors) of theta [P, C] -> [C] device."""
+        P, C_ = theta.shape
+        p = self._normreg_params(C_, P, x_obs, y_obs, lims, open_end, log_ufun, 0.0,
+                                 variant=variant)
+        out = self.empty(C_)
+        _lib.check(self.lib.pbx_normreg_logjoint(self.ctx, C.byref(p), self._ptr(theta),
+                                                 self._ptr(out)), "pbx_normreg_logjoint")
+        return out
+
     # ------------------------------------------------------- chain summaries
     def chain_stats(self, stat_sum, stat_sumsq, n_steps):
         """[D, 4] device tensor (sum_c mean, sum_c mean^2, sum_c var, C)."""
