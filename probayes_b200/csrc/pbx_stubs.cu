@@ -7,18 +7,6 @@
   return PBX_ERR_UNSUPPORTED
 
 extern "C" {
-int pbx_grid_norm_logjoint(pbx_ctx*, const double*, int64_t, const double*, int32_t, const double*,
-                           int32_t, const double*, const double*, double*) {
-  PBX_STUB("pbx_grid_norm_logjoint");
-}
-int pbx_grid_max(pbx_ctx*, const double*, int64_t, double*) { PBX_STUB("pbx_grid_max"); }
-int pbx_grid_sumexp(pbx_ctx*, const double*, int64_t, const double*, double*) {
-  PBX_STUB("pbx_grid_sumexp");
-}
-int pbx_grid_posterior(pbx_ctx*, const double*, int32_t, int32_t, const double*, const double*,
-                       double*, double*, double*) {
-  PBX_STUB("pbx_grid_posterior");
-}
 int pbx_gibbs_mvn_run(pbx_ctx*, const pbx_gibbs_mvn_params*) { PBX_STUB("pbx_gibbs_mvn_run"); }
 int pbx_mvn_logpdf(pbx_ctx*, const double*, int32_t, int64_t, const double*, const double*, double,
                    int32_t, double*) {

@@ -344,6 +344,76 @@ class Engine:
                                                  self._ptr(out)), "pbx_normreg_logjoint")
         return out
 
+    # ------------------------------------------------------ K3/K4: grid (DGEI)
+    def grid_norm_logjoint(self, x_obs, mu, sigma, logprior_mu, logprior_sigma, out=None):
+        """log-joint [M, S] = priors + sum_i norm.logpdf(x_i; mu_m, sigma_s); all
+        arguments device fp64 vectors."""
+        M, S = int(mu.numel()), int(sigma.numel())
+        if out is None:
+            out = self.empty(M, S)
+        row_cap = 65535
+        for m0 in range(0, M, row_cap):                     # slab very tall grids
+            m1 = min(M, m0 + row_cap)
+            _lib.check(self.lib.pbx_grid_norm_logjoint(
+                self.ctx, self._ptr(x_obs), int(x_obs.numel()), self._ptr(mu[m0:m1]), m1 - m0,
+                self._ptr(sigma), S, self._ptr(logprior_mu[m0:m1]), self._ptr(logprior_sigma),
+                self._ptr(out[m0:m1])), "pbx_grid_norm_logjoint")
+        return out
+
+    def grid_max(self, lj):
+        out = self.empty(1)
+        _lib.check(self.lib.pbx_grid_max(self.ctx, self._ptr(lj), int(lj.numel()),
+                                         self._ptr(out)), "pbx_grid_max")
+        return out
+
+    def grid_sumexp(self, lj, gmax):
+        out = self.empty(1)
+        _lib.check(self.lib.pbx_grid_sumexp(self.ctx, self._ptr(lj), int(lj.numel()),
+                                            self._ptr(gmax), self._ptr(out)), "pbx_grid_sumexp")
+        return out
+
+    def grid_posterior(self, lj, gmax, gsum, want_post=True, inplace=False):
+        """(post [M, S] or None, marg_mu_lin [M], marg_sigma_lin [S]) -- the
+        marginals are linear sums still to be passed through ``log_prob_``."""
+        M, S = lj.shape
+        post = (lj if inplace else self.empty(M, S)) if want_post else None
+        mm, ms = self.empty(M), self.empty(S)
+        _lib.check(self.lib.pbx_grid_posterior(self.ctx, self._ptr(lj), M, S, self._ptr(gmax),
+                                               self._ptr(gsum), self._ptr(post), self._ptr(mm),
+                                               self._ptr(ms)), "pbx_grid_posterior")
+        return post, mm, ms
+
+    def log_prob_(self, v):
+        """In-place clamped log (probayes/pscales.py:44-53)."""
+        _lib.check(self.lib.pbx_log_prob_inplace(self.ctx, self._ptr(v), int(v.numel())),
+                   "pbx_log_prob_inplace")
+        return v
+
+    def exp_logp_(self, v):
+        """In-place clamped exp (probayes/pscales.py:56-65)."""
+        _lib.check(self.lib.pbx_exp_logp_inplace(self.ctx, self._ptr(v), int(v.numel())),
+                   "pbx_exp_logp_inplace")
+        return v
+
+    def grid_conditionalise(self, lj, want_post=True, inplace=False, group=None):
+        """PD.conditionalise + both PD.marginal calls on a log-joint slab [M_local, S].
+        With ``group`` (a torch.distributed group over mu-row slabs) the normaliser
+        and the sigma marginal are all-reduced; the mu marginal stays a local slab.
+        Returns dict(post, marg_mu, marg_sigma, gmax, gsum) with log-pscale values."""
+        gmax = self.grid_max(lj)
+        dist = None
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+        gsum = self.grid_sumexp(lj, gmax)
+        if dist is not None:
+            dist.all_reduce(gsum, op=dist.ReduceOp.SUM, group=group)
+        post, mm, ms = self.grid_posterior(lj, gmax, gsum, want_post, inplace)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.SUM, group=group)
+        return dict(post=post, marg_mu=self.log_prob_(mm), marg_sigma=self.log_prob_(ms),
+                    gmax=gmax, gsum=gsum)
+
     # ------------------------------------------------------- chain summaries
     def chain_stats(self, stat_sum, stat_sumsq, n_steps):
         """[D, 4] device tensor (sum_c mean, sum_c mean^2, sum_c var, C)."""

@@ -1,0 +1,2 @@
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -x "$@" 2>&1 | tail -40

@@ -1,0 +1,125 @@
+"""K3/K4 parity (GPU, through the C ABI): discrete grid exact inference against
+the golden fixtures (live reference) and the oracles.  fp64, <= 1e-12 relative."""
+import numpy as np
+import pytest
+from conftest import load_golden, relerr
+from gpu_util import engine, dev, host
+from oracle import np_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+NNI = o.NEARLY_NEGATIVE_INF
+
+
+def _priors(M, S):
+    return np.full(M, -np.log(20.)), np.full(S, -np.log(np.log(20.) - np.log(5.)))
+
+
+def _rel_masked(a, b):
+    """relative error over the cells both sides did not clamp; clamp masks equal."""
+    ca, cb = a == NNI, b == NNI
+    assert np.array_equal(ca, cb)
+    return relerr(a[~ca], b[~cb])
+
+
+@pytest.mark.parametrize("name", ["dgei_small", "dgei_peaked"])
+def test_golden(name):
+    eng = engine()
+    g = load_golden(name)
+    M, S = len(g["mu"]), len(g["sigma"])
+    lpm, lps = _priors(M, S)
+    lj = eng.grid_norm_logjoint(dev(eng, g["data"]), dev(eng, g["mu"]), dev(eng, g["sigma"]),
+                                dev(eng, lpm), dev(eng, lps))
+    r = eng.grid_conditionalise(lj)
+    eng.sync()
+    assert relerr(host(lj), g["joint"]) <= TOL
+    assert _rel_masked(host(r["post"]), g["posterior"]) <= TOL
+    assert relerr(host(r["marg_mu"]), g["marg_mu"]) <= TOL
+    assert relerr(host(r["marg_sigma"]), g["marg_sigma"]) <= TOL
+    lin = host(eng.exp_logp_(r["post"].clone()))
+    eng.sync()
+    assert np.abs(lin - g["post_linear"]).max() <= 1e-12 * g["post_linear"].max()
+
+
+@pytest.mark.parametrize("N,M,S", [(1, 3, 5), (1023, 7, 1030), (4097, 33, 257), (20000, 64, 96)])
+def test_oracle_ragged(N, M, S):
+    """Ragged observation counts (below / across the 1024-obs tile) and grid edges
+    that do not fill a CTA tile."""
+    from oracle.c import liboracle as lo
+    eng = engine()
+    rng = np.random.default_rng(N + M + S)
+    data = rng.normal(50., 10., N)
+    mu = o.uniform_grid(40, 60, M, True, True)
+    sg = np.exp(o.uniform_grid(np.log(5), np.log(20), S, True, True))
+    lpm, lps = rng.normal(-3, .1, M), rng.normal(-1, .1, S)
+    want = lo.grid_norm_logjoint(data, mu, sg, lpm, lps)
+    lj = eng.grid_norm_logjoint(dev(eng, data), dev(eng, mu), dev(eng, sg), dev(eng, lpm),
+                                dev(eng, lps))
+    r = eng.grid_conditionalise(lj)
+    eng.sync()
+    assert relerr(host(lj), want) <= TOL
+    post = o.grid_conditionalise(want)
+    assert _rel_masked(host(r["post"]), post) <= 5e-12
+    assert relerr(host(r["marg_mu"]), o.grid_marginal(post, 1)) <= 5e-12
+    assert relerr(host(r["marg_sigma"]), o.grid_marginal(post, 0)) <= 5e-12
+
+
+def test_slab_sharded_equals_whole():
+    """mu-row slabs (the multi-GPU partitioning) reproduce the whole-grid result:
+    max of maxes, sum of sums, summed sigma marginal, concatenated mu marginal."""
+    import torch
+    eng = engine()
+    rng = np.random.default_rng(3)
+    N, M, S = 3000, 96, 130
+    data = rng.normal(50., 10., N)
+    mu = o.uniform_grid(40, 60, M, True, True)
+    sg = np.exp(o.uniform_grid(np.log(5), np.log(20), S, True, True))
+    lpm, lps = _priors(M, S)
+    xd, sd, lpsd = dev(eng, data), dev(eng, sg), dev(eng, lps)
+    whole = eng.grid_conditionalise(eng.grid_norm_logjoint(xd, dev(eng, mu), sd, dev(eng, lpm),
+                                                          lpsd))
+    slabs = [eng.grid_norm_logjoint(xd, dev(eng, mu[a:b]), sd, dev(eng, lpm[a:b]), lpsd)
+             for a, b in [(0, 40), (40, 41), (41, 96)]]
+    gmax = torch.stack([eng.grid_max(s) for s in slabs]).max(dim=0).values
+    gsum = torch.stack([eng.grid_sumexp(s, gmax) for s in slabs]).sum(dim=0)
+    parts = [eng.grid_posterior(s, gmax, gsum) for s in slabs]
+    post = torch.cat([p[0] for p in parts])
+    mm = eng.log_prob_(torch.cat([p[1] for p in parts]))
+    ms = eng.log_prob_(torch.stack([p[2] for p in parts]).sum(dim=0))
+    eng.sync()
+    assert float(gmax) == float(whole["gmax"])
+    assert _rel_masked(host(post), host(whole["post"])) <= 1e-13
+    assert relerr(host(mm), host(whole["marg_mu"])) <= 1e-13
+    assert relerr(host(ms), host(whole["marg_sigma"])) <= 1e-13
+
+
+def test_full_size_properties():
+    """BASELINE config C4 shape at reduced N (4096 x 4096 grid, N = 2000): the
+    posterior is normalised, marginals agree with row/column sums of the
+    posterior, and a random sample of cells matches the C restatement."""
+    from oracle.c import liboracle as lo
+    eng = engine()
+    rng = np.random.default_rng(7)
+    N, M, S = 2000, 4096, 4096
+    data = rng.normal(50., 10., N)
+    mu = o.uniform_grid(40, 60, M, True, True)
+    sg = np.exp(o.uniform_grid(np.log(5), np.log(20), S, True, True))
+    lpm, lps = _priors(M, S)
+    lj = eng.grid_norm_logjoint(dev(eng, data), dev(eng, mu), dev(eng, sg), dev(eng, lpm),
+                                dev(eng, lps))
+    r = eng.grid_conditionalise(lj)
+    eng.sync()
+    ljh = host(lj)
+    rows = rng.choice(M, 6, replace=False); cols = rng.choice(S, 7, replace=False)
+    want = lo.grid_norm_logjoint(data, mu[rows], sg[cols], lpm[rows], lps[cols])
+    assert relerr(ljh[np.ix_(rows, cols)], want) <= TOL
+    post = host(r["post"])
+    lin = np.where(post == NNI, 0.0, np.exp(np.maximum(post, -745.)))
+    assert abs(lin.sum() - 1.0) <= 1e-10
+    mm, ms = host(r["marg_mu"]), host(r["marg_sigma"])
+    ok = mm > -700
+    assert relerr(np.exp(mm[ok]), lin.sum(axis=1)[ok]) <= 1e-10
+    ok = ms > -700
+    assert relerr(np.exp(ms[ok]), lin.sum(axis=0)[ok]) <= 1e-10
+    assert np.unravel_index(np.argmax(ljh), ljh.shape) == \
+        np.unravel_index(np.argmax(post), post.shape)
