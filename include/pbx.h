@@ -78,8 +78,11 @@ PBX_API const char* pbx_last_error(void);
 PBX_API int pbx_device_count(int* n);
 PBX_API int pbx_device_info(int device, pbx_devinfo* out);
 
-/* stream: a cudaStream_t (as void*) to run on, or NULL to let the context own one. */
-PBX_API int pbx_ctx_create(int device, void* stream, pbx_ctx** out);
+/* own_stream != 0: the context creates (and later destroys) its own non-blocking
+ * stream and `stream` is ignored.  own_stream == 0: run on the caller's
+ * cudaStream_t `stream` (passed as void*; NULL is the default stream), e.g. torch's
+ * current stream so that kernels are ordered with the caller's allocations/copies. */
+PBX_API int pbx_ctx_create(int device, void* stream, int32_t own_stream, pbx_ctx** out);
 PBX_API int pbx_ctx_destroy(pbx_ctx* ctx);
 PBX_API int pbx_ctx_sync(pbx_ctx* ctx);
 /* number of kernels this context has launched since creation (bench: gpu_launches) */

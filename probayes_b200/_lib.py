@@ -85,7 +85,7 @@ SIGNATURES = {
     "pbx_last_error": (C.c_char_p, []),
     "pbx_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pbx_device_info": (C.c_int, [C.c_int, C.POINTER(DevInfo)]),
-    "pbx_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pbx_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
     "pbx_ctx_destroy": (C.c_int, [C.c_void_p]),
     "pbx_ctx_sync": (C.c_int, [C.c_void_p]),
     "pbx_ctx_launch_count": (C.c_int64, [C.c_void_p]),

@@ -63,7 +63,7 @@ int pbx_device_info(int device, pbx_devinfo* out) {
   return PBX_OK;
 }
 
-int pbx_ctx_create(int device, void* stream, pbx_ctx** out) {
+int pbx_ctx_create(int device, void* stream, int32_t own_stream, pbx_ctx** out) {
   PBX_REQUIRE(out != nullptr, "pbx_ctx_create: null out");
   *out = nullptr;
   int n = 0;
@@ -82,12 +82,12 @@ int pbx_ctx_create(int device, void* stream, pbx_ctx** out) {
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
-  if (stream) {
-    c->stream = (cudaStream_t)stream;
-    c->own_stream = false;
-  } else {
+  if (own_stream) {
     PBX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->own_stream = true;
+  } else {
+    c->stream = (cudaStream_t)stream;                  // NULL = the default stream
+    c->own_stream = false;
   }
   PBX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   PBX_CUDA(cudaEventCreate(&c->ev0));

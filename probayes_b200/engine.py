@@ -75,8 +75,9 @@ class Engine:
         torch.cuda.set_device(self.device)
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
         h = C.c_void_p()
+        # run on torch's current stream (0 = the default stream), never on a private one
         _lib.check(self.lib.pbx_ctx_create(self.device_index,
-                                           C.c_void_p(self.stream.cuda_stream), C.byref(h)),
+                                           C.c_void_p(self.stream.cuda_stream), 0, C.byref(h)),
                    "pbx_ctx_create")
         self.ctx = h
         info = DevInfo()

@@ -22,6 +22,18 @@ def _rel_masked(a, b):
     return relerr(a[~ca], b[~cb])
 
 
+def _abs_masked(a, b):
+    ca, cb = a == NNI, b == NNI
+    assert np.array_equal(ca, cb)
+    return float(np.abs(a[~ca] - b[~cb]).max())
+
+
+# The posterior / marginals are DIFFERENCES of log-joints of magnitude |lj| ~ N, so
+# they inherit an absolute error |lj|*eps from the summation order of either side
+# (SURVEY.md "DGEI conditioning", probe B.8).  The 1e-12 relative bound of the
+# log-densities therefore translates into an absolute bound 1e-12 * max|lj| here.
+
+
 @pytest.mark.parametrize("name", ["dgei_small", "dgei_peaked"])
 def test_golden(name):
     eng = engine()
@@ -33,12 +45,14 @@ def test_golden(name):
     r = eng.grid_conditionalise(lj)
     eng.sync()
     assert relerr(host(lj), g["joint"]) <= TOL
-    assert _rel_masked(host(r["post"]), g["posterior"]) <= TOL
-    assert relerr(host(r["marg_mu"]), g["marg_mu"]) <= TOL
-    assert relerr(host(r["marg_sigma"]), g["marg_sigma"]) <= TOL
+    atol = TOL * np.abs(g["joint"]).max()
+    assert _abs_masked(host(r["post"]), g["posterior"]) <= atol
+    assert _abs_masked(host(r["marg_mu"]), g["marg_mu"]) <= atol
+    assert _abs_masked(host(r["marg_sigma"]), g["marg_sigma"]) <= atol
     lin = host(eng.exp_logp_(r["post"].clone()))
     eng.sync()
-    assert np.abs(lin - g["post_linear"]).max() <= 1e-12 * g["post_linear"].max()
+    # linear cells: relative error = absolute error of the log cell
+    assert np.abs(lin - g["post_linear"]).max() <= atol * g["post_linear"].max()
 
 
 @pytest.mark.parametrize("N,M,S", [(1, 3, 5), (1023, 7, 1030), (4097, 33, 257), (20000, 64, 96)])
@@ -59,9 +73,10 @@ def test_oracle_ragged(N, M, S):
     eng.sync()
     assert relerr(host(lj), want) <= TOL
     post = o.grid_conditionalise(want)
-    assert _rel_masked(host(r["post"]), post) <= 5e-12
-    assert relerr(host(r["marg_mu"]), o.grid_marginal(post, 1)) <= 5e-12
-    assert relerr(host(r["marg_sigma"]), o.grid_marginal(post, 0)) <= 5e-12
+    atol = TOL * np.abs(want).max()
+    assert _abs_masked(host(r["post"]), post) <= atol
+    assert _abs_masked(host(r["marg_mu"]), o.grid_marginal(post, 1)) <= atol
+    assert _abs_masked(host(r["marg_sigma"]), o.grid_marginal(post, 0)) <= atol
 
 
 def test_slab_sharded_equals_whole():
