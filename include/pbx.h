@@ -254,12 +254,14 @@ typedef struct {
   const double* cdf_lo;    /* device [d] fixed cdf limits (cond_cov.py:38-39) */
   const double* cdf_hi;    /* device [d] */
   const double* whiten;    /* device [d][d] row-major, value permutation folded in */
+  const double* dens_mean; /* device [d] mean of the density in natural order with the
+                              permutation folded in (NULL = mean); see prob.py:349-358 */
   double norm_c;           /* d log 2pi + log_pdet */
   double* state;           /* [d][C] in/out */
   const double* inj_runif; /* [T][C] injected U(0,1) draws or NULL = Philox */
   double* out_x;           /* [T/thin][d][C] or NULL */
   double* out_prob;        /* [T/thin][C] or NULL */
-  double* stat_sum;        /* [d][C] or NULL */
+  double* stat_sum;        /* [d][C] accumulated over the RECORDED states, or NULL */
   double* stat_sumsq;      /* [d][C] or NULL */
 } pbx_gibbs_mvn_params;
 

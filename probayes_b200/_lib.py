@@ -72,7 +72,7 @@ class GibbsMvnParams(C.Structure):
         ("seed", C.c_uint64), ("log_pscale", C.c_int32), ("want_prob", C.c_int32),
         ("mean", C.c_void_p), ("coef", C.c_void_p), ("stdv", C.c_void_p),
         ("cdf_lo", C.c_void_p), ("cdf_hi", C.c_void_p), ("whiten", C.c_void_p),
-        ("norm_c", C.c_double),
+        ("dens_mean", C.c_void_p), ("norm_c", C.c_double),
         ("state", C.c_void_p), ("inj_runif", C.c_void_p),
         ("out_x", C.c_void_p), ("out_prob", C.c_void_p),
         ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p),

@@ -415,6 +415,73 @@ class Engine:
         return dict(post=post, marg_mu=self.log_prob_(mm), marg_sigma=self.log_prob_(ms),
                     gmax=gmax, gsum=gsum)
 
+    # ------------------------------------------------------------ K5: Gibbs
+    def mvn_logpdf(self, x, mean, cov, log_pscale=True, reorder=True):
+        """Batched mvn density of x [d, n] (device) -> [n]; d = 64 runs the
+        whitening product on the FP64 tensor cores."""
+        d, n = x.shape
+        mean_nat, W, norm_c = mvn_setup(mean, cov, reorder)
+        md, Wd = self.to_device(mean_nat), self.to_device(W)
+        out = self.empty(n)
+        _lib.check(self.lib.pbx_mvn_logpdf(self.ctx, self._ptr(x), d, n, self._ptr(md),
+                                           self._ptr(Wd), norm_c, 1 if log_pscale else 0,
+                                           self._ptr(out)), "pbx_mvn_logpdf")
+        return out
+
+    def gibbs_mvn(self, state, cond_cov, steps, thin=1, seed=0, step0=0, chain0=0,
+                  log_pscale=False, reorder=True, inj_runif=None, record=True, want_prob=True,
+                  stats=False):
+        """``steps`` single-coordinate Gibbs updates (coordinate = step mod d) of
+        all chains of ``state`` [d, C] (device, in place) for the mvn described by
+        ``cond_cov`` (a :class:`probayes_b200.cond_cov.CondCov`).  Returns dict
+        with x [R, d, C] and prob [R, C] (the mvn target evaluated on every kept
+        state, as the reference's SP.next does)."""
+        d, C_ = state.shape
+        if d != cond_cov.n:
+            raise ValueError("state has %d dims, CondCov has %d" % (d, cond_cov.n))
+        if d > 64:
+            raise NotImplementedError("gibbs_mvn supports up to 64 dimensions")
+        if int(thin) < 1:
+            raise ValueError("thin must be >= 1")
+        T = int(steps)
+        R = T // thin
+        p = GibbsMvnParams()
+        p.n_chains, p.n_dims, p.n_steps, p.thin = C_, d, T, thin
+        p.step0, p.chain0, p.seed = step0, chain0, seed & 0xFFFFFFFFFFFFFFFF
+        p.log_pscale = 1 if log_pscale else 0
+        consts = getattr(cond_cov, "_dev", None)
+        if consts is None or consts[0] is not self or consts[1] != reorder:
+            mean_nat, W, norm_c = mvn_setup(cond_cov.mean, cond_cov.cov, reorder)
+            consts = (self, reorder, dict(
+                mean=self.to_device(cond_cov.mean), coef=self.to_device(cond_cov.coef_matrix()),
+                stdv=self.to_device(cond_cov.stdv), lo=self.to_device(cond_cov.cdfs[:, 0]),
+                hi=self.to_device(cond_cov.cdfs[:, 1]), W=self.to_device(W),
+                dmean=self.to_device(mean_nat), norm_c=norm_c))
+            cond_cov._dev = consts
+        k = consts[2]
+        p.mean, p.coef, p.stdv = k["mean"].data_ptr(), k["coef"].data_ptr(), k["stdv"].data_ptr()
+        p.cdf_lo, p.cdf_hi = k["lo"].data_ptr(), k["hi"].data_ptr()
+        p.whiten, p.dens_mean, p.norm_c = k["W"].data_ptr(), k["dmean"].data_ptr(), k["norm_c"]
+        out = {}
+        if record:
+            out["x"] = self.empty(R, d, C_)
+            if want_prob:
+                out["prob"] = self.empty(R, C_)
+        if stats:
+            out["stat_sum"] = self.zeros(d, C_)
+            out["stat_sumsq"] = self.zeros(d, C_)
+        if inj_runif is not None and tuple(inj_runif.shape) != (T, C_):
+            raise ValueError("injected uniforms must be [T, C]")
+        p.state = state.data_ptr()
+        p.inj_runif = 0 if inj_runif is None else inj_runif.data_ptr()
+        p.out_x = out["x"].data_ptr() if record else 0
+        p.out_prob = out["prob"].data_ptr() if (record and want_prob) else 0
+        p.want_prob = 1 if (record and want_prob) else 0
+        p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
+        p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0
+        _lib.check(self.lib.pbx_gibbs_mvn_run(self.ctx, C.byref(p)), "pbx_gibbs_mvn_run")
+        return out
+
     # ------------------------------------------------------- chain summaries
     def chain_stats(self, stat_sum, stat_sumsq, n_steps):
         """[D, 4] device tensor (sum_c mean, sum_c mean^2, sum_c var, C)."""
