@@ -60,6 +60,8 @@ typedef enum {
 /* proposal draw kind (probayes/field.py:469-531, variable.py:600-638) */
 #define PBX_PROP_NORMAL 0          /* delta_j = scale_j * z_j,  z ~ N(0,1) (then optional L) */
 #define PBX_PROP_UNIFORM 1         /* delta_j = -scale_j + 2 scale_j r_j, r ~ U(0,1)  ([delta] lists) */
+#define PBX_PROP_SPHERICAL 2       /* u_j ~ U(-R, R); delta_j = (u_j R / |u|) scale_j  ((delta,) tuples,
+                                      field.py:509-531; R = prop_radius) */
 
 typedef struct pbx_ctx pbx_ctx;
 
@@ -125,6 +127,7 @@ typedef struct {
   double norm_c;           /* D log 2pi + log_pdet;  logpdf = -0.5*(norm_c + maha), scipy's form */
   double prop_scale[PBX_MAX_DIMS];
   double prop_mat[PBX_MAX_DIMS * PBX_MAX_DIMS];   /* row-major lower-triangular L */
+  double prop_radius;      /* PBX_PROP_SPHERICAL only */
   /* device buffers */
   double* state;           /* [D][C] in/out: current state */
   double* state_lp;        /* [C]    in/out: log-density of state (ignored on input when step0 == 0) */
@@ -180,6 +183,7 @@ typedef struct {
   int32_t open_end[PBX_MAX_PARAMS][2];   /* 1 = exclusive end (tuple in vset) */
   int32_t log_ufun[PBX_MAX_PARAMS];      /* 1 = (np.log, np.exp) ufun */
   double prop_scale[PBX_MAX_PARAMS];
+  double prop_radius;      /* PBX_PROP_SPHERICAL only */
   double* state;           /* [P][C] in/out */
   double* state_lp;        /* [C] in/out */
   const double* inj_delta; /* [T][P][C] or NULL */

@@ -79,7 +79,7 @@ def mh_mvn(seed, T, init, log_pscale=False, cov_tran=None):
 
 
 # ---------------------------------------------------------------------------
-def mh_norm1d(seed, T, N, scores):
+def mh_norm1d(seed, T, N, scores, spherical=False):
     """examples/mcmc/metrohast_norm1d.py:23-42 ((mu, sigma) posterior, log
     pscale, sigma with (np.log, np.exp) ufun, iid+joint), uniforms injected by
     patching np.random.uniform.  scores='hastings' keeps the script's
@@ -104,7 +104,7 @@ def mh_norm1d(seed, T, N, scores):
         paras.set_tran((tran, tran))
     else:
         paras.set_tran(tran)
-    paras.set_delta([step], scale=True)
+    paras.set_delta((step,) if spherical else [step], scale=True)
     sp.set_tran(paras)
     sp.set_delta(paras)
     sp.set_scores(scores)
@@ -119,6 +119,12 @@ def mh_norm1d(seed, T, N, scores):
     lengths = np.array([20., np.log(20.) - np.log(5.)])
     dmax = step * lengths                # scale=True: probayes/field.py:299-303
     delta = -dmax + (dmax - (-dmax)) * R[:, :2]
+    radius = 0.0
+    if spherical:                        # probayes/field.py:509-531
+        radius = step * np.sqrt(np.sum(lengths ** 2))
+        cube = -radius + (2 * radius) * R[:, :2]
+        delta = (cube * radius) / np.sqrt(np.sum(cube ** 2, axis=1, keepdims=True)) * lengths
+    out.update(radius=np.array(radius), lengths=lengths, spherical=np.array(spherical))
     out.update(x_obs=x_obs, delta=delta, thresh=R[:, 2], runif=R,
                init=np.array([50., 12.5]), dmax=dmax,
                lims=np.array([[40., 60.], [5., 20.]]),
@@ -298,6 +304,7 @@ def main():
         "mh_norm1d_hastings": lambda: mh_norm1d(21, 300, 60, 'hastings'),
         "mh_norm1d_metropolis": lambda: mh_norm1d(22, 300, 60, 'metropolis'),
         "mh_norm1d_underflow": lambda: mh_norm1d(23, 60, 1000, 'metropolis'),
+        "mh_norm1d_spherical": lambda: mh_norm1d(24, 300, 60, 'hastings', spherical=True),
         "mh_linreg": lambda: mh_linreg(31, 300, 100),
         "dgei_small": lambda: dgei(41, 60, 48, 40),
         "dgei_peaked": lambda: dgei(42, 2000, 40, 36),

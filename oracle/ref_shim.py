@@ -58,8 +58,10 @@ def injected_uniform(stream):
     orig = np.random.uniform
 
     def fake(low=0.0, high=1.0, size=None):
-        assert size is None, "injected stream supports scalar draws only"
-        return low + (high - low) * next(it)
+        if size is None:
+            return low + (high - low) * next(it)
+        n = int(np.prod(size))
+        return (low + (high - low) * np.array([next(it) for _ in range(n)])).reshape(size)
 
     np.random.uniform = fake
     try:

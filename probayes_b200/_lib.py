@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libpbx.so")
 PBX_MAX_DIMS = 8
 PBX_MAX_PARAMS = 3
 ACCEPT_REFERENCE, ACCEPT_LOG = 0, 1
-PROP_NORMAL, PROP_UNIFORM = 0, 1
+PROP_NORMAL, PROP_UNIFORM, PROP_SPHERICAL = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -38,6 +38,7 @@ class MhMvnParams(C.Structure):
         ("norm_c", C.c_double),
         ("prop_scale", C.c_double * PBX_MAX_DIMS),
         ("prop_mat", C.c_double * (PBX_MAX_DIMS * PBX_MAX_DIMS)),
+        ("prop_radius", C.c_double),
         ("state", C.c_void_p), ("state_lp", C.c_void_p),
         ("inj_delta", C.c_void_p), ("inj_thresh", C.c_void_p),
         ("out_x", C.c_void_p), ("out_prob", C.c_void_p),
@@ -57,6 +58,7 @@ class MhNormregParams(C.Structure):
         ("open_end", (C.c_int32 * 2) * PBX_MAX_PARAMS),
         ("log_ufun", C.c_int32 * PBX_MAX_PARAMS),
         ("prop_scale", C.c_double * PBX_MAX_PARAMS),
+        ("prop_radius", C.c_double),
         ("state", C.c_void_p), ("state_lp", C.c_void_p),
         ("inj_delta", C.c_void_p), ("inj_thresh", C.c_void_p),
         ("out_x", C.c_void_p), ("out_prob", C.c_void_p),

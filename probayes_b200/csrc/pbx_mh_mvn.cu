@@ -28,6 +28,7 @@ struct MhMvnConst {
   double L[PBX_MAX_DIMS * PBX_MAX_DIMS];
   double scale[PBX_MAX_DIMS];
   double norm_c;
+  double radius;
 };
 
 struct MhMvnArgs {
@@ -81,13 +82,24 @@ __device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_
       pbx_normal_pair(w, d0, d1);
       d0 *= m.scale[2 * s];
       if (2 * s + 1 < D) d1 *= m.scale[2 * s + 1];
-    } else {
+    } else if (prop_kind == PBX_PROP_UNIFORM) {
       double r0 = pbx_u52(w.x, w.y), r1 = pbx_u32(w.z);
       d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * r0;
       d1 = (2 * s + 1 < D) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * r1 : 0.0;
+    } else {                       // spherical: cube sample, rescaled below
+      d0 = -m.radius + (2.0 * m.radius) * pbx_u52(w.x, w.y);
+      d1 = (2 * s + 1 < D) ? -m.radius + (2.0 * m.radius) * pbx_u32(w.z) : 0.0;
     }
     dl[2 * s] = d0;
     if (2 * s + 1 < D) dl[2 * s + 1] = d1;
+  }
+  if (prop_kind == PBX_PROP_SPHERICAL) {   // field.py:509-531
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) ss += dl[j] * dl[j];
+    const double nrm = (ss >= PBX_TINY) ? sqrt(ss) : 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) dl[j] = ((dl[j] * m.radius) / nrm) * m.scale[j];
   }
 }
 
@@ -422,7 +434,7 @@ static int validate(const pbx_mh_mvn_params* p, const char* who) {
   PBX_REQUIRE(p->step0 >= 0 && p->chain0 >= 0, "%s: step0/chain0 must be >= 0", who);
   PBX_REQUIRE(p->accept_mode == PBX_ACCEPT_REFERENCE || p->accept_mode == PBX_ACCEPT_LOG,
               "%s: unknown accept_mode %d", who, p->accept_mode);
-  PBX_REQUIRE(p->prop_kind == PBX_PROP_NORMAL || p->prop_kind == PBX_PROP_UNIFORM,
+  PBX_REQUIRE(p->prop_kind >= PBX_PROP_NORMAL && p->prop_kind <= PBX_PROP_SPHERICAL,
               "%s: unknown prop_kind %d", who, p->prop_kind);
   PBX_REQUIRE(p->state && p->state_lp, "%s: state/state_lp are mandatory", who);
   PBX_REQUIRE((p->inj_delta == nullptr) == (p->inj_thresh == nullptr),
@@ -441,6 +453,7 @@ static void fill_const(const pbx_mh_mvn_params* p, MhMvnConst& m) {
     m.L[i] = i < D * D ? p->prop_mat[i] : 0.0;
   }
   m.norm_c = p->norm_c;
+  m.radius = p->prop_radius;
 }
 
 static int run_device(pbx_ctx* ctx, const pbx_mh_mvn_params* p) {

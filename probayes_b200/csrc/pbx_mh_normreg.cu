@@ -40,6 +40,7 @@ struct NrModel {
   int log_ufun[PBX_MAX_PARAMS];
   double scale[PBX_MAX_PARAMS];
   double nlhv[PBX_MAX_PARAMS];      // -log(length in ufun space): rv.py:153-166
+  double radius;
 };
 
 struct NrArgs {
@@ -92,13 +93,22 @@ __device__ __forceinline__ void nr_draw_delta(const NrArgs& a, const NrModel& m,
       pbx_normal_pair(w, d0, d1);
       d0 *= m.scale[2 * s];
       if (2 * s + 1 < m.P) d1 *= m.scale[2 * s + 1];
-    } else {
+    } else if (m.prop_kind == PBX_PROP_UNIFORM) {
       d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * pbx_u52(w.x, w.y);
       d1 = (2 * s + 1 < m.P) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * pbx_u32(w.z)
                              : 0.0;
+    } else {                       // spherical: cube sample, rescaled below
+      d0 = -m.radius + (2.0 * m.radius) * pbx_u52(w.x, w.y);
+      d1 = (2 * s + 1 < m.P) ? -m.radius + (2.0 * m.radius) * pbx_u32(w.z) : 0.0;
     }
     dl[2 * s] = d0;
     if (2 * s + 1 < m.P) dl[2 * s + 1] = d1;
+  }
+  if (m.prop_kind == PBX_PROP_SPHERICAL) {   // field.py:509-531
+    double ss = 0.0;
+    for (int j = 0; j < m.P; ++j) ss += dl[j] * dl[j];
+    const double nrm = (ss >= PBX_TINY) ? sqrt(ss) : 0.0;
+    for (int j = 0; j < m.P; ++j) dl[j] = ((dl[j] * m.radius) / nrm) * m.scale[j];
   }
 }
 
@@ -462,7 +472,7 @@ static int nr_validate(const pbx_mh_normreg_params* p, const char* who, bool nee
               "%s: observation arrays missing", who);
   PBX_REQUIRE(p->accept_mode == PBX_ACCEPT_REFERENCE || p->accept_mode == PBX_ACCEPT_LOG,
               "%s: unknown accept_mode", who);
-  PBX_REQUIRE(p->prop_kind == PBX_PROP_NORMAL || p->prop_kind == PBX_PROP_UNIFORM,
+  PBX_REQUIRE(p->prop_kind >= PBX_PROP_NORMAL && p->prop_kind <= PBX_PROP_SPHERICAL,
               "%s: unknown prop_kind", who);
   for (int j = 0; j < p->n_params; ++j) {
     PBX_REQUIRE(p->lims[j][1] > p->lims[j][0], "%s: empty prior box for parameter %d", who, j);
@@ -485,6 +495,7 @@ static void nr_fill_model(const pbx_mh_normreg_params* p, NrModel& m) {
   m.accept_mode = p->accept_mode;
   m.prop_kind = p->prop_kind;
   m.coef = p->accept_coef;
+  m.radius = p->prop_radius;
   for (int j = 0; j < PBX_MAX_PARAMS; ++j) {
     m.lims[j][0] = p->lims[j][0];
     m.lims[j][1] = p->lims[j][1];

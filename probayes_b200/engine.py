@@ -11,12 +11,13 @@ import numpy as np
 
 from . import _lib
 from ._lib import (PbxError, MhMvnParams, MhNormregParams, GibbsMvnParams, DevInfo,
-                   ACCEPT_REFERENCE, ACCEPT_LOG, PROP_NORMAL, PROP_UNIFORM, PBX_MAX_DIMS)
+                   ACCEPT_REFERENCE, ACCEPT_LOG, PROP_NORMAL, PROP_UNIFORM, PROP_SPHERICAL,
+                   PBX_MAX_DIMS)
 
 LOG_2PI = math.log(2.0 * math.pi)
 
 _ACCEPT = {"reference": ACCEPT_REFERENCE, "log": ACCEPT_LOG}
-_PROP = {"normal": PROP_NORMAL, "uniform": PROP_UNIFORM}
+_PROP = {"normal": PROP_NORMAL, "uniform": PROP_UNIFORM, "spherical": PROP_SPHERICAL}
 
 
 def _torch():
@@ -138,7 +139,8 @@ class Engine:
 
     # ------------------------------------------------------------ K1: mh mvn
     def _mvn_params(self, D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
-                    prop, prop_scale, prop_chol, mean, cov, reorder, variant=0):
+                    prop, prop_scale, prop_chol, mean, cov, reorder, variant=0,
+                    prop_radius=0.0):
         if not 1 <= D <= PBX_MAX_DIMS:
             raise NotImplementedError(
                 "mh_mvn supports 1..%d dimensions (got %d)" % (PBX_MAX_DIMS, D))
@@ -148,6 +150,7 @@ class Engine:
             raise ValueError("unknown accept/prop mode: %r / %r" % (accept, prop))
         p = MhMvnParams()
         p.kernel_variant = int(variant)
+        p.prop_radius = float(prop_radius)
         p.n_chains, p.n_dims, p.n_steps, p.thin = C_, D, T, thin
         p.step0, p.chain0, p.seed = step0, chain0, seed & 0xFFFFFFFFFFFFFFFF
         p.log_pscale = 1 if log_pscale else 0
@@ -175,7 +178,7 @@ class Engine:
                log_pscale=False, accept="reference", prop="normal", prop_scale=1.0,
                prop_chol=None, reorder=True, inj_delta=None, inj_thresh=None,
                state_lp=None, record=True, per_step=False, stats=True, variant=0,
-               out=None):
+               out=None, prop_radius=0.0):
         """Runs ``steps`` MH steps for all chains of ``state`` ([D, C] device fp64,
         updated in place).  Returns a dict of device tensors:
         x [R, D, C], prob [R, C] (record), accept [T, C] uint8 + score [T, C]
@@ -186,7 +189,8 @@ class Engine:
         D, C_ = state.shape
         T = int(steps)
         p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
-                             prop, prop_scale, prop_chol, mean, cov, reorder, variant)
+                             prop, prop_scale, prop_chol, mean, cov, reorder, variant,
+                             prop_radius)
         out = dict(out) if out else {}
         if state_lp is None:
             if step0 != 0:
@@ -227,7 +231,7 @@ class Engine:
     def mh_mvn_walk_host(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
                          log_pscale=False, accept="reference", prop="normal",
                          prop_scale=1.0, prop_chol=None, reorder=True, state_lp=None,
-                         chunk_steps=1000, out_x=None, out_prob=None):
+                         chunk_steps=1000, out_x=None, out_prob=None, prop_radius=0.0):
         """Whole walk through the host-buffer entry point: ``state`` is a HOST
         ndarray [D, C] (updated in place); samples are streamed back into pinned
         host buffers while the next chunk runs.  Returns dict of ndarrays."""
@@ -237,7 +241,7 @@ class Engine:
         T = int(steps)
         R = T // thin
         p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
-                             prop, prop_scale, prop_chol, mean, cov, reorder)
+                             prop, prop_scale, prop_chol, mean, cov, reorder, 0, prop_radius)
         if out_x is None:
             out_x = torch.empty((R, D, C_), dtype=torch.float64, pin_memory=True)
         if out_prob is None:
@@ -257,7 +261,8 @@ class Engine:
 
     # ------------------------------------------------- K2: streaming normal MH
     def _normreg_params(self, C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
-                        accept="log", accept_coef=1.0, prop="uniform", variant=0):
+                        accept="log", accept_coef=1.0, prop="uniform", variant=0,
+                        prop_radius=0.0):
         if P not in (2, 3):
             raise NotImplementedError("normal-likelihood MH supports (mu, sigma) or "
                                       "(b0, b1, sigma) parameters, got %d" % P)
@@ -271,6 +276,7 @@ class Engine:
         p.has_slope = 1 if has_slope else 0
         p.accept_mode, p.accept_coef = _ACCEPT[accept], float(accept_coef)
         p.prop_kind, p.variant = _PROP[prop], int(variant)
+        p.prop_radius = float(prop_radius)
         p.n_obs = int(y_obs.numel())
         if has_slope and int(x_obs.numel()) != p.n_obs:
             raise ValueError("x_obs and y_obs differ in length")
@@ -290,7 +296,7 @@ class Engine:
     def mh_normreg(self, state, y_obs, x_obs, steps, lims, open_end, log_ufun, prop_scale,
                    thin=1, seed=0, step0=0, chain0=0, accept="log", accept_coef=1.0,
                    prop="uniform", variant=0, inj_delta=None, inj_thresh=None, state_lp=None,
-                   record=True, per_step=False, stats=True):
+                   record=True, per_step=False, stats=True, prop_radius=0.0):
         """MH on the iid-normal posterior; ``state`` [P, C] device fp64 (in place),
         ``y_obs``/``x_obs`` device fp64 [N].  Same outputs as :meth:`mh_mvn`; the
         recorded ``prob`` is the log-joint (log pscale)."""
@@ -300,7 +306,7 @@ class Engine:
         if int(thin) < 1:
             raise ValueError("thin must be >= 1")
         p = self._normreg_params(C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
-                                 accept, accept_coef, prop, variant)
+                                 accept, accept_coef, prop, variant, prop_radius)
         p.n_steps, p.thin, p.step0, p.chain0 = T, thin, step0, chain0
         p.seed = seed & 0xFFFFFFFFFFFFFFFF
         if state_lp is None:

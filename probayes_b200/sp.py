@@ -1,0 +1,425 @@
+"""SP -- stochastic process: the Metropolis-Hastings / Gibbs sampler front end.
+
+Mirror of the reference interface (probayes/sp.py:57-100,131-198,221-295;
+sp_utils.py:8-91): ``set_scores`` / ``set_thresh`` / ``set_update`` with the
+``MCMC_SAMPLERS`` names, ``sampler(init, [obs], stop=, iid=, joint=)``,
+``walk(sampler)``, ``process(samples)`` -> ``opqrstuv`` summary.  The step loop
+itself (sp.py:221-258) never runs in Python: ``walk`` hands the whole walk to the
+batched-chain kernels of libpbx.
+
+New keyword arguments of ``sampler`` (everything else keeps its meaning):
+  chains=C      run C independent chains (default: one, reference-shaped results)
+  thin=k        record every k-th step
+  seed=s        Philox seed of the native RNG
+  accept=       'log' (default for native RNG) | 'reference' (the reference's
+                linear-space ratio with its clamps; default for injected streams)
+  inj_delta=, inj_thresh=   injected proposal / threshold streams ([T, D] or
+                [T, C, D] and [T] or [T, C]) for bit-parity runs
+  host_stream=True   stream samples straight into pinned host buffers (K1)
+"""
+import collections
+import numpy as np
+
+from .sd import SD
+from .pd import PD
+from .pscales import iscomplex
+from . import catalogue
+
+MCMC_SAMPLERS = ('metropolis', 'hastings', 'gibbs')
+
+
+class AcceptRecord:
+    """``summary.u`` of a batched run: behaves like the reference's list of
+    True/None for the one thing examples do with it -- ``u.count(True)``."""
+
+    def __init__(self, counts, steps):
+        self.counts = np.asarray(counts)
+        self.steps = int(steps)
+
+    def count(self, value=True):
+        total = int(self.counts.sum())
+        if value is True:
+            return total
+        if value is None:
+            return self.counts.size * self.steps - total
+        return 0
+
+    def __len__(self):
+        return self.counts.size * self.steps
+
+    def rate(self):
+        return self.count(True) / float(len(self))
+
+
+class Walk(list):
+    """Result of ``SP.walk``: a list of per-step ``opqrstuv`` tuples for
+    reference-shaped single-chain runs, plus the raw arrays (``.arrays``)."""
+    arrays = None
+    sampler = None
+
+
+class Sampler:
+    """Returned by ``SP.sampler``; iterating it (or ``SP.walk``) runs the walk."""
+
+    def __init__(self, sp, init, obs, stop, opts):
+        self.sp, self.init, self.obs, self.stop, self.opts = sp, init, obs, stop, opts
+        self.counter = 0
+        self.state = None           # device state between calls (resume)
+        self.state_lp = None
+
+    def __iter__(self):
+        return iter(self.sp.walk(self))
+
+
+class SP(SD):
+
+    def __init__(self, *args):
+        super().__init__(*args)
+        self._scores = self._thresh = self._update = None
+        self._samplers = []
+        self.stuv = collections.namedtuple(self._id, ['s', 't', 'u', 'v'])
+        self.opqrstuv = collections.namedtuple(self._id,
+                                               ['o', 'p', 'q', 'r', 's', 't', 'u', 'v'])
+
+    # ---- scores / thresh / update ------------------------------------------------------------
+    @property
+    def scores(self):
+        return self._scores
+
+    @property
+    def thresh(self):
+        return self._thresh
+
+    @property
+    def update(self):
+        return self._update
+
+    def _check_spec(self, spec, what):
+        if spec is None:
+            return None
+        if isinstance(spec, str) and spec in MCMC_SAMPLERS:
+            return spec
+        raise NotImplementedError(
+            "{} must be one of {} on the device path (custom Python {} functions cannot "
+            "run in the kernel)".format(what, MCMC_SAMPLERS, what))
+
+    def set_scores(self, scores=None, *args, **kwds):
+        assert not args and not kwds, \
+            "Neither args nor kwds permitted with spec '{}'".format(scores)
+        self._scores = self._check_spec(scores, 'scores')
+        if self._scores is not None:            # the reference chains these (sp.py:61-66)
+            self.set_thresh(scores)
+
+    def set_thresh(self, thresh=None, *args, **kwds):
+        assert not args and not kwds, \
+            "Neither args nor kwds permitted with spec '{}'".format(thresh)
+        self._thresh = self._check_spec(thresh, 'thresh')
+        if self._thresh is not None:
+            self.set_update(thresh)
+
+    def set_update(self, update=None, *args, **kwds):
+        assert not args and not kwds, \
+            "Neither args nor kwds permitted with spec '{}'".format(update)
+        self._update = self._check_spec(update, 'update')
+
+    # ---- sampler bookkeeping --------------------------------------------------------------------
+    def reset(self, sampler_id=None, reset_last=True):
+        if sampler_id is None:
+            self._samplers = []
+            return
+        s = self.get_sampler(sampler_id)
+        s.counter = 0
+        if reset_last:
+            s.state = s.state_lp = None
+
+    def get_sampler(self, sampler_id=None):
+        if sampler_id is None:
+            return self._samplers
+        return self._samplers[sampler_id] if isinstance(sampler_id, int) else sampler_id
+
+    def get_counter(self, sampler_id=None):
+        if sampler_id is None:
+            return {s: s.counter for s in self._samplers}
+        return self.get_sampler(sampler_id).counter
+
+    def sampler(self, *args, **kwds):
+        """sampler(init_state, [observations], stop=T, iid=, joint=, **new_kwargs)."""
+        kwds = dict(kwds)
+        stop = kwds.pop('stop', None)
+        if len(args) == 1 and type(args[0]) is int and stop is None:
+            stop, args = args[0], ()
+        if not args:
+            raise NotImplementedError("random initial states ({0}) are not in the device "
+                                      "catalogue: pass an initial-state dictionary")
+        init = self.parse_values(args[0])
+        obs = self.parse_values(args[1]) if len(args) > 1 else None
+        opts = dict(iid=kwds.pop('iid', False), joint=kwds.pop('joint', False),
+                    chains=kwds.pop('chains', None), thin=int(kwds.pop('thin', 1)),
+                    seed=kwds.pop('seed', None), accept=kwds.pop('accept', None),
+                    inj_delta=kwds.pop('inj_delta', None),
+                    inj_thresh=kwds.pop('inj_thresh', None),
+                    host_stream=kwds.pop('host_stream', False),
+                    variant=kwds.pop('variant', 0))
+        assert not kwds, "Unknown sampler keywords: {}".format(list(kwds))
+        s = Sampler(self, init, obs, stop, opts)
+        self._samplers.append(s)
+        return s
+
+    # ---- the walk ----------------------------------------------------------------------------------
+    def walk(self, sampler, stop=None):
+        """Runs the sampler for ``stop`` steps (default: its own ``stop``) on the
+        device and returns a :class:`Walk`."""
+        assert isinstance(sampler, Sampler), \
+            'Sampler must be a sampler instance returned by SP.sampler()'
+        T = stop if stop is not None else sampler.stop
+        if T is None:
+            raise ValueError("No stop specification set - a device walk needs a finite length")
+        if sampler.stop is not None:
+            T = min(T, sampler.stop - sampler.counter)
+        arrays = self._run(sampler, int(T))
+        sampler.counter += int(T)
+        if sampler.stop is not None and sampler.counter >= sampler.stop:
+            sampler.counter = 0                  # auto-reset (sp_utils.py:15-16)
+        out = Walk()
+        out.arrays, out.sampler = arrays, sampler
+        if arrays['chains'] is None and arrays['R'] <= 200000:
+            out.extend(self._per_step(arrays))
+        return out
+
+    def _run(self, sampler, T):
+        from .engine import get_engine
+        if self._scores is None:
+            raise NotImplementedError("set_scores('metropolis' | 'hastings' | 'gibbs') first")
+        opts = sampler.opts
+        eng = get_engine()
+        state_rf = self._state_rf
+        keys = state_rf.keylist
+        D = len(keys)
+        Cn = opts['chains']
+        C = 1 if Cn is None else int(Cn)
+        spec = catalogue.identify_target(self, self._leafs, self._roots)
+        injected = opts['inj_delta'] is not None
+        seed = opts['seed']
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))     # the reference draws from np.random
+        thin = opts['thin']
+        step0 = sampler.counter
+        # ---- initial / resumed state [D, C] ------------------------------------------------
+        if sampler.state is None or step0 == 0:
+            init = np.empty((D, C))
+            for j, k in enumerate(keys):
+                init[j] = np.broadcast_to(np.asarray(sampler.init[k], dtype=np.float64), (C,))
+            sampler.state, sampler.state_lp = eng.to_device(init), None
+        state = sampler.state
+        inj_d = inj_t = None
+        if opts['inj_thresh'] is not None:       # thresholds (MH) / cdf uniforms (Gibbs)
+            t = np.asarray(opts['inj_thresh'], dtype=np.float64)
+            t = (t[:, None] if t.ndim == 1 else t)[step0:step0 + T]
+            assert t.shape == (T, C), "injected threshold stream shape mismatch"
+            inj_t = eng.to_device(t)
+        if injected:
+            assert inj_t is not None, "inj_delta needs inj_thresh"
+            d = np.asarray(opts['inj_delta'], dtype=np.float64)
+            d = (d[:, None, :] if d.ndim == 2 else d)[step0:step0 + T]
+            assert d.shape == (T, C, D), "injected delta stream shape mismatch"
+            inj_d = eng.to_device(np.ascontiguousarray(np.transpose(d, (0, 2, 1))))
+        accept = opts['accept'] or ('reference' if injected else 'log')
+        per_step = Cn is None and T <= 200000
+        gibbs = self._scores == 'gibbs'
+        res = dict(keys=keys, chains=Cn, T=T, thin=thin, R=T // thin, spec=spec,
+                   inj_thresh=None if inj_t is None else np.asarray(opts['inj_thresh']),
+                   gibbs=gibbs, pscale=self._pscale)
+        if gibbs:
+            cc = self._cond_cov
+            if spec['kind'] != 'mvn' or cc is None:
+                raise NotImplementedError("Gibbs needs a scipy.stats.multivariate_normal "
+                                          "transition (set_tran(mvn, mean, cov, tsteps=1))")
+            tsteps = self._tran_obj.tsteps or D
+            if tsteps != 1:
+                raise NotImplementedError("tsteps=1 (one coordinate per step) only")
+            out = eng.gibbs_mvn(state, cc, T, thin=thin, seed=seed, step0=step0,
+                                log_pscale=spec['log_pscale'],
+                                inj_runif=inj_t)
+            res.update(x=out['x'], prob=out['prob'], accept_count=None, accept=None, score=None)
+            return self._finish(res, eng)
+        prop = catalogue.identify_proposal(self._proposal_rf(), self._pscale, injected)
+        coef = prop['coef'] if self._scores == 'hastings' else 1.0
+        if spec['kind'] == 'mvn':
+            assert spec['names'] == keys
+            if opts['host_stream'] and not injected and not per_step:
+                h = eng.mh_mvn_walk_host(state.cpu().numpy(), spec['mean'], spec['cov'], T,
+                                         thin=thin, seed=seed, step0=step0,
+                                         log_pscale=spec['log_pscale'], accept=accept,
+                                         prop=prop['kind'], prop_scale=prop['scale'],
+                                         prop_radius=prop['radius'], prop_chol=prop['chol'],
+                                         state_lp=None if sampler.state_lp is None
+                                         else sampler.state_lp.cpu().numpy())
+                sampler.state = eng.to_device(h['state'])
+                sampler.state_lp = eng.to_device(h['state_lp'])
+                res.update(x=h['x'], prob=h['prob'], accept_count=h['accept_count'],
+                           accept=None, score=None, stat_sum=h['stat_sum'],
+                           stat_sumsq=h['stat_sumsq'])
+                return self._finish(res, eng)
+            out = eng.mh_mvn(state, spec['mean'], spec['cov'], T, thin=thin, seed=seed,
+                             step0=step0, log_pscale=spec['log_pscale'], accept=accept,
+                             prop=prop['kind'], prop_scale=prop['scale'],
+                             prop_radius=prop['radius'], prop_chol=prop['chol'],
+                             inj_delta=inj_d, inj_thresh=inj_t, state_lp=sampler.state_lp,
+                             per_step=per_step, variant=opts['variant'])
+        else:
+            if not opts['iid']:
+                raise NotImplementedError("the normal-likelihood target needs iid=True")
+            if sampler.obs is None or spec['obs_y'] not in sampler.obs:
+                raise ValueError("observations for '{}' are required".format(spec['obs_y']))
+            assert spec['params'] == keys, \
+                "parameter field order {} must be {}".format(keys, spec['params'])
+            if 'obs_dev' not in sampler.__dict__:
+                y = eng.to_device(np.ravel(np.asarray(sampler.obs[spec['obs_y']], np.float64)))
+                x = None
+                if spec['has_slope']:
+                    x = eng.to_device(np.ravel(np.asarray(sampler.obs[spec['obs_x']],
+                                                          np.float64)))
+                sampler.obs_dev = (y, x)
+            y, x = sampler.obs_dev
+            rvs = [state_rf[k] for k in keys]
+            lims = np.array([rv.vlims for rv in rvs])
+            ex = np.array([rv.open_ends for rv in rvs], dtype=int)
+            lg = np.array([rv.log_ufun for rv in rvs], dtype=int)
+            if not opts['joint']:
+                raise NotImplementedError("likelihood-only sampling (joint=False) is not in the "
+                                          "device catalogue: the box priors are part of K2")
+            out = eng.mh_normreg(state, y, x, T, lims, ex, lg, prop['scale'], thin=thin,
+                                 seed=seed, step0=step0, accept=accept, accept_coef=coef,
+                                 prop=prop['kind'], prop_radius=prop['radius'],
+                                 inj_delta=inj_d, inj_thresh=inj_t,
+                                 state_lp=sampler.state_lp, per_step=per_step,
+                                 variant=opts['variant'])
+            res['n_obs'] = int(y.numel())
+        sampler.state_lp = out['state_lp']
+        res.update(x=out['x'], prob=out['prob'], accept_count=out['accept_count'],
+                   accept=out.get('accept'), score=out.get('score'),
+                   stat_sum=out.get('stat_sum'), stat_sumsq=out.get('stat_sumsq'))
+        return self._finish(res, eng)
+
+    @staticmethod
+    def _finish(res, eng):
+        """Device results -> host arrays ([R, D, C] / [R, C])."""
+        def host(a):
+            if a is None or isinstance(a, np.ndarray):
+                return a
+            return a.detach().cpu().numpy()
+        eng.sync()
+        for k in ('x', 'prob', 'accept_count', 'accept', 'score', 'stat_sum', 'stat_sumsq'):
+            res[k] = host(res.get(k))
+        return res
+
+    # ---- result marshalling --------------------------------------------------------------------------
+    def _value_pd(self, arrays, sel=None):
+        """PD of the retained states: arrays [R] per variable (single chain) or
+        [C, R] (batched), named like the reference's summate() result."""
+        keys, x, prob = arrays['keys'], arrays['x'], arrays['prob']
+        single = arrays['chains'] is None
+        vals = collections.OrderedDict()
+        for j, k in enumerate(keys):
+            v = x[:, j, 0] if single else x[:, j, :].T
+            vals[k] = v if sel is None else v[sel]
+        p = prob[:, 0] if single else prob.T
+        if sel is not None:
+            p = p[sel]
+        names = list(keys)
+        dims = collections.OrderedDict((k, 0) for k in keys)
+        spec = arrays['spec']
+        if spec['kind'] == 'normreg':
+            n = arrays['n_obs'] * (1 if sel is not None and np.ndim(p) == 0 else arrays['R'])
+            for ok in [k for k in (spec['obs_x'], spec['obs_y']) if k]:
+                vals[ok] = {n}
+                dims[ok] = None
+                names.append("{}={{{}}}".format(ok, n))
+        if sel is not None and np.ndim(p) == 0:
+            names = ["{}={}".format(k, vals[k]) if k in keys else n_
+                     for k, n_ in zip(list(vals.keys()), names)]
+            dims = collections.OrderedDict((k, None) for k in vals)
+            p = float(p)
+        return PD(','.join(names), vals, dims=dims, prob=p, pscale=arrays['pscale'])
+
+    def _per_step(self, arrays):
+        """Reference-shaped per-step tuples for a single chain (thin == 1 only for
+        s / t / u alignment)."""
+        out = []
+        R = arrays['R']
+        acc, score, thr = arrays.get('accept'), arrays.get('score'), arrays.get('inj_thresh')
+        aligned = arrays['thin'] == 1
+        for i in range(R):
+            v = self._value_pd(arrays, sel=i)
+            s = t = u = None
+            if arrays['gibbs']:
+                s, t, u = np.nan, np.nan, True
+            elif aligned and acc is not None:
+                u = True if acc[i, 0] else None
+                s = None if np.isnan(score[i, 0]) else float(score[i, 0])
+                t = None if thr is None else float(np.ravel(thr)[i])
+            out.append(self.opqrstuv(None, None, None, None, s, t, u, v))
+        return out
+
+    def __call__(self, *args, **kwds):
+        """process(samples) -> opqrstuv summary with array-valued ``v``; other
+        call signatures are the SD grid evaluation."""
+        conditionalise = kwds.pop('conditionalise', None)
+        samples = args[0] if args else None
+        if isinstance(samples, Walk) or (isinstance(samples, (list, tuple, collections.deque))
+                                         and len(samples)
+                                         and isinstance(samples[0], self.opqrstuv)):
+            return self._summary(samples, conditionalise)
+        return super().__call__(*args, **kwds)
+
+    def _summary(self, samples, conditionalise=None):
+        arrays = samples.arrays if isinstance(samples, Walk) else None
+        if arrays is None:
+            # a plain list of per-step tuples: concatenate their scalar PDs
+            vs = [s.v for s in samples if s.u is not False]
+            keys = list(vs[0].keys())
+            vals = collections.OrderedDict()
+            for k in keys:
+                if isinstance(vs[0][k], set):
+                    vals[k] = {sum(list(v[k])[0] for v in vs)}
+                else:
+                    vals[k] = np.array([v[k] for v in vs])
+            dims = collections.OrderedDict((k, None if isinstance(vals[k], set) else 0)
+                                           for k in keys)
+            names = [k if not isinstance(vals[k], set) else "{}={}".format(k, vals[k])
+                     for k in keys]
+            v = PD(','.join(names), vals, dims=dims, prob=np.array([p.prob for p in vs]),
+                   pscale=vs[0].pscale)
+            u = [s.u for s in samples if s.u is not False]
+            s_ = [s.s for s in samples if s.s is not None]
+            t_ = [s.t for s in samples if s.t is not None]
+            return self.opqrstuv(None, None, None, None, s_ or None, t_ or None, u, v)
+        v = self._value_pd(arrays)
+        if conditionalise:
+            raise NotImplementedError("conditionalise= on sample summaries is not in the "
+                                      "device catalogue")
+        if arrays['chains'] is None and len(samples):
+            u = [s.u for s in samples]
+            s_ = [s.s for s in samples if s.s is not None]
+            t_ = [s.t for s in samples if s.t is not None]
+            return self.opqrstuv(None, None, None, None, s_ or None, t_ or None, u, v)
+        if arrays['gibbs']:
+            C = 1 if arrays['chains'] is None else arrays['chains']
+            u = AcceptRecord(np.full(C, arrays['T']), arrays['T'])
+        else:
+            u = AcceptRecord(arrays['accept_count'], arrays['T'])
+        return self.opqrstuv(None, None, None, None, None, None, u, v)
+
+    # ---- chain diagnostics (new) -------------------------------------------------------------------------
+    @staticmethod
+    def rhat(summary_v):
+        """Gelman-Rubin R-hat per variable from a batched summary ``v`` ([C, R] arrays)."""
+        out = collections.OrderedDict()
+        for k, a in summary_v.items():
+            if isinstance(a, set) or np.ndim(a) != 2:
+                continue
+            T = a.shape[1]
+            W = a.var(axis=1, ddof=1).mean()
+            B = T * a.mean(axis=1).var(ddof=1)
+            out[k] = float(np.sqrt(((T - 1) / T * W + B / T) / W))
+        return out

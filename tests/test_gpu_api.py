@@ -1,0 +1,234 @@
+"""The reference's example workloads through the drop-in public API
+(import probayes_b200 as pb) on the GPU, against the golden fixtures generated
+from the live reference with the same injected streams.  The set-up code of each
+test is the example script's, unchanged except for the delta injection."""
+import numpy as np
+import pytest
+import scipy.stats
+from conftest import load_golden, relerr
+from gpu_util import engine
+import probayes_b200 as pb
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_log"])
+def test_mcmc_prob4a(name):
+    """examples/mcmc/mcmc_prob4a.py:38-54."""
+    engine()
+    g = load_golden(name)
+    n_steps = len(g["thresh"])
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    process = pb.SP(x & y)
+    if bool(g["log_pscale"]):
+        process.set_prob(scipy.stats.multivariate_normal, [0., 0.], [[2.0, 1.2], [1.2, 2.0]],
+                         pscale='log')
+    else:
+        process.set_prob(scipy.stats.multivariate_normal, [0., 0.], [[2.0, 1.2], [1.2, 2.0]])
+    process.set_tran(lambda **kwds: 1.)
+    process.set_delta(lambda: None)                      # draws are injected below
+    process.set_scores('hastings')
+    process.set_update('metropolis')
+    sampler = process.sampler({'x': 0., 'y': 1.}, stop=n_steps,
+                              inj_delta=g["delta"], inj_thresh=g["thresh"])
+    samples = [sample for sample in sampler]
+    assert len(samples) == n_steps
+    summary = process(samples)
+    n_accept = summary.u.count(True)
+    inference = summary.v.rescaled()
+    xvals, yvals, post = inference['x'], inference['y'], inference.prob
+    assert n_accept == int(g["u"].sum())
+    assert [u is True for u in summary.u] == list(g["u"])
+    assert np.abs(xvals - g["x"][:, 0]).max() <= TOL and np.abs(yvals - g["x"][:, 1]).max() <= TOL
+    want = np.exp(g["prob"]) if bool(g["log_pscale"]) else g["prob"]
+    assert relerr(post, want) <= TOL
+    assert summary.v.name == 'x,y' and len(summary.s) == n_steps - 1
+    assert relerr(np.array(summary.s), g["s"][1:]) <= TOL
+    assert samples[3].v.name.startswith('x=') and samples[3].u in (True, None)
+
+
+@pytest.mark.parametrize("name,scores,delta", [
+    ("mh_norm1d_spherical", 'hastings', (0.005,)), ("mh_norm1d_hastings", 'hastings', [0.005]),
+    ("mh_norm1d_metropolis", 'metropolis', [0.005])])
+def test_metrohast_norm1d(name, scores, delta):
+    """examples/mcmc/metrohast_norm1d.py:23-45 (tuple step = spherical proposal,
+    (tran, tran) pair = the e-exponent hastings score)."""
+    engine()
+    g = load_golden(name)
+    n_steps = len(g["thresh"])
+    mu = pb.RV('mu', vtype=float, vset=(40, 60), pscale='log')
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.), pscale='log')
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    sigma.set_ufun((np.log, np.exp))
+    paras = pb.RF(mu, sigma)
+    stats = pb.RF(x)
+    process = pb.SP(stats, paras)
+    process.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'})
+    tran = lambda **x: 1.
+    paras.set_tran((tran, tran) if scores == 'hastings' else tran)
+    paras.set_delta(delta, scale=True)
+    process.set_tran(paras)
+    process.set_delta(paras)
+    process.set_scores(scores)
+    if scores == 'hastings':
+        process.set_update('metropolis')
+    init_state = {mu: 50., sigma: 12.5}
+    sampler = process.sampler(init_state, {x: g["x_obs"]}, stop=n_steps, iid=True, joint=True,
+                              inj_delta=g["delta"], inj_thresh=g["thresh"])
+    samples = process.walk(sampler)
+    summary = process(samples)
+    inference = summary.v.rescaled()
+    assert summary.u.count(True) == int(g["u"].sum())
+    assert [u is True for u in summary.u] == list(g["u"])
+    assert relerr(summary.v['mu'], g["x"][:, 0]) <= TOL
+    assert relerr(summary.v['sigma'], g["x"][:, 1]) <= TOL
+    assert relerr(summary.v.prob, g["prob"]) <= TOL
+    assert summary.v.name == 'mu,sigma,x={{{}}}'.format(len(g["x_obs"]) * n_steps)
+    assert inference.pscale == 1.
+
+
+def test_linreg_mh_with_user_likelihood():
+    """Config C3's model at reference-feasible size (gibbs_linreg.py:28-36 priors and
+    ``norm_reg`` likelihood, driven as MH per SURVEY appendix B.5)."""
+    engine()
+    g = load_golden("mh_linreg")
+    n_steps = len(g["thresh"])
+    x = pb.RV('x', vtype=float, vset=[-3, 3])
+    y = pb.RV('y', vtype=float, vset=[-np.inf, np.inf])
+    beta_0 = pb.RV('beta_0', vtype=float, vset=[-6., 6.], pscale='log')
+    beta_1 = pb.RV('beta_1', vtype=float, vset=[-6., 6.], pscale='log')
+    y_sigma = pb.RV('y_sigma', vtype=float, vset=[(0.001), 10.], pscale='log')
+
+    def norm_reg(x, y, beta_0, beta_1, y_sigma):
+        return scipy.stats.norm.logpdf(y, loc=beta_0 + beta_1 * x, scale=y_sigma)
+
+    stats = x & y
+    paras = beta_0 & beta_1 & y_sigma
+    process = pb.SP(stats, paras)
+    process.set_prob(norm_reg, pscale='log')
+    paras.set_tran(lambda **k: 0.)
+    paras.set_delta([0.02])
+    process.set_tran(paras)
+    process.set_delta(paras)
+    process.set_scores('metropolis')
+    init = g["init"]
+    sampler = process.sampler({'beta_0': init[0], 'beta_1': init[1], 'y_sigma': init[2]},
+                              {'x,y': [g["x_obs"], g["y_obs"]]}, stop=n_steps, iid=True,
+                              joint=True, inj_delta=g["delta"], inj_thresh=g["thresh"])
+    summary = process(process.walk(sampler))
+    assert [u is True for u in summary.u] == list(g["u"])
+    for j, k in enumerate(['beta_0', 'beta_1', 'y_sigma']):
+        assert relerr(summary.v[k], g["x"][:, j]) <= TOL
+    assert relerr(summary.v.prob, g["prob"]) <= TOL
+    # native RNG, many chains, log rule: same model object, new kwargs only
+    sampler = process.sampler({'beta_0': -1., 'beta_1': 1.5, 'y_sigma': 0.5},
+                              {'x,y': [g["x_obs"], g["y_obs"]]}, stop=400, iid=True, joint=True,
+                              chains=256, thin=4, seed=3)
+    summary = process(process.walk(sampler))
+    assert summary.v['beta_0'].shape == (256, 100) and summary.v.prob.shape == (256, 100)
+    assert 0.3 < summary.u.rate() < 0.95
+    lr = scipy.stats.linregress(g["x_obs"], g["y_obs"])
+    assert abs(summary.v['beta_1'][:, 20:].mean() - lr.slope) < 0.03
+    assert all(abs(v - 1) < 0.2 for v in process.rhat(summary.v).values())
+
+
+@pytest.mark.parametrize("name", ["dgei_small", "dgei_peaked"])
+def test_dgei_norm1d_improved(name):
+    """examples/dgei/dgei_norm1d_improved.py:20-46."""
+    engine()
+    g = load_golden(name)
+    data = g["data"]
+    resolution = {'mu': {len(g["mu"])}, 'sigma': {len(g["sigma"])}}
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    paras = pb.RF(mu, sigma)
+    stats = pb.RF(x)
+    model = pb.SD(stats, paras)
+    model.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'},
+                   pscale='log')
+    joint = model({x: data, **resolution}, iid=True, joint=True)
+    posterior = joint.conditionalise('x')
+    post_expt = posterior.expectation()
+    post_expt.pop('x')
+    post_mean = posterior.marginal('mu')
+    post_stdv = posterior.marginal('sigma')
+    post_mean_medn = post_mean.quantile()
+    post_stdv_medn = post_stdv.quantile()
+    post_prob = posterior.rescaled().prob
+    assert joint.name == str(g["joint_name"]) and posterior.name == str(g["post_name"])
+    assert post_mean.name == str(g["marg_mu_name"])
+    assert joint.prob_device is not None and posterior.prob_device is not None
+    assert np.array_equal(np.ravel(posterior['mu']), g["mu"])
+    assert np.array_equal(np.ravel(posterior['sigma']), g["sigma"])
+    assert relerr(joint.prob, g["joint"]) <= TOL
+    atol = TOL * np.abs(g["joint"]).max()          # see tests/test_gpu_grid.py
+    clamp = g["posterior"] == pb.NEARLY_NEGATIVE_INF
+    assert np.array_equal(posterior.prob == pb.NEARLY_NEGATIVE_INF, clamp)
+    assert np.abs(posterior.prob[~clamp] - g["posterior"][~clamp]).max() <= atol
+    assert np.abs(post_mean.prob - g["marg_mu"]).max() <= atol
+    assert np.abs(post_stdv.prob - g["marg_sigma"]).max() <= atol
+    assert np.abs(post_prob - g["post_linear"]).max() <= atol * g["post_linear"].max()
+    assert abs(post_expt['mu'] - g["expt_mu"]) <= 1e-9
+    assert abs(post_expt['sigma'] - g["expt_sigma"]) <= 1e-9
+    assert abs(post_mean_medn['mu'] - g["med_mu"]) <= 1e-9
+    assert abs(post_stdv_medn['sigma'] - g["med_sigma"]) <= 1e-9
+
+
+def test_gibbs_norm2d():
+    """examples/mcmc/gibbs_norm2d.py:10-26."""
+    engine()
+    g = load_golden("gibbs2d")
+    lims = (-10., 10.)
+    n_steps = len(g["runif"])
+    means = [0.5, -0.5]
+    covar = [[1.5, -1.0], [-1.0, 2.]]
+    x = pb.RV('x', vtype=float, vset=lims)
+    y = pb.RV('y', vtype=float, vset=lims)
+    process = pb.SP(x & y)
+    process.set_prob(scipy.stats.multivariate_normal, means, covar)
+    process.set_tran(scipy.stats.multivariate_normal, means, covar, tsteps=1)
+    process.set_scores('gibbs')
+    sampler = process.sampler({'x': 0., 'y': 1.}, stop=n_steps, inj_thresh=g["runif"])
+    samples = [sample for sample in sampler]
+    summary = process(samples)
+    n_accept = summary.u.count(True)
+    inference = summary.v.rescaled()
+    xvals, yvals, post = inference['x'], inference['y'], inference.prob
+    assert n_accept == n_steps == int(g["n_true"])
+    assert np.abs(xvals - g["x"][:, 0]).max() <= 1e-11
+    assert np.abs(yvals - g["x"][:, 1]).max() <= 1e-11
+    assert relerr(post, g["prob"]) <= 1e-11
+    assert process._cond_cov is not None and relerr(process._cond_cov.stdv, g["stdv"]) <= TOL
+
+
+def test_batched_c2_through_api_and_host_stream():
+    """Config C2 shape (reduced length) through the public API: native RNG,
+    chains=4096, both the device-resident and the host-streaming paths."""
+    engine()
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    process = pb.SP(x & y)
+    process.set_prob(scipy.stats.multivariate_normal, [0., 0.], [[2.0, 1.2], [1.2, 2.0]])
+    process.set_tran(lambda **kwds: 1.)
+    process.set_delta(scipy.stats.norm(0., 1.))
+    process.set_scores('hastings')
+    process.set_update('metropolis')
+    a = process(process.walk(process.sampler({'x': 0., 'y': 1.}, stop=600, chains=4096,
+                                             seed=9, thin=2)))
+    b = process(process.walk(process.sampler({'x': 0., 'y': 1.}, stop=600, chains=4096,
+                                             seed=9, thin=2, host_stream=True)))
+    assert a.v['x'].shape == (4096, 300)
+    assert np.array_equal(a.v['x'], b.v['x']) and np.array_equal(a.v.prob, b.v.prob)
+    assert a.u.count(True) == b.u.count(True) and 0.55 < a.u.rate() < 0.68
+    flat = np.stack([a.v['x'][:, 100:].ravel(), a.v['y'][:, 100:].ravel()])
+    assert np.abs(np.cov(flat) - [[2.0, 1.2], [1.2, 2.0]]).max() < 0.06
+    # resume: a second walk on the same sampler continues the chain
+    s = process.sampler({'x': 0., 'y': 1.}, stop=600, chains=64, seed=9)
+    w1 = process.walk(s, stop=300)
+    w2 = process.walk(s, stop=300)
+    full = process.walk(process.sampler({'x': 0., 'y': 1.}, stop=600, chains=64, seed=9))
+    assert np.array_equal(np.concatenate([w1.arrays['x'], w2.arrays['x']]), full.arrays['x'])

@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference interface (no GPU needed): pscales, RV domain
+semantics, grids, priors, PD algebra on host arrays, catalogue recognition and
+error behaviour -- checked against the golden fixtures and, when the live
+reference is present (development container), differentially against it."""
+import numpy as np
+import pytest
+import scipy.stats
+from conftest import load_golden, relerr
+import probayes_b200 as pb
+from probayes_b200 import catalogue
+from oracle import ref_shim
+
+
+def test_pscales_table_matches_reference():
+    g = load_golden("pscales")
+    assert np.array_equal(pb.log_prob(g["p"]), g["log_prob"])
+    assert np.array_equal(pb.exp_logp(g["l"]), g["exp_logp"])
+    assert np.array_equal(pb.div_prob(g["num"], g["den"]), g["div_lin"])
+    assert np.array_equal(pb.div_prob(g["lnum"], g["lden"], 0j, 0j, pscale=1.),
+                          g["div_log_to_lin"])
+    assert np.array_equal(pb.rescale(g["p"], 1., 0j), g["resc_lin_to_log"])
+    assert np.array_equal(pb.rescale(g["l"], 0j, 1.), g["resc_log_to_lin"])
+
+
+def test_eval_pscale_and_products():
+    assert pb.eval_pscale(None) == 1. and pb.eval_pscale(1) == 1.
+    assert pb.eval_pscale('log') == 0j and pb.eval_pscale(0) == 0j and pb.eval_pscale('ln') == 0j
+    assert pb.eval_pscale(2.5) == 2.5 and pb.eval_pscale(3 + 0j) == 3 + 0j
+    with pytest.raises(ValueError):
+        pb.eval_pscale('linear')
+    assert pb.prod_pscale([1., 1.]) == 1. and pb.prod_pscale([0j, 1.]) == 0j
+    p, ps = pb.prod_rule(np.log(0.2), np.log(0.5), pscales=[0j, 0j])
+    assert ps == 0j and np.isclose(p, np.log(0.1))
+    p, ps = pb.prod_rule(0.2, np.log(0.5), pscales=[1., 0j])
+    assert ps == 0j and np.isclose(p, np.log(0.1))
+    p, ps = pb.prod_rule(0.2, 0.5, pscales=[1., 1.])
+    assert ps == 1. and np.isclose(p, 0.1)
+
+
+def test_rv_domain_semantics():
+    a = pb.RV('a', vtype=float, vset=(40, 60))                 # tuple: both ends open
+    assert a.vset == [(40.,), (60.,)] and a.open_ends == (True, True)
+    assert not a.inside(40.) and a.inside(50.) and not a.inside(60.)
+    b = pb.RV('b', vtype=float, vset=[-6., 6.])                # list: closed
+    assert b.inside(-6.) and b.inside(6.) and b.length == 12.
+    c = pb.RV('c', vtype=float, vset=[(0.001,), 10.])          # mixed
+    assert c.open_ends == (True, False) and not c.inside(0.001) and c.inside(10.)
+    d = pb.RV('d', vtype=float, vset=[(0.001), 10.])           # (0.001) is NOT a tuple
+    assert d.open_ends == (False, False)
+    e = pb.RV('e')
+    assert np.isinf(e.length) and not e.isfinite
+    with pytest.raises(NotImplementedError):
+        pb.RV('k', vtype=int, vset=[0, 1])
+    s = pb.RV('s', vtype=float, vset=(5, 20.), pscale='log')
+    s.set_ufun((np.log, np.exp))
+    assert np.isclose(s.length, np.log(4.)) and s.log_ufun
+    assert np.isclose(s.eval_prob(7.), -np.log(np.log(4.)))     # no Jacobian
+    assert s.eval_prob(25.) == pb.NEARLY_NEGATIVE_INF
+    lin = pb.RV('q', vtype=float, vset=[0., 4.])
+    assert np.isclose(lin.eval_prob(1.), 0.25) and lin.eval_prob(5.) == 0.
+    with pytest.raises(NotImplementedError):
+        s.set_ufun((np.sqrt, np.square))
+
+
+def test_grids_match_golden():
+    g = load_golden("dgei_small")
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sg = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    sg.set_ufun((np.log, np.exp))
+    assert np.array_equal(mu.evaluate({len(g["mu"])}), g["mu"])
+    assert np.array_equal(sg.evaluate({len(g["sigma"])}), g["sigma"])
+    assert np.array_equal(pb.uniform(0, 1, 4), np.linspace(0, 1, 4))
+    assert np.array_equal(pb.uniform(0, 1, 1), [0.5])
+    assert np.array_equal(pb.uniform(0, 1, 3, True, False), np.linspace(0, 1, 4)[1:])
+    assert np.array_equal(pb.uniform(0, 1, 3, False, True), np.linspace(0, 1, 4)[:-1])
+
+
+def test_pd_host_algebra_matches_golden():
+    """PD.conditionalise / marginal / expectation / quantile / rescaled on a
+    host-backed PD reproduce the reference's outputs (dgei_small)."""
+    g = load_golden("dgei_small")
+    N = len(g["data"])
+    joint = pb.PD("mu=[],sigma=[],x={{{}}}".format(N),
+                  {'mu': g["mu"], 'sigma': g["sigma"], 'x': {N}},
+                  dims={'mu': 0, 'sigma': 1, 'x': None}, prob=g["joint"], pscale='log')
+    assert joint.name == str(g["joint_name"])
+    post = joint.conditionalise('x')
+    assert post.name == str(g["post_name"])
+    assert relerr(post.prob, g["posterior"]) <= 1e-12
+    pm, psg = post.marginal('mu'), post.marginal('sigma')
+    assert pm.name == str(g["marg_mu_name"])
+    assert relerr(pm.prob, g["marg_mu"]) <= 1e-12 and relerr(psg.prob, g["marg_sigma"]) <= 1e-12
+    ex = post.expectation()
+    assert abs(ex['mu'] - g["expt_mu"]) <= 1e-10 and abs(ex['sigma'] - g["expt_sigma"]) <= 1e-10
+    assert abs(pm.quantile()['mu'] - g["med_mu"]) <= 1e-10
+    assert abs(psg.quantile()['sigma'] - g["med_sigma"]) <= 1e-10
+    q3 = pm.quantile([0.025, 0.5, 0.975])
+    assert np.abs(np.array([q['mu'] for q in q3]) - g["q3_mu"]).max() <= 1e-10
+    assert relerr(post.rescaled().prob, g["post_linear"]) <= 1e-12
+    srt = pm.sorted('mu')
+    assert np.array_equal(srt['mu'], np.sort(g["mu"]))
+    iid = pb.PD("x=[]", {'x': np.arange(3.)}, prob=np.log([.1, .2, .3]), pscale='log').prod('x')
+    assert iid.name == "x={3}" and np.isclose(iid.prob, np.log(.006))
+
+
+def _mvn_sp():
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    sp = pb.SP(x & y)
+    sp.set_prob(scipy.stats.multivariate_normal, [0., 0.], [[2.0, 1.2], [1.2, 2.0]])
+    return sp
+
+
+def test_catalogue_recognition():
+    sp = _mvn_sp()
+    spec = catalogue.identify_target(sp, sp.leafs, sp.roots)
+    assert spec['kind'] == 'mvn' and spec['names'] == ['x', 'y'] and not spec['log_pscale']
+    sp.set_delta(scipy.stats.norm(0., 0.7))
+    pr = catalogue.identify_proposal(sp._proposal_rf(), sp.pscale)
+    assert pr['kind'] == 'normal' and np.allclose(pr['scale'], 0.7)
+    sp.set_delta(lambda: None)
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_proposal(sp._proposal_rf(), sp.pscale)
+    catalogue.identify_proposal(sp._proposal_rf(), sp.pscale, injected=True)
+    sp.set_tran(np.array([[0.5, 0.2], [0.2, 0.8]]))
+    sp.set_delta(scipy.stats.norm(0., 1.))
+    pr = catalogue.identify_proposal(sp._proposal_rf(), sp.pscale)
+    assert np.allclose(pr['chol'], np.linalg.cholesky([[0.5, 0.2], [0.2, 0.8]]))
+    sp.set_prob(lambda x, y: x + y)
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_target(sp, sp.leafs, sp.roots)
+
+
+def test_catalogue_normal_likelihoods():
+    mu = pb.RV('mu', vtype=float, vset=(40, 60), pscale='log')
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.), pscale='log')
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    sigma.set_ufun((np.log, np.exp))
+    paras, stats = pb.RF(mu, sigma), pb.RF(x)
+    sp = pb.SP(stats, paras)
+    sp.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'})
+    spec = catalogue.identify_target(sp, sp.leafs, sp.roots)
+    assert spec == dict(kind='normreg', has_slope=False, obs_y='x', obs_x=None,
+                        params=['mu', 'sigma'], log_pscale=True)
+    tran = lambda **k: 1.
+    paras.set_tran((tran, tran))
+    paras.set_delta((0.005,), scale=True)
+    sp.set_tran(paras)
+    sp.set_delta(paras)
+    pr = catalogue.identify_proposal(sp._proposal_rf(), sp.pscale)
+    g = load_golden("mh_norm1d_spherical")
+    assert pr['kind'] == 'spherical' and np.isclose(pr['radius'], float(g["radius"]))
+    assert np.allclose(pr['scale'], g["lengths"]) and np.isclose(pr['coef'], np.e)
+    paras.set_delta([0.005], scale=True)
+    pr = catalogue.identify_proposal(sp._proposal_rf(), sp.pscale)
+    assert pr['kind'] == 'uniform' and np.allclose(pr['scale'], load_golden("mh_norm1d_hastings")["dmax"])
+    sp.set_prob(scipy.stats.norm.pdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'})
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_target(sp, sp.leafs, sp.roots)
+
+    # a user-written regression log-likelihood is recognised by probing it
+    xx = pb.RV('x', vtype=float, vset=[-3, 3])
+    yy = pb.RV('y', vtype=float, vset=[-np.inf, np.inf])
+    b0 = pb.RV('beta_0', vtype=float, vset=[-6., 6.], pscale='log')
+    b1 = pb.RV('beta_1', vtype=float, vset=[-6., 6.], pscale='log')
+    ys = pb.RV('y_sigma', vtype=float, vset=[(0.001), 10.], pscale='log')
+
+    def norm_reg(x, y, beta_0, beta_1, y_sigma):
+        return scipy.stats.norm.logpdf(y, loc=beta_0 + beta_1 * x, scale=y_sigma)
+
+    proc = pb.SP(xx & yy, b0 & b1 & ys)
+    proc.set_prob(norm_reg, pscale='log')
+    spec = catalogue.identify_target(proc, proc.leafs, proc.roots)
+    assert spec['kind'] == 'normreg' and spec['has_slope']
+    assert (spec['obs_x'], spec['obs_y']) == ('x', 'y')
+    assert spec['params'] == ['beta_0', 'beta_1', 'y_sigma']
+    proc.set_prob(lambda x, y, beta_0, beta_1, y_sigma: -np.abs(y - beta_0), pscale='log')
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_target(proc, proc.leafs, proc.roots)
+
+
+def test_sp_interface_errors_and_registry():
+    sp = _mvn_sp()
+    assert pb.MCMC_SAMPLERS == ('metropolis', 'hastings', 'gibbs')
+    sp.set_scores('hastings')
+    assert sp.scores == sp.thresh == sp.update == 'hastings'
+    sp.set_update('metropolis')
+    assert sp.update == 'metropolis'
+    with pytest.raises(NotImplementedError):
+        sp.set_scores(lambda opqr: 1.)
+    with pytest.raises(AssertionError):
+        sp.set_scores('metropolis', 3)
+    with pytest.raises(NotImplementedError):
+        sp.sampler(stop=10)
+    s = sp.sampler({'x': 0., 'y': 1.}, stop=10)
+    assert sp.get_counter(0) == 0 and sp.get_sampler(0) is s
+    with pytest.raises(ValueError):
+        sp.walk(sp.sampler({'x': 0., 'y': 1.}))            # no stop
+
+
+def test_condcov_mirror_matches_reference_constants():
+    g = load_golden("condcov_d8")
+    cc = pb.CondCov(g["mean"], g["cov"], g["lims"])
+    assert relerr(cc.stdv, g["stdv"]) <= 1e-12
+    assert np.abs(cc.coef_matrix() - g["coef"]).max() <= 1e-12
+    assert np.abs(cc.cdfs - g["cdfs"]).max() <= 1e-12
+    with pytest.raises(AssertionError):
+        pb.CondCov([0., 0.], np.eye(3), [[-1, 1]] * 2)
+
+
+@pytest.mark.skipif(not ref_shim.available(), reason="live reference not present")
+def test_differential_against_live_reference():
+    """RV lengths / priors / grids / pscales helpers against the live reference."""
+    ref = ref_shim.load()
+    from probayes import pscales as rps
+    rng = np.random.default_rng(0)
+    for vset, ufun in [((40, 60), None), ((5, 20.), (np.log, np.exp)), ([-6., 6.], None),
+                       ([(0.001,), 10.], None), ([0.5, (3.,)], (np.log, np.exp))]:
+        for pscale in (None, 'log'):
+            a = ref.RV('v', vtype=float, vset=vset, pscale=pscale)
+            b = pb.RV('v', vtype=float, vset=vset, pscale=pscale)
+            if ufun:
+                a.set_ufun(ufun)
+                b.set_ufun(ufun)
+            assert np.isclose(a.length, b.length, rtol=1e-15)
+            lo, hi = a.vlims
+            pts = np.concatenate([[lo, hi], rng.uniform(lo - 1, hi + 1, 12)])
+            assert np.array_equal(np.asarray(a.eval_prob(pts)), np.asarray(b.eval_prob(pts)))
+            for n in (1, 2, 7):
+                ga = np.ravel(a.evaluate({n})[a.name] if isinstance(a.evaluate({n}), dict)
+                              else a.evaluate({n}))
+                assert np.allclose(ga, b.evaluate({n}), rtol=1e-15, atol=0)
+    vals = rng.uniform(-800, 5, 40)
+    assert np.array_equal(rps.rescale(vals, 0j, 1.), pb.rescale(vals, 0j, 1.))
+    assert np.array_equal(rps.rescale(np.exp(vals), 1., 0j), pb.rescale(np.exp(vals), 1., 0j))
+    assert rps.prod_pscale([0j, 2.0]) == pb.prod_pscale([0j, 2.0])
