@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=0,
                     help="MH steps of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the C3/C4/C5 secondary kernel timings")
+    ap.add_argument("--quick", action="store_true", help="smaller secondary workloads")
     return ap.parse_args()
 
 
@@ -197,6 +200,127 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+
+# ---------------------------------------------------------------------------
+# secondary measurements: the other configs of BASELINE.json, one short pass each
+# ---------------------------------------------------------------------------
+def secondary(eng, peaks, fp64_peak, quick=False):
+    """log-likelihood evals/s (C3 shape), HBM-streaming likelihood roofline, DGEI
+    (C4 shape) and Gibbs (C5 shape) kernel timings; kernel-only, CUDA events."""
+    import torch
+    out = {}
+    rng = np.random.default_rng(2024)
+
+    def timeit(fn, reps=5, warm=3):
+        for _ in range(warm):
+            fn()
+        ms = []
+        for _ in range(reps):
+            fn()
+            ms.append(eng.last_kernel_ms())
+        return float(np.median(ms))
+
+    lims = np.array([[-6., 6.], [-6., 6.], [0.001, 10.]])
+    ex = np.array([[0, 0], [0, 0], [1, 0]]); lg = np.zeros(3, int)
+    # ---- C3: 16384 chains x N = 1e6 observations, tiles kernel (FP64 bound) --------
+    N, C = 1_000_000, 16384
+    x = eng.to_device(rng.normal(0, 1, N))
+    y = eng.to_device(-1 + 1.5 * x.cpu().numpy() + rng.normal(0, .5, N))
+    theta = eng.to_device(np.stack([rng.normal(-1, .001, C), rng.normal(1.5, .001, C),
+                                    rng.uniform(.49, .51, C)]))
+    ms = timeit(lambda: eng.normreg_logjoint(theta, y, x, lims, ex, lg, variant=1))
+    flops = 5.0 * N * C
+    out["c3_loglik"] = {"workload": "C3: normal log-likelihood, N=1e6 obs x 16384 chains "
+                                    "(obs tiles via TMA, chains in registers)",
+                        "ms": ms, "loglik_evals_per_s": C / (ms * 1e-3),
+                        "terms_per_s": N * C / (ms * 1e-3),
+                        "fp64_tflops": flops / (ms * 1e-3) / 1e12,
+                        "fp64_frac_of_measured_peak": flops / (ms * 1e-3) / 1e12 / fp64_peak,
+                        "note": "3 FP64 instr (fma, add, fma = 5 flop) per term: pipe-time "
+                                "ceiling is 5/6 of the FMA-only flop peak"}
+    sd = 0.5 / np.sqrt(N)
+    st = eng.to_device(np.tile(np.array([[-1.], [1.5], [.5]]), (1, C)))
+    T = 3 if quick else 10
+    burn = eng.mh_normreg(st, y, x, 2, lims, ex, lg, [2.4 * sd] * 3, seed=1, record=False)
+    ms_mh = timeit(lambda: eng.mh_normreg(st, y, x, T, lims, ex, lg, [2.4 * sd] * 3, seed=1,
+                                          step0=2, state_lp=burn["state_lp"], record=False),
+                   reps=3, warm=1)
+    out["c3_mh"] = {"workload": "C3: MH, 16384 chains, N=1e6, %d steps per call" % T,
+                    "ms_per_mh_step": ms_mh / T, "chain_steps_per_s": C * T / (ms_mh * 1e-3),
+                    "loglik_evals_per_s": C * T / (ms_mh * 1e-3)}
+    del theta, st
+    # ---- HBM-streaming regime: <= 8 chains, N = 2^27 (2 GiB of observations > L2) ----
+    Ns = (1 << 24) if quick else (1 << 27)
+    xs = torch.randn(Ns, dtype=torch.float64, device=eng.device)
+    ys = (-1 + 1.5 * xs + 0.5 * torch.randn(Ns, dtype=torch.float64, device=eng.device))
+    for Cs in (1, 4, 8):
+        th = eng.to_device(np.stack([np.full(Cs, -1.), np.full(Cs, 1.5), np.full(Cs, .5)]))
+        ms = timeit(lambda: eng.normreg_logjoint(th, ys, xs, lims, ex, lg, variant=2))
+        gbs = 16.0 * Ns / (ms * 1e-3) / 1e9
+        out["stream_c%d" % Cs] = {"ms": ms, "hbm_gbs": gbs, "frac": gbs / peaks["hbm_gbs"],
+                                  "loglik_evals_per_s": Cs / (ms * 1e-3),
+                                  "terms_per_s": Cs * Ns / (ms * 1e-3)}
+    out["roofline_stream"] = {"bound": "hbm", "kernel": "nr_stream_kernel<8,true>",
+                              "achieved": out["stream_c4"]["hbm_gbs"], "peak": peaks["hbm_gbs"],
+                              "unit": "GB/s", "frac": out["stream_c4"]["frac"],
+                              "algorithmic_bytes_per_launch": 16.0 * Ns,
+                              "workload": "streaming normal log-likelihood, 4 chains, N=%d "
+                                          "(16 B per observation per step)" % Ns}
+    del xs, ys
+    # ---- C4: DGEI 4096 x 4096 grid, N = 1e5 ---------------------------------------------
+    Ng, M, S = (10_000 if quick else 100_000), 4096, 4096
+    data = eng.to_device(rng.normal(50., 10., Ng))
+    mu = eng.to_device(np.linspace(40, 60, M + 2)[1:-1])
+    sg = eng.to_device(np.exp(np.linspace(np.log(5), np.log(20), S + 2)[1:-1]))
+    lpm = eng.to_device(np.full(M, -np.log(20.)))
+    lps = eng.to_device(np.full(S, -np.log(np.log(4.))))
+    lj = eng.empty(M, S)
+    ms = timeit(lambda: eng.grid_norm_logjoint(data, mu, sg, lpm, lps, out=lj), reps=3, warm=1)
+    cellobs = float(Ng) * M * S
+    out["c4_logjoint"] = {"workload": "C4: DGEI log-joint, %dx%d grid, N=%d" % (M, S, Ng),
+                          "ms": ms, "terms_per_s": cellobs / (ms * 1e-3),
+                          "loglik_evals_per_s": M * S / (ms * 1e-3),
+                          "fp64_tflops": 4.0 * cellobs / (ms * 1e-3) / 1e12,
+                          "fp64_frac_of_measured_peak": 4.0 * cellobs / (ms * 1e-3) / 1e12 / fp64_peak,
+                          "note": "2 FP64 instr (mul, fma = 3 flop; SURVEY counts 4) per cell-obs"}
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        r = eng.grid_conditionalise(lj)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(5):
+        r = eng.grid_conditionalise(lj)
+    t1.record(); torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / 5
+    alg = 2.0 * 8 * M * S + 8.0 * (M + S)
+    out["c4_normalise_marginals"] = {"ms": ms, "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
+                                     "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                     "note": "max + sumexp + posterior/marginal passes "
+                                             "(3 reads + 1 write of the grid)"}
+    del lj, r
+    # ---- C5: Gibbs d = 64, 65536 chains, one sweep = 64 coordinate steps ----------------
+    from probayes_b200.cond_cov import CondCov
+    d, Cg = 64, (8192 if quick else 65536)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + np.eye(d)
+    mean = rng.standard_normal(d)
+    cc = CondCov(mean, cov, np.tile([-10., 10.], (d, 1)))
+    stg = eng.to_device(np.tile(mean[:, None], (1, Cg)))
+    sweeps = 4
+    ms = timeit(lambda: eng.gibbs_mvn(stg, cc, sweeps * d, thin=d, seed=5, want_prob=True),
+                reps=3, warm=1)
+    out["c5_gibbs"] = {"workload": "C5: Gibbs cond_cov d=64, %d chains, %d sweeps (+ DMMA "
+                                   "density per sweep)" % (Cg, sweeps),
+                       "ms_per_sweep": ms / sweeps,
+                       "coordinate_updates_per_s": Cg * d * sweeps / (ms * 1e-3),
+                       "chain_sweeps_per_s": Cg * sweeps / (ms * 1e-3)}
+    xs64 = eng.to_device(rng.standard_normal((d, Cg)))
+    ms = timeit(lambda: eng.mvn_logpdf(xs64, mean, cov))
+    out["c5_mvn_logpdf_dmma"] = {"ms": ms, "points_per_s": Cg / (ms * 1e-3),
+                                 "fp64_tflops": 2.0 * d * d * Cg / (ms * 1e-3) / 1e12}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -312,6 +436,12 @@ def run_ours(args):
             "clocks": clocks,
             "quality": {"accept_rate": acc_rate, "rhat": [float(v) for v in rhat]},
         }
+        if not args.no_secondary:
+            try:
+                line["secondary"] = secondary(eng, peaks, fp64_peak, quick=args.quick)
+                line["roofline_stream"] = line["secondary"].pop("roofline_stream")
+            except Exception as e:                           # never lose the headline line
+                line["secondary"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             steps = args.cpu_sample_steps or auto_cpu_steps(C, args.accept)
             r, cores, detail, dt = cpu_walk_rate(C, steps, args.accept)

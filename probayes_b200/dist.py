@@ -1,0 +1,118 @@
+"""Multi-GPU partitioning of the hot path: one process per GPU, launched with
+``torch.distributed`` (NCCL on the GPU box, gloo in the CPU tests).
+
+The path shards without any data-path collective:
+  * MH / Gibbs chains are independent -> contiguous chain ranges per rank, the
+    Philox stream is keyed on the GLOBAL chain id so results do not depend on the
+    number of ranks; only the per-chain summaries (for R-hat) are all-reduced,
+    once, after the walk.
+  * DGEI grids shard by mu-row slabs; the normaliser needs all-reduce(max) and
+    all-reduce(sum) of two scalars, the sigma marginal an all-reduce(sum) of an
+    S-vector, the mu marginal an all-gather of the slabs.
+The reference has no parallelism of any kind; all of this is new.
+"""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous even split of n units: returns (start, count) for ``rank``; the
+    first n % world ranks get one extra unit."""
+    assert 0 <= rank < world
+    base, extra = divmod(int(n), int(world))
+    start = rank * base + min(rank, extra)
+    return start, base + (1 if rank < extra else 0)
+
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def allreduce_chain_stats(stats, group=None):
+    """stats [D, 4] = (sum_c mean, sum_c mean^2, sum_c var, C) per dimension, as
+    produced by ``Engine.chain_stats`` on this rank's chains -> summed over ranks
+    (in place)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+    return stats
+
+
+def rhat_from_stats(stats, n_steps):
+    """Gelman-Rubin R-hat per dimension from the (all-reduced) [D, 4] summaries:
+    W = mean_c var_c;  B = T * var_c(mean_c);  R = sqrt(((T-1)/T W + B/T) / W)."""
+    st = np.asarray(stats.detach().cpu().numpy() if hasattr(stats, "detach") else stats,
+                    dtype=np.float64)
+    T = float(n_steps)
+    C = st[:, 3]
+    W = st[:, 2] / C
+    B = T * (st[:, 1] - st[:, 0] ** 2 / C) / (C - 1.0)
+    return np.sqrt(((T - 1.0) / T * W + B / T) / W)
+
+
+def pooled_moments(stats):
+    """Pooled mean per dimension and the mean within-chain variance."""
+    st = np.asarray(stats.detach().cpu().numpy() if hasattr(stats, "detach") else stats,
+                    dtype=np.float64)
+    return st[:, 0] / st[:, 3], st[:, 2] / st[:, 3]
+
+
+def grid_normaliser(local_max, local_sumexp_fn, group=None):
+    """Two-phase normaliser of a slab-sharded log-joint.
+
+    local_max: 1-element tensor (this slab's max).  local_sumexp_fn(gmax) -> 1-element
+    tensor sum exp(lj - gmax) over this slab.  Returns (gmax, gsum) identical on
+    every rank: all-reduce(max) then all-reduce(sum)."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    gmax = local_max.clone()
+    if on:
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    gsum = local_sumexp_fn(gmax)
+    if on:
+        dist.all_reduce(gsum, op=dist.ReduceOp.SUM, group=group)
+    return gmax, gsum
+
+
+def gather_slabs(local, counts, group=None):
+    """All-gather of per-rank 1-D slabs of (possibly) different lengths ``counts``
+    into one vector (the mu marginal of a slab-sharded grid)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    m = max(counts)
+    pad = torch.zeros(m, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    parts = [torch.empty_like(pad) for _ in counts]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+
+
+def dgei_sharded(engine, x_obs, mu, sigma, logprior_mu, logprior_sigma, group=None):
+    """Slab-sharded discrete grid exact inference: every rank evaluates the
+    log-joint of its mu rows, the ranks agree on the normaliser, and each returns
+    dict(post=[M_local, S] slab, marg_mu=[M] (gathered), marg_sigma=[S], rows=(start,
+    count)).  All inputs are full-size host arrays."""
+    import torch.distributed as dist
+    rank, ws = world()
+    M = len(mu)
+    start, count = shard_range(M, rank, ws)
+    sl = slice(start, start + count)
+    lj = engine.grid_norm_logjoint(engine.to_device(x_obs), engine.to_device(mu[sl]),
+                                   engine.to_device(sigma), engine.to_device(logprior_mu[sl]),
+                                   engine.to_device(logprior_sigma))
+    gmax, gsum = grid_normaliser(engine.grid_max(lj), lambda g: engine.grid_sumexp(lj, g), group)
+    post, mm, ms = engine.grid_posterior(lj, gmax, gsum, inplace=True)
+    if ws > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.SUM, group=group)
+    counts = [shard_range(M, r, ws)[1] for r in range(ws)]
+    mm = gather_slabs(mm, counts, group)
+    return dict(post=post, marg_mu=engine.log_prob_(mm), marg_sigma=engine.log_prob_(ms),
+                rows=(start, count), gmax=gmax, gsum=gsum)
