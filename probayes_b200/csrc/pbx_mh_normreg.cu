@@ -350,50 +350,95 @@ __global__ void __launch_bounds__(NR_THREADS)
 }
 
 // ----------------------------------------------------------------------------
-// phase A, "stream": <= NR_SMAX chains, one coalesced 128-bit pass over HBM
-// grid = n_slices CTAs of 256 threads, grid-stride over pairs of observations
+// phase A, "stream": <= NR_SMAX chains, ONE pass over HBM.
+// grid = 2 CTAs per SM, 256 threads; CTA b owns tiles b, b + grid, ... of 2048
+// observations.  The tiles are fetched by 1-D TMA bulk copies into a 3-stage
+// shared-memory ring (96 KB per CTA -> ~190 KB of loads in flight per SM, which is
+// what it takes to cover HBM latency at ~6.5 TB/s) and consumed with conflict-free
+// 128-bit shared loads, every thread updating all KS chains' sums; warp-shuffle +
+// block reduction; phase B in the last CTA.
 // ----------------------------------------------------------------------------
+#define NRS_THREADS 256
 template <int KS, bool kSlope>
-__global__ void __launch_bounds__(256)
-    nr_stream_kernel(const NrArgs a, const __grid_constant__ NrModel m) {
-  __shared__ double s_b0[KS], s_b1[KS];
-  __shared__ double s_red[8][KS];
-  if (threadIdx.x < KS) {
-    const int c = threadIdx.x;
-    s_b0[c] = (c < a.C) ? a.theta_in[c] : 0.0;
-    s_b1[c] = (c < a.C && kSlope) ? a.theta_in[(int64_t)a.C + c] : 0.0;
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(NRS_THREADS)
+    nr_stream_kernel(const NrArgs a, const __grid_constant__ NrModel m, int use_tma) {
+  extern __shared__ __align__(128) double sm[];            // [NR_STAGES][2][NR_TILE]
+  __shared__ __align__(8) unsigned long long full_bar[NR_STAGES];
+  __shared__ double s_red[NRS_THREADS / 32][KS];
   double b0[KS], b1[KS], acc[KS];
 #pragma unroll
-  for (int k = 0; k < KS; ++k) { b0[k] = s_b0[k]; b1[k] = s_b1[k]; acc[k] = 0.0; }
-
-  const int64_t npair = a.N / 2;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  const double2* __restrict__ y2 = reinterpret_cast<const double2*>(a.y);
-  const double2* __restrict__ x2 = reinterpret_cast<const double2*>(a.x);
-#pragma unroll 4
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npair; i += stride) {
-    const double2 yv = __ldcs(y2 + i);                     // streaming: evict-first
-    double2 xv = make_double2(0.0, 0.0);
-    if (kSlope) xv = __ldcs(x2 + i);
+  for (int k = 0; k < KS; ++k) {
+    b0[k] = (k < a.C) ? a.theta_in[k] : 0.0;
+    b1[k] = (k < a.C && kSlope) ? a.theta_in[(int64_t)a.C + k] : 0.0;
+    acc[k] = 0.0;
+  }
+  const int64_t n_full = a.N / NR_TILE;
+  // tiles of this CTA: blockIdx.x + j * gridDim.x
+  const int64_t nt = (n_full > blockIdx.x) ? (n_full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  constexpr uint32_t kTileBytes = NR_TILE * sizeof(double);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NR_STAGES; ++s) pbx_mbar_init(&full_bar[s], 1);
+    pbx_fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t j) {                            // thread 0 only
+    const int s = (int)(j % NR_STAGES);
+    double* dx = sm + (size_t)s * 2 * NR_TILE;
+    const int64_t o = ((int64_t)blockIdx.x + j * gridDim.x) * NR_TILE;
+    pbx_mbar_expect_tx(&full_bar[s], kSlope ? 2 * kTileBytes : kTileBytes);
+    if (kSlope) pbx_bulk_g2s(dx, a.x + o, kTileBytes, &full_bar[s]);
+    pbx_bulk_g2s(dx + NR_TILE, a.y + o, kTileBytes, &full_bar[s]);
+  };
+  auto tile_math = [&](const double* sx, const double* sy, int cnt) {
+#pragma unroll 2
+    for (int i = 2 * threadIdx.x; i < cnt; i += 2 * NRS_THREADS) {
+      const double2 yv = *reinterpret_cast<const double2*>(sy + i);
+      double2 xv = make_double2(0.0, 0.0);
+      if (kSlope) xv = *reinterpret_cast<const double2*>(sx + i);
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const double r0 = yv.x - (kSlope ? fma(b1[k], xv.x, b0[k]) : b0[k]);
-      const double r1 = yv.y - (kSlope ? fma(b1[k], xv.y, b0[k]) : b0[k]);
-      acc[k] = fma(r0, r0, acc[k]);
-      acc[k] = fma(r1, r1, acc[k]);
+      for (int k = 0; k < KS; ++k) {
+        const double r0 = yv.x - (kSlope ? fma(b1[k], xv.x, b0[k]) : b0[k]);
+        const double r1 = yv.y - (kSlope ? fma(b1[k], xv.y, b0[k]) : b0[k]);
+        acc[k] = fma(r0, r0, acc[k]);
+        acc[k] = fma(r1, r1, acc[k]);
+      }
+    }
+  };
+  if (use_tma) {
+    if (threadIdx.x == 0)
+      for (int64_t j = 0; j < nt && j < NR_STAGES; ++j) issue(j);
+    for (int64_t j = 0; j < nt; ++j) {
+      const int s = (int)(j % NR_STAGES);
+      pbx_mbar_wait(&full_bar[s], (uint32_t)(j / NR_STAGES) & 1);
+      const double* sx = sm + (size_t)s * 2 * NR_TILE;
+      tile_math(sx, sx + NR_TILE, NR_TILE);
+      __syncthreads();
+      if (threadIdx.x == 0 && j + NR_STAGES < nt) issue(j + NR_STAGES);
+    }
+  } else {
+    for (int64_t j = 0; j < nt; ++j) {
+      const int64_t o = ((int64_t)blockIdx.x + j * gridDim.x) * NR_TILE;
+      for (int i = threadIdx.x; i < NR_TILE; i += NRS_THREADS) {
+        if (kSlope) sm[i] = a.x[o + i];
+        sm[NR_TILE + i] = a.y[o + i];
+      }
+      __syncthreads();
+      tile_math(sm, sm + NR_TILE, NR_TILE);
+      __syncthreads();
     }
   }
-  if ((a.N & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd tail
-    const double yv = a.y[a.N - 1], xv = kSlope ? a.x[a.N - 1] : 0.0;
+  // ragged tail (< NR_TILE observations): CTA 0, straight from global memory
+  if (blockIdx.x == 0) {
+    for (int64_t i = n_full * NR_TILE + threadIdx.x; i < a.N; i += NRS_THREADS) {
+      const double yv = a.y[i], xv = kSlope ? a.x[i] : 0.0;
 #pragma unroll
-    for (int k = 0; k < KS; ++k) {
-      const double r0 = yv - (kSlope ? fma(b1[k], xv, b0[k]) : b0[k]);
-      acc[k] = fma(r0, r0, acc[k]);
+      for (int k = 0; k < KS; ++k) {
+        const double r0 = yv - (kSlope ? fma(b1[k], xv, b0[k]) : b0[k]);
+        acc[k] = fma(r0, r0, acc[k]);
+      }
     }
   }
-  // warp-shuffle reduction, then across the 8 warps through shared memory
+  // warp-shuffle reduction, then across the warps through shared memory
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < KS; ++k) {
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(256)
   if (threadIdx.x < KS && threadIdx.x < a.C) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+    for (int w = 0; w < NRS_THREADS / 32; ++w) v += s_red[w][threadIdx.x];
     a.partial[(int64_t)blockIdx.x * a.C + threadIdx.x] = v;
   }
   if (!nr_arrive_last(&a.counters[0], gridDim.x)) return;
@@ -437,7 +482,6 @@ static NrPlan nr_plan(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
   if (variant == 2 && C > NR_SMAX) variant = 1;
   const bool aligned = (((uintptr_t)p->y_obs) % 16 == 0) &&
                        (!p->has_slope || ((uintptr_t)p->x_obs) % 16 == 0);
-  if (variant == 2 && !aligned) variant = 1;               // 128-bit loads need alignment
   pl.variant = variant;
   pl.use_tma = aligned ? 1 : 0;
   pl.smem = 0;
@@ -452,10 +496,11 @@ static NrPlan nr_plan(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
     if (slices < 1) slices = 1;
     pl.n_slices = (int)slices;
   } else {
-    pl.kc = 0;
+    pl.kc = (C <= 1) ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));    // KS: chains per thread
     pl.n_groups = 1;
-    int64_t want = (p->n_obs / 2 + 255) / 256;
-    int64_t cap = (int64_t)ctx->sm_count * 8;
+    pl.smem = (size_t)NR_STAGES * 2 * NR_TILE * sizeof(double);     // 96 KB -> 2 CTAs / SM
+    int64_t want = p->n_obs / NR_TILE;
+    int64_t cap = (int64_t)ctx->sm_count * 2;
     pl.n_slices = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   }
   return pl;
@@ -526,6 +571,23 @@ static int nr_launch_tiles(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, cons
   return PBX_OK;
 }
 
+template <int KS>
+static int nr_launch_stream(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const NrModel& m) {
+  if (m.has_slope) {
+    PBX_CUDA(cudaFuncSetAttribute(nr_stream_kernel<KS, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    nr_stream_kernel<KS, true><<<pl.n_slices, NRS_THREADS, pl.smem, ctx->stream>>>(a, m,
+                                                                                  pl.use_tma);
+  } else {
+    PBX_CUDA(cudaFuncSetAttribute(nr_stream_kernel<KS, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    nr_stream_kernel<KS, false><<<pl.n_slices, NRS_THREADS, pl.smem, ctx->stream>>>(a, m,
+                                                                                   pl.use_tma);
+  }
+  PBX_LAUNCH_CHECK(ctx);
+  return PBX_OK;
+}
+
 static int nr_launch_step(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const NrModel& m) {
   if (pl.variant == 1) {
     switch (pl.kc) {
@@ -534,12 +596,12 @@ static int nr_launch_step(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const
       default: return nr_launch_tiles<1>(ctx, pl, a, m);
     }
   }
-  if (m.has_slope)
-    nr_stream_kernel<NR_SMAX, true><<<pl.n_slices, 256, 0, ctx->stream>>>(a, m);
-  else
-    nr_stream_kernel<NR_SMAX, false><<<pl.n_slices, 256, 0, ctx->stream>>>(a, m);
-  PBX_LAUNCH_CHECK(ctx);
-  return PBX_OK;
+  switch (pl.kc) {
+    case 1: return nr_launch_stream<1>(ctx, pl, a, m);
+    case 2: return nr_launch_stream<2>(ctx, pl, a, m);
+    case 4: return nr_launch_stream<4>(ctx, pl, a, m);
+    default: return nr_launch_stream<8>(ctx, pl, a, m);
+  }
 }
 
 // workspace: partial [n_slices][C] | counters [n_groups] | prop [P][C]
