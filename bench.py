@@ -138,7 +138,7 @@ def cpu_walk_rate(chains, steps, accept, seed=1234):
     except Exception:
         lib = None
     if lib is not None:
-        cores = liboracle.num_threads()
+        cores = liboracle.use_all_cores()
         t0 = time.perf_counter()
         liboracle.mh_mvn_walk(np.tile(INIT, (chains, 1)), MEAN, COV, steps, seed,
                               accept=accept, record=True)

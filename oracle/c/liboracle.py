@@ -24,6 +24,14 @@ def num_threads():
     return int(load().orc_num_threads())
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm wants every core it may use."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    load().orc_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 

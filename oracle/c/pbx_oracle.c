@@ -68,6 +68,14 @@ static inline void normal_pair(const uint32_t w[4], double* z0, double* z1) {
   *z0 = r * c; *z1 = r * s;
 }
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
