@@ -22,6 +22,116 @@
 #include <math.h>
 #include "pbx_common.cuh"
 
+// ---------------------------------------------------------------------------
+// Table-driven double-precision log / sincos(2 pi u) / exp for the RNG path.
+// CUDA's libm versions cost ~75 / ~95 / ~45 SASS instructions each, a third of them
+// constant materialisation (FP64 ops take no 64-bit immediates).  Here: one 16-byte
+// table lookup + a short polynomial whose coefficients are constant-bank operands.
+// Absolute error <= ~3e-16 (checked against the CPU Philox replay to 1e-11 in the
+// tests); inputs are the RNG's uniforms, so no special-case handling is needed.
+// ---------------------------------------------------------------------------
+struct PbxTables {
+  double2 lg[128];   // (1/c_j, log c_j),            c_j = 1 + (j + 0.5)/128
+  double2 sc[256];   // (cos, sin) of 2 pi (k + 0.5)/256
+  double ex[64];     // 2^(j/64)
+};
+static __device__ PbxTables g_tables;
+__constant__ double kLogP[5] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0};
+__constant__ double kSinP[3] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0};
+__constant__ double kCosP[3] = {-0.5, 1.0 / 24.0, -1.0 / 720.0};
+__constant__ double kExpP[4] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
+
+// log(x) for positive normal x
+__device__ __forceinline__ double fast_log(double x, const PbxTables* tb) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int e = (hi >> 20) - 1023;
+  const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // [1, 2)
+  const double2 t = tb->lg[(hi >> 13) & 127];
+  const double r = fma(m, t.x, -1.0);                                      // |r| < 2^-8
+  double p = fma(r, kLogP[4], kLogP[3]);
+  p = fma(r, p, kLogP[2]);
+  p = fma(r, p, kLogP[1]);
+  p = fma(r, p, kLogP[0]);
+  p = fma(r * r, p, r);                                                    // log1p(r)
+  return fma((double)e, 0.693147180559945309417, t.y + p);
+}
+
+// (sin, cos)(2 pi u), u = (w + 0.5) / 2^32
+__device__ __forceinline__ void fast_sincos2pi(uint32_t w, const PbxTables* tb, double& s,
+                                               double& c) {
+  const double2 t = tb->sc[w >> 24];
+  // rho = 2 pi ((w & 0xffffff) + 0.5 - 2^23) / 2^32,  |rho| < pi/256
+  const double v = __hiloint2double(0x43300000, (int)(w & 0x00FFFFFFu)) - 4503599627370496.0;
+  const double rho = (v - 8388607.5) * 1.4629180792671596e-9;             // 2 pi / 2^32
+  const double q = rho * rho;
+  double sp = fma(q, kSinP[2], kSinP[1]);
+  sp = fma(q, sp, kSinP[0]);
+  const double sr = fma(rho * q, sp, rho);                                 // sin(rho)
+  double cp = fma(q, kCosP[2], kCosP[1]);
+  cp = fma(q, cp, kCosP[0]);
+  const double cr = fma(q, cp, 1.0);                                       // cos(rho)
+  c = fma(t.x, cr, -(t.y * sr));
+  s = fma(t.y, cr, t.x * sr);
+}
+
+// exp(x) for x in [-700, 700]
+__device__ __forceinline__ double fast_exp(double x, const PbxTables* tb) {
+  const double fn = fma(x, 92.332482616893656877, 6755399441055744.0);     // 64/ln2, 1.5*2^52
+  const int n = __double2loint(fn);
+  const double k = fn - 6755399441055744.0;
+  double r = fma(k, -0.01083042469326756, x);          // ln2/64 hi (32 bits: k*hi exact)
+  r = fma(k, -2.9815858269852933e-12, r);              // ln2/64 lo
+  double p = fma(r, kExpP[3], kExpP[2]);
+  p = fma(r, p, kExpP[1]);
+  p = fma(r, p, kExpP[0]);
+  p = fma(r * r, p, r);                                                    // expm1(r)
+  const double tj = tb->ex[n & 63];
+  const double y = fma(tj, p, tj);
+  return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
+}
+
+// sqrt(v) for positive normal v in fp32 range: fp32 rsqrt seed + 2 Newton steps on
+// 1/sqrt + one correction of the root.  Branch-free (libm's sqrt carries a special-
+// case branch that stops ptxas from interleaving independent steps), <= 1 ulp.
+__device__ __forceinline__ double fast_sqrt(double v) {
+  double y = (double)rsqrtf((float)v);
+  const double hv = 0.5 * v;
+  y = y * fma(-hv * y, y, 1.5);
+  y = y * fma(-hv * y, y, 1.5);
+  double s = v * y;
+  s = fma(fma(-s, s, v), 0.5 * y, s);
+  return s;
+}
+
+// linear-pscale output density exp(logpdf): table exp in its safe range, libm beyond
+__device__ __forceinline__ double out_exp(double l, const PbxTables* tb) {
+  return (l > -700.0 && l < 700.0) ? fast_exp(l, tb) : exp(l);
+}
+
+static int init_tables(pbx_ctx* ctx) {
+  static bool done[64] = {false};
+  if (ctx->device < 64 && done[ctx->device]) return PBX_OK;
+  static PbxTables h;
+  for (int j = 0; j < 128; ++j) {
+    const long double c = 1.0L + (j + 0.5L) / 128.0L;
+    h.lg[j].x = (double)(1.0L / c);
+    // log c_j must pair with the ROUNDED reciprocal: log(1/inv) keeps r = m*inv - 1 exact
+    h.lg[j].y = (double)(-logl((long double)h.lg[j].x));
+  }
+  const long double two_pi = 6.283185307179586476925286766559L;
+  for (int k = 0; k < 256; ++k) {
+    const long double th = two_pi * (k + 0.5L) / 256.0L;
+    h.sc[k].x = (double)cosl(th);
+    h.sc[k].y = (double)sinl(th);
+  }
+  for (int j = 0; j < 64; ++j) h.ex[j] = (double)exp2l(j / 64.0L);
+  PBX_CUDA(cudaMemcpyToSymbolAsync(g_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+  PBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->device < 64) done[ctx->device] = true;
+  return PBX_OK;
+}
+
 struct MhMvnConst {
   double mean[PBX_MAX_DIMS];
   double W[PBX_MAX_DIMS * PBX_MAX_DIMS];
@@ -69,19 +179,23 @@ __device__ __forceinline__ double mvn_logpdf(const double (&x)[D], const MhMvnCo
 
 // Native draws of one step: proposal deltas (scaled) and the threshold.  Shared by
 // both kernels so their streams are identical (layout: oracle/philox.py).
-template <int D>
+template <int D, bool kNormalOnly = false>
 __device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_t gchain,
-                                          int prop_kind, const MhMvnConst& m, double (&dl)[D],
-                                          double& t) {
+                                          int prop_kind, const MhMvnConst& m,
+                                          const PbxTables* tb, double (&dl)[D], double& t) {
+  if (kNormalOnly) prop_kind = PBX_PROP_NORMAL;          // compile-time: no kind branches
 #pragma unroll
   for (int s = 0; s < (D + 1) / 2; ++s) {
     pbx_u4 w = pbx_block(seed, gstep, gchain, (uint32_t)s);
     if (s == 0) t = pbx_t44(w.w, w.y);
     double d0, d1;
     if (prop_kind == PBX_PROP_NORMAL) {
-      pbx_normal_pair(w, d0, d1);
-      d0 *= m.scale[2 * s];
-      if (2 * s + 1 < D) d1 *= m.scale[2 * s + 1];
+      // Box-Muller: r = sqrt(-2 log u52), angle = 2 pi u32
+      const double rad = fast_sqrt(-2.0 * fast_log(pbx_u52(w.x, w.y), tb));
+      double sn, cs;
+      fast_sincos2pi(w.z, tb, sn, cs);
+      d0 = (rad * cs) * m.scale[2 * s];
+      d1 = (2 * s + 1 < D) ? (rad * sn) * m.scale[2 * s + 1] : 0.0;
     } else if (prop_kind == PBX_PROP_UNIFORM) {
       double r0 = pbx_u52(w.x, w.y), r1 = pbx_u32(w.z);
       d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * r0;
@@ -152,7 +266,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
       for (int j = 0; j < D; ++j) dl[j] = a.inj_delta[((int64_t)k * D + j) * C + c];
       t = a.inj_thresh[(int64_t)k * C + c];
     } else {
-      draw_step<D>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, dl, t);
+      draw_step<D>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, &g_tables, dl, t);
     }
     // ---- propose: x' = x + delta  (or + L delta: rf.py:346-348) -------------
     double xp[D], dv[D];
@@ -178,7 +292,9 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
         acc = true;
       } else {
         const double d = lpp - lp;
-        acc = (d >= log(t));
+        // injected thresholds go through libm's log (bit-parity with the oracle);
+        // native ones through the same table log as the warp-specialised kernel
+        acc = (d >= (kInjected ? log(t) : fast_log(t, &g_tables)));
         if (a.out_score) s = fmin(1.0, exp(fmin(d, 0.0)));
       }
     }
@@ -204,7 +320,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
         for (int j = 0; j < D; ++j) a.out_x[(r * D + j) * C + c] = x[j];
       }
       if (a.out_prob) {
-        double pv = a.log_pscale ? lp : (ref_mode ? lin : exp(lp));
+        double pv = a.log_pscale ? lp : (ref_mode ? lin : out_exp(lp, &g_tables));
         a.out_prob[r * C + c] = pv;
       }
     }
@@ -234,22 +350,38 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 // One mbarrier pair per slot: in_full (producer -> consumer), out_full (consumer
 // -> owning producer).
 // ---------------------------------------------------------------------------
-#define WS_NPROD 15
-#define WS_THREADS ((WS_NPROD + 1) * 32)
+#define WS_NPROD 12                      // producer warps: all warps with (warp % 4) != 0
+#define WS_NSLOT (2 * WS_NPROD)             // two ring slots per producer warp
+#ifndef WS_PUNROLL
+#define WS_PUNROLL 2
+#endif
+constexpr int kWsPUnroll = WS_PUNROLL;
+#define WS_THREADS 512                   // 16 warps; warps 4, 8, 12 exit at once so that
+                                         // the consumer (warp 0) has its SM sub-partition
+                                         // (scheduler + FP64 pipe) to itself
 template <int D> struct WsCfg {
   // steps per ring slot: G*(D+1) doubles per lane per slot, <= 6 KB per slot
   static constexpr int G = (D <= 2) ? 8 : (D == 3 ? 6 : (D <= 5 ? 4 : (D <= 7 ? 3 : 2)));
   static constexpr int SLOT_DOUBLES = G * (D + 1) * 32;
-  static constexpr size_t SMEM = (size_t)WS_NPROD * SLOT_DOUBLES * sizeof(double);
+  static constexpr size_t SMEM = (size_t)WS_NSLOT * SLOT_DOUBLES * sizeof(double);
 };
 
-template <int D, bool kRefAccept>
+// kFast: normal proposal without Cholesky colouring -> branch-free producer body
+template <int D, bool kRefAccept, bool kFast>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     mh_mvn_ws_kernel(const MhMvnArgs a, const __grid_constant__ MhMvnConst m) {
   constexpr int G = WsCfg<D>::G;
   constexpr int SD = WsCfg<D>::SLOT_DOUBLES;
-  extern __shared__ __align__(16) double ring[];          // [WS_NPROD][G][D+1][32]
-  __shared__ __align__(8) unsigned long long in_full[WS_NPROD], out_full[WS_NPROD];
+  extern __shared__ __align__(16) double ring[];          // [WS_NSLOT][G][D+1][32]
+  __shared__ __align__(8) unsigned long long in_full[WS_NSLOT], out_full[WS_NSLOT];
+  __shared__ __align__(16) PbxTables s_tb;                // 6.5 KB of math tables
+  {
+    const double* src = reinterpret_cast<const double*>(&g_tables);
+    double* dst = reinterpret_cast<double*>(&s_tb);
+    for (int i = threadIdx.x; i < (int)(sizeof(PbxTables) / sizeof(double)); i += WS_THREADS)
+      dst[i] = src[i];
+  }
+  const PbxTables* tb = &s_tb;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t C = a.C;
@@ -259,7 +391,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   const int nb = (a.T + G - 1) / G;                       // batches of G steps
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WS_NPROD; ++i) {
+    for (int i = 0; i < WS_NSLOT; ++i) {
       pbx_mbar_init(&in_full[i], 1);
       pbx_mbar_init(&out_full[i], 1);
     }
@@ -267,55 +399,69 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   __syncthreads();
 
   if (warp >= 1) {
-    // ================= producer / writer for ring slot p ========================
-    const int p = warp - 1;
-    double* slot = ring + (size_t)p * SD + lane;
-    uint32_t use = 0;
-    for (int b = p;; b += WS_NPROD, ++use) {
-      if (use > 0) {
-        // ---- drain the results of batch (b - WS_NPROD) ------------------------
-        pbx_mbar_wait(&out_full[p], (use - 1) & 1);
-        const int k0 = (b - WS_NPROD) * G;
+    // ================= producer / writer: owns ring slots p and p + WS_NPROD =====
+    if ((warp & 3) == 0) return;                          // keep sub-partition 0 for the consumer
+    const int p = warp - 1 - (warp >> 2);
+    const int n_mine = (nb > p) ? (nb - p + WS_NPROD - 1) / WS_NPROD : 0;
+    for (int n = 0; n < n_mine + 2; ++n) {
+      const int si = p + WS_NPROD * (n & 1);
+      double* slot = ring + (size_t)si * SD + lane;
+      if (n >= 2 && n - 2 < n_mine) {
+        // ---- drain the results of my batch n-2 (it used this slot) --------------
+        const int bd = p + WS_NPROD * (n - 2);
+        pbx_mbar_wait(&out_full[si], (uint32_t)((n - 2) >> 1) & 1);
+        const int k0 = bd * G;
         const int ng = min(G, a.T - k0);
         int rem = (k0 + 1) % a.thin;                      // (k+1) % thin of step k0
-        int64_t rec = (k0 + 1) / a.thin - 1;              // record index if rem == 0
+        const int64_t rec0 = (k0 + 1) / a.thin - 1 + (rem != 0);   // first record index
+        double* ox = a.out_x ? a.out_x + (rec0 * D) * C + c : nullptr;
+        double* op = a.out_prob ? a.out_prob + rec0 * C + c : nullptr;
+        if (rem == 0) rem = a.thin;                       // countdown form: record when == thin
         for (int g = 0; g < ng; ++g) {
-          if (rem == 0) {
+          if (rem == a.thin) {
+            rem = 0;
             if (valid) {
-              if (a.out_x) {
+              if (ox) {
 #pragma unroll
-                for (int j = 0; j < D; ++j)
-                  a.out_x[(rec * D + j) * C + c] = slot[(g * (D + 1) + j) * 32];
+                for (int j = 0; j < D; ++j) ox[j * C] = slot[(g * (D + 1) + j) * 32];
+                ox += D * C;
               }
-              if (a.out_prob) {
+              if (op) {
                 const double lpv = slot[(g * (D + 1) + D) * 32];
                 // linear pscale: pdf = exp(logpdf) as scipy does
-                a.out_prob[rec * C + c] = a.log_pscale ? lpv : exp(lpv);
+                *op = a.log_pscale ? lpv : (kRefAccept ? exp(lpv) : out_exp(lpv, tb));
+                op += C;
               }
             }
           }
-          if (++rem == a.thin) { rem = 0; ++rec; }
+          ++rem;
         }
       }
-      if (b >= nb) break;
-      // ---- refill with the draws of batch b -----------------------------------
-#pragma unroll 1
-      for (int g = 0; g < G; ++g) {
-        const int k = b * G + g;
-        if (k >= a.T) break;
-        const int64_t gstep = a.step0 + k;
+      if (n >= n_mine) continue;
+      const int b = p + WS_NPROD * n;
+      auto produce = [&](int g) {
+        const int64_t gstep = a.step0 + (int64_t)b * G + g;
         double dl[D], dv[D], t;
-        draw_step<D>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, dl, t);
-        colour_delta<D>(a.has_L, m, dl, dv);
+        draw_step<D, kFast>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, tb, dl, t);
+        colour_delta<D>(kFast ? 0 : a.has_L, m, dl, dv);
 #pragma unroll
         for (int j = 0; j < D; ++j) slot[(g * (D + 1) + j) * 32] = dv[j];
         // global step 0 accepts unconditionally (sp.py:253): threshold that always passes
-        double th = kRefAccept ? t : log(t);
+        double th = kRefAccept ? t : fast_log(t, tb);
         if (gstep == 0) th = kRefAccept ? 0.0 : -INFINITY;
         slot[(g * (D + 1) + D) * 32] = th;
+      };
+      if ((b + 1) * G <= a.T) {
+        // full batch: WS_PUNROLL independent steps in flight per thread (ILP), since a
+        // producer warp is otherwise a single chain of dependent instructions
+#pragma unroll kWsPUnroll
+        for (int g = 0; g < G; ++g) produce(g);
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < a.T - b * G; ++g) produce(g);
       }
       __syncwarp();
-      if (lane == 0) pbx_mbar_arrive(&in_full[p]);
+      if (lane == 0) pbx_mbar_arrive(&in_full[si]);
     }
     return;
   }
@@ -333,9 +479,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   int64_t nacc = 0;
 
   for (int b = 0; b < nb; ++b) {
-    const int s = b % WS_NPROD;
+    const int s = b % WS_NSLOT;
     double* slot = ring + (size_t)s * SD + lane;
-    pbx_mbar_wait(&in_full[s], (uint32_t)(b / WS_NPROD) & 1);
+    pbx_mbar_wait(&in_full[s], (uint32_t)(b / WS_NSLOT) & 1);
     const int ng = min(G, a.T - b * G);
     double dl[G][D], th[G];
 #pragma unroll
@@ -400,15 +546,19 @@ static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, 
   if (use_ws) {
     const int grid = (a.C + 31) / 32;
     const size_t smem = WsCfg<D>::SMEM;
-    if (a.accept_mode == PBX_ACCEPT_REFERENCE) {
-      PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mh_mvn_ws_kernel<D, true><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);
-    } else {
-      PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      mh_mvn_ws_kernel<D, false><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);
-    }
+    const bool ref = a.accept_mode == PBX_ACCEPT_REFERENCE;
+    const bool fast = a.prop_kind == PBX_PROP_NORMAL && !a.has_L;
+#define PBX_WS_LAUNCH(R, F)                                                                   \
+  do {                                                                                        \
+    PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, R, F>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    mh_mvn_ws_kernel<D, R, F><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);                 \
+  } while (0)
+    if (ref && fast) PBX_WS_LAUNCH(true, true);
+    else if (ref) PBX_WS_LAUNCH(true, false);
+    else if (fast) PBX_WS_LAUNCH(false, true);
+    else PBX_WS_LAUNCH(false, false);
+#undef PBX_WS_LAUNCH
     PBX_LAUNCH_CHECK(ctx);
     return PBX_OK;
   }
@@ -470,6 +620,10 @@ static int run_device(pbx_ctx* ctx, const pbx_mh_mvn_params* p) {
   a.out_accept = p->out_accept; a.out_score = p->out_score;
   a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
   if (a.T == 0) return PBX_OK;
+  {
+    int rc = init_tables(ctx);
+    if (rc) return rc;
+  }
   switch (p->n_dims) {
     case 1: return launch_mh_mvn<1>(ctx, a, m, p->kernel_variant);
     case 2: return launch_mh_mvn<2>(ctx, a, m, p->kernel_variant);
