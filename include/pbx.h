@@ -288,6 +288,9 @@ PBX_API int pbx_reduce_chain_stats(pbx_ctx* ctx, const double* stat_sum, const d
 /* FP64 FMA peak micro-benchmark (roofline denominator for the compute-bound
  * kernels; MEASURED_PEAKS.json has no FP64 figure). Returns TFLOP/s. */
 PBX_API int pbx_fp64_peak(pbx_ctx* ctx, double* tflops);
+/* Dependent-issue latency of DFMA / DADD in SM cycles (one warp, one dependent chain):
+ * the constant that bounds the sequential part of a Markov chain step. */
+PBX_API int pbx_fp64_dep_latency(pbx_ctx* ctx, double* dfma_cycles, double* dadd_cycles);
 
 #ifdef __cplusplus
 }

@@ -198,7 +198,40 @@ __global__ void __launch_bounds__(256) pbx_fp64_peak_kernel(double* out, int ite
   if (s == 12345.678) out[0] = s;   // keep the chain alive
 }
 
+// dependent chain of n DFMA / DADD in one warp, timed with clock64
+__global__ void pbx_fp64_latency_kernel(double* out, int n, double a, double b) {
+  double x = (double)threadIdx.x * 1e-3, y = x;
+  long long t0 = clock64();
+  for (int i = 0; i < n; ++i) x = fma(x, a, b);
+  long long t1 = clock64();
+  for (int i = 0; i < n; ++i) y = y + b;
+  long long t2 = clock64();
+  if (threadIdx.x == 0) {
+    out[0] = (double)(t1 - t0) / n;
+    out[1] = (double)(t2 - t1) / n;
+    out[2] = x + y;
+  }
+}
+
 extern "C" {
+
+int pbx_fp64_dep_latency(pbx_ctx* ctx, double* dfma_cycles, double* dadd_cycles) {
+  PBX_REQUIRE(ctx && dfma_cycles && dadd_cycles, "pbx_fp64_dep_latency: null argument");
+  {
+    int rc = pbx_ws_reserve(ctx, 64);
+    if (rc) return rc;
+  }
+  double h[3];
+  for (int rep = 0; rep < 2; ++rep) {
+    pbx_fp64_latency_kernel<<<1, 32, 0, ctx->stream>>>((double*)ctx->ws, 4096, 1.0000001, 1e-9);
+    PBX_LAUNCH_CHECK(ctx);
+  }
+  PBX_CUDA(cudaMemcpyAsync(h, ctx->ws, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  *dfma_cycles = h[0];
+  *dadd_cycles = h[1];
+  return PBX_OK;
+}
 
 int pbx_log_prob_inplace(pbx_ctx* ctx, double* v, int64_t n) {
   PBX_REQUIRE(ctx && v && n >= 0, "pbx_log_prob_inplace: bad argument");

@@ -156,6 +156,20 @@ __device__ __forceinline__ bool pbx_mbar_try_wait(void* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the warp for a HW time slice)
+__device__ __forceinline__ bool pbx_mbar_test_wait(void* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(pbx_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void pbx_mbar_wait(void* bar, uint32_t parity) {
   while (!pbx_mbar_try_wait(bar, parity)) {
   }

@@ -162,7 +162,7 @@ struct MhMvnArgs {
 // scipy multivariate_normal_gen._logpdf: -0.5*(rank*log(2pi) + log_pdet + maha),
 // maha = sum(square(dev @ U)).
 template <int D>
-__device__ __forceinline__ double mvn_logpdf(const double (&x)[D], const MhMvnConst& m) {
+__device__ __forceinline__ double mvn_maha(const double (&x)[D], const MhMvnConst& m) {
   double dev[D];
 #pragma unroll
   for (int j = 0; j < D; ++j) dev[j] = x[j] - m.mean[j];
@@ -174,7 +174,18 @@ __device__ __forceinline__ double mvn_logpdf(const double (&x)[D], const MhMvnCo
     for (int j = 0; j < D; ++j) y = fma(dev[j], m.W[j * D + k], y);
     maha = fma(y, y, maha);
   }
-  return -0.5 * (m.norm_c + maha);
+  return maha;
+}
+template <int D>
+__device__ __forceinline__ double mvn_logpdf(const double (&x)[D], const MhMvnConst& m) {
+  return -0.5 * (m.norm_c + mvn_maha<D>(x, m));
+}
+// Log-space accept test on the Mahalanobis distance: logp' - logp >= th with
+// logp' = -0.5 (c + maha')  <=>  maha' <= -2 (th + logp) - c.  The right-hand side
+// depends only on the CURRENT state, so it is off the sequential critical path
+// (the chain per step becomes add, sub, mul, fma, mul, fma, setp, select).
+__device__ __forceinline__ double maha_bound(double th, double lp, double norm_c) {
+  return fma(-2.0, th + lp, -norm_c);
 }
 
 // Native draws of one step: proposal deltas (scaled) and the threshold.  Shared by
@@ -274,7 +285,8 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 #pragma unroll
     for (int j = 0; j < D; ++j) xp[j] = x[j] + dv[j];
     // ---- evaluate target ----------------------------------------------------
-    const double lpp = mvn_logpdf<D>(xp, m);
+    const double maha = mvn_maha<D>(xp, m);
+    const double lpp = -0.5 * (m.norm_c + maha);
     // ---- score / threshold / update (sp_utils.py:19-37) ---------------------
     bool acc;
     double s = nan("");
@@ -291,11 +303,11 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
       if (gstep == 0) {
         acc = true;
       } else {
-        const double d = lpp - lp;
         // injected thresholds go through libm's log (bit-parity with the oracle);
         // native ones through the same table log as the warp-specialised kernel
-        acc = (d >= (kInjected ? log(t) : fast_log(t, &g_tables)));
-        if (a.out_score) s = fmin(1.0, exp(fmin(d, 0.0)));
+        const double th = kInjected ? log(t) : fast_log(t, &g_tables);
+        acc = (maha <= maha_bound(th, lp, m.norm_c));
+        if (a.out_score) s = fmin(1.0, exp(fmin(lpp - lp, 0.0)));
       }
     }
     if (acc) {
@@ -492,36 +504,42 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     }
     // every lane only ever touches its own column of the slot, so the results can
     // overwrite the inputs as soon as they are in registers
+    auto step = [&](int g) {
+      double xp[D];
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (g < ng) {
-        double xp[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[g][j];
-        const double lpp = mvn_logpdf<D>(xp, m);
-        bool acc;
-        double linp = 0.0;
-        if (kRefAccept) {
-          linp = a.log_pscale ? pbx_exp_logp(lpp) : exp(lpp);
-          acc = fmin(1.0, linp / fmax(PBX_TINY, lin)) >= th[g];
-        } else {
-          acc = (lpp - lp) >= th[g];
-        }
-        if (acc) {
-#pragma unroll
-          for (int j = 0; j < D; ++j) x[j] = xp[j];
-          lp = lpp;
-          lin = linp;
-          ++nacc;
-        }
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-          ssum[j] += x[j];
-          ssq[j] = fma(x[j], x[j], ssq[j]);
-          slot[(g * (D + 1) + j) * 32] = x[j];
-        }
-        slot[(g * (D + 1) + D) * 32] = lp;
+      for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[g][j];
+      const double maha = mvn_maha<D>(xp, m);
+      const double lpp = -0.5 * (m.norm_c + maha);
+      bool acc;
+      double linp = 0.0;
+      if (kRefAccept) {
+        linp = a.log_pscale ? pbx_exp_logp(lpp) : exp(lpp);
+        acc = fmin(1.0, linp / fmax(PBX_TINY, lin)) >= th[g];
+      } else {
+        acc = maha <= maha_bound(th[g], lp, m.norm_c);
       }
+      if (acc) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) x[j] = xp[j];
+        lp = lpp;
+        lin = linp;
+        ++nacc;
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        ssum[j] += x[j];
+        ssq[j] = fma(x[j], x[j], ssq[j]);
+        slot[(g * (D + 1) + j) * 32] = x[j];
+      }
+      slot[(g * (D + 1) + D) * 32] = lp;
+    };
+    if (ng == G) {                       // full batch: straight-line code, no predicates
+#pragma unroll
+      for (int g = 0; g < G; ++g) step(g);
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (g < ng) step(g);
     }
     __syncwarp();
     if (lane == 0) pbx_mbar_arrive(&out_full[s]);

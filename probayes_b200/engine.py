@@ -117,6 +117,13 @@ class Engine:
         _lib.check(self.lib.pbx_fp64_peak(self.ctx, C.byref(v)), "pbx_fp64_peak")
         return float(v.value)
 
+    def fp64_dep_latency(self):
+        """(DFMA, DADD) dependent-issue latency in SM cycles."""
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self.lib.pbx_fp64_dep_latency(self.ctx, C.byref(a), C.byref(b)),
+                   "pbx_fp64_dep_latency")
+        return float(a.value), float(b.value)
+
     def empty(self, *shape, dtype=None):
         torch = _torch()
         return torch.empty(*shape, dtype=dtype or torch.float64, device=self.device)
