@@ -185,7 +185,7 @@ class Engine:
                log_pscale=False, accept="reference", prop="normal", prop_scale=1.0,
                prop_chol=None, reorder=True, inj_delta=None, inj_thresh=None,
                state_lp=None, record=True, per_step=False, stats=True, variant=0,
-               out=None, prop_radius=0.0):
+               out=None, prop_radius=0.0, events=None):
         """Runs ``steps`` MH steps for all chains of ``state`` ([D, C] device fp64,
         updated in place).  Returns a dict of device tensors:
         x [R, D, C], prob [R, C] (record), accept [T, C] uint8 + score [T, C]
@@ -232,7 +232,11 @@ class Engine:
         p.accept_count = out["accept_count"].data_ptr()
         p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
         p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0
+        if events is not None:                 # torch events bracketing the kernel launch only
+            events[0].record(self.stream)
         _lib.check(self.lib.pbx_mh_mvn_run(self.ctx, C.byref(p)), "pbx_mh_mvn_run")
+        if events is not None:
+            events[1].record(self.stream)
         return out
 
     def mh_mvn_walk_host(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
