@@ -9,9 +9,9 @@
 // product is evaluated as c0_i + coef_i . x with c0_i = mean_i - coef_i . mean
 // folded on the host (coef_ii = 0).
 //
-// Kernel: one thread = one chain, the state vector lives in REGISTERS (the
-// coordinate loop is fully unrolled over a padded dimension DP), the coefficient
-// rows are broadcast from shared memory with 128-bit loads.
+// Kernel: four lanes = one chain, the state vector lives in REGISTERS (DP/4 doubles
+// per lane, coordinate loop fully unrolled), the coefficient rows come from shared
+// memory with 128-bit loads, the dot product finishes with two shuffle-adds.
 //
 // Density (probayes/prob.py:347-360 -> scipy multivariate_normal): maha = |(x -
 // mean) W|^2.  For d >= 64 the [chains, d] x [d, d] whitening product runs on the
@@ -46,19 +46,48 @@ __global__ void gibbs_c0_kernel(const double* coef, const double* mean, int d, d
   c0[i] = mean[i] - acc;
 }
 
-template <int DP>
+// State-independent part of one coordinate update, kept out of line: the coordinate
+// loop is fully unrolled (register-resident state) and inlining ~250 instructions of
+// Philox + normcdfinv at every site made the kernel 60 k instructions long and
+// instruction-fetch bound (ncu: stall_no_inst 34 %).
+__device__ __noinline__ double gibbs_draw_z(uint64_t seed, uint64_t gk, uint32_t gchain,
+                                            const double* inj, double lo, double w, double sd,
+                                            double c0) {
+  double r;
+  if (inj) {
+    r = *inj;
+  } else {
+    pbx_u4 b = pbx_block(seed, gk, gchain, 0u);
+    r = pbx_u52(b.x, b.y);
+  }
+  return normcdfinv(lo + w * r) * sd + c0;
+}
+
+// One chain = FOUR lanes (a warp = 8 chains): lane q of a chain keeps coordinates
+// j = 4m + q in registers (DQ = DP/4 doubles instead of DP, so the kernel fits ~64
+// registers instead of 255 + local-memory spills), the dot product coef_i . x is DQ
+// FMAs per lane + two shuffle-adds, and the expensive state-independent part of a
+// coordinate update -- Philox, ndtri(u) * stdv -- is computed by each lane for ITS OWN
+// next coordinate, i.e. four coordinates' worth in parallel with no redundancy.
+// kSweepRec: records fall on sweep boundaries only (thin % d == 0, call aligned to
+// sweeps) -> one copy of the record code per sweep instead of one per coordinate.
+template <int DQ, bool kSweepRec>
 __global__ void __launch_bounds__(GB_THREADS)
     gibbs_mvn_kernel(const GibbsArgs a) {
+  constexpr int DP = 4 * DQ;
+  constexpr int RS = DQ + 2;                // padded row stride: the 4 sub-lane rows of a
+                                            // coordinate land in distinct shared-memory banks
   extern __shared__ __align__(16) double sm[];
-  double* s_coef = sm;                     // [DP][DP] rows padded with zeros
-  double* s_c0 = sm + DP * DP;             // [DP]
+  double* s_coef = sm;                      // [DP][4][RS]: s_coef[i][q][m] = coef[i][4m + q]
+  double* s_c0 = sm + DP * 4 * RS;          // [DP]
   double* s_sd = s_c0 + DP;
   double* s_lo = s_sd + DP;
-  double* s_w = s_lo + DP;                 // hi - lo
+  double* s_w = s_lo + DP;                  // hi - lo
   const int d = a.d;
-  for (int idx = threadIdx.x; idx < DP * DP; idx += GB_THREADS) {
-    const int i = idx / DP, j = idx % DP;
-    s_coef[idx] = (i < d && j < d) ? a.coef[(int64_t)i * d + j] : 0.0;
+  for (int idx = threadIdx.x; idx < DP * 4 * RS; idx += GB_THREADS) {
+    const int i = idx / (4 * RS), r = idx % (4 * RS), q = r / RS, mm = r % RS;
+    const int j = 4 * mm + q;
+    s_coef[idx] = (i < d && mm < DQ && j < d) ? a.coef[(int64_t)i * d + j] : 0.0;
   }
   for (int i = threadIdx.x; i < DP; i += GB_THREADS) {
     const bool v = i < d;
@@ -68,74 +97,96 @@ __global__ void __launch_bounds__(GB_THREADS)
     s_w[i] = v ? a.cdf_hi[i] - a.cdf_lo[i] : 0.0;
   }
   __syncthreads();
-  const int c = blockIdx.x * GB_THREADS + threadIdx.x;
-  if (c >= a.C) return;
+  const int lane = threadIdx.x & 31, q = lane & 3;
   const int64_t C = a.C;
+  const int64_t c_raw = ((int64_t)blockIdx.x * (GB_THREADS / 32) + (threadIdx.x >> 5)) * 8 + (lane >> 2);
+  const bool valid = c_raw < C;
+  const int64_t c = valid ? c_raw : C - 1;          // clamp: idle lanes stay in the shuffles
   const uint32_t gchain = (uint32_t)(a.chain0 + c);
 
-  double x[DP];
+  double x[DQ];
 #pragma unroll
-  for (int j = 0; j < DP; ++j) x[j] = (j < d) ? a.state[(int64_t)j * C + c] : 0.0;
+  for (int mm = 0; mm < DQ; ++mm) {
+    const int j = 4 * mm + q;
+    x[mm] = (j < d) ? a.state[(int64_t)j * C + c] : 0.0;
+  }
   const bool stats = a.stat_sum != nullptr;
   const int64_t k_begin = a.step0, k_end = a.step0 + a.T;
   int until_rec = a.thin;
   int64_t rec = 0;
-  for (int64_t sweep = k_begin / d; sweep * d < k_end; ++sweep) {
+  auto record = [&]() {
+    if (valid) {
 #pragma unroll
-    for (int i = 0; i < DP; ++i) {
-      const int64_t gk = sweep * d + i;
-      if (i < d && gk >= k_begin && gk < k_end) {
-        double r;
-        if (a.inj_runif) {
-          r = a.inj_runif[(gk - k_begin) * C + c];
-        } else {
-          pbx_u4 w = pbx_block(a.seed, (uint64_t)gk, gchain, 0u);
-          r = pbx_u52(w.x, w.y);
-        }
-        const double u = s_lo[i] + s_w[i] * r;
-        // conditional mean: c0_i + coef_i . x   (4 partial sums for ILP)
-        double p0 = s_c0[i], p1 = 0.0, p2 = 0.0, p3 = 0.0;
-        const double2* row = reinterpret_cast<const double2*>(s_coef + i * DP);
-        if (DP >= 4) {
-#pragma unroll
-          for (int j = 0; j < DP; j += 4) {
-            const double2 ca = row[j / 2], cb = row[j / 2 + 1];
-            p0 = fma(ca.x, x[j], p0);
-            p1 = fma(ca.y, x[j + 1], p1);
-            p2 = fma(cb.x, x[j + 2], p2);
-            p3 = fma(cb.y, x[j + 3], p3);
+      for (int mm = 0; mm < DQ; ++mm) {
+        const int j = 4 * mm + q;
+        if (j < d) {
+          if (a.out_x) a.out_x[(rec * d + j) * C + c] = x[mm];
+          if (stats) {                              // running sums over RECORDED states
+            a.stat_sum[(int64_t)j * C + c] += x[mm];
+            a.stat_sumsq[(int64_t)j * C + c] =
+                fma(x[mm], x[mm], a.stat_sumsq[(int64_t)j * C + c]);
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < DP; ++j) p0 = fma(s_coef[i * DP + j], x[j], p0);
-        }
-        const double cm = (p0 + p1) + (p2 + p3);
-        x[i] = fma(normcdfinv(u), s_sd[i], cm);
-        if (--until_rec == 0) {
-          until_rec = a.thin;
-          if (a.out_x) {
-#pragma unroll
-            for (int j = 0; j < DP; ++j)
-              if (j < d) a.out_x[(rec * d + j) * C + c] = x[j];
-          }
-          if (stats) {                 // running sums over the RECORDED states
-#pragma unroll
-            for (int j = 0; j < DP; ++j) {
-              if (j < d) {
-                a.stat_sum[(int64_t)j * C + c] += x[j];
-                a.stat_sumsq[(int64_t)j * C + c] =
-                    fma(x[j], x[j], a.stat_sumsq[(int64_t)j * C + c]);
-              }
-            }
-          }
-          ++rec;
         }
       }
     }
-  }
+    ++rec;
+  };
+  for (int64_t sweep = k_begin / d; sweep * d < k_end; ++sweep) {
 #pragma unroll
-  for (int j = 0; j < DP; ++j) {
-    if (j < d) a.state[(int64_t)j * C + c] = x[j];
+    for (int l = 0; l < DQ; ++l) {
+      // ---- my own next coordinate i = 4l + q: draw and transform (state independent)
+      double z = 0.0;
+      {
+        const int i = 4 * l + q;
+        const int64_t gk = sweep * d + i;
+        if (i < d && gk >= k_begin && gk < k_end)
+          z = gibbs_draw_z(a.seed, (uint64_t)gk, gchain,
+                           a.inj_runif ? a.inj_runif + (gk - k_begin) * C + c : nullptr,
+                           s_lo[i], s_w[i], s_sd[i], s_c0[i]);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const int i = 4 * l + o;
+        const int64_t gk = sweep * d + i;
+        if (i < d && gk >= k_begin && gk < k_end) {        // warp-uniform
+          // conditional mean: coef_i . x  (my DQ coordinates, then the 4 sub-lanes)
+          const double2* row = reinterpret_cast<const double2*>(s_coef + (i * 4 + q) * RS);
+          double p0 = 0.0, p1 = 0.0;
+          if (DQ >= 2) {
+#pragma unroll
+            for (int mm = 0; mm < DQ; mm += 2) {
+              const double2 cf = row[mm / 2];
+              p0 = fma(cf.x, x[mm], p0);
+              p1 = fma(cf.y, x[mm + 1], p1);
+            }
+          } else {
+            p0 = s_coef[(i * 4 + q) * RS] * x[0];
+          }
+          double dot = p0 + p1;
+          dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+          dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+          if (q == o) x[l] = z + dot;                      // owner lane: x_i = ndtri*sd + c0 + dot
+          if (!kSweepRec && --until_rec == 0) {
+            until_rec = a.thin;
+            record();
+          }
+        }
+      }
+    }
+    if (kSweepRec) {
+      until_rec -= d;
+      if (until_rec == 0) {
+        until_rec = a.thin;
+        record();
+      }
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int mm = 0; mm < DQ; ++mm) {
+      const int j = 4 * mm + q;
+      if (j < d) a.state[(int64_t)j * C + c] = x[mm];
+    }
   }
 }
 
@@ -262,12 +313,22 @@ extern "C" int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int
   return PBX_OK;
 }
 
-template <int DP>
+template <int DQ>
 static int gibbs_launch(pbx_ctx* ctx, const GibbsArgs& a) {
-  const size_t smem = ((size_t)DP * DP + 4 * DP) * sizeof(double);
-  PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem));
-  gibbs_mvn_kernel<DP><<<(a.C + GB_THREADS - 1) / GB_THREADS, GB_THREADS, smem, ctx->stream>>>(a);
+  constexpr int DP = 4 * DQ;
+  const size_t smem = ((size_t)DP * 4 * (DQ + 2) + 4 * DP) * sizeof(double);
+  const int chains_per_cta = (GB_THREADS / 32) * 8;
+  const int grid = (a.C + chains_per_cta - 1) / chains_per_cta;
+  const bool sweep_rec = (a.thin % a.d == 0) && (a.step0 % a.d == 0) && (a.T % a.d == 0);
+  if (sweep_rec) {
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gibbs_mvn_kernel<DQ, true><<<grid, GB_THREADS, smem, ctx->stream>>>(a);
+  } else {
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gibbs_mvn_kernel<DQ, false><<<grid, GB_THREADS, smem, ctx->stream>>>(a);
+  }
   PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
 }
@@ -297,12 +358,11 @@ extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
   if (a.T > 0) {
     gibbs_c0_kernel<<<1, 64, 0, ctx->stream>>>(p->coef, p->mean, d, c0);
     PBX_LAUNCH_CHECK(ctx);
-    if (d <= 2) rc = gibbs_launch<2>(ctx, a);
-    else if (d <= 4) rc = gibbs_launch<4>(ctx, a);
-    else if (d <= 8) rc = gibbs_launch<8>(ctx, a);
-    else if (d <= 16) rc = gibbs_launch<16>(ctx, a);
-    else if (d <= 32) rc = gibbs_launch<32>(ctx, a);
-    else rc = gibbs_launch<64>(ctx, a);
+    if (d <= 4) rc = gibbs_launch<1>(ctx, a);
+    else if (d <= 8) rc = gibbs_launch<2>(ctx, a);
+    else if (d <= 16) rc = gibbs_launch<4>(ctx, a);
+    else if (d <= 32) rc = gibbs_launch<8>(ctx, a);
+    else rc = gibbs_launch<16>(ctx, a);
     if (rc) return rc;
     if (p->out_prob && p->want_prob) {
       // the target is evaluated and recorded on every kept step (sd.py:286)
