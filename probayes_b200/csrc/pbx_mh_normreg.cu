@@ -27,8 +27,9 @@
 #include <string.h>
 #include "pbx_common.cuh"
 
-#define NR_TILE 2048          // observations per shared-memory tile
+#define NR_TILE 1024          // observations per shared-memory tile (tiles kernel: 48 KB/CTA)
 #define NR_STAGES 3
+#define NRS_TILE 2048         // stream kernel tile (96 KB/CTA -> ~190 KB in flight per SM)
 #define NR_THREADS 128
 #define NR_SMAX 8             // chains per pass of the streaming kernel
 
@@ -268,6 +269,9 @@ __global__ void __launch_bounds__(NR_THREADS)
     if (kSlope) pbx_bulk_g2s(dx, a.x + o, kTileBytes, &full_bar[s]);
     pbx_bulk_g2s(dy, a.y + o, kTileBytes, &full_bar[s]);
   };
+  double acc1[KC];                                         // odd observations: breaks the
+#pragma unroll                                             // dependent fma pair per iteration
+  for (int k = 0; k < KC; ++k) acc1[k] = 0.0;
   auto tile_math = [&](const double* sx, const double* sy, int cnt) {
 #pragma unroll 2
     for (int i = 0; i < cnt; i += 2) {
@@ -279,7 +283,7 @@ __global__ void __launch_bounds__(NR_THREADS)
         const double r0 = yv.x - (kSlope ? fma(b1[k], xv.x, b0[k]) : b0[k]);
         const double r1 = yv.y - (kSlope ? fma(b1[k], xv.y, b0[k]) : b0[k]);
         acc[k] = fma(r0, r0, acc[k]);
-        acc[k] = fma(r1, r1, acc[k]);
+        acc1[k] = fma(r1, r1, acc1[k]);
       }
     }
   };
@@ -335,7 +339,7 @@ __global__ void __launch_bounds__(NR_THREADS)
 #pragma unroll
   for (int k = 0; k < KC; ++k) {
     const int c = cbase + k * NR_THREADS;
-    if (c < a.C) a.partial[(int64_t)slice * C + c] = acc[k];
+    if (c < a.C) a.partial[(int64_t)slice * C + c] = acc[k] + acc1[k];
   }
   if (!nr_arrive_last(&a.counters[group], (unsigned int)a.n_slices)) return;
   // ---- phase B: this CTA is the last of its chain group ----------------------
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(NR_THREADS)
 template <int KS, bool kSlope>
 __global__ void __launch_bounds__(NRS_THREADS)
     nr_stream_kernel(const NrArgs a, const __grid_constant__ NrModel m, int use_tma) {
-  extern __shared__ __align__(128) double sm[];            // [NR_STAGES][2][NR_TILE]
+  extern __shared__ __align__(128) double sm[];            // [NR_STAGES][2][NRS_TILE]
   __shared__ __align__(8) unsigned long long full_bar[NR_STAGES];
   __shared__ double s_red[NRS_THREADS / 32][KS];
   double b0[KS], b1[KS], acc[KS];
@@ -372,10 +376,10 @@ __global__ void __launch_bounds__(NRS_THREADS)
     b1[k] = (k < a.C && kSlope) ? a.theta_in[(int64_t)a.C + k] : 0.0;
     acc[k] = 0.0;
   }
-  const int64_t n_full = a.N / NR_TILE;
+  const int64_t n_full = a.N / NRS_TILE;
   // tiles of this CTA: blockIdx.x + j * gridDim.x
   const int64_t nt = (n_full > blockIdx.x) ? (n_full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  constexpr uint32_t kTileBytes = NR_TILE * sizeof(double);
+  constexpr uint32_t kTileBytes = NRS_TILE * sizeof(double);
   if (threadIdx.x == 0) {
     for (int s = 0; s < NR_STAGES; ++s) pbx_mbar_init(&full_bar[s], 1);
     pbx_fence_barrier_init();
@@ -383,11 +387,11 @@ __global__ void __launch_bounds__(NRS_THREADS)
   __syncthreads();
   auto issue = [&](int64_t j) {                            // thread 0 only
     const int s = (int)(j % NR_STAGES);
-    double* dx = sm + (size_t)s * 2 * NR_TILE;
-    const int64_t o = ((int64_t)blockIdx.x + j * gridDim.x) * NR_TILE;
+    double* dx = sm + (size_t)s * 2 * NRS_TILE;
+    const int64_t o = ((int64_t)blockIdx.x + j * gridDim.x) * NRS_TILE;
     pbx_mbar_expect_tx(&full_bar[s], kSlope ? 2 * kTileBytes : kTileBytes);
     if (kSlope) pbx_bulk_g2s(dx, a.x + o, kTileBytes, &full_bar[s]);
-    pbx_bulk_g2s(dx + NR_TILE, a.y + o, kTileBytes, &full_bar[s]);
+    pbx_bulk_g2s(dx + NRS_TILE, a.y + o, kTileBytes, &full_bar[s]);
   };
   auto tile_math = [&](const double* sx, const double* sy, int cnt) {
 #pragma unroll 2
@@ -410,26 +414,26 @@ __global__ void __launch_bounds__(NRS_THREADS)
     for (int64_t j = 0; j < nt; ++j) {
       const int s = (int)(j % NR_STAGES);
       pbx_mbar_wait(&full_bar[s], (uint32_t)(j / NR_STAGES) & 1);
-      const double* sx = sm + (size_t)s * 2 * NR_TILE;
-      tile_math(sx, sx + NR_TILE, NR_TILE);
+      const double* sx = sm + (size_t)s * 2 * NRS_TILE;
+      tile_math(sx, sx + NRS_TILE, NRS_TILE);
       __syncthreads();
       if (threadIdx.x == 0 && j + NR_STAGES < nt) issue(j + NR_STAGES);
     }
   } else {
     for (int64_t j = 0; j < nt; ++j) {
-      const int64_t o = ((int64_t)blockIdx.x + j * gridDim.x) * NR_TILE;
-      for (int i = threadIdx.x; i < NR_TILE; i += NRS_THREADS) {
+      const int64_t o = ((int64_t)blockIdx.x + j * gridDim.x) * NRS_TILE;
+      for (int i = threadIdx.x; i < NRS_TILE; i += NRS_THREADS) {
         if (kSlope) sm[i] = a.x[o + i];
-        sm[NR_TILE + i] = a.y[o + i];
+        sm[NRS_TILE + i] = a.y[o + i];
       }
       __syncthreads();
-      tile_math(sm, sm + NR_TILE, NR_TILE);
+      tile_math(sm, sm + NRS_TILE, NRS_TILE);
       __syncthreads();
     }
   }
-  // ragged tail (< NR_TILE observations): CTA 0, straight from global memory
+  // ragged tail (< NRS_TILE observations): CTA 0, straight from global memory
   if (blockIdx.x == 0) {
-    for (int64_t i = n_full * NR_TILE + threadIdx.x; i < a.N; i += NRS_THREADS) {
+    for (int64_t i = n_full * NRS_TILE + threadIdx.x; i < a.N; i += NRS_THREADS) {
       const double yv = a.y[i], xv = kSlope ? a.x[i] : 0.0;
 #pragma unroll
       for (int k = 0; k < KS; ++k) {
@@ -488,9 +492,9 @@ static NrPlan nr_plan(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
   if (variant == 1) {
     pl.kc = (C >= 4 * NR_THREADS * 8) ? 4 : ((C >= 2 * NR_THREADS * 8) ? 2 : 1);
     pl.n_groups = (C + NR_THREADS * pl.kc - 1) / (NR_THREADS * pl.kc);
-    pl.smem = (size_t)NR_STAGES * 2 * NR_TILE * sizeof(double);     // 96 KB -> 2 CTAs / SM
+    pl.smem = (size_t)NR_STAGES * 2 * NR_TILE * sizeof(double);     // 48 KB -> 4 CTAs / SM
     const int64_t n_full = p->n_obs / NR_TILE;
-    const int concurrent = ctx->sm_count * 2;
+    const int concurrent = ctx->sm_count * 4;
     int64_t slices = (2 * (int64_t)concurrent) / pl.n_groups;       // ~2 full waves
     if (slices > n_full) slices = n_full;
     if (slices < 1) slices = 1;
@@ -498,8 +502,8 @@ static NrPlan nr_plan(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
   } else {
     pl.kc = (C <= 1) ? 1 : (C <= 2 ? 2 : (C <= 4 ? 4 : 8));    // KS: chains per thread
     pl.n_groups = 1;
-    pl.smem = (size_t)NR_STAGES * 2 * NR_TILE * sizeof(double);     // 96 KB -> 2 CTAs / SM
-    int64_t want = p->n_obs / NR_TILE;
+    pl.smem = (size_t)NR_STAGES * 2 * NRS_TILE * sizeof(double);    // 96 KB -> 2 CTAs / SM
+    int64_t want = p->n_obs / NRS_TILE;
     int64_t cap = (int64_t)ctx->sm_count * 2;
     pl.n_slices = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   }
