@@ -392,18 +392,36 @@ def run_ours(args):
     rhat = np.sqrt(((T - 1) / T * W + B / T) / W)
     acc_rate = float(out["accept_count"].sum().item()) / (C * T)
 
-    # ---- end-to-end through the host-buffer C-ABI call -----------------------
-    pin_x = torch.empty((R, D, C), dtype=torch.float64, pin_memory=True)
-    pin_p = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
+    # ---- end-to-end through the PUBLIC API (the call a user makes) ----------------
+    # pb.SP(...).sampler(init, chains=, host_stream=True) -> walk -> process(samples):
+    # host init state -> H2D, chunked kernel launches, every recorded sample and
+    # density streamed D2H into pinned buffers, summary PDs built from them.
+    import scipy.stats
+    import probayes_b200 as pb
+    xr = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    yr = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    process = pb.SP(xr & yr)
+    process.set_prob(scipy.stats.multivariate_normal, list(MEAN), COV.tolist())
+    process.set_tran(lambda **kw: 1.)
+    process.set_delta(scipy.stats.norm(0., 1.))
+    process.set_scores('hastings')
+    process.set_update('metropolis')
+    hostbuf = {}
     e2e_steps = max(3, min(args.steps, 10))
+
+    def api_walk(seed):
+        smp = process.sampler({'x': INIT[0], 'y': INIT[1]}, stop=T, chains=C, thin=thin,
+                              seed=seed, accept=args.accept, host_stream=True,
+                              host_buffers=hostbuf)
+        summary = process(process.walk(smp))
+        return summary.v['x'][0, -1] + summary.u.count(True)     # touch the result
+
     for w in range(2):
-        eng.mh_mvn_walk_host(init_host.copy(), MEAN, COV, T, thin=thin, seed=3000 + w,
-                             chain0=chain0, accept=args.accept, out_x=pin_x, out_prob=pin_p)
+        api_walk(3000 + w)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        eng.mh_mvn_walk_host(init_host.copy(), MEAN, COV, T, thin=thin, seed=4000 + k,
-                             chain0=chain0, accept=args.accept, out_x=pin_x, out_prob=pin_p)
+        api_walk(4000 + k)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")

@@ -53,7 +53,9 @@ __device__ __forceinline__ double fast_log(double x, const PbxTables* tb) {
   p = fma(r, p, kLogP[1]);
   p = fma(r, p, kLogP[0]);
   p = fma(r * r, p, r);                                                    // log1p(r)
-  return fma((double)e, 0.693147180559945309417, t.y + p);
+  // (double)e without the conversion pipe: 2^52 + 2^31 + e built in the mantissa
+  const double ed = __hiloint2double(0x43300000, e ^ (int)0x80000000) - 4503601774854144.0;
+  return fma(ed, 0.693147180559945309417, t.y + p);
 }
 
 // (sin, cos)(2 pi u), u = (w + 0.5) / 2^32
@@ -90,11 +92,12 @@ __device__ __forceinline__ double fast_exp(double x, const PbxTables* tb) {
   return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
 
-// sqrt(v) for positive normal v in fp32 range: fp32 rsqrt seed + 2 Newton steps on
+// sqrt(v) for positive normal v: hardware rsqrt seed + 2 Newton steps on
 // 1/sqrt + one correction of the root.  Branch-free (libm's sqrt carries a special-
 // case branch that stops ptxas from interleaving independent steps), <= 1 ulp.
 __device__ __forceinline__ double fast_sqrt(double v) {
-  double y = (double)rsqrtf((float)v);
+  double y;                                  // MUFU.RSQ64H seed (rel. error ~2^-22)
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
   const double hv = 0.5 * v;
   y = y * fma(-hv * y, y, 1.5);
   y = y * fma(-hv * y, y, 1.5);
@@ -180,16 +183,13 @@ template <int D>
 __device__ __forceinline__ double mvn_logpdf(const double (&x)[D], const MhMvnConst& m) {
   return -0.5 * (m.norm_c + mvn_maha<D>(x, m));
 }
-// Log-space accept test on the Mahalanobis distance: logp' - logp >= th with
-// logp' = -0.5 (c + maha')  <=>  maha' <= -2 (th + logp) - c.  The right-hand side
-// depends only on the CURRENT state, so it is off the sequential critical path
-// (the chain per step becomes add, sub, mul, fma, mul, fma, setp, select).
-__device__ __forceinline__ double maha_bound(double th, double lp, double norm_c) {
-  return fma(-2.0, th + lp, -norm_c);
-}
+// Log-space accept test on the Mahalanobis distance: logp' - logp >= log t with
+// logp = -0.5 (c + maha)  <=>  maha' <= maha - 2 log t.  The right-hand side depends
+// only on the CURRENT state and the threshold draw, so it is off the sequential
+// critical path (the chain per step is add, sub, mul, fma, mul, fma, setp, select)
+// and the chain never needs logp itself (the writer derives it from maha).
+__device__ __forceinline__ double neg2log(double logt) { return -2.0 * logt; }
 
-// Native draws of one step: proposal deltas (scaled) and the threshold.  Shared by
-// both kernels so their streams are identical (layout: oracle/philox.py).
 template <int D, bool kNormalOnly = false>
 __device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_t gchain,
                                           int prop_kind, const MhMvnConst& m,
@@ -262,6 +262,9 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
     ssq[j] = 0.0;
   }
   double lp = (a.step0 > 0) ? a.state_lp[c] : 0.0;
+  // Mahalanobis distance of the retained state, recomputed from x (bit-identical to
+  // the value obtained when that state was proposed, so resumed walks decide alike)
+  double mcur = mvn_maha<D>(x, m);
   // linear density of the retained state (what the reference's opqr.o.prob holds)
   double lin = (a.step0 > 0) ? (a.log_pscale ? pbx_exp_logp(lp) : exp(lp)) : 0.0;
   int64_t nacc = 0;
@@ -305,8 +308,8 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
       } else {
         // injected thresholds go through libm's log (bit-parity with the oracle);
         // native ones through the same table log as the warp-specialised kernel
-        const double th = kInjected ? log(t) : fast_log(t, &g_tables);
-        acc = (maha <= maha_bound(th, lp, m.norm_c));
+        const double th2 = neg2log(kInjected ? log(t) : fast_log(t, &g_tables));
+        acc = (maha <= mcur + th2);
         if (a.out_score) s = fmin(1.0, exp(fmin(lpp - lp, 0.0)));
       }
     }
@@ -314,6 +317,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 #pragma unroll
       for (int j = 0; j < D; ++j) x[j] = xp[j];
       lp = lpp;
+      mcur = maha;
       lin = linp;
       ++nacc;
     }
@@ -353,10 +357,12 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 //                accept, select, running sums) -- ~30 instructions per step, no
 //                global traffic.  It overwrites the ring slot it just consumed
 //                with the retained states (x, logp) of that batch.
-//   warps 1..15  producer/writers: each owns one ring slot.  Per use: drain the
-//                consumer's results of the slot's previous batch (thinning, exp()
-//                for linear-pscale output, coalesced global stores), then refill
-//                it with Philox + Box-Muller deltas and log-thresholds for the next
+//   15 producer/writer warps (every warp with warp % 4 != 0; warps 4, 8, 12, 16 exit
+//                at once so that the consumer has SM sub-partition 0 -- scheduler and
+//                FP64 pipe -- to itself): each owns TWO ring slots.  Per use: drain the
+//                consumer's results of the slot's previous batch (thinning, logp and
+//                exp() for linear-pscale output, coalesced global stores), then refill
+//                it with Philox + Box-Muller deltas and -2 log(threshold) for the next
 //                batch of G steps.  Both jobs are independent of the chain state
 //                and therefore parallel over steps.
 // One mbarrier pair per slot: in_full (producer -> consumer), out_full (consumer
@@ -439,7 +445,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
                 ox += D * C;
               }
               if (op) {
-                const double lpv = slot[(g * (D + 1) + D) * 32];
+                // the consumer leaves logp (reference rule) or the Mahalanobis distance
+                // (log rule) of the retained state in the slot
+                const double sv = slot[(g * (D + 1) + D) * 32];
+                const double lpv = kRefAccept ? sv : -0.5 * (m.norm_c + sv);
                 // linear pscale: pdf = exp(logpdf) as scipy does
                 *op = a.log_pscale ? lpv : (kRefAccept ? exp(lpv) : out_exp(lpv, tb));
                 op += C;
@@ -459,8 +468,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
         for (int j = 0; j < D; ++j) slot[(g * (D + 1) + j) * 32] = dv[j];
         // global step 0 accepts unconditionally (sp.py:253): threshold that always passes
-        double th = kRefAccept ? t : fast_log(t, tb);
-        if (gstep == 0) th = kRefAccept ? 0.0 : -INFINITY;
+        // log rule: -2 log t (added to the current Mahalanobis distance by the consumer)
+        double th = kRefAccept ? t : neg2log(fast_log(t, tb));
+        if (gstep == 0) th = kRefAccept ? 0.0 : INFINITY;
         slot[(g * (D + 1) + D) * 32] = th;
       };
       if ((b + 1) * G <= a.T) {
@@ -486,6 +496,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     ssum[j] = ssq[j] = 0.0;
   }
   double lp = (a.step0 > 0 && valid) ? a.state_lp[c] : 0.0;
+  double mcur = mvn_maha<D>(x, m);        // log rule state: maha of the retained state
   double lin = 0.0;
   if (kRefAccept && a.step0 > 0) lin = a.log_pscale ? pbx_exp_logp(lp) : exp(lp);
   int64_t nacc = 0;
@@ -509,20 +520,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll
       for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[g][j];
       const double maha = mvn_maha<D>(xp, m);
-      const double lpp = -0.5 * (m.norm_c + maha);
       bool acc;
-      double linp = 0.0;
       if (kRefAccept) {
-        linp = a.log_pscale ? pbx_exp_logp(lpp) : exp(lpp);
+        const double lpp = -0.5 * (m.norm_c + maha);
+        const double linp = a.log_pscale ? pbx_exp_logp(lpp) : exp(lpp);
         acc = fmin(1.0, linp / fmax(PBX_TINY, lin)) >= th[g];
+        if (acc) {
+          lp = lpp;
+          lin = linp;
+        }
       } else {
-        acc = maha <= maha_bound(th[g], lp, m.norm_c);
+        acc = maha <= mcur + th[g];
       }
       if (acc) {
 #pragma unroll
         for (int j = 0; j < D; ++j) x[j] = xp[j];
-        lp = lpp;
-        lin = linp;
+        mcur = maha;
         ++nacc;
       }
 #pragma unroll
@@ -531,11 +544,52 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         ssq[j] = fma(x[j], x[j], ssq[j]);
         slot[(g * (D + 1) + j) * 32] = x[j];
       }
-      slot[(g * (D + 1) + D) * 32] = lp;
+      slot[(g * (D + 1) + D) * 32] = kRefAccept ? lp : mcur;
+    };
+    // Two steps at a time with the second one speculated on both outcomes of the
+    // first (log rule only): the distances of PA = S + dA, PB0 = S + dB and
+    // PB1 = PA + dB are independent, so the dependent chain per PAIR is
+    // add, add, sub, mul, fma, mul, fma, select, setp, select (10 ops instead of 16),
+    // with bit-identical arithmetic (the same operations on the same operands).
+    auto pair = [&](int g) {
+      double pa[D], pb0[D], pb1[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        pa[j] = x[j] + dl[g][j];
+        pb0[j] = x[j] + dl[g + 1][j];
+        pb1[j] = pa[j] + dl[g + 1][j];
+      }
+      const double ma = mvn_maha<D>(pa, m), mb0 = mvn_maha<D>(pb0, m), mb1 = mvn_maha<D>(pb1, m);
+      const bool aa = ma <= mcur + th[g];
+      const bool ab = aa ? (mb1 <= ma + th[g + 1]) : (mb0 <= mcur + th[g + 1]);
+      double s1[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) s1[j] = aa ? pa[j] : x[j];
+      const double m1 = aa ? ma : mcur;
+#pragma unroll
+      for (int j = 0; j < D; ++j) x[j] = ab ? (aa ? pb1[j] : pb0[j]) : s1[j];
+      mcur = ab ? (aa ? mb1 : mb0) : m1;
+      nacc += (int)aa + (int)ab;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        ssum[j] += s1[j];
+        ssq[j] = fma(s1[j], s1[j], ssq[j]);
+        ssum[j] += x[j];
+        ssq[j] = fma(x[j], x[j], ssq[j]);
+        slot[(g * (D + 1) + j) * 32] = s1[j];
+        slot[((g + 1) * (D + 1) + j) * 32] = x[j];
+      }
+      slot[(g * (D + 1) + D) * 32] = m1;
+      slot[((g + 1) * (D + 1) + D) * 32] = mcur;
     };
     if (ng == G) {                       // full batch: straight-line code, no predicates
+      if (!kRefAccept && (G % 2 == 0)) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) step(g);
+        for (int g = 0; g < G; g += 2) pair(g);
+      } else {
+#pragma unroll
+        for (int g = 0; g < G; ++g) step(g);
+      }
     } else {
 #pragma unroll
       for (int g = 0; g < G; ++g)
@@ -551,7 +605,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       if (a.stat_sum) a.stat_sum[j * C + c] += ssum[j];
       if (a.stat_sumsq) a.stat_sumsq[j * C + c] += ssq[j];
     }
-    a.state_lp[c] = lp;
+    a.state_lp[c] = kRefAccept ? lp : -0.5 * (m.norm_c + mcur);
     if (a.accept_count) a.accept_count[c] += nacc;
   }
 }

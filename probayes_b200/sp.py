@@ -16,6 +16,9 @@ New keyword arguments of ``sampler`` (everything else keeps its meaning):
   inj_delta=, inj_thresh=   injected proposal / threshold streams ([T, D] or
                 [T, C, D] and [T] or [T, C]) for bit-parity runs
   host_stream=True   stream samples straight into pinned host buffers (K1)
+  host_buffers=dict  (with host_stream) a dict the sampler fills with its pinned
+                buffers and reuses on later walks / other samplers of the same shape;
+                the returned arrays are then views into them
 """
 import collections
 import numpy as np
@@ -159,6 +162,7 @@ class SP(SD):
                     inj_delta=kwds.pop('inj_delta', None),
                     inj_thresh=kwds.pop('inj_thresh', None),
                     host_stream=kwds.pop('host_stream', False),
+                    host_buffers=kwds.pop('host_buffers', None),
                     variant=kwds.pop('variant', 0))
         assert not kwds, "Unknown sampler keywords: {}".format(list(kwds))
         s = Sampler(self, init, obs, stop, opts)
@@ -253,7 +257,8 @@ class SP(SD):
                                          prop=prop['kind'], prop_scale=prop['scale'],
                                          prop_radius=prop['radius'], prop_chol=prop['chol'],
                                          state_lp=None if sampler.state_lp is None
-                                         else sampler.state_lp.cpu().numpy())
+                                         else sampler.state_lp.cpu().numpy(),
+                                         chain0=0, **self._host_bufs(opts, T // thin, D, C))
                 sampler.state = eng.to_device(h['state'])
                 sampler.state_lp = eng.to_device(h['state_lp'])
                 res.update(x=h['x'], prob=h['prob'], accept_count=h['accept_count'],
@@ -300,6 +305,20 @@ class SP(SD):
                    accept=out.get('accept'), score=out.get('score'),
                    stat_sum=out.get('stat_sum'), stat_sumsq=out.get('stat_sumsq'))
         return self._finish(res, eng)
+
+    @staticmethod
+    def _host_bufs(opts, R, D, C):
+        """Pinned output buffers cached in the user-supplied ``host_buffers`` dict."""
+        cache = opts.get('host_buffers')
+        if cache is None:
+            return {}
+        import torch
+        key = (R, D, C)
+        if cache.get('key') != key:
+            cache['key'] = key
+            cache['x'] = torch.empty((R, D, C), dtype=torch.float64, pin_memory=True)
+            cache['prob'] = torch.empty((R, C), dtype=torch.float64, pin_memory=True)
+        return dict(out_x=cache['x'], out_prob=cache['prob'])
 
     @staticmethod
     def _finish(res, eng):
