@@ -79,6 +79,64 @@ def mh_mvn(seed, T, init, log_pscale=False, cov_tran=None):
 
 
 # ---------------------------------------------------------------------------
+def mh_mvn3d(seed, T):
+    """Three variables, non-exchangeable mean / covariance: pins the value
+    re-ordering of probayes/prob.py:349-358 for d > 2 ([v1, v0, v2])."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    Z = rng.standard_normal((T, 3)) * 0.7
+    U = rng.random(T)
+    zi, ui = iter(Z), iter(U)
+    mean = [0.3, -1.0, 2.0]
+    A = rng.standard_normal((3, 3))
+    cov = A @ A.T / 3 + np.diag([0.5, 1.0, 2.0])
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    z = pb.RV('z', vtype=float, vset=(-np.inf, np.inf))
+    sp = pb.SP(x & y & z)
+    sp.set_prob(scipy.stats.multivariate_normal, mean, cov)
+    sp.set_tran(lambda **k: 1.)
+    sp.set_delta(lambda: (lambda d: sp.Delta(x=d[0], y=d[1], z=d[2]))(next(zi)))
+    sp.set_scores('hastings')
+    sp.set_update('metropolis')
+    sp.set_thresh(lambda: next(ui))
+    init = (0.5, -0.5, 1.5)
+    sampler = sp.sampler({'x': init[0], 'y': init[1], 'z': init[2]}, stop=T)
+    samples = [s for s in sampler]
+    out = _summary_arrays(sp, samples, ['x', 'y', 'z'])
+    out.update(delta=Z, thresh=U, init=np.array(init), mean=np.array(mean), cov=cov,
+               log_pscale=np.array(False))
+    return out
+
+
+def gibbs3d(seed, T):
+    """Gibbs on a 3-D mvn (tsteps=1): conditional draws in natural order, recorded
+    density on the permuted point."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    lims = (-8., 8.)
+    means = [0.5, -0.5, 1.0]
+    A = rng.standard_normal((3, 3))
+    covar = A @ A.T / 3 + np.diag([0.6, 1.0, 1.5])
+    x = pb.RV('x', vtype=float, vset=lims)
+    y = pb.RV('y', vtype=float, vset=lims)
+    z = pb.RV('z', vtype=float, vset=lims)
+    sp = pb.SP(x & y & z)
+    sp.set_prob(scipy.stats.multivariate_normal, means, covar)
+    sp.set_tran(scipy.stats.multivariate_normal, means, covar, tsteps=1)
+    sp.set_scores('gibbs')
+    R = rng.random(T)
+    with ref_shim.injected_uniform(R):
+        sampler = sp.sampler({'x': 0., 'y': 1., 'z': -1.}, stop=T)
+        samples = [s for s in sampler]
+    summary = sp(samples)
+    xs = np.stack([np.asarray(summary.v[k], float) for k in 'xyz'], axis=-1)
+    return dict(x=xs, prob=np.asarray(summary.v.prob, float), runif=R,
+                init=np.array([0., 1., -1.]), mean=np.array(means), cov=covar,
+                lims=np.array([lims] * 3))
+
+
+# ---------------------------------------------------------------------------
 def mh_norm1d(seed, T, N, scores, spherical=False):
     """examples/mcmc/metrohast_norm1d.py:23-42 ((mu, sigma) posterior, log
     pscale, sigma with (np.log, np.exp) ufun, iid+joint), uniforms injected by
@@ -301,6 +359,8 @@ def main():
         "mh_mvn_c1": lambda: mh_mvn(11, 512, (0., 1.)),
         "mh_mvn_c1_b": lambda: mh_mvn(12, 256, (-2.5, 3.0)),
         "mh_mvn_log": lambda: mh_mvn(13, 256, (0., 1.), log_pscale=True),
+        "mh_mvn_3d": lambda: mh_mvn3d(15, 256),
+        "gibbs3d": lambda: gibbs3d(54, 300),
         "mh_norm1d_hastings": lambda: mh_norm1d(21, 300, 60, 'hastings'),
         "mh_norm1d_metropolis": lambda: mh_norm1d(22, 300, 60, 'metropolis'),
         "mh_norm1d_underflow": lambda: mh_norm1d(23, 60, 1000, 'metropolis'),

@@ -205,6 +205,45 @@ def test_gibbs_norm2d():
     assert process._cond_cov is not None and relerr(process._cond_cov.stdv, g["stdv"]) <= TOL
 
 
+def test_three_variable_mvn_through_api():
+    """SP(x & y & z) with a non-exchangeable mvn: the d > 2 value re-ordering quirk
+    (prob.py:349-358) is reproduced by the drop-in (golden from the live reference)."""
+    engine()
+    g = load_golden("mh_mvn_3d")
+    T = len(g["thresh"])
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    z = pb.RV('z', vtype=float, vset=(-np.inf, np.inf))
+    process = pb.SP(x & y & z)
+    process.set_prob(scipy.stats.multivariate_normal, g["mean"], g["cov"])
+    process.set_tran(lambda **k: 1.)
+    process.set_delta(lambda: None)
+    process.set_scores('hastings')
+    process.set_update('metropolis')
+    init = g["init"]
+    sampler = process.sampler({'x': init[0], 'y': init[1], 'z': init[2]}, stop=T,
+                              inj_delta=g["delta"], inj_thresh=g["thresh"])
+    summary = process(process.walk(sampler))
+    assert [u is True for u in summary.u] == list(g["u"])
+    for j, k in enumerate('xyz'):
+        assert np.abs(summary.v[k] - g["x"][:, j]).max() <= TOL
+    assert relerr(summary.v.prob, g["prob"]) <= TOL
+    # Gibbs on three variables
+    g = load_golden("gibbs3d")
+    lims = tuple(g["lims"][0])
+    rvs = [pb.RV(k, vtype=float, vset=lims) for k in 'xyz']
+    process = pb.SP(rvs[0] & rvs[1] & rvs[2])
+    process.set_prob(scipy.stats.multivariate_normal, g["mean"], g["cov"])
+    process.set_tran(scipy.stats.multivariate_normal, g["mean"], g["cov"], tsteps=1)
+    process.set_scores('gibbs')
+    sampler = process.sampler({'x': 0., 'y': 1., 'z': -1.}, stop=len(g["runif"]),
+                              inj_thresh=g["runif"])
+    summary = process(process.walk(sampler))
+    for j, k in enumerate('xyz'):
+        assert np.abs(summary.v[k] - g["x"][:, j]).max() <= 1e-11
+    assert relerr(summary.v.prob, g["prob"]) <= 1e-11
+
+
 def test_batched_c2_through_api_and_host_stream():
     """Config C2 shape (reduced length) through the public API: native RNG,
     chains=4096, both the device-resident and the host-streaming paths."""

@@ -23,12 +23,13 @@ def test_condcov_constants_match_reference():
         assert np.abs(cc.coef_matrix() - coef).max() <= TOL
 
 
-def test_gibbs2d_golden():
-    """examples/mcmc/gibbs_norm2d.py through the reference with injected uniforms:
-    trajectory and the recorded (permuted-order) mvn pdf."""
+@pytest.mark.parametrize("name", ["gibbs2d", "gibbs3d"])
+def test_gibbs2d_golden(name):
+    """examples/mcmc/gibbs_norm2d.py (and a 3-D variant) through the reference with
+    injected uniforms: trajectory and the recorded (permuted-order) mvn pdf."""
     from probayes_b200.cond_cov import CondCov
     eng = engine()
-    g = load_golden("gibbs2d")
+    g = load_golden(name)
     cc = CondCov(g["mean"], g["cov"], g["lims"])
     T = len(g["runif"])
     state = dev(eng, g["init"][:, None])

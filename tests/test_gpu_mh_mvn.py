@@ -14,7 +14,7 @@ TOL = 1e-12
 COV = np.array([[2.0, 1.2], [1.2, 2.0]])
 
 
-@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_c1_b", "mh_mvn_log"])
+@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_c1_b", "mh_mvn_log", "mh_mvn_3d"])
 def test_golden_injected(name):
     eng = engine()
     g = load_golden(name)

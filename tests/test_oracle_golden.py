@@ -9,7 +9,7 @@ from oracle import np_oracle as o
 TOL = 1e-12
 
 
-@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_c1_b", "mh_mvn_log"])
+@pytest.mark.parametrize("name", ["mh_mvn_c1", "mh_mvn_c1_b", "mh_mvn_log", "mh_mvn_3d"])
 def test_mh_mvn(name):
     g = load_golden(name)
     r = o.mh_mvn_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
@@ -82,6 +82,26 @@ def test_dgei(name):
         assert (g["posterior"] == o.NEARLY_NEGATIVE_INF).sum() > 0
         assert np.array_equal(post == o.NEARLY_NEGATIVE_INF,
                               g["posterior"] == o.NEARLY_NEGATIVE_INF)
+
+
+def test_mvn_value_order_quirk_is_pinned():
+    """d = 3: the reference evaluates scipy's mvn on [v1, v0, v2] (prob.py:349-358);
+    the natural order gives different accept decisions."""
+    g = load_golden("mh_mvn_3d")
+    assert o.mvn_value_order(3) == [1, 0, 2] and o.mvn_value_order(2) == [1, 0]
+    assert o.mvn_value_order(5) == [3, 2, 1, 0, 4]
+    r = o.mh_mvn_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                      g["mean"], g["cov"], reorder=False)
+    assert not np.array_equal(r["u"][:, 0], g["u"])
+
+
+@pytest.mark.parametrize("name", ["gibbs2d", "gibbs3d"])
+def test_gibbs_nd(name):
+    g = load_golden(name)
+    r = o.gibbs_mvn_walk(g["init"][None], g["runif"][:, None], g["mean"], g["cov"],
+                         g["lims"])
+    assert np.abs(r["x"][:, 0] - g["x"]).max() <= TOL
+    assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
 
 
 def test_gibbs2d():
