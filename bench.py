@@ -35,6 +35,11 @@ MEAN = np.array([0.0, 0.0])
 INIT = np.array([0.0, 1.0])
 METRIC = "mh_chain_steps_per_sec"
 UNIT = "chain-steps/s"
+# DRAM traffic of one K1 launch on the default workload (4096 chains x 10^4 steps, D=2, thin=1):
+# dram__bytes_read.sum (335 KB) + dram__bytes_write.sum (925.0 MB) from the ncu --set full capture in
+# profiles/r1e_ncu_full_k1_final.csv.  Algorithmic bytes are 983.0 MB; the difference is the tail of
+# the output still resident in the 126 MB L2 when the kernel ends.  No re-reads.
+NCU_K1_DRAM_BYTES = 335360 + 924983296
 
 
 def parse():
@@ -444,7 +449,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": NCU_K1_DRAM_BYTES if (C, T, thin, args.variant) == (4096, 10000, 1, 0) else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                                           "profiles/r1e_ncu_full_k1_final.csv",
                          "peak_source": which, "kernel": "mh_mvn_kernel<2>" if args.variant == 1 else "mh_mvn_ws_kernel<2>",
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": out_bytes,
