@@ -285,6 +285,68 @@ PBX_API int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int64_
 PBX_API int pbx_reduce_chain_stats(pbx_ctx* ctx, const double* stat_sum, const double* stat_sumsq,
                            int32_t n_dims, int64_t n_chains, int64_t n_steps, double* out);
 
+/* ---------------------------------------------------------------------------
+ * K6: PD post-processing on large grids / sample sets -- SURVEY.md section 8f rank 2.
+ * Replaces the numpy passes of PD.sorted (np.argsort + fancy indexing,
+ * probayes/pd.py:464-493), PD.quantile (rescale + np.cumsum + div_prob + np.digitize,
+ * pd.py:408-461) and PD.expectation (rescale + np.sum(prob*val), pd.py:373-405).
+ * All HBM-bound; deterministic (fixed reduction / scan order, no atomics on doubles).
+ * ------------------------------------------------------------------------- */
+
+/* bytes of device workspace pbx_argsort_f64 needs for n keys */
+PBX_API int pbx_argsort_workspace_bytes(int64_t n, size_t* bytes);
+/* Ascending STABLE argsort of n doubles (np.argsort(kind='stable') order; -0.0 sorts
+ * before +0.0, NaNs last): LSD radix sort, 8-bit digits, passes whose digit is constant
+ * over all keys are skipped.  keys: device [n] (not modified); order: device int32 [n]
+ * out; keys_sorted: device [n] out or NULL.  n < 2^31. */
+PBX_API int pbx_argsort_f64(pbx_ctx* ctx, const double* keys, int64_t n, int32_t* order,
+                            double* keys_sorted, void* workspace, size_t workspace_bytes);
+/* dst[i] = src[idx[i]]  (values / probabilities re-ordered by a sort: pd.py:478-492) */
+PBX_API int pbx_gather_f64(pbx_ctx* ctx, const double* src, const int32_t* idx, int64_t n,
+                           double* dst);
+/* 2-D take along an axis: axis 0: dst[i][j] = src[idx[i]][j]; axis 1: dst[i][j] = src[i][idx[j]]
+ * (prob[tuple(slices)] of pd.py:476-478 for a grid PD) */
+PBX_API int pbx_take_axis_f64(pbx_ctx* ctx, const double* src, int64_t rows, int64_t cols,
+                              int32_t axis, const int32_t* idx, double* dst);
+/* bytes of device workspace for pbx_cumprob_f64 / pbx_expectation_f64 */
+PBX_API int pbx_scan_workspace_bytes(int64_t n, size_t* bytes);
+/* cum[i] = (sum_{k<=i} lin(prob[k])) / max(tiny, sum_k lin(prob[k])), lin = clamped exp
+ * when log_pscale (pscales.py:56-65,100-131,219-236); total (device, 1 double, may be NULL)
+ * receives the un-normalised sum.  cum may alias prob.  Three-phase reduce-then-scan:
+ * 24 B of traffic per element, bit-reproducible. */
+PBX_API int pbx_cumprob_f64(pbx_ctx* ctx, const double* prob, int64_t n, int32_t log_pscale,
+                            double* cum, double* total, void* workspace, size_t workspace_bytes);
+/* np.maximum(0, np.digitize(q, cum) - 1) for nq quantiles (pd.py:430): idx_out device
+ * int64 [nq]; q host [nq]; cum device [n] non-decreasing. nq <= 64. */
+PBX_API int pbx_digitize_f64(pbx_ctx* ctx, const double* cum, int64_t n, const double* q,
+                             int32_t nq, int64_t* idx_out);
+/* Sums for PD.expectation over a [rows][cols] prob array (rows = 1 for sample sets):
+ * out[0] = sum lin(p); out[1+k] = sum_ij lin(p_ij) row_vals[k][i], k < n_row_vals;
+ * out[1+n_row_vals+k] = sum_ij lin(p_ij) col_vals[k][j].  row_vals: device
+ * [n_row_vals][rows], col_vals: device [n_col_vals][cols] (either may be NULL with count 0;
+ * counts <= 4).  out: device [1 + n_row_vals + n_col_vals].  The quotient
+ * div_prob(numerator, total) is left to the caller (2 scalars). */
+PBX_API int pbx_expectation_f64(pbx_ctx* ctx, const double* prob, int64_t rows, int64_t cols,
+                                int32_t log_pscale, const double* row_vals, int32_t n_row_vals,
+                                const double* col_vals, int32_t n_col_vals, double* out,
+                                void* workspace, size_t workspace_bytes);
+
+/* ---------------------------------------------------------------------------
+ * Ordinary Monte Carlo random sampling of box-bounded parameters -- SURVEY.md section 8f
+ * rank 3.  Replaces Variable.evaluate({0}) -> vtypes.uniform(ulims, n=0) -> ufun^-1
+ * (probayes/variable.py:558-583, vtypes.py:186) called once per sampler step by
+ * SP.next's no-proposal branch (sp.py:229-234), as in examples/omc/omc_rs_sp_norm1d.py:
+ * theta[j][t] = ufun_j^-1( ulo_j + (uhi_j - ulo_j) r ),  r ~ U(0,1); the log-joint of
+ * the samples is then pbx_normreg_logjoint.  Draws: injected uniforms inj_unif
+ * [n_samples][n_params] (reference draw order: parameters in field order per step), or
+ * Philox block (seed, step = sample0 + t, chain = 0, slot j/2) -> (u52, u32).
+ * lims host [n_params][2] (value space), log_ufun host [n_params]; out device
+ * [n_params][n_samples]. n_params <= 8.
+ * ------------------------------------------------------------------------- */
+PBX_API int pbx_box_sample(pbx_ctx* ctx, int32_t n_params, int64_t n_samples, const double* lims,
+                           const int32_t* log_ufun, uint64_t seed, int64_t sample0,
+                           const double* inj_unif, double* out);
+
 /* FP64 FMA peak micro-benchmark (roofline denominator for the compute-bound
  * kernels; MEASURED_PEAKS.json has no FP64 figure). Returns TFLOP/s. */
 PBX_API int pbx_fp64_peak(pbx_ctx* ctx, double* tflops);

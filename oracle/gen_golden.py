@@ -274,6 +274,51 @@ def dgei(seed, N, M, S):
 
 
 # ---------------------------------------------------------------------------
+def omc_rs_norm1d(seed, N, T):
+    """examples/omc/omc_rs_sp_norm1d.py:17-52 with the prior draws injected:
+    random sampling of (mu, sigma) through SP.sampler without a proposal, the
+    summary PD, and its post-processing (rescaled / sorted / quantile /
+    expectation: probayes/pd.py:373-499)."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    data = rng.normal(50., 10., size=N)
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset=[-np.inf, np.inf])
+    sigma.set_ufun((np.log, np.exp))
+    process = pb.SP(pb.RF(x), pb.RF(mu, sigma))
+    process.set_prob(scipy.stats.norm.logpdf,
+                     order={'x': 0, 'mu': 'loc', 'sigma': 'scale'}, pscale='log')
+    R = rng.random((T, 2))
+    with ref_shim.injected_uniform(np.ravel(R)):
+        sampler = process.sampler({'mu': {0}, 'sigma': {0}, 'x': data},
+                                  iid=True, joint=True, stop=T)
+        samples = [s for s in sampler]
+    summary = process(samples)
+    inference = summary.rescaled()
+    mu_sort = inference.sorted('mu')
+    sigma_sort = inference.sorted('sigma')
+    qs = [0.025, 0.25, 0.5, 0.75, 0.975]
+    expt = inference.expectation()
+    expt2 = inference.expectation(['mu', 'sigma'], exponent=2)
+    return dict(data=data, runif=R, mu=np.asarray(summary['mu'], float),
+                sigma=np.asarray(summary['sigma'], float),
+                logp=np.asarray(summary.prob, float), lin=np.asarray(inference.prob, float),
+                name=np.array(summary.name), first_name=np.array(samples[0].name),
+                mu_sorted=np.asarray(mu_sort['mu'], float),
+                mu_sorted_sigma=np.asarray(mu_sort['sigma'], float),
+                mu_sorted_prob=np.asarray(mu_sort.prob, float),
+                sigma_sorted=np.asarray(sigma_sort['sigma'], float),
+                sigma_sorted_prob=np.asarray(sigma_sort.prob, float),
+                qs=np.array(qs),
+                q_mu=np.array([float(q['mu']) for q in mu_sort.quantile(qs)]),
+                q_sigma=np.array([float(q['sigma']) for q in sigma_sort.quantile(qs)]),
+                med_mu=np.array(float(mu_sort.quantile(0.5)['mu'])),
+                expt=np.array([float(expt['mu']), float(expt['sigma'])]),
+                expt2=np.array([float(expt2['mu']), float(expt2['sigma'])]))
+
+
+# ---------------------------------------------------------------------------
 def gibbs2d(seed, T):
     """examples/mcmc/gibbs_norm2d.py:15-22 with the cdf uniforms injected."""
     pb = ref_shim.load()
@@ -369,6 +414,7 @@ def main():
         "dgei_small": lambda: dgei(41, 60, 48, 40),
         "dgei_peaked": lambda: dgei(42, 2000, 40, 36),
         "gibbs2d": lambda: gibbs2d(51, 400),
+        "omc_rs_norm1d": lambda: omc_rs_norm1d(61, 60, 400),
         "condcov_d8": lambda: condcov_bare(52, 8, 160),
         "condcov_d64": lambda: condcov_bare(53, 64, 256),
         "pscales": pscales_table,

@@ -426,3 +426,73 @@ def rhat(X):
     W = v.mean(axis=0)
     B = T * m.var(axis=0, ddof=1)
     return np.sqrt(((T - 1) / T * W + B / T) / W)
+
+
+# ----------------------------------------------------------------------------
+# PD post-processing and OMC random sampling (rank 3)
+# ----------------------------------------------------------------------------
+def box_sample(lims, log_ufun, runif):
+    """Variable.evaluate({0}): probayes/variable.py:558-583 with vtypes.uniform
+    (vtypes.py:186): one uniform in ufun space per variable, mapped back through
+    ufun^-1.  runif [T, P] in draw order (variables in field order per step)."""
+    lims = np.asarray(lims, dtype=float)
+    runif = np.asarray(runif, dtype=float)
+    out = np.empty(runif.shape[::-1])
+    for j in range(lims.shape[0]):
+        lo, hi = lims[j]
+        if log_ufun[j]:
+            ulo, uhi = np.log(lo), np.log(hi)
+            out[j] = np.exp(ulo + (uhi - ulo) * runif[:, j])
+        else:
+            out[j] = lo + (hi - lo) * runif[:, j]
+    return out
+
+
+def pd_sorted_order(keys):
+    """PD.sorted: probayes/pd.py:473-474 (np.argsort; the stable variant so that
+    ties have a defined order)."""
+    return np.argsort(np.ravel(keys), kind='stable')
+
+
+def pd_cumprob(prob, log_pscale):
+    """PD.quantile: probayes/pd.py:426-429 -- rescale to linear, cumsum,
+    div_prob by the last element."""
+    rav = to_linear(np.ravel(np.asarray(prob, dtype=float)), log_pscale)
+    cum = np.cumsum(rav)
+    return div_prob_linear(cum, cum[-1]), rav
+
+
+def pd_quantile_index(cum, q):
+    """probayes/pd.py:430."""
+    return np.maximum(0, np.digitize(np.atleast_1d(np.asarray(q, float)), cum) - 1)
+
+
+def pd_quantile_1d(vals, prob, log_pscale, q):
+    """PD.quantile for a 1-D distribution whose ``vals`` are monotonic
+    (probayes/pd.py:433-457): the bracketing cell from the cumulative
+    probability, then interpolation in cumulative probability when the two
+    cell probabilities are close, else their probability-weighted mean."""
+    vals = np.ravel(np.asarray(vals, dtype=float))
+    cum, rav = pd_cumprob(prob, log_pscale)
+    out = []
+    for qq, i in zip(np.atleast_1d(q), pd_quantile_index(cum, q)):
+        i = int(min(i, len(vals) - 1))
+        if i == len(vals) - 1:
+            out.append(vals[i])
+        elif abs(rav[i + 1] - rav[i]) < min(qq, 1. - qq):
+            out.append(float(np.interp(qq, cum[i:i + 2], vals[i:i + 2])))
+        else:
+            w = rav[i:i + 2]
+            out.append(float(np.sum(w * vals[i:i + 2]) / np.sum(w)))
+    return np.array(out)
+
+
+def pd_expectation(prob, log_pscale, row_vals=None, col_vals=None):
+    """PD.expectation over every array axis: probayes/pd.py:387-402 -- returns
+    (total, [sum p*row_val], [sum p*col_val]) for a [rows, cols] prob."""
+    p = to_linear(np.atleast_2d(np.asarray(prob, dtype=float)), log_pscale)
+    rv = [] if row_vals is None else [float(np.sum(p * np.asarray(v, float)[:, None]))
+                                      for v in row_vals]
+    cv = [] if col_vals is None else [float(np.sum(p * np.asarray(v, float)[None, :]))
+                                      for v in col_vals]
+    return float(np.sum(p)), rv, cv

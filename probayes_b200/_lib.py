@@ -114,6 +114,23 @@ SIGNATURES = {
                                  C.c_void_p, C.c_double, C.c_int32, C.c_void_p]),
     "pbx_reduce_chain_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_int64, C.c_void_p]),
+    "pbx_argsort_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    "pbx_argsort_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_size_t]),
+    "pbx_gather_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pbx_take_axis_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                    C.c_void_p, C.c_void_p]),
+    "pbx_scan_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),
+    "pbx_cumprob_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pbx_digitize_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.POINTER(C.c_double), C.c_int32, C.c_void_p]),
+    "pbx_expectation_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                      C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_size_t]),
+    "pbx_box_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_int32), C.c_uint64, C.c_int64, C.c_void_p,
+                                 C.c_void_p]),
     "pbx_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pbx_fp64_dep_latency": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

@@ -499,6 +499,98 @@ class Engine:
         _lib.check(self.lib.pbx_gibbs_mvn_run(self.ctx, C.byref(p)), "pbx_gibbs_mvn_run")
         return out
 
+    # ------------------------------------------------- K6: PD post-processing
+    def _workspace(self, nbytes):
+        torch = _torch()
+        return torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+
+    def argsort(self, keys, want_keys=False):
+        """Ascending stable argsort of a 1-D fp64 device tensor -> int32 order
+        (and the sorted keys): np.argsort of PD.sorted (pd.py:473-474)."""
+        torch = _torch()
+        n = int(keys.numel())
+        nb = C.c_size_t()
+        _lib.check(self.lib.pbx_argsort_workspace_bytes(n, C.byref(nb)), "pbx_argsort_workspace_bytes")
+        ws = self._workspace(max(nb.value, 1))
+        order = torch.empty(n, dtype=torch.int32, device=self.device)
+        ks = self.empty(n) if want_keys else None
+        _lib.check(self.lib.pbx_argsort_f64(self.ctx, self._ptr(keys), n, order.data_ptr(),
+                                            0 if ks is None else ks.data_ptr(),
+                                            ws.data_ptr(), nb.value), "pbx_argsort_f64")
+        return (order, ks) if want_keys else order
+
+    def gather(self, src, order):
+        out = self.empty(int(order.numel()))
+        _lib.check(self.lib.pbx_gather_f64(self.ctx, self._ptr(src), order.data_ptr(),
+                                           int(order.numel()), out.data_ptr()), "pbx_gather_f64")
+        return out
+
+    def take_axis(self, src, order, axis):
+        rows, cols = src.shape
+        out = self.empty(rows, cols)
+        _lib.check(self.lib.pbx_take_axis_f64(self.ctx, self._ptr(src), rows, cols, int(axis),
+                                              order.data_ptr(), out.data_ptr()),
+                   "pbx_take_axis_f64")
+        return out
+
+    def _scan_ws(self, n):
+        nb = C.c_size_t()
+        _lib.check(self.lib.pbx_scan_workspace_bytes(int(n), C.byref(nb)), "pbx_scan_workspace_bytes")
+        return self._workspace(nb.value), nb.value
+
+    def cumprob(self, prob, log_pscale, out=None):
+        """Normalised cumulative probability of the ravelled ``prob`` and the
+        un-normalised total (1-element device tensor): pd.py:426-429."""
+        n = int(prob.numel())
+        ws, nb = self._scan_ws(n)
+        cum = self.empty(n) if out is None else out
+        total = self.empty(1)
+        _lib.check(self.lib.pbx_cumprob_f64(self.ctx, self._ptr(prob), n, int(bool(log_pscale)),
+                                            cum.data_ptr(), total.data_ptr(), ws.data_ptr(), nb),
+                   "pbx_cumprob_f64")
+        return cum, total
+
+    def digitize(self, cum, q):
+        """np.maximum(0, np.digitize(q, cum) - 1) -> int64 device tensor (pd.py:430)."""
+        torch = _torch()
+        q = np.ascontiguousarray(np.atleast_1d(np.asarray(q, dtype=np.float64)))
+        out = torch.empty(q.size, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.pbx_digitize_f64(self.ctx, self._ptr(cum), int(cum.numel()),
+                                             q.ctypes.data_as(C.POINTER(C.c_double)), q.size,
+                                             out.data_ptr()), "pbx_digitize_f64")
+        return out
+
+    def expectation_sums(self, prob, log_pscale, row_vals=None, col_vals=None):
+        """[1 + KR + KC] device sums: total, sum p*row_vals[k][i], sum p*col_vals[k][j]
+        over a [rows, cols] (or 1-D = [1, n]) prob tensor (pd.py:387-402)."""
+        if prob.dim() == 1:
+            rows, cols = 1, int(prob.numel())
+        else:
+            rows, cols = prob.shape
+        kr = 0 if row_vals is None else int(row_vals.shape[0])
+        kc = 0 if col_vals is None else int(col_vals.shape[0])
+        ws, nb = self._scan_ws(rows * cols)
+        out = self.empty(1 + kr + kc)
+        _lib.check(self.lib.pbx_expectation_f64(
+            self.ctx, self._ptr(prob), rows, cols, int(bool(log_pscale)),
+            0 if kr == 0 else self._ptr(row_vals), kr,
+            0 if kc == 0 else self._ptr(col_vals), kc, out.data_ptr(), ws.data_ptr(), nb),
+            "pbx_expectation_f64")
+        return out
+
+    def box_sample(self, lims, log_ufun, n_samples, seed=0, sample0=0, inj_unif=None):
+        """theta [P, T] device: uniform draws in ufun space mapped back
+        (variable.py:558-583); inj_unif [T, P] device or None = Philox."""
+        lims = np.ascontiguousarray(np.asarray(lims, dtype=np.float64))
+        P = lims.shape[0]
+        lg = np.ascontiguousarray(np.asarray(log_ufun, dtype=np.int32))
+        out = self.empty(P, int(n_samples))
+        _lib.check(self.lib.pbx_box_sample(
+            self.ctx, P, int(n_samples), lims.ctypes.data_as(C.POINTER(C.c_double)),
+            lg.ctypes.data_as(C.POINTER(C.c_int32)), int(seed), int(sample0),
+            0 if inj_unif is None else self._ptr(inj_unif), out.data_ptr()), "pbx_box_sample")
+        return out
+
     # ------------------------------------------------------- chain summaries
     def chain_stats(self, stat_sum, stat_sumsq, n_steps):
         """[D, 4] device tensor (sum_c mean, sum_c mean^2, sum_c var, C)."""

@@ -9,8 +9,12 @@ array algebra of the path running in libpbx:
   * ``conditionalise`` / ``marginal`` / ``marginalise`` / ``rescaled`` on a
     2-D device-backed PD are the K4 kernels (probayes/pd.py:136-165,168-211,
     214-295,496-499);
-  * ``expectation`` / ``quantile`` / ``sorted`` are the "next" rows of the scope
-    table; here they operate on marginals / sample sets on the host.
+  * ``expectation`` / ``quantile`` / ``sorted`` on a device-backed PD (1-D sample
+    sets / marginals, 2-D grids) are the K6 kernels: radix argsort + gathers,
+    reduce-then-scan cumulative probability + digitize, one-pass weighted sums
+    (probayes/pd.py:373-405,408-461,464-493); only the O(1) bracket interpolation
+    and the name/dims bookkeeping stay in Python.  Host-backed PDs (scalars, small
+    user-built arrays) keep the reference's numpy arithmetic.
 
 Names follow the reference: ``"mu=[],sigma=[]|x={60}"`` -- ``key=[]`` for array
 values, ``key={n}`` for an iid-reduced set, ``key=value`` for scalars; marginal
@@ -70,6 +74,8 @@ class PD(collections.OrderedDict):
         self._prob_dev = None
         self._prob = None
         self._cache = {}            # device-side by-products (marginals of a posterior)
+        self._vals_dev = {}         # key -> 1-D device tensor mirroring an array value
+        self._monotonic = {}        # key -> True where known (set by sorted())
         self.prob = prob
 
     # ---- bookkeeping ------------------------------------------------------------
@@ -176,6 +182,22 @@ class PD(collections.OrderedDict):
         """The device tensor behind ``prob`` (None for host-backed PDs)."""
         return self._prob_dev
 
+    def set_device_vals(self, vals_dev):
+        """Registers device mirrors of array values (so sorted() / expectation() need
+        no upload).  vals_dev: {key: 1-D fp64 device tensor}."""
+        for k, t in vals_dev.items():
+            assert k in self and int(t.numel()) == int(np.size(self[k]))
+            self._vals_dev[k] = t
+
+    def _dev_val(self, key, exponent=None):
+        """1-D device tensor of the values of ``key`` (uploaded on first use)."""
+        eng = self._engine()
+        if exponent:
+            return eng.to_device(np.ravel(np.asarray(self[key], dtype=float)) ** exponent)
+        if key not in self._vals_dev:
+            self._vals_dev[key] = eng.to_device(np.ravel(np.asarray(self[key], dtype=float)))
+        return self._vals_dev[key]
+
     def _new(self, name, vals, dims, prob, pscale=None):
         return PD(name, vals, dims=dims, prob=prob,
                   pscale=self._pscale if pscale is None else pscale)
@@ -193,7 +215,9 @@ class PD(collections.OrderedDict):
             eng = self._engine()
             out = self._prob_dev.clone()
             out = eng.exp_logp_(out) if iscomplex(self._pscale) else eng.log_prob_(out)
-            return self._new(self._name, collections.OrderedDict(self), self._dims, out, dst)
+            res = self._new(self._name, collections.OrderedDict(self), self._dims, out, dst)
+            res._vals_dev, res._monotonic = dict(self._vals_dev), dict(self._monotonic)
+            return res
         prob = rescale(np.copy(self.prob), self._pscale, dst)
         return self._new(self._name, collections.OrderedDict(self), self._dims, prob, dst)
 
@@ -277,6 +301,11 @@ class PD(collections.OrderedDict):
         if not normalise:
             return self._new(name, vals, self._dims, self._prob_dev
                              if self._prob_dev is not None else self.prob)
+        if self._prob_dev is not None and self.ndim == 1 and self._pscale == 0j:
+            r = self._engine().grid_conditionalise(self._prob_dev.reshape(1, -1))
+            out = self._new(name, vals, self._dims, r["post"].reshape(-1))
+            out._vals_dev = dict(self._vals_dev)
+            return out
         if self._prob_dev is not None and self.ndim == 2 and self._pscale == 0j:
             eng = self._engine()
             r = eng.grid_conditionalise(self._prob_dev)
@@ -317,56 +346,125 @@ class PD(collections.OrderedDict):
             else np.prod(self.prob, axis=tuple(axes))
         return self._new(margcond_str(marg, self._cond), vals, dims, prob)
 
+    def _log_flag(self):
+        if self._pscale == 0j:
+            return True
+        if self._pscale == 1.:
+            return False
+        raise NotImplementedError("device post-processing handles pscale 'log' and 1 only")
+
     def expectation(self, keys=None, exponent=None):
         """E[key] = sum(prob*val) / max(tiny, sum(prob)) over all array axes
         (pd.py:373-405)."""
         keys = list(self._marg.keys()) if keys is None else \
             ([keys] if isinstance(keys, str) else list(keys))
-        prob = rescale(self.prob, self._pscale, 1.)
-        total = np.sum(prob)
+        for key in keys:
+            assert key in self._marg, \
+                "Key {} not marginal in distribution {}".format(key, self._name)
+        akeys = [k for k, single in zip(self.keys(), self._aresingleton)
+                 if k in keys and not single]
+        sums = {}
+        if self._prob_dev is not None and akeys:
+            # K6: one pass over prob for the total and every numerator
+            if self.ndim > 2:
+                raise NotImplementedError("device expectation handles 1-D and 2-D PDs")
+            if {self._dims[k] for k in akeys} != set(range(self.ndim)):
+                raise NotImplementedError("device expectation sums over every array axis: "
+                                          "request keys on all of them")
+            import torch
+            last = self.ndim - 1                       # 1-D: everything is a 'column' value
+            rk = [k for k in akeys if self._dims[k] != last]
+            ck = [k for k in akeys if self._dims[k] == last]
+            if len(rk) > 4 or len(ck) > 4:
+                raise NotImplementedError("at most 4 array keys per axis")
+            rv = torch.stack([self._dev_val(k, exponent) for k in rk]) if rk else None
+            cv = torch.stack([self._dev_val(k, exponent) for k in ck]) if ck else None
+            res = self._engine().expectation_sums(self._prob_dev, self._log_flag(), rv, cv)
+            res = res.cpu().numpy()
+            total = res[0]
+            for j, k in enumerate(rk + ck):
+                sums[k] = res[1 + j]
+        elif akeys:
+            prob = rescale(self.prob, self._pscale, 1.)
+            total = np.sum(prob)
+            for key in akeys:
+                val = self[key] if not exponent else self[key] ** exponent
+                shape = [1] * self.ndim
+                shape[self._dims[key]] = -1
+                sums[key] = np.sum(prob * np.asarray(val, dtype=float).reshape(shape))
         out = collections.OrderedDict()
         for key, single in zip(self.keys(), self._aresingleton):
             if key in keys:
-                val = self[key] if not exponent else self[key] ** exponent
                 if single:
-                    out[key] = val
+                    out[key] = self[key] if not exponent or isinstance(self[key], set) \
+                        else self[key] ** exponent
                 else:
-                    shape = [1] * self.ndim
-                    shape[self._dims[key]] = -1
-                    v = np.asarray(val, dtype=float).reshape(shape)
-                    out[key] = div_prob(np.sum(prob * v), total)
+                    out[key] = div_prob(sums[key], total)
             elif key in self._cond:
                 out[key] = self[key]
         return out
 
+    def _ismonotonic(self, key):
+        if key in self._monotonic:
+            return self._monotonic[key]
+        v = np.ravel(self[key])
+        ge = v[1:] >= v[:-1]
+        self._monotonic[key] = bool(v.size < 2 or np.all(ge) or not np.any(ge))
+        return self._monotonic[key]
+
+    def _cum_brackets(self, quants):
+        """For each quantile: (ravelled index i of the bracketing cell, linear probs of
+        cells i, i+1, cumulative probs of cells i, i+1) -- pd.py:426-430."""
+        n = self.size
+        if self._prob_dev is not None:
+            eng = self._engine()
+            flat = self._prob_dev.reshape(-1)
+            cum, _ = eng.cumprob(flat, self._log_flag())
+            idx = eng.digitize(cum, quants).cpu().numpy()
+            out = []
+            for i in idx:
+                i = int(i)
+                j = min(i + 2, n)
+                rav = rescale(flat[i:j].cpu().numpy(), self._pscale, 1.)
+                out.append((i, rav, cum[i:j].cpu().numpy()))
+            return out
+        rav = rescale(np.ravel(self.prob), self._pscale, 1.)
+        cum = np.cumsum(rav)
+        cum = div_prob(cum, cum[-1])
+        idx = np.maximum(0, np.digitize(np.array(quants), cum) - 1).tolist()
+        return [(int(i), rav[int(i):int(i) + 2], cum[int(i):int(i) + 2]) for i in idx]
+
     def quantile(self, q=0.5):
-        """Quantiles of a 1-D distribution from the cumulative probability with
-        linear interpolation inside the bracketing cell (pd.py:408-461)."""
+        """Quantiles from the cumulative probability of the ravelled distribution;
+        values of the last axis are interpolated inside the bracketing cell, other
+        axes take the cell's value, non-monotonic values are returned as the set
+        {size} (pd.py:408-461)."""
         quants = [q] if isscalar(q) else list(q)
         if self.issingleton:
             res = [collections.OrderedDict(self)] * len(quants)
             return res[0] if isscalar(q) else res
-        assert self.ndim == 1, "quantile() is implemented for 1-D distributions"
-        rav = rescale(np.ravel(self.prob), self._pscale, 1.)
-        cum = np.cumsum(rav)
-        cum = div_prob(cum, cum[-1])
-        idxs = np.maximum(0, np.digitize(np.array(quants), cum) - 1).tolist()
+        unsorted = {k for k, single in zip(self.keys(), self._aresingleton)
+                    if not single and not self._ismonotonic(k)}
         res = []
-        for qq, i in zip(quants, idxs):
+        for qq, (rav_idx, ravp, cump) in zip(quants, self._cum_brackets(quants)):
+            unr_idx = np.unravel_index(rav_idx, self._shape)
             item = collections.OrderedDict()
             for key, single in zip(self.keys(), self._aresingleton):
                 if single:
                     item[key] = self[key]
                     continue
+                if key in unsorted:
+                    item[key] = {int(np.size(self[key]))}
+                    continue
+                dim = self._dims[key]
                 val = np.ravel(self[key])
-                i = int(min(i, len(val) - 1))
-                if i == len(val) - 1:
+                i = int(min(unr_idx[dim], len(val) - 1))
+                if dim < self.ndim - 1 or i == len(val) - 1:
                     item[key] = val[i]
-                elif abs(rav[i + 1] - rav[i]) < min(qq, 1. - qq):
-                    item[key] = float(np.interp(qq, cum[i:i + 2], val[i:i + 2]))
+                elif abs(ravp[1] - ravp[0]) < min(qq, 1. - qq):
+                    item[key] = np.interp(qq, cump, val[i:i + 2])
                 else:
-                    w = rav[i:i + 2]
-                    item[key] = float(np.sum(w * val[i:i + 2]) / np.sum(w))
+                    item[key] = np.sum(ravp * val[i:i + 2]) / np.sum(ravp)
             res.append(item)
         return res[0] if isscalar(q) else res
 
@@ -374,7 +472,30 @@ class PD(collections.OrderedDict):
         """Distribution re-ordered by ascending ``key`` (pd.py:464-493)."""
         dim = self._dims[key]
         if dim is None:
-            return self._new(self._name, collections.OrderedDict(self), self._dims, self.prob)
+            return self._new(self._name, collections.OrderedDict(self), self._dims,
+                             self._prob_dev if self._prob_dev is not None else self.prob)
+        if self._prob_dev is not None:
+            # K6: radix argsort of the key, gathers of prob and of the values on that axis
+            if self.ndim > 2:
+                raise NotImplementedError("device sorted() handles 1-D and 2-D PDs")
+            eng = self._engine()
+            order, ks = eng.argsort(self._dev_val(key), want_keys=True)
+            prob = eng.gather(self._prob_dev, order) if self.ndim == 1 else \
+                eng.take_axis(self._prob_dev, order, dim)
+            vals, vdev = collections.OrderedDict(), {}
+            for k, v in self.items():
+                if self._dims[k] != dim:
+                    vals[k] = v
+                    if k in self._vals_dev:
+                        vdev[k] = self._vals_dev[k]
+                    continue
+                vdev[k] = ks if k == key else eng.gather(self._dev_val(k), order)
+                vals[k] = vdev[k].cpu().numpy()
+            out = self._new(self._name, vals, self._dims, prob)
+            out._vals_dev = vdev
+            out._monotonic = {k: m for k, m in self._monotonic.items() if self._dims[k] != dim}
+            out._monotonic[key] = True
+            return out
         order = np.argsort(np.ravel(self[key]))
         vals = collections.OrderedDict()
         for k, v in self.items():

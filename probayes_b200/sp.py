@@ -19,6 +19,15 @@ New keyword arguments of ``sampler`` (everything else keeps its meaning):
   host_buffers=dict  (with host_stream) a dict the sampler fills with its pinned
                 buffers and reuses on later walks / other samplers of the same shape;
                 the returned arrays are then views into them
+  inj_unif=     injected prior draws [T, P] for ordinary Monte Carlo random sampling
+
+Ordinary Monte Carlo random sampling (sp.py:229-234, the no-proposal branch of
+``SP.next``; examples/omc/omc_rs_sp_norm1d.py): with neither transition nor delta set,
+``sampler({'mu': {0}, 'sigma': {0}, 'x': data}, iid=True, joint=True, stop=T)`` draws
+every parameter afresh from its box (uniform in ufun space) at each step and evaluates
+the joint; ``process(samples)`` is then ONE PD over the T samples (summate,
+pd_utils.py:332-383), device-backed, whose ``rescaled / sorted / quantile /
+expectation`` run as K6 kernels.
 """
 import collections
 import numpy as np
@@ -26,6 +35,7 @@ import numpy as np
 from .sd import SD
 from .pd import PD
 from .pscales import iscomplex
+from .vtypes import isunitsetint
 from . import catalogue
 
 MCMC_SAMPLERS = ('metropolis', 'hastings', 'gibbs')
@@ -156,6 +166,10 @@ class SP(SD):
                                       "catalogue: pass an initial-state dictionary")
         init = self.parse_values(args[0])
         obs = self.parse_values(args[1]) if len(args) > 1 else None
+        omc = self._is_random_sampling(init)
+        if omc:                     # one dict holds the {0} requests and the observations
+            obs = collections.OrderedDict((k, v) for k, v in init.items()
+                                          if k not in self._state_rf.keyset)
         opts = dict(iid=kwds.pop('iid', False), joint=kwds.pop('joint', False),
                     chains=kwds.pop('chains', None), thin=int(kwds.pop('thin', 1)),
                     seed=kwds.pop('seed', None), accept=kwds.pop('accept', None),
@@ -163,11 +177,25 @@ class SP(SD):
                     inj_thresh=kwds.pop('inj_thresh', None),
                     host_stream=kwds.pop('host_stream', False),
                     host_buffers=kwds.pop('host_buffers', None),
-                    variant=kwds.pop('variant', 0))
+                    variant=kwds.pop('variant', 0),
+                    inj_unif=kwds.pop('inj_unif', None), omc=omc)
         assert not kwds, "Unknown sampler keywords: {}".format(list(kwds))
         s = Sampler(self, init, obs, stop, opts)
         self._samplers.append(s)
         return s
+
+    def _is_random_sampling(self, init):
+        """No proposal configured and every sampled variable requested as {0}
+        (sp.py:227-234: such a sampler is a plain distribution call per step)."""
+        rf = self._proposal_rf()
+        if rf._delta is not None or rf._tran is not None or rf._tfun is not None:
+            return False
+        req = [init.get(k) for k in self._state_rf.keylist]
+        if not all(isunitsetint(v) for v in req):
+            return False
+        if any(list(v)[0] != 0 for v in req):
+            raise NotImplementedError("random sampling draws one value per step: use {0}")
+        return True
 
     # ---- the walk ----------------------------------------------------------------------------------
     def walk(self, sampler, stop=None):
@@ -180,15 +208,103 @@ class SP(SD):
             raise ValueError("No stop specification set - a device walk needs a finite length")
         if sampler.stop is not None:
             T = min(T, sampler.stop - sampler.counter)
-        arrays = self._run(sampler, int(T))
+        arrays = self._run_omc(sampler, int(T)) if sampler.opts['omc'] \
+            else self._run(sampler, int(T))
         sampler.counter += int(T)
         if sampler.stop is not None and sampler.counter >= sampler.stop:
             sampler.counter = 0                  # auto-reset (sp_utils.py:15-16)
         out = Walk()
         out.arrays, out.sampler = arrays, sampler
+        if arrays.get('omc'):
+            if arrays['T'] <= 200000:
+                out.extend(self._omc_per_step(arrays))
+            return out
         if arrays['chains'] is None and arrays['R'] <= 200000:
             out.extend(self._per_step(arrays))
         return out
+
+    # ---- ordinary Monte Carlo random sampling ------------------------------------------------
+    def _run_omc(self, sampler, T):
+        from .engine import get_engine
+        opts = sampler.opts
+        eng = get_engine()
+        spec = catalogue.identify_target(self, self._leafs, self._roots)
+        if spec['kind'] != 'normreg':
+            raise NotImplementedError("random sampling is in the device catalogue for the iid "
+                                      "normal likelihood targets")
+        if not (opts['iid'] and opts['joint']):
+            raise NotImplementedError("random sampling needs iid=True, joint=True")
+        keys = self._state_rf.keylist
+        assert spec['params'] == keys, \
+            "parameter field order {} must be {}".format(keys, spec['params'])
+        rvs = [self._state_rf[k] for k in keys]
+        for rv in rvs:
+            assert rv.isfinite, "Cannot evaluate {{0}} values for bounds: {}".format(rv.ulims)
+        lims = np.array([rv.vlims for rv in rvs])
+        ex = np.array([rv.open_ends for rv in rvs], dtype=int)
+        lg = np.array([rv.log_ufun for rv in rvs], dtype=int)
+        if sampler.obs is None or spec['obs_y'] not in sampler.obs:
+            raise ValueError("observations for '{}' are required".format(spec['obs_y']))
+        if 'obs_dev' not in sampler.__dict__:
+            y = eng.to_device(np.ravel(np.asarray(sampler.obs[spec['obs_y']], np.float64)))
+            x = None
+            if spec['has_slope']:
+                x = eng.to_device(np.ravel(np.asarray(sampler.obs[spec['obs_x']], np.float64)))
+            sampler.obs_dev = (y, x)
+        y, x = sampler.obs_dev
+        inj = None
+        if opts['inj_unif'] is not None:
+            u = np.asarray(opts['inj_unif'], dtype=np.float64)[sampler.counter:sampler.counter + T]
+            assert u.shape == (T, len(keys)), "injected uniform stream shape mismatch"
+            inj = eng.to_device(u)
+        seed = opts['seed']
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        theta = eng.box_sample(lims, lg, T, seed=seed, sample0=sampler.counter, inj_unif=inj)
+        logp = eng.normreg_logjoint(theta, y, x, lims, ex, lg)
+        return dict(omc=True, keys=keys, T=T, spec=spec, theta=theta, logp=logp,
+                    n_obs=int(y.numel()), pscale=self._pscale, chains=None)
+
+    def _omc_names(self, arrays, n):
+        spec = arrays['spec']
+        return ["{}={{{}}}".format(ok, n) for ok in (spec['obs_x'], spec['obs_y']) if ok], \
+            [ok for ok in (spec['obs_x'], spec['obs_y']) if ok]
+
+    def _omc_per_step(self, arrays):
+        """One scalar PD per step, named like the reference's per-step joint call
+        ("mu=55.8,sigma=19.1,x={60}")."""
+        th = arrays['theta'].detach().cpu().numpy()
+        lp = arrays['logp'].detach().cpu().numpy()
+        arrays['theta_host'], arrays['logp_host'] = th, lp
+        labels, okeys = self._omc_names(arrays, arrays['n_obs'])
+        out = []
+        for t in range(arrays['T']):
+            vals = collections.OrderedDict((k, th[j, t]) for j, k in enumerate(arrays['keys']))
+            for ok in okeys:
+                vals[ok] = {arrays['n_obs']}
+            name = ','.join(["{}={}".format(k, vals[k]) for k in arrays['keys']] + labels)
+            out.append(PD(name, vals, dims=collections.OrderedDict((k, None) for k in vals),
+                          prob=float(lp[t]), pscale=arrays['pscale']))
+            out[-1]._origin = (arrays, t)       # lets process([...]) find the device arrays
+        return out
+
+    def _omc_summary(self, arrays):
+        """summate() of the per-step PDs (pd_utils.py:332-383): arrays on dim 0, the
+        iid sets added up, prob device-backed."""
+        th = arrays.get('theta_host')
+        if th is None:
+            th = arrays['theta'].detach().cpu().numpy()
+        n = arrays['n_obs'] * arrays['T']
+        labels, okeys = self._omc_names(arrays, n)
+        vals = collections.OrderedDict((k, th[j]) for j, k in enumerate(arrays['keys']))
+        dims = collections.OrderedDict((k, 0) for k in arrays['keys'])
+        for ok in okeys:
+            vals[ok] = {n}
+            dims[ok] = None
+        pd = PD(','.join(list(arrays['keys']) + labels), vals, dims=dims, prob=arrays['logp'],
+                pscale=arrays['pscale'])
+        pd.set_device_vals({k: arrays['theta'][j] for j, k in enumerate(arrays['keys'])})
+        return pd
 
     def _run(self, sampler, T):
         from .engine import get_engine
@@ -389,10 +505,25 @@ class SP(SD):
                                          and len(samples)
                                          and isinstance(samples[0], self.opqrstuv)):
             return self._summary(samples, conditionalise)
+        if isinstance(samples, (list, tuple, collections.deque)) and len(samples) \
+                and isinstance(samples[0], PD):
+            # [sample for sample in sampler] of a random-sampling run: all T per-step PDs
+            # of one walk, in order -> the device-backed summary; anything else is outside
+            # the catalogue (a host-side concatenation would be a CPU path)
+            first, last = getattr(samples[0], '_origin', None), getattr(samples[-1], '_origin', None)
+            if first is None or last is None or first[0] is not last[0] or first[1] != 0 \
+                    or last[1] != first[0]['T'] - 1 or len(samples) != first[0]['T']:
+                raise NotImplementedError("process(list of PDs) needs the complete, ordered "
+                                          "output of one sampler (or pass SP.walk(sampler))")
+            pd = self._omc_summary(first[0])
+            return pd.conditionalise(self._leafs.keyset) if conditionalise else pd
         return super().__call__(*args, **kwds)
 
     def _summary(self, samples, conditionalise=None):
         arrays = samples.arrays if isinstance(samples, Walk) else None
+        if arrays is not None and arrays.get('omc'):
+            pd = self._omc_summary(arrays)
+            return pd.conditionalise(self._leafs.keyset) if conditionalise else pd
         if arrays is None:
             # a plain list of per-step tuples: concatenate their scalar PDs
             vs = [s.v for s in samples if s.u is not False]

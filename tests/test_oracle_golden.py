@@ -143,3 +143,41 @@ def test_pscales_table():
             g["div_log_to_lin"])
     assert np.array_equal(o.from_linear(g["p"], True), g["resc_lin_to_log"])
     assert np.array_equal(o.to_linear(g["l"], True), g["resc_log_to_lin"])
+
+
+OMC_LIMS = np.array([[40., 60.], [5., 20.]])
+OMC_EX = np.array([[1, 1], [1, 1]])
+OMC_LOG = np.array([0, 1])
+
+
+def test_omc_random_sampling():
+    """examples/omc/omc_rs_sp_norm1d.py: prior draws, log-joint, summary name."""
+    g = load_golden("omc_rs_norm1d")
+    th = o.box_sample(OMC_LIMS, OMC_LOG, g["runif"])
+    assert np.array_equal(th[0], g["mu"]) and np.array_equal(th[1], g["sigma"])
+    lj = o.normreg_logjoint(th.T, None, g["data"], OMC_LIMS, OMC_EX, OMC_LOG, has_slope=False)
+    assert relerr(lj, g["logp"]) <= TOL
+    assert relerr(o.exp_logp(lj), g["lin"]) <= 1e-11       # exp amplifies |lj| * eps
+    assert str(g["name"]) == "mu,sigma,x={%d}" % (g["data"].size * g["mu"].size)
+
+
+def test_pd_sorted_quantile_expectation():
+    """PD.sorted / quantile / expectation on the OMC summary (pd.py:373-493)."""
+    g = load_golden("omc_rs_norm1d")
+    order = o.pd_sorted_order(g["mu"])
+    assert np.array_equal(g["mu"][order], g["mu_sorted"])
+    assert np.array_equal(g["sigma"][order], g["mu_sorted_sigma"])
+    assert np.array_equal(g["lin"][order], g["mu_sorted_prob"])
+    q = o.pd_quantile_1d(g["mu_sorted"], g["mu_sorted_prob"], False, g["qs"])
+    assert relerr(q, g["q_mu"]) <= TOL
+    so = o.pd_sorted_order(g["sigma"])
+    assert np.array_equal(g["sigma"][so], g["sigma_sorted"])
+    q = o.pd_quantile_1d(g["sigma_sorted"], g["lin"][so], False, g["qs"])
+    assert relerr(q, g["q_sigma"]) <= TOL
+    # the same quantiles straight from the log-pscale summary (rescale folded in)
+    q = o.pd_quantile_1d(g["mu_sorted"], g["logp"][order], True, g["qs"])
+    assert relerr(q, g["q_mu"]) <= 1e-10
+    tot, _, cv = o.pd_expectation(g["lin"], False, col_vals=[g["mu"], g["sigma"],
+                                                             g["mu"] ** 2, g["sigma"] ** 2])
+    e = np.array(cv) / max(o.NEARLY_POSITIVE_ZERO, tot)
+    assert relerr(e[:2], g["expt"]) <= TOL and relerr(e[2:], g["expt2"]) <= TOL
