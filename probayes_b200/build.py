@@ -64,7 +64,8 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+            cmd = [nvcc] + NVCC_FLAGS + os.environ.get("PBX_NVCC_EXTRA", "").split() + \
+                  (["-Xptxas", "-v"] if verbose else []) + \
                   ["-c", src, "-o", obj]
             jobs.append(cmd)
 

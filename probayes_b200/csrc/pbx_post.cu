@@ -35,6 +35,9 @@
 #define RS_TILE (RS_THREADS * RS_ITEMS)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_PASSES 8
+#ifndef RS_MINB
+#define RS_MINB 3
+#endif
 
 struct RsPlan {
   int skip[RS_PASSES];
@@ -118,35 +121,45 @@ __device__ __forceinline__ unsigned long long rs_load_key(const RsBufs& b, int s
   return (src == 1 ? b.ka : b.kb)[e];
 }
 
+// Tile digit counts without votes or contended atomics: every LANE owns a private copy
+// of the histogram, laid out [digit pair][lane] so that lane l only ever touches bank l
+// (two 16-bit counters per word; a lane sees at most 16 x 8 = 128 keys of a tile).  The
+// shared-memory atomics of a warp therefore never collide, whatever the digit skew.
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const RsBufs b, long long n, int pass,
                                                              const RsPlan* __restrict__ plan,
                                                              unsigned* __restrict__ counts,
                                                              int ntiles) {
   if (plan->skip[pass]) return;
-  __shared__ unsigned h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
+  __shared__ unsigned h[128 * 32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) h[i * RS_THREADS + threadIdx.x] = 0;
   const int src = plan->src[pass];
   const int lane = threadIdx.x & 31;
+  const int shift = 8 * pass;
   const long long base = (long long)blockIdx.x * RS_TILE;
-  unsigned dg[RS_ITEMS];
-  unsigned okm = 0;
+  const unsigned long long* kp = (src == 0) ? b.keys : (src == 1 ? b.ka : b.kb);
+  unsigned long long k[RS_ITEMS];
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {             // all loads in flight at once
     const long long e = base + r * RS_THREADS + threadIdx.x;
-    const bool ok = e < n;
-    okm |= (unsigned)ok << r;
-    dg[r] = ok ? (unsigned)(rs_load_key(b, src, e) >> (8 * pass)) & 255u : 0u;
-  }
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const bool ok = (okm >> r) & 1u;
-    const unsigned act = __ballot_sync(0xffffffffu, ok);
-    const unsigned m = rs_match8(dg[r]) & act;
-    if (ok && lane == __ffs(m) - 1) atomicAdd(&h[dg[r]], (unsigned)__popc(m));
+    k[r] = (e < n) ? kp[e] : 0ull;
   }
   __syncthreads();
-  counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const long long e = base + r * RS_THREADS + threadIdx.x;
+    const unsigned long long u = (src == 0) ? rs_encode(k[r]) : k[r];
+    const unsigned d = (unsigned)(u >> shift) & 255u;
+    if (e < n) atomicAdd(&h[(d >> 1) * 32 + lane], 1u << ((d & 1u) * 16));
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    unsigned acc = 0;                              // both halves stay below 2^16 (<= 4096)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += h[threadIdx.x * 32 + ((j + threadIdx.x) & 31)];
+    counts[(size_t)(2 * threadIdx.x) * ntiles + blockIdx.x] = acc & 0xFFFFu;
+    counts[(size_t)(2 * threadIdx.x + 1) * ntiles + blockIdx.x] = acc >> 16;
+  }
 }
 
 // CTA d: exclusive scan of counts[d][0..ntiles) in place
@@ -192,19 +205,18 @@ __global__ void __launch_bounds__(256) rs_rowscan_kernel(unsigned* __restrict__ 
 }
 
 struct RsSmem {
-  unsigned long long keys[RS_TILE];
-  int idx[RS_TILE];
-  unsigned wc[RS_WARPS][256];
-  unsigned gofs[256];
+  unsigned long long keys[RS_TILE];   // tile re-ordered by digit; re-used for the indices
+  unsigned wc[RS_WARPS][256];         // per-warp digit counters -> local offsets
+  unsigned gofs[256];                 // global position of local slot j of digit d = gofs[d] + j
   unsigned wsum[RS_WARPS];
   unsigned gsum[RS_WARPS];
 };
 
-__global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter_kernel(const RsBufs b, long long n,
-                                                                int pass,
-                                                                const RsPlan* __restrict__ plan,
-                                                                const unsigned* __restrict__ counts,
-                                                                int ntiles) {
+__global__ void __launch_bounds__(RS_THREADS, RS_MINB) rs_scatter_kernel(const RsBufs b, long long n,
+                                                                   int pass,
+                                                                   const RsPlan* __restrict__ plan,
+                                                                   const unsigned* __restrict__ counts,
+                                                                   int ntiles) {
   if (plan->skip[pass]) return;
   extern __shared__ __align__(16) unsigned char rs_raw[];
   RsSmem& s = *reinterpret_cast<RsSmem*>(rs_raw);
@@ -213,41 +225,40 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter_kernel(const RsBufs 
   const int shift = 8 * pass;
   const long long base = (long long)blockIdx.x * RS_TILE;
   const int tile_n = (int)min((long long)RS_TILE, n - base);
-  const int* src_idx = (src == 1) ? b.ia : b.ib;
+  // thread = digit: this tile's exclusive count and the digit's global total (loaded
+  // early so that their latency hides behind the key loads)
+  const unsigned tile_ofs = counts[(size_t)tid * ntiles + blockIdx.x];
+  const unsigned dt = plan->dtot[tid];
 
-  for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&s.wc[0][0])[i] = 0;
+#pragma unroll
+  for (int i = 0; i < RS_WARPS; ++i) s.wc[i][tid] = 0;
 
   // tile order: warp w owns elements [w*512, (w+1)*512), item r is element r*32 + lane of it
+  const unsigned long long* kp = (src == 0) ? b.keys : (src == 1 ? b.ka : b.kb);
   unsigned long long key[RS_ITEMS];
-  int idv[RS_ITEMS];
   const int seg = warp * (RS_ITEMS * 32);
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const int t = seg + r * 32 + lane;
-    const long long e = base + t;
-    if (t < tile_n) {
-      key[r] = rs_load_key(b, src, e);
-      idv[r] = (src == 0) ? (int)e : src_idx[e];
-    } else {
-      key[r] = 0xFFFFFFFFFFFFFFFFull;       // padding ranks after every real key of the tile
-      idv[r] = 0;
-    }
+    key[r] = (t < tile_n) ? kp[base + t] : 0ull;
+  }
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int t = seg + r * 32 + lane;
+    if (src == 0) key[r] = rs_encode(key[r]);
+    if (t >= tile_n) key[r] = 0xFFFFFFFFFFFFFFFFull;   // padding ranks after every real key
   }
   __syncthreads();
 
-  // stable rank of each key among the keys of its digit within the warp segment.
-  // First all 16 match masks (independent: the ballots overlap), then the running
-  // per-warp digit counters: the first lane of each digit group adds the group's size
-  // with one shared-memory atomic and broadcasts the old value to its group.
-  unsigned mask[RS_ITEMS];
-#pragma unroll
-  for (int r = 0; r < RS_ITEMS; ++r) mask[r] = rs_match8((unsigned)(key[r] >> shift) & 255u);
+  // stable rank of each key among the keys of its digit within the warp segment: the
+  // first lane of each digit group adds the group's size to the warp's running counter
+  // with one shared-memory atomic and broadcasts the old value to its group
   unsigned short rank[RS_ITEMS];
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const unsigned d = (unsigned)(key[r] >> shift) & 255u;
-    const unsigned m = mask[r];
+    const unsigned m = rs_match8(d);
     const int leader = __ffs(m) - 1;
     unsigned prev = 0;
     if (lane == leader) prev = atomicAdd(&s.wc[warp][d], (unsigned)__popc(m));
@@ -264,42 +275,49 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter_kernel(const RsBufs 
     s.wc[w][tid] = cnt;
     cnt += t;
   }
-  // exclusive scan of the tile's digit counts over the 256 digits
-  unsigned inc = cnt;
+  // exclusive scans over the 256 digits: the tile's counts, and the pass's digit totals
+  unsigned inc = cnt, ginc = dt;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     const unsigned t = __shfl_up_sync(0xffffffffu, inc, off);
-    if (lane >= off) inc += t;
+    const unsigned g = __shfl_up_sync(0xffffffffu, ginc, off);
+    if (lane >= off) {
+      inc += t;
+      ginc += g;
+    }
   }
-  if (lane == 31) s.wsum[warp] = inc;
-  __syncthreads();
-  unsigned excl = inc - cnt;
-  for (int w = 0; w < warp; ++w) excl += s.wsum[w];
-  // global base of digit d: exclusive scan of the pass's digit totals
-  const unsigned dt = plan->dtot[tid];
-  unsigned ginc = dt;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, ginc, off);
-    if (lane >= off) ginc += t;
+  if (lane == 31) {
+    s.wsum[warp] = inc;
+    s.gsum[warp] = ginc;
   }
-  if (lane == 31) s.gsum[warp] = ginc;
   __syncthreads();
-  unsigned gbase = ginc - dt;
-  for (int w = 0; w < warp; ++w) gbase += s.gsum[w];
-  // global position of local slot j of digit d: gofs[d] + j
-  s.gofs[tid] = gbase + counts[(size_t)tid * ntiles + blockIdx.x] - excl;
+  unsigned excl = inc - cnt, gbase = ginc - dt;
+  for (int w = 0; w < warp; ++w) {
+    excl += s.wsum[w];
+    gbase += s.gsum[w];
+  }
+  s.gofs[tid] = gbase + tile_ofs - excl;               // mod 2^32; + j >= excl restores it
 #pragma unroll
   for (int w = 0; w < RS_WARPS; ++w) s.wc[w][tid] += excl;
   __syncthreads();
 
-  // re-order the tile by digit in shared memory
+  // re-order the tile's keys by digit in shared memory; rank[] becomes the local slot
 #pragma unroll
   for (int r = 0; r < RS_ITEMS; ++r) {
     const unsigned d = (unsigned)(key[r] >> shift) & 255u;
     const unsigned lp = s.wc[warp][d] + rank[r];
+    rank[r] = (unsigned short)lp;
     s.keys[lp] = key[r];
-    s.idx[lp] = idv[r];
+  }
+  // the indices travelling with the keys (their loads overlap the key write-out)
+  int idv[RS_ITEMS];
+  {
+    const int* src_idx = (src == 1) ? b.ia : b.ib;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const int t = seg + r * 32 + lane;
+      idv[r] = (src == 0) ? (int)(base + t) : ((t < tile_n) ? src_idx[base + t] : 0);
+    }
   }
   __syncthreads();
 
@@ -307,12 +325,23 @@ __global__ void __launch_bounds__(RS_THREADS, 3) rs_scatter_kernel(const RsBufs 
   unsigned long long* dk = (dst == 1) ? b.ka : (dst == 2 ? b.kb : b.keys_sorted);
   int* di = (dst == 1) ? b.ia : (dst == 2 ? b.ib : b.order);
   const bool final_pass = dst == 3;
-  for (int j = tid; j < tile_n; j += RS_THREADS) {
+  unsigned g[RS_ITEMS];
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int j = tid + i * RS_THREADS;
     const unsigned long long k = s.keys[j];
-    const unsigned d = (unsigned)(k >> shift) & 255u;
-    const unsigned g = s.gofs[d] + (unsigned)j;       // mod 2^32: gofs holds base - excl
-    if (dk) dk[g] = final_pass ? rs_decode(k) : k;
-    di[g] = s.idx[j];
+    g[i] = s.gofs[(unsigned)(k >> shift) & 255u] + (unsigned)j;
+    if (dk && j < tile_n) dk[g[i]] = final_pass ? rs_decode(k) : k;
+  }
+  __syncthreads();
+  int* sidx = reinterpret_cast<int*>(s.keys);
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) sidx[rank[r]] = idv[r];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < RS_ITEMS; ++i) {
+    const int j = tid + i * RS_THREADS;
+    if (j < tile_n) di[g[i]] = sidx[j];
   }
 }
 
