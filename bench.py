@@ -323,6 +323,43 @@ def secondary(eng, peaks, fp64_peak, quick=False):
     ms = timeit(lambda: eng.mvn_logpdf(xs64, mean, cov))
     out["c5_mvn_logpdf_dmma"] = {"ms": ms, "points_per_s": Cg / (ms * 1e-3),
                                  "fp64_tflops": 2.0 * d * d * Cg / (ms * 1e-3) / 1e12}
+    del xs64, stg
+    # ---- K6: PD post-processing on a 4096^2 grid's worth of doubles / a sample set -------
+    def timeit_ev(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+              for _ in range(reps)]
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in ev]))
+
+    n6 = (1 << 22) if quick else (1 << 26)
+    keys = torch.randn(n6, dtype=torch.float64, device=eng.device)
+    ms = timeit_ev(lambda: eng.argsort(keys, want_keys=True))
+    # 8 executed passes x (8 B histogram read + 12 B read + 12 B write) + 8 B and/or read
+    sort_bytes = (8 * 32 + 8) * float(n6)
+    out["k6_argsort"] = {"workload": "PD.sorted: stable argsort of %d fp64 keys (+ sorted keys)" % n6,
+                         "ms": ms, "keys_per_s": n6 / (ms * 1e-3),
+                         "algorithmic_gbs": sort_bytes / (ms * 1e-3) / 1e9,
+                         "frac": sort_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                         "note": "LSD radix, 8 passes of an 8-bit digit: 264 B of traffic per key"}
+    lp = torch.log(torch.rand(n6, dtype=torch.float64, device=eng.device)) - 100.0
+    ms = timeit_ev(lambda: eng.cumprob(lp, True))
+    out["k6_cumprob"] = {"workload": "PD.quantile: normalised cumulative probability of %d "
+                                     "log-pscale cells (exp + reduce-then-scan)" % n6,
+                         "ms": ms, "algorithmic_gbs": 24.0 * n6 / (ms * 1e-3) / 1e9,
+                         "frac": 24.0 * n6 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    vals = torch.rand(2, n6, dtype=torch.float64, device=eng.device)
+    ms = timeit_ev(lambda: eng.expectation_sums(lp, True, None, vals))
+    out["k6_expectation"] = {"workload": "PD.expectation: sum p, sum p*v for 2 value arrays "
+                                         "over %d log-pscale samples" % n6,
+                             "ms": ms, "algorithmic_gbs": 24.0 * n6 / (ms * 1e-3) / 1e9,
+                             "frac": 24.0 * n6 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     return out
 
 
