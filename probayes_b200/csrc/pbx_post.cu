@@ -754,8 +754,8 @@ __global__ void __launch_bounds__(EX_THREADS) ex_partial_kernel(
 #pragma unroll
   for (int a = 0; a < 1 + KR + KC; ++a) acc[a] = 0.0;
   const bool small = n < 0xFFFFFFFFll;
-  for (long long e = e0 + threadIdx.x; e < e1; e += EX_THREADS) {
-    const double p = cp_lin(prob[e], log_pscale);
+  auto term = [&](long long e, double praw) {
+    const double p = cp_lin(praw, log_pscale);
     long long i = 0, j = e;
     if (rows > 1) {
       if (small) {
@@ -772,7 +772,17 @@ __global__ void __launch_bounds__(EX_THREADS) ex_partial_kernel(
     for (int k = 0; k < KR; ++k) acc[1 + k] = fma(p, row_vals[k * rows + i], acc[1 + k]);
 #pragma unroll
     for (int k = 0; k < KC; ++k) acc[1 + KR + k] = fma(p, col_vals[k * cols + j], acc[1 + KR + k]);
+  };
+  // four independent cells in flight per thread (the loads are issued before the exps)
+  long long e = e0 + threadIdx.x;
+  for (; e + 3 * EX_THREADS < e1; e += 4 * EX_THREADS) {
+    double pr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) pr[u] = prob[e + u * EX_THREADS];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) term(e + u * EX_THREADS, pr[u]);
   }
+  for (; e < e1; e += EX_THREADS) term(e, prob[e]);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int a = 0; a < 1 + KR + KC; ++a) {

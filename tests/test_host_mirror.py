@@ -103,6 +103,59 @@ def test_pd_host_algebra_matches_golden():
     assert iid.name == "x={3}" and np.isclose(iid.prob, np.log(.006))
 
 
+def test_pd_host_postprocessing_matches_omc_golden():
+    """PD.sorted / quantile (incl. the {size} answer for non-monotonic values) /
+    expectation(exponent=) on a host-backed sample-set PD reproduce the reference's
+    outputs on the OMC fixture (pd.py:373-493)."""
+    g = load_golden("omc_rs_norm1d")
+    T, n = len(g["mu"]), len(g["data"]) * len(g["mu"])
+    inf = pb.PD(str(g["name"]), {'mu': g["mu"], 'sigma': g["sigma"], 'x': {n}},
+                dims={'mu': 0, 'sigma': 0, 'x': None}, prob=g["lin"], pscale=1.)
+    assert inf.name == str(g["name"]) and inf.shape == [T]
+    ms = inf.sorted('mu')
+    assert np.array_equal(ms['mu'], g["mu_sorted"])
+    assert np.array_equal(ms['sigma'], g["mu_sorted_sigma"])
+    assert np.array_equal(ms.prob, g["mu_sorted_prob"])
+    q = ms.quantile(g["qs"].tolist())
+    assert relerr([v['mu'] for v in q], g["q_mu"]) <= 1e-12
+    assert q[2]['sigma'] == {T} and q[2]['x'] == {n}
+    assert abs(ms.quantile(0.5)['mu'] - g["med_mu"]) <= 1e-12 * g["med_mu"]
+    ss = inf.sorted('sigma')
+    assert np.array_equal(ss.prob, g["sigma_sorted_prob"])
+    assert relerr([v['sigma'] for v in ss.quantile(g["qs"].tolist())], g["q_sigma"]) <= 1e-12
+    e = inf.expectation()
+    assert relerr([e['mu'], e['sigma']], g["expt"]) <= 1e-12 and e['x'] == {n}
+    e2 = inf.expectation(['mu', 'sigma'], exponent=2)
+    assert relerr([e2['mu'], e2['sigma']], g["expt2"]) <= 1e-12
+    # 2-D: mu (axis 0) takes the cell's value, sigma (last axis) is interpolated
+    d = load_golden("dgei_small")
+    post = pb.PD("mu=[],sigma=[]|x={60}", {'mu': d["mu"], 'sigma': d["sigma"], 'x': {60}},
+                 dims={'mu': 0, 'sigma': 1, 'x': None}, prob=d["posterior"], pscale='log')
+    q2 = post.quantile(0.5)
+    assert q2['mu'] in d["mu"] and d["sigma"].min() <= q2['sigma'] <= d["sigma"].max()
+
+
+def test_sp_random_sampling_recognition():
+    """The proposal-free sampler with {0} requests is the OMC mode (sp.py:227-234);
+    {n != 0} and a configured delta are not."""
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset=[-np.inf, np.inf])
+    sigma.set_ufun((np.log, np.exp))
+    sp = pb.SP(pb.RF(x), pb.RF(mu, sigma))
+    sp.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'},
+                pscale='log')
+    data = np.arange(5.)
+    s = sp.sampler({'mu': {0}, 'sigma': {0}, 'x': data}, iid=True, joint=True, stop=10)
+    assert s.opts['omc'] and list(s.obs.keys()) == ['x']
+    with pytest.raises(NotImplementedError, match="one value per step"):
+        sp.sampler({'mu': {3}, 'sigma': {0}, 'x': data}, stop=10)
+    s2 = sp.sampler({'mu': 50., 'sigma': 10.}, {'x': data}, stop=10)
+    assert not s2.opts['omc']
+    sp.set_delta([0.5])
+    assert not sp.sampler({'mu': {0}, 'sigma': {0}, 'x': data}, stop=10).opts['omc']
+
+
 def _mvn_sp():
     x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
     y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
