@@ -9,6 +9,9 @@ The path shards without any data-path collective:
   * DGEI grids shard by mu-row slabs; the normaliser needs all-reduce(max) and
     all-reduce(sum) of two scalars, the sigma marginal an all-reduce(sum) of an
     S-vector, the mu marginal an all-gather of the slabs.
+  * Ordinary-MC random samples are independent -> contiguous sample ranges per rank
+    (Philox keyed on the GLOBAL sample id); posterior expectations need the same
+    two-scalar normaliser plus one all-reduce of the 1 + P weighted sums.
 The reference has no parallelism of any kind; all of this is new.
 """
 import numpy as np
@@ -116,3 +119,36 @@ def dgei_sharded(engine, x_obs, mu, sigma, logprior_mu, logprior_sigma, group=No
     mm = gather_slabs(mm, counts, group)
     return dict(post=post, marg_mu=engine.log_prob_(mm), marg_sigma=engine.log_prob_(ms),
                 rows=(start, count), gmax=gmax, gsum=gsum)
+
+
+def allreduce_expectation(sums, group=None):
+    """sums [1 + K] = (sum p, sum p*v_1, ...) over this rank's cells (Engine.
+    expectation_sums) -> expectations [K] over all ranks: all-reduce(sum), then the
+    reference's safe division (probayes/pd.py:402, pscales.py:219-236)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    st = np.asarray(sums.detach().cpu().numpy() if hasattr(sums, "detach") else sums,
+                    dtype=np.float64)
+    return st[1:] / max(2.2250738585072014e-308, st[0])
+
+
+def omc_sharded(engine, y_obs, lims, open_end, log_ufun, n_samples, seed=0, x_obs=None,
+                group=None):
+    """Sample-sharded ordinary Monte Carlo random sampling of a normal-likelihood
+    posterior: rank r draws samples [start, start + count) of the global Philox stream,
+    evaluates their log-joint, the ranks agree on the normaliser, and the posterior
+    means of the parameters are all-reduced.  Returns dict(theta [P, count], logpost
+    [count] (normalised over ALL ranks), expectation [P], samples=(start, count))."""
+    rank, ws = world()
+    start, count = shard_range(n_samples, rank, ws)
+    theta = engine.box_sample(lims, log_ufun, count, seed=seed, sample0=start)
+    y = engine.to_device(np.ravel(np.asarray(y_obs, dtype=np.float64)))
+    x = None if x_obs is None else engine.to_device(np.ravel(np.asarray(x_obs, np.float64)))
+    logp = engine.normreg_logjoint(theta, y, x, lims, open_end, log_ufun)
+    gmax, gsum = grid_normaliser(engine.grid_max(logp),
+                                 lambda g: engine.grid_sumexp(logp, g), group)
+    post, _, _ = engine.grid_posterior(logp.reshape(1, -1), gmax, gsum, inplace=True)
+    sums = engine.expectation_sums(post.reshape(-1), True, None, theta)
+    return dict(theta=theta, logpost=post.reshape(-1), samples=(start, count),
+                expectation=allreduce_expectation(sums, group))

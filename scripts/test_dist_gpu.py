@@ -1,7 +1,9 @@
 """Multi-GPU check of the sharded paths with real NCCL (run under torchrun):
   * MH chains sharded over ranks == the same global chains on one GPU (Philox keyed
     on the global chain id), R-hat from all-reduced summaries;
-  * DGEI mu-row slabs: normaliser / marginals agree with the single-GPU result.
+  * DGEI mu-row slabs: normaliser / marginals agree with the single-GPU result;
+  * OMC random samples sharded over ranks: same global Philox stream, posterior means
+    from all-reduced sums agree with the single-GPU result.
 Prints PASS lines on rank 0; exits non-zero on mismatch."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -56,6 +58,22 @@ if rank == 0:
     same_mask = bool(torch.equal(post > -1e300, keep))
     print("dgei sharded vs single: post %.2e marg_mu %.2e marg_sigma %.2e mask %s" % (e1, e2, e3, same_mask))
     ok &= same_mask and e1 < 1e-9 and e2 < 1e-9 and e3 < 1e-9
+# OMC random sampling, samples sharded over ranks
+lims = np.array([[40., 60.], [5., 20.]]); logu = np.array([0, 1]); ex = np.ones((2, 2), int)
+Tn = 100003
+ro = pd_.omc_sharded(eng, data[:300], lims, ex, logu, Tn, seed=21)
+ths = [torch.empty((2, pd_.shard_range(Tn, q, world)[1]), dtype=torch.float64, device="cuda")
+       for q in range(world)]
+dist.all_gather(ths, ro["theta"].contiguous())
+if rank == 0:
+    th1 = eng.box_sample(lims, logu, Tn, seed=21)
+    same = torch.equal(torch.cat(ths, dim=1), th1)
+    lp1 = eng.normreg_logjoint(th1, eng.to_device(data[:300]), None, lims, ex, logu)
+    w1 = eng.grid_conditionalise(lp1.reshape(1, -1))
+    s1 = eng.expectation_sums(w1["post"].reshape(-1), True, None, th1).cpu().numpy()
+    e1 = s1[1:] / s1[0]
+    print("omc sharded == single GPU draws:", same, "expectation", ro["expectation"], e1)
+    ok &= same and np.allclose(ro["expectation"], e1, rtol=1e-11)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)
 dist.destroy_process_group()

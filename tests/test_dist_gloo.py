@@ -83,6 +83,38 @@ def test_slab_sharded_grid_normaliser(world, port):
         assert max_ok and e_post <= 1e-9 and e_mm <= 1e-9 and e_ms <= 1e-9
 
 
+def _omc_job(rank, world):
+    """Per-rank arithmetic of dist.omc_sharded stood in for by the oracle: the global
+    Philox sample stream is cut into contiguous ranges, the normaliser and the weighted
+    sums are all-reduced."""
+    from probayes_b200 import dist as pd_
+    from oracle import np_oracle as o, philox
+    T, seed = 1001, 17
+    lims = np.array([[40., 60.], [5., 20.]]); logu = np.array([0, 1])
+    data = np.random.default_rng(3).normal(50., 10., 40)
+    start, count = pd_.shard_range(T, rank, world)
+    th = o.box_sample(lims, logu, philox.uniforms(seed, count, 1, 2, step0=start)[:, 0, :])
+    lj = o.normreg_logjoint(th.T, None, data, lims, np.ones((2, 2), int), logu, has_slope=False)
+    gmax, gsum = pd_.grid_normaliser(torch.tensor([lj.max()]),
+                                     lambda g: torch.tensor([o.exp_logp(lj - float(g)).sum()]))
+    lin = o.exp_logp(lj - float(gmax)) / max(o.NEARLY_POSITIVE_ZERO, float(gsum))
+    sums = torch.tensor([lin.sum(), (lin * th[0]).sum(), (lin * th[1]).sum()])
+    e = pd_.allreduce_expectation(sums)
+    # single-process answer over the whole stream
+    tha = o.box_sample(lims, logu, philox.uniforms(seed, T, 1, 2)[:, 0, :])
+    lja = o.normreg_logjoint(tha.T, None, data, lims, np.ones((2, 2), int), logu, has_slope=False)
+    w = o.exp_logp(lja - lja.max())
+    want = np.array([(w * tha[0]).sum(), (w * tha[1]).sum()]) / w.sum()
+    return e, want, np.array_equal(th, tha[:, start:start + count])
+
+
+@pytest.mark.parametrize("world,port", [(2, 29619), (3, 29621)])
+def test_sample_sharded_omc_expectation(world, port):
+    for e, want, same_stream in _spawn(_omc_job, world, port):
+        assert same_stream                       # results do not depend on the rank count
+        assert np.allclose(e, want, rtol=1e-12)
+
+
 def test_shard_range_covers_everything():
     from probayes_b200.dist import shard_range
     for n in (1, 7, 4096, 16384, 65537):
