@@ -77,16 +77,45 @@ def config(args, n_gpus):
 # clocks: sample nvidia-smi during the timed region
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle-reason samples DURING the timed region.  The timed region of
+    the headline is a few tens of milliseconds, shorter than one `nvidia-smi` query, so
+    the samples come from NVML in-process (pynvml, ~1 kHz from a thread that runs while
+    the main thread waits in cudaStreamSynchronize); `nvidia-smi -lms` is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []
+        self._stop = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(
+                ("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
+        try:
+            self.nvml, self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle,
+                                                                     self.nvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -97,11 +126,43 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop:
+            try:
+                mhz = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                try:
+                    pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = 0.0
+                self.samples.append((float(mhz), int(rs), pw))
+            except Exception:
+                break
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            reasons = set()
+            for _, rs, _ in self.samples:
+                for bit, name in self.REASONS.items():
+                    if rs & bit:
+                        reasons.add(name)
+            return {"sm_mhz": float(np.median([m for m, _, _ in self.samples])),
+                    "sm_max_mhz": self.max_mhz,
+                    "power_w_max": float(max(p for _, _, p in self.samples)),
+                    "samples": len(self.samples), "source": "nvml", "reasons": sorted(reasons)}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -126,7 +187,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "power_w_max": float(max(power)), "samples": len(sm),
+                "power_w_max": float(max(power)), "samples": len(sm), "source": "nvidia-smi",
                 "reasons": sorted(reasons)}
 
 
