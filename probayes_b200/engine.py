@@ -199,10 +199,13 @@ class Engine:
                              prop, prop_scale, prop_chol, mean, cov, reorder, variant,
                              prop_radius)
         out = dict(out) if out else {}
+        if state_lp is None and step0 != 0:
+            raise ValueError("state_lp is required when resuming (step0 > 0)")
+        # one zero-fill for every accumulator of the walk: [state_lp | accept_count |
+        # stat_sum | stat_sumsq]
+        zbuf = self.zeros(C_ * (2 + (2 * D if stats else 0)))
         if state_lp is None:
-            if step0 != 0:
-                raise ValueError("state_lp is required when resuming (step0 > 0)")
-            state_lp = self.zeros(C_)
+            state_lp = zbuf[:C_]
         R = T // thin
         if record:
             if "x" not in out:
@@ -214,10 +217,10 @@ class Engine:
         if per_step:
             out["accept"] = self.empty(T, C_, dtype=torch.uint8)
             out["score"] = self.empty(T, C_)
-        out["accept_count"] = self.zeros(C_, dtype=torch.int64)
+        out["accept_count"] = zbuf[C_:2 * C_].view(torch.int64)
         if stats:
-            out["stat_sum"] = self.zeros(D, C_)
-            out["stat_sumsq"] = self.zeros(D, C_)
+            out["stat_sum"] = zbuf[2 * C_:(2 + D) * C_].view(D, C_)
+            out["stat_sumsq"] = zbuf[(2 + D) * C_:].view(D, C_)
         out["state_lp"] = state_lp
         if inj_delta is not None:
             if tuple(inj_delta.shape) != (T, D, C_) or tuple(inj_thresh.shape) != (T, C_):
