@@ -45,7 +45,7 @@ NCU_K1_DRAM_BYTES = 335360 + 924983296
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
@@ -142,7 +142,7 @@ class ClockSampler:
                 self.samples.append((float(mhz), int(rs), pw))
             except Exception:
                 break
-            time.sleep(0.001)
+            time.sleep(0.0003)
 
     def _read(self):
         for line in self.proc.stdout:
