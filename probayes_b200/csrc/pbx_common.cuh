@@ -92,6 +92,34 @@ __host__ __device__ __forceinline__ pbx_u4 pbx_philox(uint32_t c0, uint32_t c1, 
   return o;
 }
 
+// Same rounds with the 20 round keys precomputed on the host (they depend on the seed
+// only): as constant-bank operands of the XORs they cost no instruction, the key
+// schedule above costs two integer adds per round.
+struct pbx_round_keys { uint32_t k[20]; };
+static inline void pbx_make_round_keys(uint64_t seed, pbx_round_keys& rk) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    rk.k[2 * r] = k0;
+    rk.k[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ pbx_u4 pbx_philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                const pbx_round_keys& rk) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ rk.k[2 * r], n2 = hi0 ^ c3 ^ rk.k[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  pbx_u4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+#endif
+
 __host__ __device__ __forceinline__ pbx_u4 pbx_block(uint64_t seed, uint64_t step, uint32_t chain,
                                                      uint32_t slot) {
   return pbx_philox((uint32_t)step, (uint32_t)(step >> 32), chain, slot, (uint32_t)seed,

@@ -107,8 +107,10 @@ __device__ __forceinline__ double fast_sqrt(double v) {
 }
 
 // linear-pscale output density exp(logpdf): table exp in its safe range, libm beyond
+// (out of line: the unrolled writers carry one call site each instead of libm's body)
+__device__ __noinline__ double out_exp_slow(double l) { return exp(l); }
 __device__ __forceinline__ double out_exp(double l, const PbxTables* tb) {
-  return (l > -700.0 && l < 700.0) ? fast_exp(l, tb) : exp(l);
+  return (l > -700.0 && l < 700.0) ? fast_exp(l, tb) : out_exp_slow(l);
 }
 
 static int init_tables(pbx_ctx* ctx) {
@@ -142,6 +144,7 @@ struct MhMvnConst {
   double scale[PBX_MAX_DIMS];
   double norm_c;
   double radius;
+  pbx_round_keys rk;         // Philox round keys of the walk's seed
 };
 
 struct MhMvnArgs {
@@ -197,7 +200,7 @@ __device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_
   if (kNormalOnly) prop_kind = PBX_PROP_NORMAL;          // compile-time: no kind branches
 #pragma unroll
   for (int s = 0; s < (D + 1) / 2; ++s) {
-    pbx_u4 w = pbx_block(seed, gstep, gchain, (uint32_t)s);
+    pbx_u4 w = pbx_philox_rk((uint32_t)gstep, (uint32_t)(gstep >> 32), gchain, (uint32_t)s, m.rk);
     if (s == 0) t = pbx_t44(w.w, w.y);
     double d0, d1;
     if (prop_kind == PBX_PROP_NORMAL) {
@@ -430,6 +433,32 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         pbx_mbar_wait(&out_full[si], (uint32_t)((n - 2) >> 1) & 1);
         const int k0 = bd * G;
         const int ng = min(G, a.T - k0);
+        if (a.thin == 1 && ng == G && a.out_x != nullptr && a.out_prob != nullptr) {
+          // common case (every step recorded, full batch): straight-line code, record
+          // index = step index, addresses as base + compile-time multiples of C
+          if (valid) {
+            double* ox = a.out_x + ((int64_t)k0 * D) * C + c;
+            double* op = a.out_prob + (int64_t)k0 * C + c;
+            if (a.log_pscale) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) ox[(g * D + j) * C] = slot[(g * (D + 1) + j) * 32];
+                const double sv = slot[(g * (D + 1) + D) * 32];
+                op[g * C] = kRefAccept ? sv : -0.5 * (m.norm_c + sv);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+#pragma unroll
+                for (int j = 0; j < D; ++j) ox[(g * D + j) * C] = slot[(g * (D + 1) + j) * 32];
+                const double sv = slot[(g * (D + 1) + D) * 32];
+                const double lpv = kRefAccept ? sv : -0.5 * (m.norm_c + sv);
+                op[g * C] = kRefAccept ? exp(lpv) : out_exp(lpv, tb);
+              }
+            }
+          }
+        } else {
         int rem = (k0 + 1) % a.thin;                      // (k+1) % thin of step k0
         const int64_t rec0 = (k0 + 1) / a.thin - 1 + (rem != 0);   // first record index
         double* ox = a.out_x ? a.out_x + (rec0 * D) * C + c : nullptr;
@@ -456,6 +485,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
             }
           }
           ++rem;
+        }
         }
       }
       if (n >= n_mine) continue;
@@ -676,6 +706,7 @@ static void fill_const(const pbx_mh_mvn_params* p, MhMvnConst& m) {
   }
   m.norm_c = p->norm_c;
   m.radius = p->prop_radius;
+  pbx_make_round_keys(p->seed, m.rk);
 }
 
 static int run_device(pbx_ctx* ctx, const pbx_mh_mvn_params* p) {
