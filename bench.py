@@ -379,7 +379,13 @@ def secondary(eng, peaks, fp64_peak, quick=False):
                                    "density per sweep)" % (Cg, sweeps),
                        "ms_per_sweep": ms / sweeps,
                        "coordinate_updates_per_s": Cg * d * sweeps / (ms * 1e-3),
-                       "chain_sweeps_per_s": Cg * sweeps / (ms * 1e-3)}
+                       "chain_sweeps_per_s": Cg * sweeps / (ms * 1e-3),
+                       # 2 d^2 flop of conditional means + 2 d^2 + 2 d of density
+                       "fp64_tflops": (4.0 * d * d + 2 * d) * Cg * sweeps / (ms * 1e-3) / 1e12,
+                       "fp64_frac_of_measured_peak": (4.0 * d * d + 2 * d) * Cg * sweeps
+                       / (ms * 1e-3) / 1e12 / fp64_peak,
+                       "note": "bounded by the serial coordinate dependency: per update one "
+                               "Philox block + ndtri (~100 instr) next to 2 d flop"}
     xs64 = eng.to_device(rng.standard_normal((d, Cg)))
     ms = timeit(lambda: eng.mvn_logpdf(xs64, mean, cov))
     out["c5_mvn_logpdf_dmma"] = {"ms": ms, "points_per_s": Cg / (ms * 1e-3),
