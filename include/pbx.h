@@ -354,6 +354,12 @@ PBX_API int pbx_fp64_peak(pbx_ctx* ctx, double* tflops);
  * the constant that bounds the sequential part of a Markov chain step. */
 PBX_API int pbx_fp64_dep_latency(pbx_ctx* ctx, double* dfma_cycles, double* dadd_cycles);
 
+/* Self-test of the table-driven math K1's RNG path uses instead of libm (-2 log u,
+ * sqrt, sincos(2 pi .), exp): u device [n] in (0,1), w device uint32 [n], out device
+ * [5][n] = (-2 log u, sqrt(-2 log u), sin, cos of 2 pi (w + 0.5)/2^32, exp(-700 u)). */
+PBX_API int pbx_selftest_fastmath(pbx_ctx* ctx, const double* u, const uint32_t* w, int64_t n,
+                                  double* out);
+
 #ifdef __cplusplus
 }
 #endif

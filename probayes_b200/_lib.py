@@ -131,6 +131,8 @@ SIGNATURES = {
     "pbx_box_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double),
                                  C.POINTER(C.c_int32), C.c_uint64, C.c_int64, C.c_void_p,
                                  C.c_void_p]),
+    "pbx_selftest_fastmath": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p]),
     "pbx_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "pbx_fp64_dep_latency": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

@@ -31,31 +31,33 @@
 // tests); inputs are the RNG's uniforms, so no special-case handling is needed.
 // ---------------------------------------------------------------------------
 struct PbxTables {
-  double2 lg[128];   // (1/c_j, log c_j),            c_j = 1 + (j + 0.5)/128
+  double2 lg[128];   // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/128
   double2 sc[256];   // (cos, sin) of 2 pi (k + 0.5)/256
   double ex[64];     // 2^(j/64)
 };
 static __device__ PbxTables g_tables;
-__constant__ double kLogP[5] = {-0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0};
 __constant__ double kSinP[3] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0};
 __constant__ double kCosP[3] = {-0.5, 1.0 / 24.0, -1.0 / 720.0};
 __constant__ double kExpP[4] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
 
-// log(x) for positive normal x
-__device__ __forceinline__ double fast_log(double x, const PbxTables* tb) {
+// -2 log(x) for positive normal x (what both Box-Muller and the accept threshold need):
+// the same reduction with the factor -2 folded into the table value, the polynomial
+// and the exponent term -- one multiply less than -2 * fast_log(x)
+__constant__ double kN2LogP[5] = {1.0, -2.0 / 3.0, 0.5, -0.4, 1.0 / 3.0};
+__device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const int e = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // [1, 2)
   const double2 t = tb->lg[(hi >> 13) & 127];
   const double r = fma(m, t.x, -1.0);                                      // |r| < 2^-8
-  double p = fma(r, kLogP[4], kLogP[3]);
-  p = fma(r, p, kLogP[2]);
-  p = fma(r, p, kLogP[1]);
-  p = fma(r, p, kLogP[0]);
-  p = fma(r * r, p, r);                                                    // log1p(r)
-  // (double)e without the conversion pipe: 2^52 + 2^31 + e built in the mantissa
+  double p = fma(r, kN2LogP[4], kN2LogP[3]);
+  p = fma(r, p, kN2LogP[2]);
+  p = fma(r, p, kN2LogP[1]);
+  p = fma(r, p, kN2LogP[0]);
+  p = fma(r * r, p, t.y);                        // -2 log c + r^2 (1 - 2r/3 + ...)
+  p = fma(r, -2.0, p);                           // ... - 2r  = -2 log(c (1 + r))
   const double ed = __hiloint2double(0x43300000, e ^ (int)0x80000000) - 4503601774854144.0;
-  return fma(ed, 0.693147180559945309417, t.y + p);
+  return fma(ed, -1.386294361119890618835, p);   // -2 ln 2
 }
 
 // (sin, cos)(2 pi u), u = (w + 0.5) / 2^32
@@ -92,14 +94,15 @@ __device__ __forceinline__ double fast_exp(double x, const PbxTables* tb) {
   return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
 
-// sqrt(v) for positive normal v: hardware rsqrt seed + 2 Newton steps on
-// 1/sqrt + one correction of the root.  Branch-free (libm's sqrt carries a special-
-// case branch that stops ptxas from interleaving independent steps), <= 1 ulp.
+// sqrt(v) for positive normal v: hardware rsqrt seed (relative error < 2^-22), ONE
+// Newton step on 1/sqrt (-> 2^-43) and one correction of the root (-> < 2^-80, i.e.
+// the rounding of the last fma decides: faithfully rounded).  Branch-free (libm's
+// sqrt carries a special-case branch that stops ptxas from interleaving independent
+// steps).
 __device__ __forceinline__ double fast_sqrt(double v) {
-  double y;                                  // MUFU.RSQ64H seed (rel. error ~2^-22)
+  double y;                                  // MUFU.RSQ64H
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
   const double hv = 0.5 * v;
-  y = y * fma(-hv * y, y, 1.5);
   y = y * fma(-hv * y, y, 1.5);
   double s = v * y;
   s = fma(fma(-s, s, v), 0.5 * y, s);
@@ -121,7 +124,7 @@ static int init_tables(pbx_ctx* ctx) {
     const long double c = 1.0L + (j + 0.5L) / 128.0L;
     h.lg[j].x = (double)(1.0L / c);
     // log c_j must pair with the ROUNDED reciprocal: log(1/inv) keeps r = m*inv - 1 exact
-    h.lg[j].y = (double)(-logl((long double)h.lg[j].x));
+    h.lg[j].y = (double)(2.0L * logl((long double)h.lg[j].x));        // = -2 log c_j
   }
   const long double two_pi = 6.283185307179586476925286766559L;
   for (int k = 0; k < 256; ++k) {
@@ -205,7 +208,7 @@ __device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_
     double d0, d1;
     if (prop_kind == PBX_PROP_NORMAL) {
       // Box-Muller: r = sqrt(-2 log u52), angle = 2 pi u32
-      const double rad = fast_sqrt(-2.0 * fast_log(pbx_u52(w.x, w.y), tb));
+      const double rad = fast_sqrt(fast_neg2log(pbx_u52(w.x, w.y), tb));
       double sn, cs;
       fast_sincos2pi(w.z, tb, sn, cs);
       d0 = (rad * cs) * m.scale[2 * s];
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
       } else {
         // injected thresholds go through libm's log (bit-parity with the oracle);
         // native ones through the same table log as the warp-specialised kernel
-        const double th2 = neg2log(kInjected ? log(t) : fast_log(t, &g_tables));
+        const double th2 = kInjected ? neg2log(log(t)) : fast_neg2log(t, &g_tables);
         acc = (maha <= mcur + th2);
         if (a.out_score) s = fmin(1.0, exp(fmin(lpp - lp, 0.0)));
       }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         for (int j = 0; j < D; ++j) slot[(g * (D + 1) + j) * 32] = dv[j];
         // global step 0 accepts unconditionally (sp.py:253): threshold that always passes
         // log rule: -2 log t (added to the current Mahalanobis distance by the consumer)
-        double th = kRefAccept ? t : neg2log(fast_log(t, tb));
+        double th = kRefAccept ? t : fast_neg2log(t, tb);
         if (gstep == 0) th = kRefAccept ? 0.0 : INFINITY;
         slot[(g * (D + 1) + D) * 32] = th;
       };
@@ -841,5 +844,38 @@ extern "C" int pbx_mh_mvn_walk_host(pbx_ctx* ctx, const pbx_mh_mvn_params* p,
     cudaEventDestroy(done[b]);
     cudaEventDestroy(copied[b]);
   }
+  return PBX_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Self-test hook for the table-driven math of the RNG path (tests/test_gpu_mh_mvn.py
+// checks it against libm to a few ulp): u[n] in (0, 1), w[n] raw 32-bit words ->
+// out[0][n] = -2 log(u), out[1][n] = sqrt(-2 log u), out[2][n] = sin(2 pi (w + .5)/2^32),
+// out[3][n] = cos(same), out[4][n] = exp(-700 u).
+// ---------------------------------------------------------------------------
+__global__ void fastmath_selftest_kernel(const double* __restrict__ u, const uint32_t* __restrict__ w,
+                                         int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double l = fast_neg2log(u[i], &g_tables);
+  double sn, cs;
+  fast_sincos2pi(w[i], &g_tables, sn, cs);
+  out[i] = l;
+  out[n + i] = fast_sqrt(l);
+  out[2 * n + i] = sn;
+  out[3 * n + i] = cs;
+  out[4 * n + i] = fast_exp(-700.0 * u[i], &g_tables);
+}
+
+extern "C" int pbx_selftest_fastmath(pbx_ctx* ctx, const double* u, const uint32_t* w, int64_t n,
+                                     double* out) {
+  PBX_REQUIRE(ctx && u && w && out && n >= 0, "pbx_selftest_fastmath: bad argument");
+  if (n == 0) return PBX_OK;
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  int rc = init_tables(ctx);
+  if (rc) return rc;
+  fastmath_selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(u, w, n, out);
+  PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
 }

@@ -206,3 +206,36 @@ def test_errors_are_loud():
     with pytest.raises(PbxError):          # the C ABI validates too
         eng.mh_mvn(eng.zeros(2, 4), np.zeros(2), np.eye(2), 10, step0=-1,
                    state_lp=eng.zeros(4))
+
+
+def test_table_driven_math_accuracy():
+    """The RNG path's -2 log / sqrt / sincos(2 pi .) / exp replacements stay within a few
+    ulp of libm over the ranges the kernels feed them (uniforms, 32-bit angle words)."""
+    import torch
+    from probayes_b200 import _lib
+    eng = engine()
+    rng = np.random.default_rng(123)
+    n = 1 << 20
+    u = rng.random(n)
+    u[:4] = [2.0 ** -53, 1.0 - 2.0 ** -53, 0.5, 2.0 ** -45]
+    w = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    w[:4] = [0, 0xFFFFFFFF, 0x80000000, 0x40000000]
+    ud = dev(eng, u)
+    wd = torch.from_numpy(w.view(np.int32)).to(eng.device)
+    out = eng.empty(5, n)
+    _lib.check(eng.lib.pbx_selftest_fastmath(eng.ctx, ud.data_ptr(), wd.data_ptr(), n,
+                                             out.data_ptr()))
+    o5 = host(out)
+    l = -2.0 * np.log(u)
+    ulp = lambda got, want: np.max(np.abs(got - want) / np.spacing(np.abs(want)))
+    # -2 log u: table value + polynomial, so the error is absolute (~1 ulp of 1) for u near 1
+    # -- the normal variates built from it are O(1) quantities
+    assert np.max(np.abs(o5[0] - l) / np.spacing(np.maximum(1.0, l))) <= 2.0
+    assert ulp(o5[1], np.sqrt(o5[0])) <= 1.0          # sqrt of the value it was given
+    # extended-precision reference: in fp64 the argument 2 pi u alone carries 4e-16
+    ang = 2.0 * np.longdouble("3.14159265358979323846264338327950288") * \
+        ((w.astype(np.longdouble) + 0.5) / np.longdouble(2.0 ** 32))
+    # absolute error (the functions are O(1); near their zeros an ulp bound is meaningless)
+    assert float(np.max(np.abs(o5[2] - np.sin(ang)))) <= 4e-16
+    assert float(np.max(np.abs(o5[3] - np.cos(ang)))) <= 4e-16
+    assert ulp(o5[4], np.exp(-700.0 * u)) <= 2.0
