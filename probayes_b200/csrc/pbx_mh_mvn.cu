@@ -170,11 +170,14 @@ struct MhMvnArgs {
 
 // scipy multivariate_normal_gen._logpdf: -0.5*(rank*log(2pi) + log_pdet + maha),
 // maha = sum(square(dev @ U)).
-template <int D>
+// kZeroMean: the target mean is exactly 0 in every dimension; x - 0.0 == x bit for
+// bit, so the subtraction is dropped (one FP64 op per dimension off the consumer's
+// instruction budget).
+template <int D, bool kZeroMean = false>
 __device__ __forceinline__ double mvn_maha(const double (&x)[D], const MhMvnConst& m) {
   double dev[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) dev[j] = x[j] - m.mean[j];
+  for (int j = 0; j < D; ++j) dev[j] = kZeroMean ? x[j] : x[j] - m.mean[j];
   double maha = 0.0;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
@@ -391,7 +394,8 @@ template <int D> struct WsCfg {
 };
 
 // kFast: normal proposal without Cholesky colouring -> branch-free producer body
-template <int D, bool kRefAccept, bool kFast>
+// kZeroMean: see mvn_maha
+template <int D, bool kRefAccept, bool kFast, bool kZeroMean = false>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     mh_mvn_ws_kernel(const MhMvnArgs a, const __grid_constant__ MhMvnConst m) {
   constexpr int G = WsCfg<D>::G;
@@ -529,7 +533,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     ssum[j] = ssq[j] = 0.0;
   }
   double lp = (a.step0 > 0 && valid) ? a.state_lp[c] : 0.0;
-  double mcur = mvn_maha<D>(x, m);        // log rule state: maha of the retained state
+  double mcur = mvn_maha<D, kZeroMean>(x, m);   // log rule state: maha of the retained state
   double lin = 0.0;
   if (kRefAccept && a.step0 > 0) lin = a.log_pscale ? pbx_exp_logp(lp) : exp(lp);
   int64_t nacc = 0;
@@ -552,7 +556,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       double xp[D];
 #pragma unroll
       for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[g][j];
-      const double maha = mvn_maha<D>(xp, m);
+      const double maha = mvn_maha<D, kZeroMean>(xp, m);
       bool acc;
       if (kRefAccept) {
         const double lpp = -0.5 * (m.norm_c + maha);
@@ -592,7 +596,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         pb0[j] = x[j] + dl[g + 1][j];
         pb1[j] = pa[j] + dl[g + 1][j];
       }
-      const double ma = mvn_maha<D>(pa, m), mb0 = mvn_maha<D>(pb0, m), mb1 = mvn_maha<D>(pb1, m);
+      const double ma = mvn_maha<D, kZeroMean>(pa, m), mb0 = mvn_maha<D, kZeroMean>(pb0, m),
+                   mb1 = mvn_maha<D, kZeroMean>(pb1, m);
       const bool aa = ma <= mcur + th[g];
       const bool ab = aa ? (mb1 <= ma + th[g + 1]) : (mb0 <= mcur + th[g + 1]);
       double s1[D];
@@ -653,16 +658,19 @@ static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, 
     const size_t smem = WsCfg<D>::SMEM;
     const bool ref = a.accept_mode == PBX_ACCEPT_REFERENCE;
     const bool fast = a.prop_kind == PBX_PROP_NORMAL && !a.has_L;
-#define PBX_WS_LAUNCH(R, F)                                                                   \
+#define PBX_WS_LAUNCH(R, F, Z)                                                                \
   do {                                                                                        \
-    PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, R, F>,                                  \
+    PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, R, F, Z>,                               \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    mh_mvn_ws_kernel<D, R, F><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);                 \
+    mh_mvn_ws_kernel<D, R, F, Z><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);              \
   } while (0)
-    if (ref && fast) PBX_WS_LAUNCH(true, true);
-    else if (ref) PBX_WS_LAUNCH(true, false);
-    else if (fast) PBX_WS_LAUNCH(false, true);
-    else PBX_WS_LAUNCH(false, false);
+    bool zero_mean = true;
+    for (int j = 0; j < D; ++j) zero_mean = zero_mean && m.mean[j] == 0.0;
+    if (ref && fast) PBX_WS_LAUNCH(true, true, false);
+    else if (ref) PBX_WS_LAUNCH(true, false, false);
+    else if (fast && zero_mean) PBX_WS_LAUNCH(false, true, true);
+    else if (fast) PBX_WS_LAUNCH(false, true, false);
+    else PBX_WS_LAUNCH(false, false, false);
 #undef PBX_WS_LAUNCH
     PBX_LAUNCH_CHECK(ctx);
     return PBX_OK;
