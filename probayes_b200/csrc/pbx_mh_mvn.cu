@@ -610,10 +610,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       nacc += (int)aa + (int)ab;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
+#ifndef PBX_K1_NOSTATS
         ssum[j] += s1[j];
         ssq[j] = fma(s1[j], s1[j], ssq[j]);
         ssum[j] += x[j];
         ssq[j] = fma(x[j], x[j], ssq[j]);
+#endif
         slot[(g * (D + 1) + j) * 32] = s1[j];
         slot[((g + 1) * (D + 1) + j) * 32] = x[j];
       }
