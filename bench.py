@@ -430,6 +430,34 @@ def secondary(eng, peaks, fp64_peak, quick=False):
     return out
 
 
+def bind_to_gpu_cpus(index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU (same NUMA node /
+    PCIe root), before any pinned host buffer is allocated: with 8 ranks streaming
+    samples device->host at once, remote-node pinned memory halves the aggregate rate.
+    Returns a short description for the bench line."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(
+                ("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        bind_to_gpu_cpus.original = allowed
+        use = ideal & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return "bound to %d of %d allowed CPUs (GPU-local)" % (len(use), len(allowed))
+        return "no narrower GPU-local CPU set (%d ideal, %d allowed)" % (len(ideal), len(allowed))
+    except Exception as e:                                   # diagnostics only
+        return "unbound (%s)" % type(e).__name__
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -437,6 +465,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_binding = bind_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from probayes_b200.engine import get_engine
@@ -564,6 +593,7 @@ def run_ours(args):
                                  "FP64-pipe/latency bound, not HBM bound (see fp64)"},
             "fp64": {"peak_tflops_measured": fp64_peak},
             "clocks": clocks,
+            "cpu_binding": cpu_binding,
             "quality": {"accept_rate": acc_rate, "rhat": [float(v) for v in rhat]},
         }
         if not args.no_secondary:
@@ -573,6 +603,8 @@ def run_ours(args):
             except Exception as e:                           # never lose the headline line
                 line["secondary"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
+            if getattr(bind_to_gpu_cpus, "original", None):     # the CPU arm gets every core
+                os.sched_setaffinity(0, bind_to_gpu_cpus.original)
             steps = args.cpu_sample_steps or auto_cpu_steps(C, args.accept)
             r, cores, detail, dt = cpu_walk_rate(C, steps, args.accept)
             line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
