@@ -377,13 +377,17 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 // One mbarrier pair per slot: in_full (producer -> consumer), out_full (consumer
 // -> owning producer).
 // ---------------------------------------------------------------------------
+#ifndef WS_NPROD
 #define WS_NPROD 15                      // producer warps: all warps with (warp % 4) != 0
+#endif
 #define WS_NSLOT (2 * WS_NPROD)             // two ring slots per producer warp
 #ifndef WS_PUNROLL
 #define WS_PUNROLL 2
 #endif
 constexpr int kWsPUnroll = WS_PUNROLL;
+#ifndef WS_THREADS
 #define WS_THREADS 640                   // 20 warps; warps 4, 8, 12, 16 exit at once so that
+#endif
                                          // the consumer (warp 0) has its SM sub-partition
                                          // (scheduler + FP64 pipe) to itself
 template <int D> struct WsCfg {
