@@ -182,6 +182,9 @@ typedef struct {
   double lims[PBX_MAX_PARAMS][2];        /* vlims */
   int32_t open_end[PBX_MAX_PARAMS][2];   /* 1 = exclusive end (tuple in vset) */
   int32_t log_ufun[PBX_MAX_PARAMS];      /* 1 = (np.log, np.exp) ufun */
+  int32_t prop_bound;      /* set_delta(..., bound=True): proposals are constrained to the
+                              vset (variable.py:700-739) -- closed ends clip, a proposal
+                              beyond an open end bounces back to the current value */
   double prop_scale[PBX_MAX_PARAMS];
   double prop_radius;      /* PBX_PROP_SPHERICAL only */
   double* state;           /* [P][C] in/out */

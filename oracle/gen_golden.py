@@ -137,7 +137,7 @@ def gibbs3d(seed, T):
 
 
 # ---------------------------------------------------------------------------
-def mh_norm1d(seed, T, N, scores, spherical=False):
+def mh_norm1d(seed, T, N, scores, spherical=False, bound=None):
     """examples/mcmc/metrohast_norm1d.py:23-42 ((mu, sigma) posterior, log
     pscale, sigma with (np.log, np.exp) ufun, iid+joint), uniforms injected by
     patching np.random.uniform.  scores='hastings' keeps the script's
@@ -148,6 +148,14 @@ def mh_norm1d(seed, T, N, scores, spherical=False):
     x_obs = rng.normal(50., 10., size=N)
     mu_lims, sigma_lims = (40, 60), (5, 20.)
     step = 0.005
+    ex = [[True, True], [True, True]]
+    init_vals = (50., 12.5)
+    if bound == 'open':             # bound=True, both ends open: bounce back
+        step, init_vals = 0.6, (58.5, 18.)
+    elif bound == 'mixed':          # mu closed (clip), sigma open below / closed above
+        step, init_vals = 0.6, (41., 6.)
+        mu_lims, sigma_lims = [40, 60], [(5,), 20.]
+        ex = [[False, False], [True, False]]
     mu = pb.RV('mu', vtype=float, vset=mu_lims, pscale='log')
     sigma = pb.RV('sigma', vtype=float, vset=sigma_lims, pscale='log')
     x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
@@ -162,14 +170,17 @@ def mh_norm1d(seed, T, N, scores, spherical=False):
         paras.set_tran((tran, tran))
     else:
         paras.set_tran(tran)
-    paras.set_delta((step,) if spherical else [step], scale=True)
+    if bound:
+        paras.set_delta([step], scale=True, bound=True)
+    else:
+        paras.set_delta((step,) if spherical else [step], scale=True)
     sp.set_tran(paras)
     sp.set_delta(paras)
     sp.set_scores(scores)
     if scores == 'hastings':
         sp.set_update('metropolis')
     R = rng.random((T, 3))               # per step: d_mu, d_sigma, threshold
-    init = {mu: 50., sigma: 12.5}
+    init = {mu: init_vals[0], sigma: init_vals[1]}
     with ref_shim.injected_uniform(R.ravel()):
         sampler = sp.sampler(init, {x: x_obs}, stop=T, iid=True, joint=True)
         samples = [s for s in sampler]
@@ -184,9 +195,9 @@ def mh_norm1d(seed, T, N, scores, spherical=False):
         delta = (cube * radius) / np.sqrt(np.sum(cube ** 2, axis=1, keepdims=True)) * lengths
     out.update(radius=np.array(radius), lengths=lengths, spherical=np.array(spherical))
     out.update(x_obs=x_obs, delta=delta, thresh=R[:, 2], runif=R,
-               init=np.array([50., 12.5]), dmax=dmax,
+               init=np.array(init_vals), dmax=dmax,
                lims=np.array([[40., 60.], [5., 20.]]),
-               ex=np.array([[True, True], [True, True]]),
+               ex=np.array(ex), bound=np.array(bool(bound)),
                log_ufun=np.array([False, True]),
                coef=np.array(np.e if scores == 'hastings' else 1.0))
     return out
@@ -410,6 +421,8 @@ def main():
         "mh_norm1d_metropolis": lambda: mh_norm1d(22, 300, 60, 'metropolis'),
         "mh_norm1d_underflow": lambda: mh_norm1d(23, 60, 1000, 'metropolis'),
         "mh_norm1d_spherical": lambda: mh_norm1d(24, 300, 60, 'hastings', spherical=True),
+        "mh_norm1d_bound_open": lambda: mh_norm1d(25, 300, 60, 'metropolis', bound='open'),
+        "mh_norm1d_bound_mixed": lambda: mh_norm1d(26, 300, 60, 'metropolis', bound='mixed'),
         "mh_linreg": lambda: mh_linreg(31, 300, 100),
         "dgei_small": lambda: dgei(41, 60, 48, 40),
         "dgei_peaked": lambda: dgei(42, 2000, 40, 36),

@@ -273,18 +273,34 @@ def normreg_logjoint(theta, x_obs, y_obs, lims, ex, log_ufun, has_slope=True):
     return prior + out
 
 
-def ufun_propose(theta, delta, log_ufun):
+def ufun_propose(theta, delta, log_ufun, bound=None):
     """probayes/variable.py:693-697: x' = x + d, or ufun^-1(ufun(x) + d) with
-    the (np.log, np.exp) tuple ufun."""
+    the (np.log, np.exp) tuple ufun.  bound = (lims [P, 2], ex [P, 2]) applies
+    set_delta(..., bound=True) (variable.py:700-727, the scalar branch the sampler
+    takes): closed ends clip, a proposal beyond an open end bounces back."""
     out = theta + delta
     for j, lg in enumerate(log_ufun):
         if lg:
             out[:, j] = np.exp(np.log(theta[:, j]) + delta[:, j])
+    if bound is not None:
+        lims, ex = bound
+        for j in range(theta.shape[1]):
+            lo, hi = lims[j]
+            olo, ohi = bool(ex[j][0]), bool(ex[j][1])
+            v, old = out[:, j], theta[:, j]
+            if not olo and not ohi:
+                out[:, j] = np.maximum(lo, np.minimum(hi, v))
+            elif olo and ohi:
+                out[:, j] = np.where((v > lo) & (v < hi), v, old)
+            elif olo:
+                out[:, j] = np.where(v < lo, old, np.minimum(hi, v))
+            else:
+                out[:, j] = np.where(v > hi, old, np.maximum(lo, v))
     return out
 
 
 def mh_normreg_walk(init, delta, thresh, x_obs, y_obs, lims, ex, log_ufun,
-                    has_slope=True, accept="reference", coef=1.0):
+                    has_slope=True, accept="reference", coef=1.0, bound=False):
     """MH for the (mu, sigma) / (beta_0, beta_1, y_sigma) posterior in log
     pscale with iid=True, joint=True: examples/mcmc/metrohast_norm1d.py:23-42,
     examples/mcmc/gibbs_linreg.py:28-36 + SURVEY appendix B.5."""
@@ -292,7 +308,7 @@ def mh_normreg_walk(init, delta, thresh, x_obs, y_obs, lims, ex, log_ufun,
         return normreg_logjoint(th, x_obs, y_obs, lims, ex, log_ufun, has_slope)
 
     def propose(th, dl):
-        return ufun_propose(th, dl, log_ufun)
+        return ufun_propose(th, dl, log_ufun, (lims, ex) if bound else None)
 
     return mh_walk(init, delta, thresh, target, propose, True, accept, coef)
 

@@ -56,7 +56,7 @@ class MhNormregParams(C.Structure):
         ("n_obs", C.c_int64), ("x_obs", C.c_void_p), ("y_obs", C.c_void_p),
         ("lims", (C.c_double * 2) * PBX_MAX_PARAMS),
         ("open_end", (C.c_int32 * 2) * PBX_MAX_PARAMS),
-        ("log_ufun", C.c_int32 * PBX_MAX_PARAMS),
+        ("log_ufun", C.c_int32 * PBX_MAX_PARAMS), ("prop_bound", C.c_int32),
         ("prop_scale", C.c_double * PBX_MAX_PARAMS),
         ("prop_radius", C.c_double),
         ("state", C.c_void_p), ("state_lp", C.c_void_p),

@@ -152,7 +152,8 @@ def identify_proposal(rf, target_pscale, injected=False):
     D = rf.nvars
     delta, kw = rf._delta, rf._delta_kwds
     lengths = rf.lengths
-    out = dict(kind='normal', scale=np.ones(D), radius=0.0, chol=None, coef=1.0)
+    out = dict(kind='normal', scale=np.ones(D), radius=0.0, chol=None, coef=1.0,
+               bound=bool(kw.get('bound')))
     if isinstance(rf._tfun, np.ndarray):
         out['chol'] = np.asarray(rf._tfun, dtype=float)
     fro = _frozen_norm_scale(delta)
@@ -190,8 +191,6 @@ def identify_proposal(rf, target_pscale, injected=False):
                 "a frozen scipy.stats.norm(0, s), or inject the draws (inj_delta=...)")
     else:
         raise NotImplementedError("unrecognised delta specification {!r}".format(delta))
-    if kw.get('bound'):
-        raise NotImplementedError("bound=True deltas are not in the device catalogue yet")
     # asymmetric (q, r) pair: hastings_scores multiplies the linear proposal density
     # into the target *in the target's pscale* (sp_utils.py:52-64, rf.py:531-536)
     tran = rf._tran

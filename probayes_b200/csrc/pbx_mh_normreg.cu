@@ -34,7 +34,7 @@
 #define NR_SMAX 8             // chains per pass of the streaming kernel
 
 struct NrModel {
-  int P, has_slope, accept_mode, prop_kind;
+  int P, has_slope, accept_mode, prop_kind, bound;
   double coef;
   double lims[PBX_MAX_PARAMS][2];
   int open_end[PBX_MAX_PARAMS][2];
@@ -125,6 +125,16 @@ __device__ __forceinline__ void nr_propose(const NrArgs& a, const NrModel& m, in
   nr_draw_delta(a, m, gstep, kk, c, dl);
   for (int j = 0; j < m.P; ++j) {
     double v = m.log_ufun[j] ? exp(log(th[j]) + dl[j]) : th[j] + dl[j];
+    if (m.bound) {
+      // Variable.apply_delta(bound=True), scalar branch (variable.py:700-727): closed
+      // ends clip; beyond an open end the proposal bounces back to the current value
+      const double lo = m.lims[j][0], hi = m.lims[j][1];
+      const bool olo = m.open_end[j][0] != 0, ohi = m.open_end[j][1] != 0;
+      if (!olo && !ohi) v = fmax(lo, fmin(hi, v));
+      else if (olo && ohi) v = (v > lo && v < hi) ? v : th[j];
+      else if (olo) v = (v < lo) ? th[j] : fmin(hi, v);
+      else v = (v > hi) ? th[j] : fmax(lo, v);
+    }
     a.prop[(int64_t)j * a.C + c] = v;
   }
 }
@@ -541,6 +551,7 @@ static int nr_validate(const pbx_mh_normreg_params* p, const char* who, bool nee
 static void nr_fill_model(const pbx_mh_normreg_params* p, NrModel& m) {
   m.P = p->n_params;
   m.has_slope = p->has_slope;
+  m.bound = p->prop_bound != 0;
   m.accept_mode = p->accept_mode;
   m.prop_kind = p->prop_kind;
   m.coef = p->accept_coef;

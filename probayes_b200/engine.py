@@ -276,7 +276,7 @@ class Engine:
     # ------------------------------------------------- K2: streaming normal MH
     def _normreg_params(self, C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
                         accept="log", accept_coef=1.0, prop="uniform", variant=0,
-                        prop_radius=0.0):
+                        prop_radius=0.0, prop_bound=False):
         if P not in (2, 3):
             raise NotImplementedError("normal-likelihood MH supports (mu, sigma) or "
                                       "(b0, b1, sigma) parameters, got %d" % P)
@@ -291,6 +291,7 @@ class Engine:
         p.accept_mode, p.accept_coef = _ACCEPT[accept], float(accept_coef)
         p.prop_kind, p.variant = _PROP[prop], int(variant)
         p.prop_radius = float(prop_radius)
+        p.prop_bound = 1 if prop_bound else 0
         p.n_obs = int(y_obs.numel())
         if has_slope and int(x_obs.numel()) != p.n_obs:
             raise ValueError("x_obs and y_obs differ in length")
@@ -310,7 +311,8 @@ class Engine:
     def mh_normreg(self, state, y_obs, x_obs, steps, lims, open_end, log_ufun, prop_scale,
                    thin=1, seed=0, step0=0, chain0=0, accept="log", accept_coef=1.0,
                    prop="uniform", variant=0, inj_delta=None, inj_thresh=None, state_lp=None,
-                   record=True, per_step=False, stats=True, prop_radius=0.0):
+                   record=True, per_step=False, stats=True, prop_radius=0.0,
+                   prop_bound=False):
         """MH on the iid-normal posterior; ``state`` [P, C] device fp64 (in place),
         ``y_obs``/``x_obs`` device fp64 [N].  Same outputs as :meth:`mh_mvn`; the
         recorded ``prob`` is the log-joint (log pscale)."""
@@ -320,7 +322,7 @@ class Engine:
         if int(thin) < 1:
             raise ValueError("thin must be >= 1")
         p = self._normreg_params(C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
-                                 accept, accept_coef, prop, variant, prop_radius)
+                                 accept, accept_coef, prop, variant, prop_radius, prop_bound)
         p.n_steps, p.thin, p.step0, p.chain0 = T, thin, step0, chain0
         p.seed = seed & 0xFFFFFFFFFFFFFFFF
         if state_lp is None:

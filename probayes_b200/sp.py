@@ -366,6 +366,9 @@ class SP(SD):
         coef = prop['coef'] if self._scores == 'hastings' else 1.0
         if spec['kind'] == 'mvn':
             assert spec['names'] == keys
+            if prop['bound'] and any(np.isfinite(state_rf[k].vlims).any() for k in keys):
+                raise NotImplementedError("bound=True on a bounded RV is in the device catalogue "
+                                          "for the normal-likelihood targets (K2) only")
             if opts['host_stream'] and not injected and not per_step:
                 h = eng.mh_mvn_walk_host(state.cpu().numpy(), spec['mean'], spec['cov'], T,
                                          thin=thin, seed=seed, step0=step0,
@@ -412,6 +415,7 @@ class SP(SD):
             out = eng.mh_normreg(state, y, x, T, lims, ex, lg, prop['scale'], thin=thin,
                                  seed=seed, step0=step0, accept=accept, accept_coef=coef,
                                  prop=prop['kind'], prop_radius=prop['radius'],
+                                 prop_bound=prop['bound'],
                                  inj_delta=inj_d, inj_thresh=inj_t,
                                  state_lp=sampler.state_lp, per_step=per_step,
                                  variant=opts['variant'])

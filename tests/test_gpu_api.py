@@ -51,15 +51,18 @@ def test_mcmc_prob4a(name):
 
 @pytest.mark.parametrize("name,scores,delta", [
     ("mh_norm1d_spherical", 'hastings', (0.005,)), ("mh_norm1d_hastings", 'hastings', [0.005]),
-    ("mh_norm1d_metropolis", 'metropolis', [0.005])])
+    ("mh_norm1d_metropolis", 'metropolis', [0.005]),
+    ("mh_norm1d_bound_open", 'metropolis', [0.6]), ("mh_norm1d_bound_mixed", 'metropolis', [0.6])])
 def test_metrohast_norm1d(name, scores, delta):
     """examples/mcmc/metrohast_norm1d.py:23-45 (tuple step = spherical proposal,
     (tran, tran) pair = the e-exponent hastings score)."""
     engine()
     g = load_golden(name)
     n_steps = len(g["thresh"])
-    mu = pb.RV('mu', vtype=float, vset=(40, 60), pscale='log')
-    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.), pscale='log')
+    bound = 'bound' in name
+    mixed = name.endswith('mixed')       # mu closed (clips), sigma open below / closed above
+    mu = pb.RV('mu', vtype=float, vset=[40, 60] if mixed else (40, 60), pscale='log')
+    sigma = pb.RV('sigma', vtype=float, vset=[(5,), 20.] if mixed else (5, 20.), pscale='log')
     x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
     sigma.set_ufun((np.log, np.exp))
     paras = pb.RF(mu, sigma)
@@ -68,13 +71,16 @@ def test_metrohast_norm1d(name, scores, delta):
     process.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'})
     tran = lambda **x: 1.
     paras.set_tran((tran, tran) if scores == 'hastings' else tran)
-    paras.set_delta(delta, scale=True)
+    if bound:                            # variable.py:700-739
+        paras.set_delta(delta, scale=True, bound=True)
+    else:
+        paras.set_delta(delta, scale=True)
     process.set_tran(paras)
     process.set_delta(paras)
     process.set_scores(scores)
     if scores == 'hastings':
         process.set_update('metropolis')
-    init_state = {mu: 50., sigma: 12.5}
+    init_state = {mu: float(g["init"][0]), sigma: float(g["init"][1])}
     sampler = process.sampler(init_state, {x: g["x_obs"]}, stop=n_steps, iid=True, joint=True,
                               inj_delta=g["delta"], inj_thresh=g["thresh"])
     samples = process.walk(sampler)

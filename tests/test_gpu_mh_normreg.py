@@ -19,6 +19,7 @@ def _run_golden(eng, g, has_slope, accept, variant):
     state = dev(eng, g["init"][:, None])
     out = eng.mh_normreg(state, y, x, T, g["lims"], g["ex"], g["log_ufun"], g["dmax"],
                          accept=accept, accept_coef=float(g["coef"]), variant=variant,
+                         prop_bound=bool(g["bound"]) if "bound" in g.files else False,
                          inj_delta=dev(eng, tcd_to_tdc(g["delta"][:, None, :])),
                          inj_thresh=dev(eng, g["thresh"][:, None]), per_step=True)
     eng.sync()
@@ -28,7 +29,8 @@ def _run_golden(eng, g, has_slope, accept, variant):
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("name,has_slope", [
     ("mh_norm1d_hastings", False), ("mh_norm1d_metropolis", False),
-    ("mh_norm1d_underflow", False), ("mh_linreg", True)])
+    ("mh_norm1d_underflow", False), ("mh_linreg", True),
+    ("mh_norm1d_bound_open", False), ("mh_norm1d_bound_mixed", False)])
 def test_golden_injected_reference_rule(name, has_slope, variant):
     eng = engine()
     g = load_golden(name)
@@ -219,3 +221,29 @@ def test_linreg_posterior_moments_philox():
     assert 0.8 * sd / np.sqrt(2) < s[2] < 1.2 * sd / np.sqrt(2)
     rate = host(out["accept_count"]).sum() / (C * 1500)
     assert 0.15 < rate < 0.6
+
+
+def test_bound_native_rng_stays_inside_and_matches_oracle():
+    """set_delta([d], bound=True) with the Philox stream, many chains: closed ends clip,
+    open ends bounce (variable.py:700-727) -- replayed on the oracle with the same draws."""
+    eng = engine()
+    rng = np.random.default_rng(4)
+    C, T, N, seed = 257, 60, 500, 99
+    y = rng.normal(50., 10., N)
+    lims = np.array([[40., 60.], [5., 20.]])
+    ex = np.array([[0, 0], [1, 0]])
+    lg = np.array([0, 1])
+    scale = np.array([6.0, 0.5])
+    init = np.stack([rng.uniform(41, 59, C), rng.uniform(6, 19, C)])
+    out = eng.mh_normreg(dev(eng, init), dev(eng, y), None, T, lims, ex, lg, scale, seed=seed,
+                         accept="log", prop="uniform", prop_bound=True, per_step=True)
+    eng.sync()
+    R = philox.uniforms(seed, T, C, 2)
+    delta = -scale + 2.0 * scale * R
+    U = philox.thresholds(seed, T, C)
+    ref = o.mh_normreg_walk(init.T, delta, U, None, y, lims, ex, lg, has_slope=False,
+                            accept="log", bound=True)
+    assert np.array_equal(host(out["accept"]).astype(bool), ref["u"])
+    x = host(out["x"])
+    assert relerr(x, tcd_to_tdc(ref["x"])) <= 1e-11
+    assert x[:, 0].min() >= 40. and x[:, 0].max() <= 60. and x[:, 1].min() > 5. and x[:, 1].max() <= 20.

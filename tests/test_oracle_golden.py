@@ -24,12 +24,14 @@ def test_mh_mvn(name):
 
 
 @pytest.mark.parametrize("name", ["mh_norm1d_hastings", "mh_norm1d_metropolis",
-                                  "mh_norm1d_underflow"])
+                                  "mh_norm1d_underflow", "mh_norm1d_bound_open",
+                                  "mh_norm1d_bound_mixed"])
 def test_mh_norm1d(name):
     g = load_golden(name)
     r = o.mh_normreg_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
                           None, g["x_obs"], g["lims"], g["ex"], g["log_ufun"],
-                          has_slope=False, coef=float(g["coef"]))
+                          has_slope=False, coef=float(g["coef"]),
+                          bound=bool(g["bound"]) if "bound" in g.files else False)
     assert np.array_equal(r["u"][:, 0], g["u"])
     assert relerr(r["x"][:, 0], g["x"]) <= TOL
     assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
