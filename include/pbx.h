@@ -334,6 +334,17 @@ PBX_API int pbx_expectation_f64(pbx_ctx* ctx, const double* prob, int64_t rows, 
                                 const double* col_vals, int32_t n_col_vals, double* out,
                                 void* workspace, size_t workspace_bytes);
 
+/* Binary PD algebra with broadcasting: op 0 = product rule
+ * (PD.__mul__ -> pd_utils.product -> pscales.prod_rule, probayes/pd.py:564-565,
+ * pd_utils.py:85-328, pscales.py:160-216), op 1 = safe division (PD.__truediv__ ->
+ * pscales.div_prob, pd.py:572-615, pscales.py:219-236).  a: device [a_rows][a_cols] with
+ * a_rows in {1, rows}, a_cols in {1, cols}; b likewise; *_log: 1 = log pscale, 0 = linear;
+ * out: device [rows][cols].  Product: out_log must be (a_log || b_log). */
+PBX_API int pbx_pd_binary_f64(pbx_ctx* ctx, int32_t op, const double* a, int64_t a_rows,
+                              int64_t a_cols, int32_t a_log, const double* b, int64_t b_rows,
+                              int64_t b_cols, int32_t b_log, int64_t rows, int64_t cols,
+                              int32_t out_log, double* out);
+
 /* ---------------------------------------------------------------------------
  * Ordinary Monte Carlo random sampling of box-bounded parameters -- SURVEY.md section 8f
  * rank 3.  Replaces Variable.evaluate({0}) -> vtypes.uniform(ulims, n=0) -> ufun^-1

@@ -330,6 +330,43 @@ def omc_rs_norm1d(seed, N, T):
 
 
 # ---------------------------------------------------------------------------
+def pd_algebra(seed, N, M, S):
+    """The joint-product / division algebra around the DGEI model
+    (probayes/pd.py:564-615, pd_utils.py:85-328, pscales.py:160-236): RV and RF prior
+    PDs, prior * likelihood, joint / evidence, joint / p(mu, x)."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    data = rng.normal(50., 10., size=N)
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    paras = pb.RF(mu, sigma)
+    model = pb.SD(pb.RF(x), paras)
+    model.set_prob(scipy.stats.norm.logpdf,
+                   order={'x': 0, 'mu': 'loc', 'sigma': 'scale'}, pscale='log')
+    grid = {'mu': {M}, 'sigma': {S}}
+    joint = model({x: data, **grid}, iid=True, joint=True)
+    like = model({x: data, **grid}, iid=True, joint=False)
+    prior = paras(dict(grid))
+    pmu, psg = mu({M}), sigma({S})
+    pp = pmu * psg
+    j2 = prior * like
+    ev = joint.marginal('x')
+    post = joint / ev
+    mm = joint.marginal(['mu', 'x'])
+    pc = joint / mm
+    return dict(data=data, mu=np.ravel(joint['mu']), sigma=np.ravel(joint['sigma']),
+                pmu=np.ravel(pmu.prob), psg=np.ravel(psg.prob), prior=np.asarray(prior.prob),
+                pmu_psg=np.asarray(pp.prob), like=np.asarray(like.prob),
+                joint=np.asarray(joint.prob), prior_like=np.asarray(j2.prob),
+                evidence=np.array(float(ev.prob)), post=np.asarray(post.prob),
+                marg_mu_x=np.asarray(mm.prob), cond_sigma=np.asarray(pc.prob),
+                names=np.array([pmu.name, prior.name, pp.name, like.name, j2.name, ev.name,
+                                post.name, mm.name, pc.name]))
+
+
+# ---------------------------------------------------------------------------
 def gibbs2d(seed, T):
     """examples/mcmc/gibbs_norm2d.py:15-22 with the cdf uniforms injected."""
     pb = ref_shim.load()
@@ -427,6 +464,7 @@ def main():
         "dgei_small": lambda: dgei(41, 60, 48, 40),
         "dgei_peaked": lambda: dgei(42, 2000, 40, 36),
         "gibbs2d": lambda: gibbs2d(51, 400),
+        "pd_algebra": lambda: pd_algebra(71, 40, 9, 7),
         "omc_rs_norm1d": lambda: omc_rs_norm1d(61, 60, 400),
         "condcov_d8": lambda: condcov_bare(52, 8, 160),
         "condcov_d64": lambda: condcov_bare(53, 64, 256),

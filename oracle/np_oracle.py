@@ -512,3 +512,26 @@ def pd_expectation(prob, log_pscale, row_vals=None, col_vals=None):
     cv = [] if col_vals is None else [float(np.sum(p * np.asarray(v, float)[None, :]))
                                       for v in col_vals]
     return float(np.sum(p)), rv, cv
+
+
+# ----------------------------------------------------------------------------
+# joint-product / division algebra
+# ----------------------------------------------------------------------------
+def pd_product(a, a_log, b, b_log):
+    """pscales.prod_rule for two factors (probayes/pscales.py:160-216): sum in log
+    space as soon as one factor is in log pscale (the linear one through the
+    clamped log), plain product otherwise.  Returns (prob, is_log)."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    if a_log or b_log:
+        return (a if a_log else log_prob(a)) + (b if b_log else log_prob(b)), True
+    return a * b, False
+
+
+def pd_divide(a, a_log, b, b_log):
+    """pscales.div_prob (probayes/pscales.py:219-236) as PD.__truediv__ calls it
+    (pd.py:614): both to linear, num / max(tiny, den), back to the dividend's
+    pscale."""
+    with np.errstate(over="ignore"):
+        q = div_prob_linear(to_linear(np.asarray(a, dtype=float), a_log),
+                            to_linear(np.asarray(b, dtype=float), b_log))
+    return from_linear(q, a_log)

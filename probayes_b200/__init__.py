@@ -15,7 +15,7 @@ from .rv import RV
 from .rf import RF
 from .sd import SD
 from .sp import SP, MCMC_SAMPLERS, Walk, Sampler, AcceptRecord
-from .pd import PD
+from .pd import PD, product
 from .cond_cov import CondCov
 from .catalogue import NormalRegression
 from ._lib import PbxError

@@ -128,6 +128,9 @@ SIGNATURES = {
     "pbx_expectation_f64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_size_t]),
+    "pbx_pd_binary_f64": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                    C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                    C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "pbx_box_sample": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_double),
                                  C.POINTER(C.c_int32), C.c_uint64, C.c_int64, C.c_void_p,
                                  C.c_void_p]),

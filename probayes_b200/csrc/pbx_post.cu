@@ -867,6 +867,75 @@ extern "C" int pbx_expectation_f64(pbx_ctx* ctx, const double* prob, int64_t row
 }
 
 // ===========================================================================
+// Binary PD algebra with broadcasting: the product rule (PD.__mul__ -> pd_utils.product
+// -> pscales.prod_rule, probayes/pscales.py:160-216) and the safe division
+// (PD.__truediv__ -> pscales.div_prob, pscales.py:219-236) of two probability arrays
+// whose shapes are [rows or 1][cols or 1].  One streaming pass, 8 B out per cell.
+// ===========================================================================
+__global__ void __launch_bounds__(256) pd_binary_kernel(int op, const double* __restrict__ a,
+                                                        long long a_rs, long long a_cs, int a_log,
+                                                        const double* __restrict__ b,
+                                                        long long b_rs, long long b_cs, int b_log,
+                                                        long long rows, long long cols, int out_log,
+                                                        double* __restrict__ out) {
+  const long long n = rows * cols;
+  const bool small = n < 0xFFFFFFFFll;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long i, j;
+    if (small) {
+      const unsigned ii = (unsigned)e / (unsigned)cols;
+      i = ii;
+      j = (unsigned)e - ii * (unsigned)cols;
+    } else {
+      i = e / cols;
+      j = e - i * cols;
+    }
+    const double av = a[i * a_rs + j * a_cs], bv = b[i * b_rs + j * b_cs];
+    double r;
+    if (op == 0) {
+      // product rule: log space as soon as one factor is in log pscale (clamped log of
+      // the linear one), plain product otherwise
+      if (out_log) r = (a_log ? av : pbx_log_prob(av)) + (b_log ? bv : pbx_log_prob(bv));
+      else r = av * bv;
+    } else {
+      // div_prob: both to linear, num / max(tiny, den), back to the output pscale
+      const double num = a_log ? pbx_exp_logp(av) : av;
+      const double den = b_log ? pbx_exp_logp(bv) : bv;
+      const double q = num / fmax(PBX_TINY, den);
+      r = out_log ? pbx_log_prob(q) : q;
+    }
+    out[e] = r;
+  }
+}
+
+extern "C" int pbx_pd_binary_f64(pbx_ctx* ctx, int32_t op, const double* a, int64_t a_rows,
+                                 int64_t a_cols, int32_t a_log, const double* b, int64_t b_rows,
+                                 int64_t b_cols, int32_t b_log, int64_t rows, int64_t cols,
+                                 int32_t out_log, double* out) {
+  PBX_REQUIRE(ctx != nullptr, "pbx_pd_binary_f64: null context");
+  PBX_REQUIRE(op == 0 || op == 1, "pbx_pd_binary_f64: op must be 0 (product) or 1 (division)");
+  PBX_REQUIRE(rows >= 0 && cols >= 0, "pbx_pd_binary_f64: negative shape");
+  if (rows == 0 || cols == 0) return PBX_OK;
+  PBX_REQUIRE(a && b && out, "pbx_pd_binary_f64: null pointer");
+  PBX_REQUIRE((a_rows == 1 || a_rows == rows) && (a_cols == 1 || a_cols == cols) &&
+                  (b_rows == 1 || b_rows == rows) && (b_cols == 1 || b_cols == cols),
+              "pbx_pd_binary_f64: operand shapes must be [rows or 1][cols or 1]");
+  PBX_REQUIRE(op == 1 || (out_log != 0) == (a_log != 0 || b_log != 0),
+              "pbx_pd_binary_f64: the product is in log pscale iff a factor is "
+              "(pscales.py:170-172)");
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  const long long a_rs = a_rows == 1 ? 0 : a_cols, a_cs = a_cols == 1 ? 0 : 1;
+  const long long b_rs = b_rows == 1 ? 0 : b_cols, b_cs = b_cols == 1 ? 0 : 1;
+  const int64_t n = rows * cols;
+  const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  pd_binary_kernel<<<grid, 256, 0, ctx->stream>>>(op, a, a_rs, a_cs, a_log, b, b_rs, b_cs, b_log,
+                                                  (long long)rows, (long long)cols, out_log, out);
+  PBX_LAUNCH_CHECK(ctx);
+  return PBX_OK;
+}
+
+// ===========================================================================
 // Box sampler of ordinary Monte Carlo random sampling
 // ===========================================================================
 struct BoxConst {

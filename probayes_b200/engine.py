@@ -583,6 +583,20 @@ class Engine:
             "pbx_expectation_f64")
         return out
 
+    def pd_binary(self, op, a, a_log, b, b_log, out_log):
+        """Product rule (op='mul') / safe division (op='div') of two probability
+        tensors of shapes [rows or 1, cols or 1] -> [rows, cols] device tensor."""
+        a2 = a.reshape(1, -1) if a.dim() < 2 else a
+        b2 = b.reshape(1, -1) if b.dim() < 2 else b
+        rows, cols = max(a2.shape[0], b2.shape[0]), max(a2.shape[1], b2.shape[1])
+        out = self.empty(rows, cols)
+        _lib.check(self.lib.pbx_pd_binary_f64(
+            self.ctx, 0 if op == 'mul' else 1, self._ptr(a2.contiguous()), a2.shape[0],
+            a2.shape[1], int(bool(a_log)), self._ptr(b2.contiguous()), b2.shape[0], b2.shape[1],
+            int(bool(b_log)), rows, cols, int(bool(out_log)), out.data_ptr()),
+            "pbx_pd_binary_f64")
+        return out
+
     def box_sample(self, lims, log_ufun, n_samples, seed=0, sample0=0, inj_unif=None):
         """theta [P, T] device: uniform draws in ufun space mapped back
         (variable.py:558-583); inj_unif [T, P] device or None = Philox."""

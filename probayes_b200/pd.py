@@ -23,8 +23,8 @@ keys before the ``|``, conditional keys after it.
 import collections
 import numpy as np
 
-from .pscales import eval_pscale, iscomplex, rescale, div_prob, log_prob, exp_logp
-from .vtypes import isscalar, isunitset
+from .pscales import eval_pscale, iscomplex, rescale, div_prob, log_prob, exp_logp, prod_rule
+from .vtypes import isscalar, isunitset, isunitsetint
 
 
 def str_margcond(name):
@@ -250,6 +250,14 @@ class PD(collections.OrderedDict):
         cached = self._cache.get(("marginalise", frozenset(keys)))
         if cached is not None:
             return self._new(name, vals, dims, cached)
+        if self._prob_dev is not None and len(axes) == self.ndim and self._pscale == 0j:
+            # every array axis goes: log_prob(sum exp_logp(p)) without a max shift, as the
+            # reference evaluates it (underflows like the reference for large |log p|)
+            eng = self._engine()
+            import torch
+            zero = torch.zeros(1, dtype=torch.float64, device=self._prob_dev.device)
+            tot = eng.log_prob_(eng.grid_sumexp(self._prob_dev.reshape(-1), zero))
+            return self._new(name, vals, dims, float(tot.item()))
         if self._prob_dev is not None and self.ndim == 2 and len(axes) == 1 \
                 and iscomplex(self._pscale) and self._pscale == 0j:
             eng = self._engine()
@@ -503,5 +511,181 @@ class PD(collections.OrderedDict):
         prob = np.take(self.prob, order, axis=dim)
         return self._new(self._name, vals, self._dims, prob)
 
+    # ---- joint-product algebra -----------------------------------------------------------
+    def __mul__(self, other):
+        """Product rule: p(A | ..) * p(B | A, ..) -> p(A, B | ..) (pd.py:564-565)."""
+        return product(self, other)
+
+    def __truediv__(self, other):
+        """If self is p(A, B | C) and other is p(A | C), returns p(B | C, A): the safe
+        division ``num / max(tiny, den)`` in linear space (pd.py:572-615,
+        pscales.py:219-236).  For log-pscale grids of large |log p| the reference's linear
+        detour underflows -- use conditionalise() there, as its examples do."""
+        assert set(self._cond.keys()) == set(other.cond.keys()), "Conditionals must match"
+        divs = other.issingleton
+        if divs:
+            scalars = {k for k, single in zip(self.keys(), self._aresingleton)
+                       if k in self._marg and single}
+            assert scalars == set(other.marg.keys()), \
+                "For divisor singletons, scalar marginals must match"
+        keys = list(other.marg.keys())
+        marg = collections.OrderedDict(self._marg)
+        cond = collections.OrderedDict(self._cond)
+        vals = collections.OrderedDict((k, self[k]) for k in self._cond)
+        re_shape = [1] * self.ndim
+        for key, single in zip(self.keys(), self._aresingleton):
+            if key in keys:
+                cond[key] = marg.pop(key)
+                if not single and not divs:
+                    re_shape[self._dims[key]] = int(np.size(other[key]))
+            elif key not in vals:
+                vals[key] = self[key]
+        for key in self.keys():
+            if key in keys:
+                vals[key] = self[key]
+        name = margcond_str(marg, cond)
+        dims = collections.OrderedDict((k, self._dims[k]) for k in vals)
+        a_log, b_log = _log_flag_of(self._pscale), _log_flag_of(other.pscale)
+        if self._prob_dev is not None or other.prob_device is not None:
+            if self.ndim > 2:
+                raise NotImplementedError("device division handles 1-D and 2-D PDs")
+            eng = (self if self._prob_dev is not None else other)._engine()
+            a = self._prob_dev if self._prob_dev is not None else eng.to_device(self.prob)
+            b = other.prob_device if other.prob_device is not None else \
+                eng.to_device(np.atleast_1d(np.asarray(other.prob, dtype=float)))
+            a2 = a.reshape(1, -1) if self.ndim < 2 else a
+            shape_b = [1, 1] if divs else ([1] + re_shape if self.ndim < 2 else re_shape)
+            out = eng.pd_binary('div', a2, a_log, b.reshape(shape_b), b_log, a_log)
+            return self._new(name, vals, dims, out.reshape(self._shape))
+        divp = other.prob if divs else np.reshape(other.prob, re_shape)
+        prob = div_prob(self.prob, divp, self._pscale, other.pscale)
+        return self._new(name, vals, dims, prob)
+
     def __repr__(self):
         return "PD({!r}, shape={}, pscale={})".format(self._name, self._shape, self._pscale)
+
+
+def _log_flag_of(pscale):
+    if pscale == 0j:
+        return True
+    if pscale == 1.:
+        return False
+    raise NotImplementedError("the joint-product algebra handles pscale 'log' and 1 only")
+
+
+def product(*args):
+    """Product rule over PDs with distinct marginal variables (pd_utils.py:85-328):
+    conditionals that another factor carries as marginals become marginals of the
+    product, the remaining conditionals must agree, array values get consecutive axes
+    in name order (keys that share an axis in a factor keep sharing it), iid-reduced sets
+    ``{n}`` add up, and the probabilities are combined by the product rule of
+    pscales.py:160-216 -- on the device as soon as one factor is device-backed.
+    Products of up to two array axes are in the device catalogue."""
+    assert args, "product() needs at least one distribution"
+    if len(args) == 1:
+        return args[0]
+    all_marg = [k for a in args for k in a.marg.keys()]
+    assert len(all_marg) == len(set(all_marg)), \
+        "Non-unique marginal variables for currently not supported: {}".format(all_marg)
+    logs = [_log_flag_of(a.pscale) for a in args]
+    out_log = any(logs)
+    marg_names = [name for a in args for name in a.marg.values()]
+    marg_keys = set(all_marg)
+    cond_items = [(k, name) for a in args for k, name in a.cond.items()]
+    prod_cond = collections.OrderedDict((k, n) for k, n in cond_items if k not in marg_keys)
+    for a in args:
+        rest = {k for k in a.cond.keys() if k not in marg_keys}
+        if rest:
+            assert rest == set(prod_cond.keys()), \
+                "Incompatible product conditional {} for conditional set {}".format(
+                    set(prod_cond.keys()), rest)
+    prod_keys = all_marg + list(prod_cond.keys())
+    # values: the first factor that has the key provides it; {n} sets add up
+    vals = collections.OrderedDict()
+    for key in prod_keys:
+        found = [a[key] for a in args if key in a]
+        assert found, "Values for key {} not found".format(key)
+        if isunitsetint(found[0]):
+            assert all(isunitsetint(v) for v in found), "Mismatch in variables"
+            vals[key] = {sum(list(v)[0] for v in found)}
+        else:
+            vals[key] = found[0]
+            for v in found[1:]:
+                if not np.allclose(np.ravel(v), np.ravel(found[0])):
+                    raise ValueError("Mismatch in values for condition {}".format(key))
+    # axes: consecutive in key order; keys sharing an axis inside a factor share it here
+    dims, ndim, groups = collections.OrderedDict(), 0, {}
+    for key in prod_keys:
+        if isscalar(vals[key]) or isunitset(vals[key]):
+            dims[key] = None
+            continue
+        tag = None
+        for ai, a in enumerate(args):
+            if key in a and a.dims[key] is not None:
+                tag = (ai, a.dims[key])
+                break
+        if tag in groups:
+            dims[key] = groups[tag]
+        else:
+            dims[key] = groups[tag] = ndim
+            ndim += 1
+    # product labels ("mu=[]", "x={40}", "mu=50.0") are refreshed by the constructor
+    name = ','.join(marg_names)
+    if prod_cond:
+        name += '|' + ','.join(prod_cond.values())
+    pscale = 0j if out_log else 1.
+    if ndim == 0:
+        prob, _ = prod_rule(*[a.prob for a in args], pscales=[a.pscale for a in args])
+        return PD(name, vals, dims=dims, prob=float(prob), pscale=pscale)
+    if ndim > 2:
+        raise NotImplementedError("products of more than two array axes are outside the "
+                                  "device catalogue")
+    shape = [0] * ndim
+    for key, d in dims.items():
+        if d is not None:
+            shape[d] = int(np.size(vals[key]))
+
+    def aligned(a):
+        """(array-like prob of factor a, its shape broadcast into the product axes)"""
+        olddims = sorted({d for d in a.dims.values() if d is not None})
+        newdims = []
+        for od in olddims:
+            key = next(k for k, d in a.dims.items() if d == od)
+            newdims.append(dims[key])
+        tgt = [1] * ndim
+        for nd in newdims:
+            tgt[nd] = shape[nd]
+        return olddims, newdims, tgt
+
+    device = any(a.prob_device is not None for a in args)
+    if not device:
+        probs = []
+        for a in args:
+            _, newdims, tgt = aligned(a)
+            p = a.prob
+            if not isscalar(p):
+                p = np.asarray(p, dtype=float)
+                if len(newdims) == 2 and newdims[0] > newdims[1]:
+                    p = p.T
+                p = p.reshape(tgt)
+            probs.append(p)
+        prob, _ = prod_rule(*probs, pscales=[a.pscale for a in args])
+        return PD(name, vals, dims=dims, prob=np.broadcast_to(prob, shape).copy(), pscale=pscale)
+    eng = next(a for a in args if a.prob_device is not None)._engine()
+    acc, acc_log = None, None
+    for a, lg in zip(args, logs):
+        _, newdims, tgt = aligned(a)
+        t = a.prob_device if a.prob_device is not None else \
+            eng.to_device(np.atleast_1d(np.asarray(a.prob, dtype=float)))
+        if len(newdims) == 2 and newdims[0] > newdims[1]:
+            t = t.t().contiguous()
+        t = t.reshape(tgt if ndim == 2 else [1] + tgt)
+        if acc is None:
+            acc, acc_log = t, lg
+            continue
+        step_log = acc_log or lg
+        acc = eng.pd_binary('mul', acc, acc_log, t, lg, step_log)
+        acc_log = step_log
+    if acc_log != out_log:                       # single log factor among linear ones, last
+        acc = eng.log_prob_(acc.clone())
+    return PD(name, vals, dims=dims, prob=acc.reshape(shape), pscale=pscale)

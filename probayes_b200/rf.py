@@ -114,6 +114,14 @@ class RF:
         kwds.pop('passdims', None)
         self._prob, self._prob_args, self._prob_kwds = prob, tuple(args), kwds
 
+    def __call__(self, values=None):
+        """Joint PD of the independent default RV priors over a dictionary of values /
+        {n} grid requests (probayes/rf.py:565-581 without a set_prob: rf_utils.py:10-42)."""
+        from .pd import product
+        values = {} if values is None else values
+        values = {self.parse_key(k): v for k, v in values.items()}
+        return product(*[rv(values.get(rv.name)) for rv in self.varlist])
+
     def eval_prior(self, values):
         """Product of the independent default RV priors (rf_utils.py:10-42)."""
         rvs = self.varlist

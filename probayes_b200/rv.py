@@ -172,6 +172,20 @@ class RV:
         vals = uniform(lo, hi, n, self._open[0], self._open[1])
         return np.exp(vals) if self._log_ufun else vals
 
+    def __call__(self, values=None):
+        """PD of this RV's default prior over ``values`` ({n} grids included):
+        probayes/rv.py:323-343."""
+        from .pd import PD
+        vals = self.evaluate(values)
+        if isunitsetint(vals):
+            vals = self.evaluate(vals)
+        prob = self.eval_prob(vals)
+        if not isscalar(vals):
+            vals = np.ravel(vals)
+            prob = np.ravel(prob)
+        name = "{}={}".format(self._name, vals) if isscalar(vals) else self._name + "=[]"
+        return PD(name, {self._name: vals}, prob=prob, pscale=self._pscale)
+
     # ---- deltas ---------------------------------------------------------------------------
     def set_delta(self, delta=None, scale=False, bound=False):
         self._delta = delta

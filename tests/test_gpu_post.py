@@ -322,3 +322,87 @@ def collections_copy(pd, key, newval):
     vals = collections.OrderedDict(pd)
     vals[key] = newval
     return vals
+
+
+# ---- joint-product / division algebra -------------------------------------------------------
+@pytest.mark.parametrize("op", ["mul", "div"])
+@pytest.mark.parametrize("a_shape,b_shape", [
+    ((37, 53), (37, 53)), ((37, 1), (1, 53)), ((37, 53), (1, 53)), ((37, 53), (37, 1)),
+    ((1, 7000), (1, 7000)), ((1, 1), (300, 200)), ((1300, 1), (1300, 1))])
+@pytest.mark.parametrize("a_log,b_log", [(False, False), (True, True), (False, True), (True, False)])
+def test_pd_binary_kernel(op, a_shape, b_shape, a_log, b_log):
+    eng = engine()
+    rng = np.random.default_rng(a_shape[0] * 31 + b_shape[1] + 2 * a_log + b_log)
+
+    def draw(shape, lg):
+        p = rng.random(shape) + 0.01
+        p.flat[rng.integers(0, p.size, max(1, p.size // 20))] = 0.0       # clamp edge: log(0)
+        if not lg:
+            return p
+        with np.errstate(divide="ignore"):
+            l = np.log(p) - 300.0 * rng.random(shape)
+        l[~np.isfinite(l)] = o.NEARLY_NEGATIVE_INF
+        return l
+    a, b = draw(a_shape, a_log), draw(b_shape, b_log)
+    if op == "mul":
+        want, out_log = o.pd_product(a, a_log, b, b_log)
+    else:
+        want, out_log = o.pd_divide(a, a_log, b, b_log), a_log
+    got = host(eng.pd_binary(op, dev(eng, a), a_log, dev(eng, b), b_log, out_log))
+    want = np.broadcast_to(want, got.shape)
+    # clamped cells (-1.797e308) and the -inf two of them add up to (as in numpy) match
+    # exactly; everything else to 1e-12
+    special = (want == o.NEARLY_NEGATIVE_INF) | np.isneginf(want)
+    assert np.array_equal(got[special], want[special])
+    assert np.all(np.isfinite(got[~special]))
+    assert relerr(got[~special], want[~special]) <= TOL
+
+
+def test_pd_binary_rejects_bad_shapes():
+    from probayes_b200 import _lib
+    eng = engine()
+    a, b = dev(eng, np.ones((3, 4))), dev(eng, np.ones((2, 4)))
+    out = eng.empty(3, 4)
+    with pytest.raises(_lib.PbxError, match="rows or 1"):
+        _lib.check(eng.lib.pbx_pd_binary_f64(eng.ctx, 0, a.data_ptr(), 3, 4, 0, b.data_ptr(), 2, 4,
+                                             0, 3, 4, 0, out.data_ptr()))
+    with pytest.raises(_lib.PbxError, match="log pscale iff"):
+        _lib.check(eng.lib.pbx_pd_binary_f64(eng.ctx, 0, a.data_ptr(), 3, 4, 1, a.data_ptr(), 3, 4,
+                                             0, 3, 4, 0, out.data_ptr()))
+
+
+def test_api_pd_algebra_golden():
+    """prior * likelihood, joint / evidence and joint / p(mu, x) with device-backed PDs
+    against the live-reference fixture (pd.py:564-615)."""
+    engine()
+    import probayes_b200 as pb
+    g = load_golden("pd_algebra")
+    names = [str(n) for n in g["names"]]
+    M, S = len(g["mu"]), len(g["sigma"])
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    paras = pb.RF(mu, sigma)
+    model = pb.SD(pb.RF(x), paras)
+    model.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'},
+                   pscale='log')
+    grid = {'mu': {M}, 'sigma': {S}}
+    joint = model({x: g["data"], **grid}, iid=True, joint=True)
+    like = model({x: g["data"], **grid}, iid=True, joint=False)
+    assert like.name == names[3] and like.prob_device is not None
+    assert relerr(like.prob, g["like"]) <= TOL
+    prior = paras(dict(grid))
+    j2 = prior * like
+    assert j2.name == names[4] and j2.prob_device is not None and j2.pscale == 0j
+    assert relerr(j2.prob, g["prior_like"]) <= TOL and relerr(joint.prob, g["joint"]) <= TOL
+    ev = joint.marginal('x')
+    assert ev.name == names[5] and abs(float(ev.prob) - g["evidence"]) <= 1e-11 * abs(g["evidence"])
+    post = joint / ev
+    assert post.name == names[6] and post.prob_device is not None
+    assert np.abs(post.prob - g["post"]).max() <= 1e-12 * np.abs(g["joint"]).max()
+    mm = joint.marginal(['mu', 'x'])
+    assert mm.name == names[7] and relerr(mm.prob, g["marg_mu_x"]) <= 1e-11
+    pc = joint / mm
+    assert pc.name == names[8]
+    assert np.abs(pc.prob - g["cond_sigma"]).max() <= 1e-12 * np.abs(g["joint"]).max()

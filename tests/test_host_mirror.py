@@ -135,6 +135,47 @@ def test_pd_host_postprocessing_matches_omc_golden():
     assert q2['mu'] in d["mu"] and d["sigma"].min() <= q2['sigma'] <= d["sigma"].max()
 
 
+def test_pd_product_division_match_reference():
+    """RV / RF prior PDs, PD.__mul__ (pd_utils.product) and PD.__truediv__ on host-backed
+    PDs reproduce the reference's names, dims and arrays (pd_algebra fixture)."""
+    g = load_golden("pd_algebra")
+    names = [str(n) for n in g["names"]]
+    M, S, N = len(g["mu"]), len(g["sigma"]), len(g["data"])
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    sigma.set_ufun((np.log, np.exp))
+    pmu, psg = mu({M}), sigma({S})
+    assert pmu.name == names[0] and np.array_equal(pmu.prob, g["pmu"]) and pmu.pscale == 1.
+    assert np.array_equal(pmu['mu'], g["mu"]) and relerr(psg['sigma'], g["sigma"]) <= 1e-15
+    prior = pb.RF(mu, sigma)({'mu': {M}, 'sigma': {S}})
+    pp = pmu * psg
+    for d in (prior, pp):
+        assert d.name == names[1] and d.shape == [M, S] and d.pscale == 1.
+        assert dict(d.dims) == {'mu': 0, 'sigma': 1} and np.array_equal(d.prob, g["prior"])
+    like = pb.PD(names[3], {'mu': g["mu"], 'sigma': g["sigma"], 'x': {N}},
+                 dims={'mu': 0, 'sigma': 1, 'x': None}, prob=g["like"], pscale='log')
+    joint = prior * like
+    assert joint.name == names[4] and joint.pscale == 0j and joint['x'] == {N}
+    assert np.array_equal(joint.prob, g["prior_like"])
+    assert (like * prior).name == 'x={%d},mu=[],sigma=[]' % N
+    ev = joint.marginal('x')
+    assert ev.name == names[5] and abs(ev.prob - g["evidence"]) <= 1e-12 * abs(g["evidence"])
+    post = joint / ev
+    assert post.name == names[6] and relerr(post.prob, g["post"]) <= 1e-12
+    mm = joint.marginal(['mu', 'x'])
+    assert mm.name == names[7] and relerr(mm.prob, g["marg_mu_x"]) <= 1e-12
+    pc = joint / mm
+    assert pc.name == names[8] and dict(pc.dims) == {'sigma': 1, 'mu': 0, 'x': None}
+    assert relerr(pc.prob, g["cond_sigma"]) <= 1e-12
+    # scalars: product of two scalar PDs, mismatching marginals refused
+    a = pb.PD('a=1.0', {'a': 1.0}, prob=0.25)
+    b = pb.PD('b=2.0|a=1.0', {'b': 2.0, 'a': 1.0}, prob=0.5)
+    ab = a * b
+    assert ab.name == 'a=1.0,b=2.0' and ab.prob == 0.125
+    with pytest.raises(AssertionError, match="Non-unique"):
+        pmu * pmu
+
+
 def test_sp_random_sampling_recognition():
     """The proposal-free sampler with {0} requests is the OMC mode (sp.py:227-234);
     {n != 0} and a configured delta are not."""

@@ -183,3 +183,15 @@ def test_pd_sorted_quantile_expectation():
                                                              g["mu"] ** 2, g["sigma"] ** 2])
     e = np.array(cv) / max(o.NEARLY_POSITIVE_ZERO, tot)
     assert relerr(e[:2], g["expt"]) <= TOL and relerr(e[2:], g["expt2"]) <= TOL
+
+
+def test_pd_product_and_division_algebra():
+    """prod_rule / div_prob with broadcasting on the DGEI pieces (pscales.py:160-236)."""
+    g = load_golden("pd_algebra")
+    p, lg = o.pd_product(g["pmu"][:, None], False, g["psg"][None, :], False)
+    assert not lg and np.array_equal(p, g["prior"]) and np.array_equal(p, g["pmu_psg"])
+    j, lg = o.pd_product(g["prior"], False, g["like"], True)
+    assert lg and np.array_equal(j, g["joint"]) and np.array_equal(j, g["prior_like"])
+    assert np.array_equal(o.pd_divide(g["joint"], True, g["evidence"], True), g["post"])
+    assert np.array_equal(o.pd_divide(g["joint"], True, g["marg_mu_x"][:, None], True),
+                          g["cond_sigma"])
