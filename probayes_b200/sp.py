@@ -549,9 +549,8 @@ class SP(SD):
             t_ = [s.t for s in samples if s.t is not None]
             return self.opqrstuv(None, None, None, None, s_ or None, t_ or None, u, v)
         v = self._value_pd(arrays)
-        if conditionalise:
-            raise NotImplementedError("conditionalise= on sample summaries is not in the "
-                                      "device catalogue")
+        if conditionalise:                      # sp.py:194-196: condition on the leaf (data) keys
+            v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])
         if arrays['chains'] is None and len(samples):
             u = [s.u for s in samples]
             s_ = [s.s for s in samples if s.s is not None]

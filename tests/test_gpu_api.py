@@ -93,6 +93,12 @@ def test_metrohast_norm1d(name, scores, delta):
     assert relerr(summary.v.prob, g["prob"]) <= TOL
     assert summary.v.name == 'mu,sigma,x={{{}}}'.format(len(g["x_obs"]) * n_steps)
     assert inference.pscale == 1.
+    # process(samples, conditionalise=True): normalised over the samples (sp.py:194-196)
+    cond = process(samples, conditionalise=True).v
+    assert cond.name == 'mu,sigma|x={{{}}}'.format(len(g["x_obs"]) * n_steps)
+    assert abs(np.exp(cond.prob).sum() - 1.0) <= 1e-12
+    lin = np.exp(g["prob"] - g["prob"].max())
+    assert relerr(np.exp(cond.prob), lin / lin.sum()) <= 1e-10
 
 
 def test_linreg_mh_with_user_likelihood():
