@@ -140,6 +140,8 @@ typedef struct {
   int64_t* accept_count;   /* [C] accumulated, or NULL */
   double* stat_sum;        /* [D][C] accumulated sum of the retained state, or NULL */
   double* stat_sumsq;      /* [D][C] accumulated sum of squares, or NULL */
+  double* out_xprop;       /* [T][D][C] or NULL: the proposal of every step (opqr.p values) */
+  double* out_pprop;       /* [T][C] or NULL: the target density at the proposal (opqr.p.prob) */
 } pbx_mh_mvn_params;
 
 PBX_API int pbx_mh_mvn_run(pbx_ctx* ctx, const pbx_mh_mvn_params* p);
@@ -198,6 +200,8 @@ typedef struct {
   int64_t* accept_count;   /* [C] or NULL */
   double* stat_sum;        /* [P][C] or NULL */
   double* stat_sumsq;      /* [P][C] or NULL */
+  double* out_xprop;       /* [T][P][C] or NULL: the proposal of every step (opqr.p values) */
+  double* out_pprop;       /* [T][C] or NULL: the log-joint at the proposal (opqr.p.prob) */
 } pbx_mh_normreg_params;
 
 PBX_API int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p);

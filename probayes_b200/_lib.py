@@ -44,6 +44,7 @@ class MhMvnParams(C.Structure):
         ("out_x", C.c_void_p), ("out_prob", C.c_void_p),
         ("out_accept", C.c_void_p), ("out_score", C.c_void_p),
         ("accept_count", C.c_void_p), ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p),
+        ("out_xprop", C.c_void_p), ("out_pprop", C.c_void_p),
     ]
 
 
@@ -64,6 +65,7 @@ class MhNormregParams(C.Structure):
         ("out_x", C.c_void_p), ("out_prob", C.c_void_p),
         ("out_accept", C.c_void_p), ("out_score", C.c_void_p),
         ("accept_count", C.c_void_p), ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p),
+        ("out_xprop", C.c_void_p), ("out_pprop", C.c_void_p),
     ]
 
 

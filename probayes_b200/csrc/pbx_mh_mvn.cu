@@ -166,6 +166,8 @@ struct MhMvnArgs {
   int64_t* accept_count;
   double* stat_sum;
   double* stat_sumsq;
+  double* out_xprop;
+  double* out_pprop;
 };
 
 // scipy multivariate_normal_gen._logpdf: -0.5*(rank*log(2pi) + log_pdet + maha),
@@ -338,6 +340,12 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
     }
     if (a.out_accept) a.out_accept[(int64_t)k * C + c] = acc ? 1 : 0;
     if (a.out_score) a.out_score[(int64_t)k * C + c] = s;
+    if (a.out_xprop) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) a.out_xprop[((int64_t)k * D + j) * C + c] = xp[j];
+    }
+    if (a.out_pprop)
+      a.out_pprop[(int64_t)k * C + c] = a.log_pscale ? lpp : (ref_mode ? linp : exp(lpp));
     if ((k + 1) % a.thin == 0) {
       const int64_t r = (k + 1) / a.thin - 1;
       if (a.out_x) {
@@ -657,7 +665,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 template <int D>
 static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, int kernel_variant) {
   const bool injected = a.inj_delta != nullptr;
-  const bool per_step = a.out_accept != nullptr || a.out_score != nullptr;
+  const bool per_step = a.out_accept != nullptr || a.out_score != nullptr ||
+                        a.out_xprop != nullptr || a.out_pprop != nullptr;
   const bool use_ws = !injected && !per_step && kernel_variant != 1;
   if (use_ws) {
     const int grid = (a.C + 31) / 32;
@@ -738,6 +747,7 @@ static int run_device(pbx_ctx* ctx, const pbx_mh_mvn_params* p) {
   a.inj_delta = p->inj_delta; a.inj_thresh = p->inj_thresh;
   a.out_x = p->out_x; a.out_prob = p->out_prob;
   a.out_accept = p->out_accept; a.out_score = p->out_score;
+  a.out_xprop = p->out_xprop; a.out_pprop = p->out_pprop;
   a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
   if (a.T == 0) return PBX_OK;
   {
@@ -777,7 +787,7 @@ extern "C" int pbx_mh_mvn_walk_host(pbx_ctx* ctx, const pbx_mh_mvn_params* p,
   PBX_REQUIRE(ctx != nullptr, "pbx_mh_mvn_walk_host: null ctx");
   int rc = validate(p, "pbx_mh_mvn_walk_host");
   if (rc) return rc;
-  PBX_REQUIRE(!p->inj_delta && !p->out_accept && !p->out_score,
+  PBX_REQUIRE(!p->inj_delta && !p->out_accept && !p->out_score && !p->out_xprop && !p->out_pprop,
               "pbx_mh_mvn_walk_host: injected streams / per-step accept+score outputs are "
               "device-only (use pbx_mh_mvn_run)");
   PBX_CUDA(cudaSetDevice(ctx->device));

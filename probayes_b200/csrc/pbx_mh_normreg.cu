@@ -71,6 +71,8 @@ struct NrArgs {
   double* out_prob;
   uint8_t* out_accept;
   double* out_score;
+  double* out_xprop;
+  double* out_pprop;
   int64_t* accept_count;
   double* stat_sum;
   double* stat_sumsq;
@@ -199,6 +201,9 @@ __device__ void nr_phase_b(const NrArgs& a, const NrModel& m, int c, double S) {
   }
   if (a.out_accept) a.out_accept[(int64_t)a.k * C + c] = acc ? 1 : 0;
   if (a.out_score) a.out_score[(int64_t)a.k * C + c] = s;
+  if (a.out_xprop)
+    for (int j = 0; j < m.P; ++j) a.out_xprop[((int64_t)a.k * m.P + j) * C + c] = thp[j];
+  if (a.out_pprop) a.out_pprop[(int64_t)a.k * C + c] = lpp;
   if ((a.k + 1) % a.thin == 0) {
     const int64_t r = (a.k + 1) / a.thin - 1;
     if (a.out_x)
@@ -659,6 +664,7 @@ extern "C" int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p) 
   a.inj_delta = p->inj_delta; a.inj_thresh = p->inj_thresh;
   a.out_x = p->out_x; a.out_prob = p->out_prob;
   a.out_accept = p->out_accept; a.out_score = p->out_score;
+  a.out_xprop = p->out_xprop; a.out_pprop = p->out_pprop;
   a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   if (a.T > 0) {

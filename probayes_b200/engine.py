@@ -217,6 +217,8 @@ class Engine:
         if per_step:
             out["accept"] = self.empty(T, C_, dtype=torch.uint8)
             out["score"] = self.empty(T, C_)
+            out["xprop"] = self.empty(T, D, C_)
+            out["pprop"] = self.empty(T, C_)
         out["accept_count"] = zbuf[C_:2 * C_].view(torch.int64)
         if stats:
             out["stat_sum"] = zbuf[2 * C_:(2 + D) * C_].view(D, C_)
@@ -232,6 +234,8 @@ class Engine:
         p.out_prob = out["prob"].data_ptr() if record else 0
         p.out_accept = out["accept"].data_ptr() if per_step else 0
         p.out_score = out["score"].data_ptr() if per_step else 0
+        p.out_xprop = out["xprop"].data_ptr() if per_step else 0
+        p.out_pprop = out["pprop"].data_ptr() if per_step else 0
         p.accept_count = out["accept_count"].data_ptr()
         p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
         p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0
@@ -337,6 +341,8 @@ class Engine:
         if per_step:
             out["accept"] = self.empty(T, C_, dtype=torch.uint8)
             out["score"] = self.empty(T, C_)
+            out["xprop"] = self.empty(T, P, C_)
+            out["pprop"] = self.empty(T, C_)
         out["accept_count"] = self.zeros(C_, dtype=torch.int64)
         if stats:
             out["stat_sum"] = self.zeros(P, C_)
@@ -351,6 +357,8 @@ class Engine:
         p.out_prob = out["prob"].data_ptr() if record else 0
         p.out_accept = out["accept"].data_ptr() if per_step else 0
         p.out_score = out["score"].data_ptr() if per_step else 0
+        p.out_xprop = out["xprop"].data_ptr() if per_step else 0
+        p.out_pprop = out["pprop"].data_ptr() if per_step else 0
         p.accept_count = out["accept_count"].data_ptr()
         p.stat_sum = out["stat_sum"].data_ptr() if stats else 0
         p.stat_sumsq = out["stat_sumsq"].data_ptr() if stats else 0

@@ -423,6 +423,7 @@ class SP(SD):
         sampler.state_lp = out['state_lp']
         res.update(x=out['x'], prob=out['prob'], accept_count=out['accept_count'],
                    accept=out.get('accept'), score=out.get('score'),
+                   xprop=out.get('xprop'), pprop=out.get('pprop'),
                    stat_sum=out.get('stat_sum'), stat_sumsq=out.get('stat_sumsq'))
         return self._finish(res, eng)
 
@@ -448,15 +449,19 @@ class SP(SD):
                 return a
             return a.detach().cpu().numpy()
         eng.sync()
-        for k in ('x', 'prob', 'accept_count', 'accept', 'score', 'stat_sum', 'stat_sumsq'):
+        for k in ('x', 'prob', 'accept_count', 'accept', 'score', 'stat_sum', 'stat_sumsq',
+                  'xprop', 'pprop'):
             res[k] = host(res.get(k))
         return res
 
     # ---- result marshalling --------------------------------------------------------------------------
-    def _value_pd(self, arrays, sel=None):
-        """PD of the retained states: arrays [R] per variable (single chain) or
-        [C, R] (batched), named like the reference's summate() result."""
-        keys, x, prob = arrays['keys'], arrays['x'], arrays['prob']
+    def _value_pd(self, arrays, sel=None, x=None, prob=None):
+        """PD of the retained states (or, with ``x`` / ``prob``, of any [R, D, C] / [R, C]
+        pair such as the proposals): arrays [R] per variable (single chain) or [C, R]
+        (batched), named like the reference's summate() result."""
+        keys = arrays['keys']
+        x = arrays['x'] if x is None else x
+        prob = arrays['prob'] if prob is None else prob
         single = arrays['chains'] is None
         vals = collections.OrderedDict()
         for j, k in enumerate(keys):
@@ -469,7 +474,7 @@ class SP(SD):
         dims = collections.OrderedDict((k, 0) for k in keys)
         spec = arrays['spec']
         if spec['kind'] == 'normreg':
-            n = arrays['n_obs'] * (1 if sel is not None and np.ndim(p) == 0 else arrays['R'])
+            n = arrays['n_obs'] * (1 if sel is not None and np.ndim(p) == 0 else x.shape[0])
             for ok in [k for k in (spec['obs_x'], spec['obs_y']) if k]:
                 vals[ok] = {n}
                 dims[ok] = None
@@ -481,23 +486,33 @@ class SP(SD):
             p = float(p)
         return PD(','.join(names), vals, dims=dims, prob=p, pscale=arrays['pscale'])
 
+    @staticmethod
+    def _has_proposals(arrays):
+        return arrays.get('xprop') is not None and arrays['thin'] == 1
+
     def _per_step(self, arrays):
-        """Reference-shaped per-step tuples for a single chain (thin == 1 only for
-        s / t / u alignment)."""
+        """Reference-shaped per-step tuples for a single chain: ``v`` the retained state,
+        and (thin == 1) ``p`` the proposal with its target density, ``o`` the predecessor
+        (None on the first step of a fresh sampler), ``s / t / u`` (sp.py:244-258)."""
         out = []
         R = arrays['R']
         acc, score, thr = arrays.get('accept'), arrays.get('score'), arrays.get('inj_thresh')
         aligned = arrays['thin'] == 1
+        props = self._has_proposals(arrays)
+        prev = None
         for i in range(R):
             v = self._value_pd(arrays, sel=i)
-            s = t = u = None
+            s = t = u = p = None
             if arrays['gibbs']:
                 s, t, u = np.nan, np.nan, True
             elif aligned and acc is not None:
                 u = True if acc[i, 0] else None
                 s = None if np.isnan(score[i, 0]) else float(score[i, 0])
                 t = None if thr is None else float(np.ravel(thr)[i])
-            out.append(self.opqrstuv(None, None, None, None, s, t, u, v))
+            if props:
+                p = self._value_pd(arrays, sel=i, x=arrays['xprop'], prob=arrays['pprop'])
+            out.append(self.opqrstuv(prev if aligned else None, p, None, None, s, t, u, v))
+            prev = v
         return out
 
     def __call__(self, *args, **kwds):
@@ -530,32 +545,47 @@ class SP(SD):
             return pd.conditionalise(self._leafs.keyset) if conditionalise else pd
         if arrays is None:
             # a plain list of per-step tuples: concatenate their scalar PDs
-            vs = [s.v for s in samples if s.u is not False]
-            keys = list(vs[0].keys())
-            vals = collections.OrderedDict()
-            for k in keys:
-                if isinstance(vs[0][k], set):
-                    vals[k] = {sum(list(v[k])[0] for v in vs)}
-                else:
-                    vals[k] = np.array([v[k] for v in vs])
-            dims = collections.OrderedDict((k, None if isinstance(vals[k], set) else 0)
-                                           for k in keys)
-            names = [k if not isinstance(vals[k], set) else "{}={}".format(k, vals[k])
-                     for k in keys]
-            v = PD(','.join(names), vals, dims=dims, prob=np.array([p.prob for p in vs]),
-                   pscale=vs[0].pscale)
-            u = [s.u for s in samples if s.u is not False]
+            def concat(pds):
+                pds = [d for d in pds if d is not None]
+                if not pds:
+                    return None
+                keys = list(pds[0].keys())
+                vals = collections.OrderedDict()
+                for k in keys:
+                    if isinstance(pds[0][k], set):
+                        vals[k] = {sum(list(d[k])[0] for d in pds)}
+                    else:
+                        vals[k] = np.array([d[k] for d in pds])
+                dims = collections.OrderedDict((k, None if isinstance(vals[k], set) else 0)
+                                               for k in keys)
+                names = [k if not isinstance(vals[k], set) else "{}={}".format(k, vals[k])
+                         for k in keys]
+                return PD(','.join(names), vals, dims=dims,
+                          prob=np.array([d.prob for d in pds]), pscale=pds[0].pscale)
+            kept = [s for s in samples if s.u is not False]
+            v = concat([s.v for s in kept])
+            if conditionalise:
+                v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])
+            u = [s.u for s in kept]
             s_ = [s.s for s in samples if s.s is not None]
             t_ = [s.t for s in samples if s.t is not None]
-            return self.opqrstuv(None, None, None, None, s_ or None, t_ or None, u, v)
+            return self.opqrstuv(concat([s.o for s in kept]), concat([s.p for s in kept]),
+                                 None, None, s_ or None, t_ or None, u, v)
         v = self._value_pd(arrays)
         if conditionalise:                      # sp.py:194-196: condition on the leaf (data) keys
             v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])
+        o = p = None
+        if self._has_proposals(arrays) and not conditionalise:
+            # summate() of the per-step p / o PDs (sp.py:170-198): every proposal, and the
+            # predecessor of every step but the first
+            p = self._value_pd(arrays, x=arrays['xprop'], prob=arrays['pprop'])
+            if arrays['R'] > 1:
+                o = self._value_pd(arrays, x=arrays['x'][:-1], prob=arrays['prob'][:-1])
         if arrays['chains'] is None and len(samples):
             u = [s.u for s in samples]
             s_ = [s.s for s in samples if s.s is not None]
             t_ = [s.t for s in samples if s.t is not None]
-            return self.opqrstuv(None, None, None, None, s_ or None, t_ or None, u, v)
+            return self.opqrstuv(o, p, None, None, s_ or None, t_ or None, u, v)
         if arrays['gibbs']:
             C = 1 if arrays['chains'] is None else arrays['chains']
             u = AcceptRecord(np.full(C, arrays['T']), arrays['T'])

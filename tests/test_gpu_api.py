@@ -47,6 +47,18 @@ def test_mcmc_prob4a(name):
     assert summary.v.name == 'x,y' and len(summary.s) == n_steps - 1
     assert relerr(np.array(summary.s), g["s"][1:]) <= TOL
     assert samples[3].v.name.startswith('x=') and samples[3].u in (True, None)
+    # proposals (opqr.p) and predecessors (opqr.o): sp.py:244-258, summated sp.py:170-198
+    assert summary.p.name == 'x,y' and summary.p.shape == [n_steps]
+    assert relerr(np.stack([summary.p['x'], summary.p['y']], 1), g["xprop"]) <= TOL
+    assert relerr(summary.p.prob, g["pprop"]) <= TOL
+    assert summary.o.shape == [n_steps - 1] and samples[0].o is None
+    assert np.array_equal(summary.o['x'], summary.v['x'][:-1])
+    assert np.array_equal(summary.o.prob, summary.v.prob[:-1])
+    assert samples[5].o['x'] == samples[4].v['x'] and samples[5].p['x'] == summary.p['x'][5]
+    walk = process.walk(process.sampler({'x': 0., 'y': 1.}, stop=n_steps,
+                                        inj_delta=g["delta"], inj_thresh=g["thresh"]))
+    s2 = process(walk)                       # the Walk path builds the same PDs from arrays
+    assert np.array_equal(s2.p['y'], summary.p['y']) and np.array_equal(s2.o.prob, summary.o.prob)
 
 
 @pytest.mark.parametrize("name,scores,delta", [
@@ -93,6 +105,10 @@ def test_metrohast_norm1d(name, scores, delta):
     assert relerr(summary.v.prob, g["prob"]) <= TOL
     assert summary.v.name == 'mu,sigma,x={{{}}}'.format(len(g["x_obs"]) * n_steps)
     assert inference.pscale == 1.
+    assert relerr(np.stack([summary.p['mu'], summary.p['sigma']], 1), g["xprop"]) <= TOL
+    assert relerr(summary.p.prob, g["pprop"]) <= TOL
+    assert summary.p.name == summary.v.name
+    assert summary.o.name == 'mu,sigma,x={{{}}}'.format(len(g["x_obs"]) * (n_steps - 1))
     # process(samples, conditionalise=True): normalised over the samples (sp.py:194-196)
     cond = process(samples, conditionalise=True).v
     assert cond.name == 'mu,sigma|x={{{}}}'.format(len(g["x_obs"]) * n_steps)
