@@ -27,8 +27,9 @@
 // CUDA's libm versions cost ~75 / ~95 / ~45 SASS instructions each, a third of them
 // constant materialisation (FP64 ops take no 64-bit immediates).  Here: one 16-byte
 // table lookup + a short polynomial whose coefficients are constant-bank operands.
-// Absolute error <= ~3e-16 (checked against the CPU Philox replay to 1e-11 in the
-// tests); inputs are the RNG's uniforms, so no special-case handling is needed.
+// Absolute error <= ~3e-16 (pinned by pbx_selftest_fastmath in the tests: <= 2 ulp of
+// max(1, |value|), sin/cos <= 4e-16 against an extended-precision reference); inputs
+// are the RNG's uniforms, so no special-case handling is needed.
 // ---------------------------------------------------------------------------
 struct PbxTables {
   double2 lg[128];   // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/128
@@ -42,7 +43,7 @@ __constant__ double kExpP[4] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
 
 // -2 log(x) for positive normal x (what both Box-Muller and the accept threshold need):
 // the same reduction with the factor -2 folded into the table value, the polynomial
-// and the exponent term -- one multiply less than -2 * fast_log(x)
+// and the exponent term -- one multiply less than scaling a plain log afterwards
 __constant__ double kN2LogP[5] = {1.0, -2.0 / 3.0, 0.5, -0.4, 1.0 / 3.0};
 __device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
