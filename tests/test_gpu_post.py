@@ -406,3 +406,50 @@ def test_api_pd_algebra_golden():
     pc = joint / mm
     assert pc.name == names[8]
     assert np.abs(pc.prob - g["cond_sigma"]).max() <= 1e-12 * np.abs(g["joint"]).max()
+
+
+# ---- full-size properties (no CPU oracle at these sizes) --------------------------------------
+def test_argsort_full_size_properties():
+    """2^26 keys: the result is sorted, is a permutation, is stable for ties, and sorting
+    the sorted keys again is the identity (size-independent properties of PD.sorted)."""
+    import torch
+    eng = engine()
+    n = 1 << 26
+    g = torch.Generator(device=eng.device).manual_seed(7)
+    keys = torch.randn(n, dtype=torch.float64, device=eng.device, generator=g)
+    keys[::3] = torch.round(keys[::3]) + 0.0                # a third of the keys are heavy ties
+    # (+ 0.0 turns round()'s -0.0 into +0.0: the sort orders -0.0 before +0.0, == does not)
+    order, ks = eng.argsort(keys, want_keys=True)
+    assert bool((ks[1:] >= ks[:-1]).all())                  # sorted
+    assert bool(torch.equal(ks, keys[order.long()]))        # consistent with the order
+    seen = torch.zeros(n, dtype=torch.int32, device=eng.device)
+    seen.index_add_(0, order.long(), torch.ones(n, dtype=torch.int32, device=eng.device))
+    assert int(seen.min()) == 1 and int(seen.max()) == 1    # a permutation
+    ties = ks[1:] == ks[:-1]
+    assert bool((order[1:][ties] > order[:-1][ties]).all()) # stable: input order among equals
+    order2, ks2 = eng.argsort(ks, want_keys=True)
+    assert bool(torch.equal(ks2, ks))
+    assert bool(torch.equal(order2, torch.arange(n, dtype=torch.int32, device=eng.device)))
+
+
+def test_cumprob_and_expectation_full_size_properties():
+    """2^26 cells: cum is non-decreasing, ends at exactly 1, its increments are the
+    normalised cells; expectation of a constant is the constant, and linear in the values."""
+    import torch
+    eng = engine()
+    n = 1 << 26
+    g = torch.Generator(device=eng.device).manual_seed(11)
+    p = torch.rand(n, dtype=torch.float64, device=eng.device, generator=g)
+    cum, total = eng.cumprob(p, False)
+    assert bool((cum[1:] >= cum[:-1]).all()) and float(cum[-1]) == 1.0
+    assert abs(float(total) - float(p.sum())) <= 1e-12 * float(total)
+    inc = cum[1:] - cum[:-1]
+    assert float((inc - p[1:] / total).abs().max()) <= 5e-15         # a few ulp of cum ~ 1 (increments ~ 1e-8)
+    v = torch.rand(n, dtype=torch.float64, device=eng.device, generator=g)
+    vals = torch.stack([torch.full_like(v, 3.25), v, 2.0 * v - 1.0])
+    s = eng.expectation_sums(p, False, None, vals).cpu().numpy()
+    e = s[1:] / s[0]
+    assert abs(e[0] - 3.25) <= 1e-12 and abs(e[2] - (2.0 * e[1] - 1.0)) <= 1e-12
+    lp = torch.log(p) - 500.0                                # same weights in log pscale
+    s2 = eng.expectation_sums(lp, True, None, vals).cpu().numpy()
+    assert np.abs(s2[1:] / s2[0] - e).max() <= 1e-11
