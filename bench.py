@@ -596,13 +596,13 @@ def run_ours(args):
             "cpu_binding": cpu_binding,
             "quality": {"accept_rate": acc_rate, "rhat": [float(v) for v in rhat]},
         }
-        if not args.no_secondary:
+        if not args.no_secondary and world == 1:        # the other configs: N = 1 only
             try:
                 line["secondary"] = secondary(eng, peaks, fp64_peak, quick=args.quick)
                 line["roofline_stream"] = line["secondary"].pop("roofline_stream")
             except Exception as e:                           # never lose the headline line
                 line["secondary"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:     # reported on rank 0 at N = 1 only
             if getattr(bind_to_gpu_cpus, "original", None):     # the CPU arm gets every core
                 os.sched_setaffinity(0, bind_to_gpu_cpus.original)
             steps = args.cpu_sample_steps or auto_cpu_steps(C, args.accept)
