@@ -596,13 +596,13 @@ class Engine:
         tensors of shapes [rows or 1, cols or 1] -> [rows, cols] device tensor."""
         a2 = a.reshape(1, -1) if a.dim() < 2 else a
         b2 = b.reshape(1, -1) if b.dim() < 2 else b
+        a2, b2 = a2.contiguous(), b2.contiguous()       # kept alive until after the launch
         rows, cols = max(a2.shape[0], b2.shape[0]), max(a2.shape[1], b2.shape[1])
         out = self.empty(rows, cols)
         _lib.check(self.lib.pbx_pd_binary_f64(
-            self.ctx, 0 if op == 'mul' else 1, self._ptr(a2.contiguous()), a2.shape[0],
-            a2.shape[1], int(bool(a_log)), self._ptr(b2.contiguous()), b2.shape[0], b2.shape[1],
-            int(bool(b_log)), rows, cols, int(bool(out_log)), out.data_ptr()),
-            "pbx_pd_binary_f64")
+            self.ctx, 0 if op == 'mul' else 1, self._ptr(a2), a2.shape[0], a2.shape[1],
+            int(bool(a_log)), self._ptr(b2), b2.shape[0], b2.shape[1], int(bool(b_log)),
+            rows, cols, int(bool(out_log)), out.data_ptr()), "pbx_pd_binary_f64")
         return out
 
     def box_sample(self, lims, log_ufun, n_samples, seed=0, sample0=0, inj_unif=None):
