@@ -65,9 +65,11 @@ __device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
 __device__ __forceinline__ void fast_sincos2pi(uint32_t w, const PbxTables* tb, double& s,
                                                double& c) {
   const double2 t = tb->sc[w >> 24];
-  // rho = 2 pi ((w & 0xffffff) + 0.5 - 2^23) / 2^32,  |rho| < pi/256
-  const double v = __hiloint2double(0x43300000, (int)(w & 0x00FFFFFFu)) - 4503599627370496.0;
-  const double rho = (v - 8388607.5) * 1.4629180792671596e-9;             // 2 pi / 2^32
+  // rho = 2 pi ((w & 0xffffff) + 0.5 - 2^23) / 2^32,  |rho| < pi/256.  The 24 bits go
+  // into the mantissa of 2^51 (unit in the last place 1/2) doubled, so that 2^51 + k is
+  // exact and one subtraction of 2^51 + 2^23 - 0.5 (representable) centres it
+  const double v = __hiloint2double(0x43200000, (int)((w & 0x00FFFFFFu) << 1));
+  const double rho = (v - 2251799822073855.5) * 1.4629180792671596e-9;    // 2 pi / 2^32
   const double q = rho * rho;
   double sp = fma(q, kSinP[2], kSinP[1]);
   sp = fma(q, sp, kSinP[0]);
@@ -517,11 +519,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         colour_delta<D>(kFast ? 0 : a.has_L, m, dl, dv);
 #pragma unroll
         for (int j = 0; j < D; ++j) slot[(g * (D + 1) + j) * 32] = dv[j];
-        // global step 0 accepts unconditionally (sp.py:253): threshold that always passes
         // log rule: -2 log t (added to the current Mahalanobis distance by the consumer)
-        double th = kRefAccept ? t : fast_neg2log(t, tb);
-        if (gstep == 0) th = kRefAccept ? 0.0 : INFINITY;
-        slot[(g * (D + 1) + D) * 32] = th;
+        slot[(g * (D + 1) + D) * 32] = kRefAccept ? t : fast_neg2log(t, tb);
       };
       if ((b + 1) * G <= a.T) {
         // full batch: WS_PUNROLL independent steps in flight per thread (ILP), since a
@@ -532,6 +531,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 #pragma unroll 1
         for (int g = 0; g < a.T - b * G; ++g) produce(g);
       }
+      // global step 0 accepts unconditionally (sp.py:253): a threshold that always passes
+      if (b == 0 && a.step0 == 0) slot[D * 32] = kRefAccept ? 0.0 : INFINITY;
       __syncwarp();
       if (lane == 0) pbx_mbar_arrive(&in_full[si]);
     }
