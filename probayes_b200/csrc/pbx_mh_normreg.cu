@@ -121,13 +121,17 @@ __device__ __forceinline__ double nr_threshold(const NrArgs& a, int64_t gstep, i
   return pbx_t44(w.w, w.y);
 }
 
+// kExtras gates the rarely used per-step extras (bounded deltas, proposal outputs) at
+// compile time, so that adding to them never perturbs the register allocation of the
+// hot likelihood loops of the common configuration (a 9 % effect when it happened)
+template <bool kExtras>
 __device__ __forceinline__ void nr_propose(const NrArgs& a, const NrModel& m, int64_t gstep,
                                            int kk, int c, const double* th) {
   double dl[PBX_MAX_PARAMS];
   nr_draw_delta(a, m, gstep, kk, c, dl);
   for (int j = 0; j < m.P; ++j) {
     double v = m.log_ufun[j] ? exp(log(th[j]) + dl[j]) : th[j] + dl[j];
-    if (m.bound) {
+    if (kExtras && m.bound) {
       // Variable.apply_delta(bound=True), scalar branch (variable.py:700-727): closed
       // ends clip; beyond an open end the proposal bounces back to the current value
       const double lo = m.lims[j][0], hi = m.lims[j][1];
@@ -158,6 +162,7 @@ __device__ __forceinline__ double nr_logjoint(const NrArgs& a, const NrModel& m,
 }
 
 // phase B for one chain: S is the complete residual sum of squares of the proposal
+template <bool kExtras>
 __device__ void nr_phase_b(const NrArgs& a, const NrModel& m, int c, double S) {
   const int64_t C = a.C;
   double thp[PBX_MAX_PARAMS];
@@ -201,9 +206,9 @@ __device__ void nr_phase_b(const NrArgs& a, const NrModel& m, int c, double S) {
   }
   if (a.out_accept) a.out_accept[(int64_t)a.k * C + c] = acc ? 1 : 0;
   if (a.out_score) a.out_score[(int64_t)a.k * C + c] = s;
-  if (a.out_xprop)
+  if (kExtras && a.out_xprop)
     for (int j = 0; j < m.P; ++j) a.out_xprop[((int64_t)a.k * m.P + j) * C + c] = thp[j];
-  if (a.out_pprop) a.out_pprop[(int64_t)a.k * C + c] = lpp;
+  if (kExtras && a.out_pprop) a.out_pprop[(int64_t)a.k * C + c] = lpp;
   if ((a.k + 1) % a.thin == 0) {
     const int64_t r = (a.k + 1) / a.thin - 1;
     if (a.out_x)
@@ -211,16 +216,17 @@ __device__ void nr_phase_b(const NrArgs& a, const NrModel& m, int c, double S) {
     if (a.out_prob) a.out_prob[r * C + c] = lp;
   }
   // draw the proposal of the NEXT step (none after the last step of the call)
-  if (a.k + 1 < a.T) nr_propose(a, m, a.gstep + 1, a.k + 1, c, th);
+  if (a.k + 1 < a.T) nr_propose<kExtras>(a, m, a.gstep + 1, a.k + 1, c, th);
 }
 
 // first proposal of a call, from the current state
+template <bool kExtras>
 __global__ void __launch_bounds__(256) nr_init_kernel(const NrArgs a, const __grid_constant__ NrModel m) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= a.C) return;
   double th[PBX_MAX_PARAMS];
   for (int j = 0; j < m.P; ++j) th[j] = a.state[(int64_t)j * a.C + c];
-  nr_propose(a, m, a.step0, 0, c, th);
+  nr_propose<kExtras>(a, m, a.step0, 0, c, th);
 }
 
 // "last CTA of the group" election; returns true in the CTA that arrives last
@@ -242,7 +248,7 @@ __device__ __forceinline__ bool nr_arrive_last(unsigned int* counter, unsigned i
 // phase A, "tiles": chains in registers, observation tiles via TMA bulk copies
 // grid = (n_slices, n_groups); group = NR_THREADS*KC chains
 // ----------------------------------------------------------------------------
-template <int KC, bool kSlope>
+template <int KC, bool kSlope, bool kExtras>
 __global__ void __launch_bounds__(NR_THREADS)
     nr_tiles_kernel(const NrArgs a, const __grid_constant__ NrModel m, int use_tma) {
   extern __shared__ __align__(128) double sm[];            // [NR_STAGES][2][NR_TILE]
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(NR_THREADS)
     if (c >= a.C) continue;
     double S = 0.0;
     for (int s = 0; s < a.n_slices; ++s) S += __ldcg(&a.partial[(int64_t)s * C + c]);
-    nr_phase_b(a, m, c, S);
+    nr_phase_b<kExtras>(a, m, c, S);
   }
 }
 
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(NR_THREADS)
 // block reduction; phase B in the last CTA.
 // ----------------------------------------------------------------------------
 #define NRS_THREADS 256
-template <int KS, bool kSlope>
+template <int KS, bool kSlope, bool kExtras>
 __global__ void __launch_bounds__(NRS_THREADS)
     nr_stream_kernel(const NrArgs a, const __grid_constant__ NrModel m, int use_tma) {
   extern __shared__ __align__(128) double sm[];            // [NR_STAGES][2][NRS_TILE]
@@ -478,7 +484,7 @@ __global__ void __launch_bounds__(NRS_THREADS)
     const int c = threadIdx.x;
     double S = 0.0;
     for (int s = 0; s < (int)gridDim.x; ++s) S += __ldcg(&a.partial[(int64_t)s * a.C + c]);
-    nr_phase_b(a, m, c, S);
+    nr_phase_b<kExtras>(a, m, c, S);
   }
 }
 
@@ -575,35 +581,44 @@ static void nr_fill_model(const pbx_mh_normreg_params* p, NrModel& m) {
   }
 }
 
+static bool nr_extras(const NrArgs& a, const NrModel& m) {
+  return m.bound != 0 || a.out_xprop != nullptr || a.out_pprop != nullptr;
+}
+
 template <int KC>
 static int nr_launch_tiles(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const NrModel& m) {
   dim3 grid(pl.n_slices, pl.n_groups);
-  if (m.has_slope) {
-    PBX_CUDA(cudaFuncSetAttribute(nr_tiles_kernel<KC, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    nr_tiles_kernel<KC, true><<<grid, NR_THREADS, pl.smem, ctx->stream>>>(a, m, pl.use_tma);
-  } else {
-    PBX_CUDA(cudaFuncSetAttribute(nr_tiles_kernel<KC, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    nr_tiles_kernel<KC, false><<<grid, NR_THREADS, pl.smem, ctx->stream>>>(a, m, pl.use_tma);
-  }
+#define NR_TILES_GO(S, E)                                                                      \
+  do {                                                                                         \
+    PBX_CUDA(cudaFuncSetAttribute(nr_tiles_kernel<KC, S, E>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    nr_tiles_kernel<KC, S, E><<<grid, NR_THREADS, pl.smem, ctx->stream>>>(a, m, pl.use_tma);   \
+  } while (0)
+  const bool ex = nr_extras(a, m);
+  if (m.has_slope && ex) NR_TILES_GO(true, true);
+  else if (m.has_slope) NR_TILES_GO(true, false);
+  else if (ex) NR_TILES_GO(false, true);
+  else NR_TILES_GO(false, false);
+#undef NR_TILES_GO
   PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
 }
 
 template <int KS>
 static int nr_launch_stream(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const NrModel& m) {
-  if (m.has_slope) {
-    PBX_CUDA(cudaFuncSetAttribute(nr_stream_kernel<KS, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    nr_stream_kernel<KS, true><<<pl.n_slices, NRS_THREADS, pl.smem, ctx->stream>>>(a, m,
-                                                                                  pl.use_tma);
-  } else {
-    PBX_CUDA(cudaFuncSetAttribute(nr_stream_kernel<KS, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    nr_stream_kernel<KS, false><<<pl.n_slices, NRS_THREADS, pl.smem, ctx->stream>>>(a, m,
-                                                                                   pl.use_tma);
-  }
+#define NR_STREAM_GO(S, E)                                                                     \
+  do {                                                                                         \
+    PBX_CUDA(cudaFuncSetAttribute(nr_stream_kernel<KS, S, E>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    nr_stream_kernel<KS, S, E><<<pl.n_slices, NRS_THREADS, pl.smem, ctx->stream>>>(a, m,       \
+                                                                                  pl.use_tma); \
+  } while (0)
+  const bool ex = nr_extras(a, m);
+  if (m.has_slope && ex) NR_STREAM_GO(true, true);
+  else if (m.has_slope) NR_STREAM_GO(true, false);
+  else if (ex) NR_STREAM_GO(false, true);
+  else NR_STREAM_GO(false, false);
+#undef NR_STREAM_GO
   PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
 }
@@ -668,7 +683,8 @@ extern "C" int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p) 
   a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   if (a.T > 0) {
-    nr_init_kernel<<<(a.C + 255) / 256, 256, 0, ctx->stream>>>(a, m);
+    if (nr_extras(a, m)) nr_init_kernel<true><<<(a.C + 255) / 256, 256, 0, ctx->stream>>>(a, m);
+    else nr_init_kernel<false><<<(a.C + 255) / 256, 256, 0, ctx->stream>>>(a, m);
     PBX_LAUNCH_CHECK(ctx);
     for (int k = 0; k < a.T; ++k) {
       a.k = k;
