@@ -314,7 +314,20 @@ def secondary(eng, peaks, fp64_peak, quick=False):
     out["c3_mh"] = {"workload": "C3: MH, 16384 chains, N=1e6, %d steps per call" % T,
                     "ms_per_mh_step": ms_mh / T, "chain_steps_per_s": C * T / (ms_mh * 1e-3),
                     "loglik_evals_per_s": C * T / (ms_mh * 1e-3)}
-    del theta, st
+    # opt-in algorithmic variant (NOT the measured path of the roofline figures): the same
+    # walk from centred sufficient statistics, O(1) per likelihood evaluation
+    st2 = eng.to_device(np.tile(np.array([[-1.], [1.5], [.5]]), (1, C)))
+    Tss = 1000
+    ms_ss = timeit(lambda: eng.mh_normreg(st2, y, x, Tss, lims, ex, lg, [2.4 * sd] * 3, seed=1,
+                                          variant=3, record=False), reps=3, warm=1)
+    out["c3_mh_suffstat"] = {"workload": "C3 with variant 3 (sufficient statistics, opt-in): "
+                                         "16384 chains x %d steps, N=1e6, one launch" % Tss,
+                             "ms_per_walk": ms_ss,
+                             "chain_steps_per_s": C * Tss / (ms_ss * 1e-3),
+                             "note": "same values as the term-by-term kernels to fp64 round-off; "
+                                     "3 passes over the observations per call, then O(1) per "
+                                     "evaluation"}
+    del theta, st, st2
     # ---- HBM-streaming regime: <= 8 chains, N = 2^27 (2 GiB of observations > L2) ----
     Ns = (1 << 24) if quick else (1 << 27)
     xs = torch.randn(Ns, dtype=torch.float64, device=eng.device)
@@ -349,6 +362,12 @@ def secondary(eng, peaks, fp64_peak, quick=False):
                           "fp64_tflops": 4.0 * cellobs / (ms * 1e-3) / 1e12,
                           "fp64_frac_of_measured_peak": 4.0 * cellobs / (ms * 1e-3) / 1e12 / fp64_peak,
                           "note": "2 FP64 instr (mul, fma = 3 flop; SURVEY counts 4) per cell-obs"}
+    ms_ss = timeit(lambda: eng.grid_norm_logjoint(data, mu, sg, lpm, lps, out=lj, suffstat=True),
+                   reps=3, warm=1)
+    out["c4_logjoint_suffstat"] = {"workload": "C4 log-joint from sufficient statistics (opt-in)",
+                                   "ms": ms_ss, "algorithmic_gbs": 8.0 * M * S / (ms_ss * 1e-3) / 1e9,
+                                   "frac": 8.0 * M * S / (ms_ss * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                   "note": "HBM-bound on writing the 134 MB grid"}
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     for _ in range(2):
         r = eng.grid_conditionalise(lj)

@@ -177,7 +177,10 @@ typedef struct {
                               hastings_scores (sp_utils.py:62-64); 1.0 for metropolis */
   int32_t prop_kind;
   int32_t variant;         /* 0 auto; 1 chains-in-registers + TMA-staged obs tiles;
-                              2 obs-per-thread streaming + warp-shuffle reduction */
+                              2 obs-per-thread streaming + warp-shuffle reduction;
+                              3 (opt-in) centred sufficient statistics: one reduction over
+                              the observations, then O(1) per likelihood evaluation and the
+                              whole walk in one launch -- same values to <= 1e-15 */
   int64_t n_obs;
   const double* x_obs;     /* device [N] (unused when !has_slope) */
   const double* y_obs;     /* device [N] */
@@ -225,6 +228,12 @@ PBX_API int pbx_grid_norm_logjoint(pbx_ctx* ctx, const double* x_obs, int64_t n_
                            const double* logprior_mu, const double* logprior_sigma,
                            double* out);
 /* out[0] = max over n entries (device scalar) */
+/* opt-in: the same values (<= 1e-15) from centred sufficient statistics of the
+ * observations: one reduction over x_obs, then O(1) per cell instead of O(N) */
+PBX_API int pbx_grid_norm_logjoint_ss(pbx_ctx* ctx, const double* x_obs, int64_t n_obs,
+                                      const double* mu, int32_t n_mu, const double* sigma,
+                                      int32_t n_sigma, const double* logprior_mu,
+                                      const double* logprior_sigma, double* out);
 PBX_API int pbx_grid_max(pbx_ctx* ctx, const double* logjoint, int64_t n, double* out);
 /* out[0] = sum exp_logp(logjoint - gmax[0]) (device scalars) */
 PBX_API int pbx_grid_sumexp(pbx_ctx* ctx, const double* logjoint, int64_t n,

@@ -104,6 +104,9 @@ SIGNATURES = {
     "pbx_grid_norm_logjoint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
+    "pbx_grid_norm_logjoint_ss": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                            C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]),
     "pbx_grid_max": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pbx_grid_sumexp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pbx_grid_posterior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,

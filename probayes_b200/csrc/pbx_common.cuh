@@ -48,6 +48,11 @@ int pbx_ws_reserve(pbx_ctx* ctx, size_t bytes);
     PBX_CUDA(cudaGetLastError());                                               \
   } while (0)
 
+// centred sufficient statistics of (x, y) observations for the normal likelihoods
+// (pbx_mh_normreg.cu, "variant 3"); computed into the context workspace
+struct NrStats { double N, cx, cy, Sxx, b1s, RSS, Su, Se, Seu, pad; };
+int pbx_ss_compute(pbx_ctx* ctx, const double* x, const double* y, int64_t n, NrStats** out);
+
 // ---------------------------------------------------------------------------
 // probayes/constants.py:9-32 (fp64)
 // ---------------------------------------------------------------------------

@@ -25,6 +25,7 @@
 //          reduce.  This is the HBM-roofline regime (16 B per observation per step).
 #include <math.h>
 #include <string.h>
+#include <algorithm>
 #include "pbx_common.cuh"
 
 #define NR_TILE 1024          // observations per shared-memory tile (tiles kernel: 48 KB/CTA)
@@ -639,6 +640,226 @@ static int nr_launch_step(pbx_ctx* ctx, const NrPlan& pl, const NrArgs& a, const
   }
 }
 
+// ============================================================================
+// variant 3: sufficient statistics.  For a NORMAL likelihood the residual sum of squares
+// of any (b0, b1) is a quadratic form in a few sums over the observations, so after a
+// one-time reduction every likelihood evaluation is O(1) instead of O(N) and a whole
+// walk is ONE launch.  To stay at the accuracy of the per-observation sum (<= 3e-16
+// relative against a long-double evaluation, the same as the streaming kernels) the
+// statistics are centred -- three deterministic passes over the data:
+//   1. cx = mean x, cy = mean y
+//   2. u = x - cx, v = y - cy:  Sxx = sum u^2, Sxy = sum u v, Su = sum u  -> b1* = Sxy / Sxx
+//   3. e = v - b1* u:           RSS = sum e^2, Se = sum e, Seu = sum e u
+// and with D = b1 - b1*, a = b0 + b1 cx - cy every term of
+//   sum (y - b0 - b1 x)^2 = RSS + D^2 Sxx + N a^2 - 2 D Seu - 2 a Se + 2 a D Su
+// is either non-negative or a rounding residual: no cancellation, whatever the fit.
+// (Without a slope: u = 0, b1 = 0, e = v.)  Opt-in: the default variants evaluate the
+// likelihood term by term as the reference does.
+// ============================================================================
+
+#define SS_THREADS 256
+#define SS_MAXCTA 1024
+// pass 1: (sum x, sum y);  pass 2: (Sxx, Sxy, Su, -);  pass 3: (RSS, Se, Seu, -)
+template <int PASS>
+__global__ void __launch_bounds__(SS_THREADS) ss_partial_kernel(const double* __restrict__ x,
+                                                                const double* __restrict__ y,
+                                                                long long n, long long per_cta,
+                                                                const NrStats* __restrict__ st,
+                                                                double* __restrict__ part) {
+  __shared__ double s_red[SS_THREADS / 32][4];
+  const long long e0 = (long long)blockIdx.x * per_cta, e1 = min(n, e0 + per_cta);
+  const double cx = PASS > 1 ? st->cx : 0.0, cy = PASS > 1 ? st->cy : 0.0;
+  const double b1 = PASS > 2 ? st->b1s : 0.0;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (long long e = e0 + threadIdx.x; e < e1; e += SS_THREADS) {
+    const double xv = x ? x[e] : 0.0, yv = y[e];
+    if (PASS == 1) {
+      acc[0] += xv;
+      acc[1] += yv;
+    } else if (PASS == 2) {
+      const double u = xv - cx, v = yv - cy;
+      acc[0] = fma(u, u, acc[0]);
+      acc[1] = fma(u, v, acc[1]);
+      acc[2] += u;
+    } else {
+      const double u = xv - cx, ee = (yv - cy) - b1 * u;
+      acc[0] = fma(ee, ee, acc[0]);
+      acc[1] += ee;
+      acc[2] = fma(ee, u, acc[2]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < SS_THREADS / 32; ++w) v += s_red[w][threadIdx.x];
+    part[(size_t)blockIdx.x * 4 + threadIdx.x] = v;
+  }
+}
+
+// one warp: adds the partials in index order and updates the statistics
+template <int PASS>
+__global__ void ss_final_kernel(const double* __restrict__ part, int nparts, long long n,
+                                int has_x, NrStats* st) {
+  const int k = threadIdx.x;
+  double v = 0.0;
+  if (k < 4)
+    for (int p = 0; p < nparts; ++p) v += part[(size_t)p * 4 + k];
+  const double v0 = __shfl_sync(0xffffffffu, v, 0), v1 = __shfl_sync(0xffffffffu, v, 1);
+  const double v2 = __shfl_sync(0xffffffffu, v, 2);
+  if (k != 0) return;
+  if (PASS == 1) {
+    st->N = (double)n;
+    st->cx = has_x ? v0 / (double)n : 0.0;
+    st->cy = v1 / (double)n;
+  } else if (PASS == 2) {
+    st->Sxx = v0;
+    st->b1s = (has_x && v0 > 0.0) ? v1 / v0 : 0.0;
+    st->Su = v2;
+  } else {
+    st->RSS = v0;
+    st->Se = v1;
+    st->Seu = v2;
+  }
+}
+
+__device__ __forceinline__ double ss_rss(const NrStats& st, const NrModel& m, const double* th) {
+  const double b0 = th[0], b1 = m.has_slope ? th[1] : 0.0;
+  const double D = b1 - st.b1s;
+  const double a = fma(b1, st.cx, b0) - st.cy;
+  double S = st.RSS;
+  S = fma(D * D, st.Sxx, S);
+  S = fma(st.N * a, a, S);
+  S = fma(-2.0 * D, st.Seu, S);
+  S = fma(-2.0 * a, st.Se, S);
+  S = fma(2.0 * a * D, st.Su, S);
+  return S;
+}
+
+// evaluate-only: log-joint of theta[P][C] from the statistics
+__global__ void __launch_bounds__(256) ss_eval_kernel(const NrArgs a, const __grid_constant__ NrModel m,
+                                                      const NrStats* __restrict__ stp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const NrStats st = *stp;
+  double th[PBX_MAX_PARAMS];
+  for (int j = 0; j < m.P; ++j) th[j] = a.theta_in[(int64_t)j * a.C + c];
+  a.eval_out[c] = nr_logjoint(a, m, th, ss_rss(st, m, th));
+}
+
+// the whole walk of one chain in one thread (the same draws, accept rule and records as
+// nr_phase_b, with the O(1) likelihood)
+__global__ void __launch_bounds__(128) ss_walk_kernel(const NrArgs a, const __grid_constant__ NrModel m,
+                                                      const NrStats* __restrict__ stp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.C) return;
+  const int64_t C = a.C;
+  const NrStats st = *stp;
+  double th[PBX_MAX_PARAMS], ssum[PBX_MAX_PARAMS], ssq[PBX_MAX_PARAMS];
+  for (int j = 0; j < m.P; ++j) {
+    th[j] = a.state[(int64_t)j * C + c];
+    ssum[j] = ssq[j] = 0.0;
+  }
+  double lp = a.state_lp[c];
+  int64_t nacc = 0;
+  for (int k = 0; k < a.T; ++k) {
+    const int64_t gstep = a.step0 + k;
+    double dl[PBX_MAX_PARAMS], thp[PBX_MAX_PARAMS];
+    nr_draw_delta(a, m, gstep, k, c, dl);
+    for (int j = 0; j < m.P; ++j) {
+      double v = m.log_ufun[j] ? exp(log(th[j]) + dl[j]) : th[j] + dl[j];
+      if (m.bound) {                                   // variable.py:700-727
+        const double lo = m.lims[j][0], hi = m.lims[j][1];
+        const bool olo = m.open_end[j][0] != 0, ohi = m.open_end[j][1] != 0;
+        if (!olo && !ohi) v = fmax(lo, fmin(hi, v));
+        else if (olo && ohi) v = (v > lo && v < hi) ? v : th[j];
+        else if (olo) v = (v < lo) ? th[j] : fmin(hi, v);
+        else v = (v > hi) ? th[j] : fmax(lo, v);
+      }
+      thp[j] = v;
+    }
+    const double lpp = nr_logjoint(a, m, thp, ss_rss(st, m, thp));
+    const double t = nr_threshold(a, gstep, k, c);
+    bool acc;
+    double s = nan("");
+    if (gstep == 0) {
+      acc = true;
+    } else if (m.accept_mode == PBX_ACCEPT_REFERENCE) {
+      const double num = pbx_exp_logp(lpp * m.coef), den = pbx_exp_logp(lp * m.coef);
+      s = fmin(1.0, num / fmax(PBX_TINY, den));
+      acc = (s >= t);
+    } else {
+      const double d = m.coef * (lpp - lp);
+      acc = (d >= log(t));
+      if (a.out_score) s = fmin(1.0, exp(fmin(d, 0.0)));
+    }
+    if (acc) {
+      for (int j = 0; j < m.P; ++j) th[j] = thp[j];
+      lp = lpp;
+      ++nacc;
+    }
+    for (int j = 0; j < m.P; ++j) {
+      ssum[j] += th[j];
+      ssq[j] = fma(th[j], th[j], ssq[j]);
+    }
+    if (a.out_accept) a.out_accept[(int64_t)k * C + c] = acc ? 1 : 0;
+    if (a.out_score) a.out_score[(int64_t)k * C + c] = s;
+    if (a.out_xprop)
+      for (int j = 0; j < m.P; ++j) a.out_xprop[((int64_t)k * m.P + j) * C + c] = thp[j];
+    if (a.out_pprop) a.out_pprop[(int64_t)k * C + c] = lpp;
+    if ((k + 1) % a.thin == 0) {
+      const int64_t r = (k + 1) / a.thin - 1;
+      if (a.out_x)
+        for (int j = 0; j < m.P; ++j) a.out_x[(r * m.P + j) * C + c] = th[j];
+      if (a.out_prob) a.out_prob[r * C + c] = lp;
+    }
+  }
+  for (int j = 0; j < m.P; ++j) {
+    a.state[(int64_t)j * C + c] = th[j];
+    if (a.stat_sum) a.stat_sum[(int64_t)j * C + c] += ssum[j];
+    if (a.stat_sumsq) a.stat_sumsq[(int64_t)j * C + c] += ssq[j];
+  }
+  a.state_lp[c] = lp;
+  if (a.accept_count) a.accept_count[c] += nacc;
+}
+
+// computes the statistics into the context workspace; *out points at them
+int pbx_ss_compute(pbx_ctx* ctx, const double* x, const double* y, int64_t n, NrStats** out) {
+  const int64_t chunk = 8192;
+  int64_t grid = std::min<int64_t>((n + chunk - 1) / chunk, SS_MAXCTA);
+  if (grid < 1) grid = 1;
+  int64_t per_cta = ((n + grid - 1) / grid + chunk - 1) / chunk * chunk;
+  grid = (n + per_cta - 1) / per_cta;
+  const size_t part_bytes = ((size_t)SS_MAXCTA * 4 * 8 + 255) / 256 * 256;
+  int rc = pbx_ws_reserve(ctx, part_bytes + 256);
+  if (rc) return rc;
+  double* part = (double*)ctx->ws;
+  NrStats* st = (NrStats*)((char*)ctx->ws + part_bytes);
+  const int has_x = x != nullptr;
+  ss_partial_kernel<1><<<(int)grid, SS_THREADS, 0, ctx->stream>>>(x, y, n, per_cta, st, part);
+  PBX_LAUNCH_CHECK(ctx);
+  ss_final_kernel<1><<<1, 32, 0, ctx->stream>>>(part, (int)grid, n, has_x, st);
+  PBX_LAUNCH_CHECK(ctx);
+  ss_partial_kernel<2><<<(int)grid, SS_THREADS, 0, ctx->stream>>>(x, y, n, per_cta, st, part);
+  PBX_LAUNCH_CHECK(ctx);
+  ss_final_kernel<2><<<1, 32, 0, ctx->stream>>>(part, (int)grid, n, has_x, st);
+  PBX_LAUNCH_CHECK(ctx);
+  ss_partial_kernel<3><<<(int)grid, SS_THREADS, 0, ctx->stream>>>(x, y, n, per_cta, st, part);
+  PBX_LAUNCH_CHECK(ctx);
+  ss_final_kernel<3><<<1, 32, 0, ctx->stream>>>(part, (int)grid, n, has_x, st);
+  PBX_LAUNCH_CHECK(ctx);
+  *out = st;
+  return PBX_OK;
+}
+
 // workspace: partial [n_slices][C] | counters [n_groups] | prop [P][C]
 static int nr_workspace(pbx_ctx* ctx, const NrPlan& pl, int C, int P, double** partial,
                         unsigned int** counters, double** prop) {
@@ -664,6 +885,29 @@ extern "C" int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p) 
   PBX_CUDA(cudaSetDevice(ctx->device));
   NrModel m;
   nr_fill_model(p, m);
+  if (p->variant == 3) {                       // sufficient statistics: the walk in one launch
+    NrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = p->n_chains; a.N = p->n_obs;
+    a.state = p->state; a.state_lp = p->state_lp;
+    a.step0 = p->step0; a.T = p->n_steps; a.thin = p->thin;
+    a.chain0 = p->chain0; a.seed = p->seed;
+    a.inj_delta = p->inj_delta; a.inj_thresh = p->inj_thresh;
+    a.out_x = p->out_x; a.out_prob = p->out_prob;
+    a.out_accept = p->out_accept; a.out_score = p->out_score;
+    a.out_xprop = p->out_xprop; a.out_pprop = p->out_pprop;
+    a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
+    PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (a.T > 0) {
+      NrStats* st = nullptr;
+      rc = pbx_ss_compute(ctx, m.has_slope ? p->x_obs : nullptr, p->y_obs, p->n_obs, &st);
+      if (rc) return rc;
+      ss_walk_kernel<<<(a.C + 127) / 128, 128, 0, ctx->stream>>>(a, m, st);
+      PBX_LAUNCH_CHECK(ctx);
+    }
+    PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    return PBX_OK;
+  }
   const NrPlan pl = nr_plan(ctx, p);
   NrArgs a;
   memset(&a, 0, sizeof(a));
@@ -706,6 +950,21 @@ extern "C" int pbx_normreg_logjoint(pbx_ctx* ctx, const pbx_mh_normreg_params* p
   PBX_CUDA(cudaSetDevice(ctx->device));
   NrModel m;
   nr_fill_model(p, m);
+  if (p->variant == 3) {
+    NrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = p->n_chains; a.N = p->n_obs;
+    a.theta_in = theta;
+    a.eval_out = out;
+    PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    NrStats* st = nullptr;
+    rc = pbx_ss_compute(ctx, m.has_slope ? p->x_obs : nullptr, p->y_obs, p->n_obs, &st);
+    if (rc) return rc;
+    ss_eval_kernel<<<(a.C + 255) / 256, 256, 0, ctx->stream>>>(a, m, st);
+    PBX_LAUNCH_CHECK(ctx);
+    PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    return PBX_OK;
+  }
   const NrPlan pl = nr_plan(ctx, p);
   NrArgs a;
   memset(&a, 0, sizeof(a));

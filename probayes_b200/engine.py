@@ -376,19 +376,23 @@ class Engine:
         return out
 
     # ------------------------------------------------------ K3/K4: grid (DGEI)
-    def grid_norm_logjoint(self, x_obs, mu, sigma, logprior_mu, logprior_sigma, out=None):
+    def grid_norm_logjoint(self, x_obs, mu, sigma, logprior_mu, logprior_sigma, out=None,
+                           suffstat=False):
         """log-joint [M, S] = priors + sum_i norm.logpdf(x_i; mu_m, sigma_s); all
-        arguments device fp64 vectors."""
+        arguments device fp64 vectors.  ``suffstat=True`` (opt-in) evaluates it from
+        centred sufficient statistics of the observations: O(M S) instead of O(N M S)."""
         M, S = int(mu.numel()), int(sigma.numel())
+        fn, what = (self.lib.pbx_grid_norm_logjoint_ss, "pbx_grid_norm_logjoint_ss") \
+            if suffstat else (self.lib.pbx_grid_norm_logjoint, "pbx_grid_norm_logjoint")
         if out is None:
             out = self.empty(M, S)
         row_cap = 65535
         for m0 in range(0, M, row_cap):                     # slab very tall grids
             m1 = min(M, m0 + row_cap)
-            _lib.check(self.lib.pbx_grid_norm_logjoint(
+            _lib.check(fn(
                 self.ctx, self._ptr(x_obs), int(x_obs.numel()), self._ptr(mu[m0:m1]), m1 - m0,
                 self._ptr(sigma), S, self._ptr(logprior_mu[m0:m1]), self._ptr(logprior_sigma),
-                self._ptr(out[m0:m1])), "pbx_grid_norm_logjoint")
+                self._ptr(out[m0:m1])), what)
         return out
 
     def grid_max(self, lj):

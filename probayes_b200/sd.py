@@ -145,7 +145,10 @@ class SD:
     # ---- discrete grid exact inference ---------------------------------------------------------
     def __call__(self, values=None, iid=False, joint=False, **kwds):
         """model({x: data, 'mu': {M}, 'sigma': {S}}, iid=True, joint=True) -> PD of the
-        log-joint over the (mu, sigma) grid (examples/dgei/dgei_norm1d_improved.py:36-37)."""
+        log-joint over the (mu, sigma) grid (examples/dgei/dgei_norm1d_improved.py:36-37).
+        ``suffstat=True`` (new, opt-in): evaluate it from centred sufficient statistics of
+        the observations -- O(M S) instead of O(N M S), same values to fp64 round-off."""
+        suffstat = bool(kwds.pop('suffstat', False))
         from .engine import get_engine
         assert isinstance(values, dict), "values must be a dictionary keyed by variable"
         values = self.parse_values(values)
@@ -176,7 +179,7 @@ class SD:
         eng = get_engine()
         lj = eng.grid_norm_logjoint(eng.to_device(data), eng.to_device(grids[kmu]),
                                     eng.to_device(grids[ksg]), eng.to_device(lpm),
-                                    eng.to_device(lps))
+                                    eng.to_device(lps), suffstat=suffstat)
         order = [k for k in self._roots.keylist if k in (kmu, ksg)]
         vals = collections.OrderedDict()
         dims = collections.OrderedDict()

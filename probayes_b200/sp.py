@@ -20,6 +20,10 @@ New keyword arguments of ``sampler`` (everything else keeps its meaning):
                 buffers and reuses on later walks / other samplers of the same shape;
                 the returned arrays are then views into them
   inj_unif=     injected prior draws [T, P] for ordinary Monte Carlo random sampling
+  suffstat=True (opt-in, normal-likelihood targets) evaluate the likelihood from centred
+                sufficient statistics of the observations: one reduction over the data,
+                then O(1) per evaluation and the whole walk in one launch; same values as
+                the term-by-term kernels to fp64 round-off
 
 Ordinary Monte Carlo random sampling (sp.py:229-234, the no-proposal branch of
 ``SP.next``; examples/omc/omc_rs_sp_norm1d.py): with neither transition nor delta set,
@@ -179,6 +183,8 @@ class SP(SD):
                     host_buffers=kwds.pop('host_buffers', None),
                     variant=kwds.pop('variant', 0),
                     inj_unif=kwds.pop('inj_unif', None), omc=omc)
+        if kwds.pop('suffstat', False):
+            opts['variant'] = 3
         assert not kwds, "Unknown sampler keywords: {}".format(list(kwds))
         s = Sampler(self, init, obs, stop, opts)
         self._samplers.append(s)
@@ -261,7 +267,8 @@ class SP(SD):
         if seed is None:
             seed = int(np.random.randint(0, 2 ** 31 - 1))
         theta = eng.box_sample(lims, lg, T, seed=seed, sample0=sampler.counter, inj_unif=inj)
-        logp = eng.normreg_logjoint(theta, y, x, lims, ex, lg)
+        logp = eng.normreg_logjoint(theta, y, x, lims, ex, lg,
+                                    variant=3 if opts['variant'] == 3 else 0)
         return dict(omc=True, keys=keys, T=T, spec=spec, theta=theta, logp=logp,
                     n_obs=int(y.numel()), pscale=self._pscale, chains=None)
 
