@@ -525,7 +525,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       if ((b + 1) * G <= a.T) {
         // full batch: WS_PUNROLL independent steps in flight per thread (ILP), since a
         // producer warp is otherwise a single chain of dependent instructions
-#pragma unroll kWsPUnroll
+        // (one step at a time for D > 4: two sets of D draws + D deltas do not fit 96 registers)
+        constexpr int kUnroll = (D <= 4) ? kWsPUnroll : 1;
+#pragma unroll kUnroll
         for (int g = 0; g < G; ++g) produce(g);
       } else {
 #pragma unroll 1
@@ -557,31 +559,39 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     double* slot = ring + (size_t)s * SD + lane;
     pbx_mbar_wait(&in_full[s], (uint32_t)(b / WS_NSLOT) & 1);
     const int ng = min(G, a.T - b * G);
-    double dl[G][D], th[G];
+    // D <= 4: the whole batch is loaded into registers up front; beyond that G * (D + 1)
+    // doubles no longer fit next to the state and each step loads its own inputs
+    constexpr bool kPreload = D <= 4;
+    constexpr int GP = kPreload ? G : 1;
+    double dl[GP][D], th[GP];
+    if (kPreload) {
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
+      for (int g = 0; g < G; ++g) {
 #pragma unroll
-      for (int j = 0; j < D; ++j) dl[g][j] = slot[(g * (D + 1) + j) * 32];
-      th[g] = slot[(g * (D + 1) + D) * 32];
+        for (int j = 0; j < D; ++j) dl[g][j] = slot[(g * (D + 1) + j) * 32];
+        th[g] = slot[(g * (D + 1) + D) * 32];
+      }
     }
     // every lane only ever touches its own column of the slot, so the results can
     // overwrite the inputs as soon as they are in registers
     auto step = [&](int g) {
       double xp[D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) xp[j] = x[j] + dl[g][j];
+      for (int j = 0; j < D; ++j)
+        xp[j] = x[j] + (kPreload ? dl[kPreload ? g : 0][j] : slot[(g * (D + 1) + j) * 32]);
+      const double thg = kPreload ? th[kPreload ? g : 0] : slot[(g * (D + 1) + D) * 32];
       const double maha = mvn_maha<D, kZeroMean>(xp, m);
       bool acc;
       if (kRefAccept) {
         const double lpp = -0.5 * (m.norm_c + maha);
         const double linp = a.log_pscale ? pbx_exp_logp(lpp) : exp(lpp);
-        acc = fmin(1.0, linp / fmax(PBX_TINY, lin)) >= th[g];
+        acc = fmin(1.0, linp / fmax(PBX_TINY, lin)) >= thg;
         if (acc) {
           lp = lpp;
           lin = linp;
         }
       } else {
-        acc = maha <= mcur + th[g];
+        acc = maha <= mcur + thg;
       }
       if (acc) {
 #pragma unroll
@@ -637,7 +647,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       slot[((g + 1) * (D + 1) + D) * 32] = mcur;
     };
     if (ng == G) {                       // full batch: straight-line code, no predicates
-      if (!kRefAccept && (G % 2 == 0)) {
+      if (!kRefAccept && (G % 2 == 0) && D <= 4) {   // speculation needs 3 states in registers
 #pragma unroll
         for (int g = 0; g < G; g += 2) pair(g);
       } else {
