@@ -11,7 +11,7 @@
 //                      Philox4x32-10 + Box-Muller in-thread or INJECTED streams (the
 //                      bit-parity path), per-step accept/score outputs.
 //  * mh_mvn_ws_kernel  warp-specialised native-RNG fast path.  A CTA owns 32 chains:
-//                      15 producer warps draw Philox blocks and turn them into
+//                      12 (D <= 3) or 9 producer warps draw Philox blocks and turn them into
 //                      proposal deltas and log-thresholds for batches of steps (that
 //                      work does not depend on the chain state, so it parallelises
 //                      over steps), hand them through a shared-memory ring guarded
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 //                accept, select, running sums) -- ~30 instructions per step, no
 //                global traffic.  It overwrites the ring slot it just consumed
 //                with the retained states (x, logp) of that batch.
-//   15 producer/writer warps (every warp with warp % 4 != 0; warps 4, 8, 12, 16 exit
+//   12 or 9 producer/writer warps (every warp with warp % 4 != 0; warps 4, 8, 12 exit
 //                at once so that the consumer has SM sub-partition 0 -- scheduler and
 //                FP64 pipe -- to itself): each owns TWO ring slots.  Per use: drain the
 //                consumer's results of the slot's previous batch (thinning, logp and
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 // -> owning producer).
 // ---------------------------------------------------------------------------
 #ifndef WS_NPROD
-#define WS_NPROD 15                      // producer warps: all warps with (warp % 4) != 0
+#define WS_NPROD 12                      // producer warps: all warps with (warp % 4) != 0
 #endif
 #define WS_NSLOT (2 * WS_NPROD)             // two ring slots per producer warp
 #ifndef WS_PUNROLL
@@ -397,31 +397,49 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 #endif
 constexpr int kWsPUnroll = WS_PUNROLL;
 #ifndef WS_THREADS
-#define WS_THREADS 640                   // 20 warps; warps 4, 8, 12, 16 exit at once so that
+#define WS_THREADS 512                   // 16 warps; warps 4, 8, 12 exit at once so that
 #endif
                                          // the consumer (warp 0) has its SM sub-partition
                                          // (scheduler + FP64 pipe) to itself
+#ifndef WS_BIGCTA_MAXD
+#define WS_BIGCTA_MAXD 3                 // largest D that runs the 512-thread CTA
+#endif
+#ifndef WS_SMALL_NPROD
+#define WS_SMALL_NPROD 9                 // producers of the small CTA (+ consumer + idle warps)
+#endif
 template <int D> struct WsCfg {
   // steps per ring slot: G*(D+1) doubles per lane per slot, <= 6 KB per slot
   static constexpr int G = (D <= 2) ? 8 : (D == 3 ? 6 : (D <= 5 ? 4 : (D <= 7 ? 3 : 2)));
   static constexpr int SLOT_DOUBLES = G * (D + 1) * 32;
-  static constexpr size_t SMEM = (size_t)WS_NSLOT * SLOT_DOUBLES * sizeof(double);
+  // CTA shape (measured, 4096 chains x 10^4 steps): 12 producer warps in a 512-thread CTA
+  // (128 registers per thread) for D <= 3 -- 0.546 ms at D = 2 against 0.559 with 15
+  // producers / 96 registers and 0.598 with 9; the producer count must be a multiple of 3
+  // so that the three producer sub-partitions carry equal load (11 or 13 are 7-14 % slower).
+  // From D = 4 on the consumer's state + D x D quadratic form dominate and want registers:
+  // 9 producers / 384 threads (up to 168 registers; D = 6: 1.70 -> 1.39 ms, D = 8: 6.5 ->
+  // 3.9 ms against the 15-producer shape).
+  static constexpr int NPROD = (D <= WS_BIGCTA_MAXD) ? WS_NPROD : WS_SMALL_NPROD;
+  static constexpr int NSLOT = 2 * NPROD;
+  static constexpr int THREADS =
+      (D <= WS_BIGCTA_MAXD) ? WS_THREADS : 32 * (WS_SMALL_NPROD + 1 + (WS_SMALL_NPROD - 1) / 3);
+  static constexpr size_t SMEM = (size_t)NSLOT * SLOT_DOUBLES * sizeof(double);
 };
 
 // kFast: normal proposal without Cholesky colouring -> branch-free producer body
 // kZeroMean: see mvn_maha
 template <int D, bool kRefAccept, bool kFast, bool kZeroMean = false>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WsCfg<D>::THREADS, 1)
     mh_mvn_ws_kernel(const MhMvnArgs a, const __grid_constant__ MhMvnConst m) {
   constexpr int G = WsCfg<D>::G;
   constexpr int SD = WsCfg<D>::SLOT_DOUBLES;
-  extern __shared__ __align__(16) double ring[];          // [WS_NSLOT][G][D+1][32]
-  __shared__ __align__(8) unsigned long long in_full[WS_NSLOT], out_full[WS_NSLOT];
+  constexpr int NP = WsCfg<D>::NPROD, NS = WsCfg<D>::NSLOT;
+  extern __shared__ __align__(16) double ring[];          // [NS][G][D+1][32]
+  __shared__ __align__(8) unsigned long long in_full[NS], out_full[NS];
   __shared__ __align__(16) PbxTables s_tb;                // 6.5 KB of math tables
   {
     const double* src = reinterpret_cast<const double*>(&g_tables);
     double* dst = reinterpret_cast<double*>(&s_tb);
-    for (int i = threadIdx.x; i < (int)(sizeof(PbxTables) / sizeof(double)); i += WS_THREADS)
+    for (int i = threadIdx.x; i < (int)(sizeof(PbxTables) / sizeof(double)); i += WsCfg<D>::THREADS)
       dst[i] = src[i];
   }
   const PbxTables* tb = &s_tb;
@@ -434,7 +452,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   const int nb = (a.T + G - 1) / G;                       // batches of G steps
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < WS_NSLOT; ++i) {
+    for (int i = 0; i < NS; ++i) {
       pbx_mbar_init(&in_full[i], 1);
       pbx_mbar_init(&out_full[i], 1);
     }
@@ -442,16 +460,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   __syncthreads();
 
   if (warp >= 1) {
-    // ================= producer / writer: owns ring slots p and p + WS_NPROD =====
+    // ================= producer / writer: owns ring slots p and p + NP ===========
     if ((warp & 3) == 0) return;                          // keep sub-partition 0 for the consumer
     const int p = warp - 1 - (warp >> 2);
-    const int n_mine = (nb > p) ? (nb - p + WS_NPROD - 1) / WS_NPROD : 0;
+    const int n_mine = (nb > p) ? (nb - p + NP - 1) / NP : 0;
     for (int n = 0; n < n_mine + 2; ++n) {
-      const int si = p + WS_NPROD * (n & 1);
+      const int si = p + NP * (n & 1);
       double* slot = ring + (size_t)si * SD + lane;
       if (n >= 2 && n - 2 < n_mine) {
         // ---- drain the results of my batch n-2 (it used this slot) --------------
-        const int bd = p + WS_NPROD * (n - 2);
+        const int bd = p + NP * (n - 2);
         pbx_mbar_wait(&out_full[si], (uint32_t)((n - 2) >> 1) & 1);
         const int k0 = bd * G;
         const int ng = min(G, a.T - k0);
@@ -511,7 +529,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
         }
       }
       if (n >= n_mine) continue;
-      const int b = p + WS_NPROD * n;
+      const int b = p + NP * n;
       auto produce = [&](int g) {
         const int64_t gstep = a.step0 + (int64_t)b * G + g;
         double dl[D], dv[D], t;
@@ -555,9 +573,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   int64_t nacc = 0;
 
   for (int b = 0; b < nb; ++b) {
-    const int s = b % WS_NSLOT;
+    const int s = b % NS;
     double* slot = ring + (size_t)s * SD + lane;
-    pbx_mbar_wait(&in_full[s], (uint32_t)(b / WS_NSLOT) & 1);
+    pbx_mbar_wait(&in_full[s], (uint32_t)(b / NS) & 1);
     const int ng = min(G, a.T - b * G);
     // D <= 4: the whole batch is loaded into registers up front; beyond that G * (D + 1)
     // doubles no longer fit next to the state and each step loads its own inputs
@@ -689,7 +707,7 @@ static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, 
   do {                                                                                        \
     PBX_CUDA(cudaFuncSetAttribute(mh_mvn_ws_kernel<D, R, F, Z>,                               \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
-    mh_mvn_ws_kernel<D, R, F, Z><<<grid, WS_THREADS, smem, ctx->stream>>>(a, m);              \
+    mh_mvn_ws_kernel<D, R, F, Z><<<grid, WsCfg<D>::THREADS, smem, ctx->stream>>>(a, m);     \
   } while (0)
     bool zero_mean = true;
     for (int j = 0; j < D; ++j) zero_mean = zero_mean && m.mean[j] == 0.0;

@@ -7,7 +7,7 @@ from probayes_b200.engine import get_engine
 eng = get_engine(0)
 C, T = 4096, 10000
 rng = np.random.default_rng(0)
-for D in (1, 2, 3, 4, 6, 8):
+for D in (1, 2, 3, 4, 5, 6, 7, 8):
     A = rng.standard_normal((D, D))
     cov = A @ A.T / D + np.eye(D)
     mean = np.zeros(D)

@@ -89,7 +89,8 @@ def test_philox_replay(accept):
     (2, 4096, 333, "log", False, "normal", False), (2, 100, 257, "reference", False, "normal", False),
     (2, 33, 100, "log", True, "uniform", False), (3, 65, 130, "log", True, "normal", True),
     (5, 40, 90, "reference", True, "normal", False), (8, 64, 64, "log", False, "normal", True),
-    (1, 50, 77, "log", False, "normal", False)])
+    (1, 50, 77, "log", False, "normal", False), (7, 48, 70, "log", False, "normal", False),
+    (6, 33, 50, "log", True, "normal", False), (8, 40, 61, "reference", True, "uniform", False)])
 def test_warp_specialised_equals_per_thread_kernel(D, C, T, accept, logp, prop, chol):
     """The warp-specialised fast path is bit-identical to the per-thread kernel
     (same Philox stream, same arithmetic), for every D and both accept rules."""
