@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
 #endif
 #define WS_NSLOT (2 * WS_NPROD)             // two ring slots per producer warp
 #ifndef WS_PUNROLL
-#define WS_PUNROLL 2
+#define WS_PUNROLL 4
 #endif
 constexpr int kWsPUnroll = WS_PUNROLL;
 #ifndef WS_THREADS
@@ -543,8 +543,9 @@ __global__ void __launch_bounds__(WsCfg<D>::THREADS, 1)
       if ((b + 1) * G <= a.T) {
         // full batch: WS_PUNROLL independent steps in flight per thread (ILP), since a
         // producer warp is otherwise a single chain of dependent instructions
-        // (one step at a time for D > 4: two sets of D draws + D deltas do not fit 96 registers)
-        constexpr int kUnroll = (D <= 4) ? kWsPUnroll : 1;
+        // (D <= 3: four independent steps in flight in the 128-register shape -- 0.547 ->
+        // 0.532 ms at D = 2; D = 4: two; beyond that one, the draws of a step fill the file)
+        constexpr int kUnroll = (D <= 3) ? (kRefAccept ? 2 : kWsPUnroll) : (D == 4 ? 2 : 1);
 #pragma unroll kUnroll
         for (int g = 0; g < G; ++g) produce(g);
       } else {
