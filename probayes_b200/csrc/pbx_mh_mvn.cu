@@ -401,6 +401,9 @@ constexpr int kWsPUnroll = WS_PUNROLL;
 #endif
                                          // the consumer (warp 0) has its SM sub-partition
                                          // (scheduler + FP64 pipe) to itself
+#ifndef WS_G2
+#define WS_G2 8                          // steps per ring slot for D <= 2
+#endif
 #ifndef WS_BIGCTA_MAXD
 #define WS_BIGCTA_MAXD 3                 // largest D that runs the 512-thread CTA
 #endif
@@ -409,7 +412,7 @@ constexpr int kWsPUnroll = WS_PUNROLL;
 #endif
 template <int D> struct WsCfg {
   // steps per ring slot: G*(D+1) doubles per lane per slot, <= 6 KB per slot
-  static constexpr int G = (D <= 2) ? 8 : (D == 3 ? 6 : (D <= 5 ? 4 : (D <= 7 ? 3 : 2)));
+  static constexpr int G = (D <= 2) ? WS_G2 : (D == 3 ? 6 : (D <= 5 ? 4 : (D <= 7 ? 3 : 2)));
   static constexpr int SLOT_DOUBLES = G * (D + 1) * 32;
   // CTA shape (measured, 4096 chains x 10^4 steps): 12 producer warps in a 512-thread CTA
   // (128 registers per thread) for D <= 3 -- 0.546 ms at D = 2 against 0.559 with 15
