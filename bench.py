@@ -36,10 +36,10 @@ INIT = np.array([0.0, 1.0])
 METRIC = "mh_chain_steps_per_sec"
 UNIT = "chain-steps/s"
 # DRAM traffic of one K1 launch on the default workload (4096 chains x 10^4 steps, D=2, thin=1):
-# dram__bytes_read.sum (294 KB) + dram__bytes_write.sum (924.0 MB) from the ncu --set full capture in
-# profiles/r1g_ncu_full_k1.csv.  Algorithmic bytes are 983.0 MB; the difference is the tail of
+# dram__bytes_read.sum (290 KB) + dram__bytes_write.sum (925.7 MB) from the ncu --set full capture in
+# profiles/r1i_ncu_full_k1.csv.  Algorithmic bytes are 983.0 MB; the difference is the tail of
 # the output still resident in the 126 MB L2 when the kernel ends.  No re-reads.
-NCU_K1_DRAM_BYTES = 294400 + 923982848
+NCU_K1_DRAM_BYTES = 289536 + 925711104
 
 
 def parse():
@@ -604,7 +604,7 @@ def run_ours(args):
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": NCU_K1_DRAM_BYTES if (C, T, thin, args.variant) == (4096, 10000, 1, 0) else None,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                                           "profiles/r1g_ncu_full_k1.csv",
+                                           "profiles/r1i_ncu_full_k1.csv",
                          "peak_source": which, "kernel": "mh_mvn_kernel<2>" if args.variant == 1 else "mh_mvn_ws_kernel<2>",
                          "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": out_bytes,
