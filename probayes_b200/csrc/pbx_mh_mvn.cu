@@ -32,7 +32,7 @@
 // are the RNG's uniforms, so no special-case handling is needed.
 // ---------------------------------------------------------------------------
 struct PbxTables {
-  double2 lg[128];   // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/128
+  double2 lg[1024];  // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/1024
   double2 sc[256];   // (cos, sin) of 2 pi (k + 0.5)/256
   double ex[64];     // 2^(j/64)
 };
@@ -44,18 +44,17 @@ __constant__ double kExpP[4] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
 // -2 log(x) for positive normal x (what both Box-Muller and the accept threshold need):
 // the same reduction with the factor -2 folded into the table value, the polynomial
 // and the exponent term -- one multiply less than scaling a plain log afterwards
-__constant__ double kN2LogP[5] = {1.0, -2.0 / 3.0, 0.5, -0.4, 1.0 / 3.0};
+__constant__ double kN2LogP[3] = {1.0, -2.0 / 3.0, 0.5};
 __device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const int e = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // [1, 2)
-  const double2 t = tb->lg[(hi >> 13) & 127];
-  const double r = fma(m, t.x, -1.0);                                      // |r| < 2^-8
-  double p = fma(r, kN2LogP[4], kN2LogP[3]);
-  p = fma(r, p, kN2LogP[2]);
-  p = fma(r, p, kN2LogP[1]);
+  const double2 t = tb->lg[(hi >> 10) & 1023];
+  const double r = fma(m, t.x, -1.0);                                      // |r| < 2^-11
+  // -2 log1p(r) = -2r + r^2 (1 - 2r/3 + r^2/2 - ...); the next term is < 0.4 * 2^-55
+  double p = fma(r, kN2LogP[2], kN2LogP[1]);
   p = fma(r, p, kN2LogP[0]);
-  p = fma(r * r, p, t.y);                        // -2 log c + r^2 (1 - 2r/3 + ...)
+  p = fma(r * r, p, t.y);                        // -2 log c + r^2 (1 - 2r/3 + r^2/2)
   p = fma(r, -2.0, p);                           // ... - 2r  = -2 log(c (1 + r))
   const double ed = __hiloint2double(0x43300000, e ^ (int)0x80000000) - 4503601774854144.0;
   return fma(ed, -1.386294361119890618835, p);   // -2 ln 2
@@ -123,8 +122,8 @@ static int init_tables(pbx_ctx* ctx) {
   static bool done[64] = {false};
   if (ctx->device < 64 && done[ctx->device]) return PBX_OK;
   static PbxTables h;
-  for (int j = 0; j < 128; ++j) {
-    const long double c = 1.0L + (j + 0.5L) / 128.0L;
+  for (int j = 0; j < 1024; ++j) {
+    const long double c = 1.0L + (j + 0.5L) / 1024.0L;
     h.lg[j].x = (double)(1.0L / c);
     // log c_j must pair with the ROUNDED reciprocal: log(1/inv) keeps r = m*inv - 1 exact
     h.lg[j].y = (double)(2.0L * logl((long double)h.lg[j].x));        // = -2 log c_j
@@ -216,7 +215,9 @@ __device__ __forceinline__ void draw_step(uint64_t seed, uint64_t gstep, uint32_
     double d0, d1;
     if (prop_kind == PBX_PROP_NORMAL) {
       // Box-Muller: r = sqrt(-2 log u52), angle = 2 pi u32
-      const double rad = fast_sqrt(fast_neg2log(pbx_u52(w.x, w.y), tb));
+      // (the table log is accurate to ~1e-16 ABSOLUTE: for u within a few ulp of 1 it may
+      // return 0 or -1e-16, which the rsqrt-based root would turn into NaN -- clamp)
+      const double rad = fast_sqrt(fmax(fast_neg2log(pbx_u52(w.x, w.y), tb), PBX_TINY));
       double sn, cs;
       fast_sincos2pi(w.z, tb, sn, cs);
       d0 = (rad * cs) * m.scale[2 * s];
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(WsCfg<D>::THREADS, 1)
   constexpr int NP = WsCfg<D>::NPROD, NS = WsCfg<D>::NSLOT;
   extern __shared__ __align__(16) double ring[];          // [NS][G][D+1][32]
   __shared__ __align__(8) unsigned long long in_full[NS], out_full[NS];
-  __shared__ __align__(16) PbxTables s_tb;                // 6.5 KB of math tables
+  __shared__ __align__(16) PbxTables s_tb;                // 20.5 KB of math tables
   {
     const double* src = reinterpret_cast<const double*>(&g_tables);
     double* dst = reinterpret_cast<double*>(&s_tb);
@@ -920,7 +921,7 @@ __global__ void fastmath_selftest_kernel(const double* __restrict__ u, const uin
   double sn, cs;
   fast_sincos2pi(w[i], &g_tables, sn, cs);
   out[i] = l;
-  out[n + i] = fast_sqrt(l);
+  out[n + i] = fast_sqrt(fmax(l, PBX_TINY));
   out[2 * n + i] = sn;
   out[3 * n + i] = cs;
   out[4 * n + i] = fast_exp(-700.0 * u[i], &g_tables);
