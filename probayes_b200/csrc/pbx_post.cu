@@ -31,7 +31,9 @@
 // the hardware match.any instruction is several times slower than that.
 // ===========================================================================
 #define RS_THREADS 256
+#ifndef RS_ITEMS
 #define RS_ITEMS 16
+#endif
 #define RS_TILE (RS_THREADS * RS_ITEMS)
 #define RS_WARPS (RS_THREADS / 32)
 #define RS_PASSES 8
