@@ -33,7 +33,7 @@
 // ---------------------------------------------------------------------------
 struct PbxTables {
   double2 lg[1024];  // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/1024
-  double2 sc[256];   // (cos, sin) of 2 pi (k + 0.5)/256
+  double2 sc[1024];  // (cos, sin) of 2 pi (k + 0.5)/1024
   double ex[64];     // 2^(j/64)
 };
 static __device__ PbxTables g_tables;
@@ -63,19 +63,16 @@ __device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
 // (sin, cos)(2 pi u), u = (w + 0.5) / 2^32
 __device__ __forceinline__ void fast_sincos2pi(uint32_t w, const PbxTables* tb, double& s,
                                                double& c) {
-  const double2 t = tb->sc[w >> 24];
-  // rho = 2 pi ((w & 0xffffff) + 0.5 - 2^23) / 2^32,  |rho| < pi/256.  The 24 bits go
+  const double2 t = tb->sc[w >> 22];
+  // rho = 2 pi ((w & 0x3fffff) + 0.5 - 2^21) / 2^32,  |rho| < pi/1024.  The 22 bits go
   // into the mantissa of 2^51 (unit in the last place 1/2) doubled, so that 2^51 + k is
-  // exact and one subtraction of 2^51 + 2^23 - 0.5 (representable) centres it
-  const double v = __hiloint2double(0x43200000, (int)((w & 0x00FFFFFFu) << 1));
-  const double rho = (v - 2251799822073855.5) * 1.4629180792671596e-9;    // 2 pi / 2^32
+  // exact and one subtraction of 2^51 + 2^21 - 0.5 (representable) centres it
+  const double v = __hiloint2double(0x43200000, (int)((w & 0x003FFFFFu) << 1));
+  const double rho = (v - 2251799815782399.5) * 1.4629180792671596e-9;    // 2 pi / 2^32
   const double q = rho * rho;
-  double sp = fma(q, kSinP[2], kSinP[1]);
-  sp = fma(q, sp, kSinP[0]);
-  const double sr = fma(rho * q, sp, rho);                                 // sin(rho)
-  double cp = fma(q, kCosP[2], kCosP[1]);
-  cp = fma(q, cp, kCosP[0]);
-  const double cr = fma(q, cp, 1.0);                                       // cos(rho)
+  // |rho| < 3.1e-3: the dropped terms are rho^7/5040 < 1e-21 and rho^6/720 < 2e-18
+  const double sr = fma(rho * q, fma(q, kSinP[1], kSinP[0]), rho);         // sin(rho)
+  const double cr = fma(q, fma(q, kCosP[1], kCosP[0]), 1.0);               // cos(rho)
   c = fma(t.x, cr, -(t.y * sr));
   s = fma(t.y, cr, t.x * sr);
 }
@@ -129,8 +126,8 @@ static int init_tables(pbx_ctx* ctx) {
     h.lg[j].y = (double)(2.0L * logl((long double)h.lg[j].x));        // = -2 log c_j
   }
   const long double two_pi = 6.283185307179586476925286766559L;
-  for (int k = 0; k < 256; ++k) {
-    const long double th = two_pi * (k + 0.5L) / 256.0L;
+  for (int k = 0; k < 1024; ++k) {
+    const long double th = two_pi * (k + 0.5L) / 1024.0L;
     h.sc[k].x = (double)cosl(th);
     h.sc[k].y = (double)sinl(th);
   }
@@ -439,7 +436,7 @@ __global__ void __launch_bounds__(WsCfg<D>::THREADS, 1)
   constexpr int NP = WsCfg<D>::NPROD, NS = WsCfg<D>::NSLOT;
   extern __shared__ __align__(16) double ring[];          // [NS][G][D+1][32]
   __shared__ __align__(8) unsigned long long in_full[NS], out_full[NS];
-  __shared__ __align__(16) PbxTables s_tb;                // 20.5 KB of math tables
+  __shared__ __align__(16) PbxTables s_tb;                // 32.5 KB of math tables
   {
     const double* src = reinterpret_cast<const double*>(&g_tables);
     double* dst = reinterpret_cast<double*>(&s_tb);
