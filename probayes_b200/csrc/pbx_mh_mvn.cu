@@ -405,6 +405,9 @@ constexpr int kWsPUnroll = WS_PUNROLL;
 #ifndef WS_BIGCTA_MAXD
 #define WS_BIGCTA_MAXD 3                 // largest D that runs the 512-thread CTA
 #endif
+#ifndef WS_BIGCTA_MIND
+#define WS_BIGCTA_MIND 99                // smallest D (beyond MAXD) that runs it again
+#endif
 #ifndef WS_SMALL_NPROD
 #define WS_SMALL_NPROD 9                 // producers of the small CTA (+ consumer + idle warps)
 #endif
@@ -419,10 +422,11 @@ template <int D> struct WsCfg {
   // From D = 4 on the consumer's state + D x D quadratic form dominate and want registers:
   // 9 producers / 384 threads (up to 168 registers; D = 6: 1.70 -> 1.39 ms, D = 8: 6.5 ->
   // 3.9 ms against the 15-producer shape).
-  static constexpr int NPROD = (D <= WS_BIGCTA_MAXD) ? WS_NPROD : WS_SMALL_NPROD;
+  static constexpr bool BIG = (D <= WS_BIGCTA_MAXD) || (D >= WS_BIGCTA_MIND);
+  static constexpr int NPROD = BIG ? WS_NPROD : WS_SMALL_NPROD;
   static constexpr int NSLOT = 2 * NPROD;
   static constexpr int THREADS =
-      (D <= WS_BIGCTA_MAXD) ? WS_THREADS : 32 * (WS_SMALL_NPROD + 1 + (WS_SMALL_NPROD - 1) / 3);
+      BIG ? WS_THREADS : 32 * (WS_SMALL_NPROD + 1 + (WS_SMALL_NPROD - 1) / 3);
   static constexpr size_t SMEM = (size_t)NSLOT * SLOT_DOUBLES * sizeof(double);
 };
 
