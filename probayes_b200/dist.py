@@ -37,6 +37,13 @@ def world():
     return 0, 1
 
 
+def default_chain0(chains):
+    """Global id of this rank's first chain when every rank runs ``chains`` chains
+    through ``SP.sampler`` without an explicit ``chain0``: rank * chains (0 outside a
+    process group), so that sharded public-API runs never duplicate chains."""
+    return world()[0] * int(chains)
+
+
 def allreduce_chain_stats(stats, group=None):
     """stats [D, 4] = (sum_c mean, sum_c mean^2, sum_c var, C) per dimension, as
     produced by ``Engine.chain_stats`` on this rank's chains -> summed over ranks

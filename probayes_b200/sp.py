@@ -11,6 +11,10 @@ New keyword arguments of ``sampler`` (everything else keeps its meaning):
   chains=C      run C independent chains (default: one, reference-shaped results)
   thin=k        record every k-th step
   seed=s        Philox seed of the native RNG
+  chain0=g      global id of this process's first chain (the Philox stream is keyed on
+                chain0 + c).  Default: 0, or rank * chains when a torch.distributed
+                process group is initialised, so that the ranks of a sharded run draw
+                DIFFERENT chains and their concatenation equals the single-process run
   accept=       'log' (default for native RNG) | 'reference' (the reference's
                 linear-space ratio with its clamps; default for injected streams)
   inj_delta=, inj_thresh=   injected proposal / threshold streams ([T, D] or
@@ -177,6 +181,7 @@ class SP(SD):
         opts = dict(iid=kwds.pop('iid', False), joint=kwds.pop('joint', False),
                     chains=kwds.pop('chains', None), thin=int(kwds.pop('thin', 1)),
                     seed=kwds.pop('seed', None), accept=kwds.pop('accept', None),
+                    chain0=kwds.pop('chain0', None),
                     inj_delta=kwds.pop('inj_delta', None),
                     inj_thresh=kwds.pop('inj_thresh', None),
                     host_stream=kwds.pop('host_stream', False),
@@ -331,6 +336,11 @@ class SP(SD):
             seed = int(np.random.randint(0, 2 ** 31 - 1))     # the reference draws from np.random
         thin = opts['thin']
         step0 = sampler.counter
+        chain0 = opts['chain0']
+        if chain0 is None:                       # sharded run: rank r owns chains [r*C, (r+1)*C)
+            from .dist import default_chain0
+            chain0 = default_chain0(C)
+        chain0 = int(chain0)
         # ---- initial / resumed state [D, C] ------------------------------------------------
         if sampler.state is None or step0 == 0:
             init = np.empty((D, C))
@@ -365,7 +375,7 @@ class SP(SD):
             if tsteps != 1:
                 raise NotImplementedError("tsteps=1 (one coordinate per step) only")
             out = eng.gibbs_mvn(state, cc, T, thin=thin, seed=seed, step0=step0,
-                                log_pscale=spec['log_pscale'],
+                                chain0=chain0, log_pscale=spec['log_pscale'],
                                 inj_runif=inj_t)
             res.update(x=out['x'], prob=out['prob'], accept_count=None, accept=None, score=None)
             return self._finish(res, eng)
@@ -384,7 +394,7 @@ class SP(SD):
                                          prop_radius=prop['radius'], prop_chol=prop['chol'],
                                          state_lp=None if sampler.state_lp is None
                                          else sampler.state_lp.cpu().numpy(),
-                                         chain0=0, **self._host_bufs(opts, T // thin, D, C))
+                                         chain0=chain0, **self._host_bufs(opts, T // thin, D, C))
                 sampler.state = eng.to_device(h['state'])
                 sampler.state_lp = eng.to_device(h['state_lp'])
                 res.update(x=h['x'], prob=h['prob'], accept_count=h['accept_count'],
@@ -396,7 +406,7 @@ class SP(SD):
                              prop=prop['kind'], prop_scale=prop['scale'],
                              prop_radius=prop['radius'], prop_chol=prop['chol'],
                              inj_delta=inj_d, inj_thresh=inj_t, state_lp=sampler.state_lp,
-                             per_step=per_step, variant=opts['variant'])
+                             per_step=per_step, variant=opts['variant'], chain0=chain0)
         else:
             if not opts['iid']:
                 raise NotImplementedError("the normal-likelihood target needs iid=True")
@@ -425,7 +435,7 @@ class SP(SD):
                                  prop_bound=prop['bound'],
                                  inj_delta=inj_d, inj_thresh=inj_t,
                                  state_lp=sampler.state_lp, per_step=per_step,
-                                 variant=opts['variant'])
+                                 variant=opts['variant'], chain0=chain0)
             res['n_obs'] = int(y.numel())
         sampler.state_lp = out['state_lp']
         res.update(x=out['x'], prob=out['prob'], accept_count=out['accept_count'],

@@ -115,6 +115,19 @@ def test_sample_sharded_omc_expectation(world, port):
         assert np.allclose(e, want, rtol=1e-12)
 
 
+def _chain0_job(rank, world):
+    from probayes_b200 import dist as pd_
+    return pd_.default_chain0(4096)
+
+
+def test_default_chain0_is_rank_times_chains():
+    """SP.sampler's default chain offset under a process group (all ranks
+    used to draw the same chains)."""
+    from probayes_b200 import dist as pd_
+    assert pd_.default_chain0(4096) == 0                    # no process group
+    assert _spawn(_chain0_job, 2, 29617) == [0, 4096]
+
+
 def test_shard_range_covers_everything():
     from probayes_b200.dist import shard_range
     for n in (1, 7, 4096, 16384, 65537):

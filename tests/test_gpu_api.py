@@ -299,3 +299,35 @@ def test_batched_c2_through_api_and_host_stream():
     w2 = process.walk(s, stop=300)
     full = process.walk(process.sampler({'x': 0., 'y': 1.}, stop=600, chains=64, seed=9))
     assert np.array_equal(np.concatenate([w1.arrays['x'], w2.arrays['x']]), full.arrays['x'])
+
+
+def _prob4a_process():
+    x = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+    y = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+    process = pb.SP(x & y)
+    process.set_prob(scipy.stats.multivariate_normal, [0., 0.], [[2.0, 1.2], [1.2, 2.0]])
+    process.set_tran(lambda **kwds: 1.)
+    process.set_delta(scipy.stats.norm(0., 1.))
+    process.set_scores('hastings')
+    process.set_update('metropolis')
+    return process
+
+
+@pytest.mark.parametrize("host_stream", [False, True])
+def test_sampler_chain0_shards_the_public_api(host_stream):
+    """Two 'ranks' of a sharded run through SP.sampler(chain0=) draw different chains
+    and their concatenation is the single-process run (Philox is keyed on the global
+    chain id): the public-API counterpart of Engine.mh_mvn(chain0=)."""
+    engine()
+    process = _prob4a_process()
+
+    def run(chains, chain0):
+        smp = process.sampler({'x': 0., 'y': 1.}, stop=64, chains=chains, seed=77,
+                              chain0=chain0, host_stream=host_stream)
+        return process(process.walk(smp))
+
+    full, lo, hi = run(64, 0), run(32, 0), run(32, 32)
+    assert not np.array_equal(lo.v['x'], hi.v['x'])
+    assert np.array_equal(np.concatenate([lo.v['x'], hi.v['x']]), full.v['x'])
+    assert np.array_equal(np.concatenate([lo.v.prob, hi.v.prob]), full.v.prob)
+    assert lo.u.count(True) + hi.u.count(True) == full.u.count(True)
