@@ -1,21 +1,42 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the probayes hot path on B200.
+"""bench.py -- benchmarks of the probayes hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload c2] [--chains C] [--walk-steps T]
+                    [--workload c2|c3|c4|c5]
 
-Workload (BASELINE.json configs[1], "C2"): 4096 independent Metropolis-Hastings
-chains x 10^4 steps on the 2-D correlated normal of examples/mcmc/mcmc_prob4a.py,
-fp64, native Philox RNG, every step recorded (thin=1).  One bench "step" = one
-whole walk (C x T chain-steps).  Under torchrun each rank runs its own 4096
-chains (chains are independent: weak scaling, no data-path collective; the
-per-chain summaries are all-reduced once after the timed region).
+Workloads = the configurations of BASELINE.json:
+  c2 (default, the headline) 4096 independent Metropolis-Hastings chains per GPU x 10^4
+      steps on the 2-D correlated normal of examples/mcmc/mcmc_prob4a.py, fp64, native
+      Philox RNG, every step recorded.  One bench "step" = --walks-per-step whole walks
+      (so that a step is >= 50 ms of GPU work and the timed region >= 1 s).  Weak scaling:
+      every rank runs its own 4096 chains (global Philox chain ids rank*4096 + c).
+      metric: mh_chain_steps_per_sec.
+  c3  Bayesian linear regression, N = 10^6 observations, 3 parameters, 16384 MH chains
+      SHARDED over the ranks (strong scaling); one bench step = --mh-steps MH steps of
+      all chains (one log-likelihood evaluation of N terms per chain per MH step).
+      metric: loglik_evals_per_sec.
+  c4  discrete grid exact inference, 4096 x 4096 (mu, sigma) grid, N = 10^5 observations,
+      mu-row slabs SHARDED over the ranks; one bench step = log-joint of every cell +
+      normaliser (all-reduce max / sum) + posterior + both marginals (all-reduce of the
+      sigma marginal, all-gather of the mu slabs).  metric: loglik_evals_per_sec (one
+      evaluation = one grid cell = N terms).
+  c5  Gibbs sampling of a d = 64 multivariate normal through its conditional covariances,
+      65536 chains SHARDED over the ranks; one bench step = --sweeps sweeps of 64 coordinate
+      updates, the target density of every kept state on the FP64 tensor cores.
+      metric: mh_chain_steps_per_sec (one chain-step = one coordinate update, the
+      reference's step with tsteps=1).
 
 Prints ONE JSON line (rank 0):
-  value   chain-steps/s, device-resident (outputs written to HBM)
-  e2e     same metric through the host-buffer C-ABI call: H2D of the initial
-          state + D2H of every recorded sample and density inside the timed region
-  roofline / cpu_baseline / clocks / gpu_launches as the bench contract asks.
+  value     whole-job throughput, inputs resident in HBM, CUDA events, max over ranks
+  e2e       the same metric through the public API (pb.SP / pb.SD / dist.dgei_sharded) with
+            HOST inputs and results: H2D and D2H copies inside the timed region
+  roofline  the bound that applies to the dominant kernel (FP64 pipe for all four; the
+            HBM-streaming likelihood regime is reported under roofline_stream)
+  cpu_baseline   the oracle's C restatement on the box's host cores (kind "port") and, for
+            c2, the REAL reference's NumPy sampler from oracle/_ref timed in the same run
+  secondary_n    (default workload only) short c3 / c4 / c5 passes at the same N GPUs
+  secondary      (N = 1 only) kernel-level timings of every kernel family
+`--impl reference` times the CPU implementation of the same workload on the host cores.
 """
 import argparse
 import json
@@ -33,49 +54,39 @@ sys.path.insert(0, ROOT)
 COV = np.array([[2.0, 1.2], [1.2, 2.0]])
 MEAN = np.array([0.0, 0.0])
 INIT = np.array([0.0, 1.0])
-METRIC = "mh_chain_steps_per_sec"
-UNIT = "chain-steps/s"
-# DRAM traffic of one K1 launch on the default workload (4096 chains x 10^4 steps, D=2, thin=1):
-# dram__bytes_read.sum (290 KB) + dram__bytes_write.sum (925.7 MB) from the ncu --set full capture in
-# profiles/r1i_ncu_full_k1.csv.  Algorithmic bytes are 983.0 MB; the difference is the tail of
-# the output still resident in the 126 MB L2 when the kernel ends.  No re-reads.
-NCU_K1_DRAM_BYTES = 289536 + 925711104
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--chains", type=int, default=4096, help="chains per GPU")
-    ap.add_argument("--walk-steps", type=int, default=10000, help="MH steps per walk")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    # c2
+    ap.add_argument("--chains", type=int, default=0,
+                    help="chains (c2: per GPU, default 4096; c3: total 16384; c5: total 65536)")
+    ap.add_argument("--walk-steps", type=int, default=10000, help="c2: MH steps per walk")
+    ap.add_argument("--walks-per-step", type=int, default=100, help="c2: walks per bench step")
     ap.add_argument("--thin", type=int, default=1)
     ap.add_argument("--accept", default="log", choices=["reference", "log"])
-    ap.add_argument("--variant", type=int, default=0, help="K1 kernel: 0 auto, 1 per-thread, 2 warp-specialised")
+    ap.add_argument("--variant", type=int, default=0,
+                    help="c2 K1 kernel: 0 auto, 1 per-thread, 2 warp-specialised")
+    # c3 / c4 / c5
+    ap.add_argument("--n-obs", type=int, default=0, help="c3: 10^6, c4: 10^5 by default")
+    ap.add_argument("--mh-steps", type=int, default=20, help="c3: MH steps per bench step")
+    ap.add_argument("--grid", type=int, default=4096, help="c4: grid points per axis")
+    ap.add_argument("--sweeps", type=int, default=100, help="c5: sweeps per bench step")
     ap.add_argument("--cpu-sample-steps", type=int, default=0,
-                    help="MH steps of the bounded CPU sample (0 = auto)")
+                    help="c2: MH steps of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
-                    help="skip the C3/C4/C5 secondary kernel timings")
+                    help="skip the secondary / secondary_n blocks")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--quick", action="store_true", help="smaller secondary workloads")
     return ap.parse_args()
 
 
-def config(args, n_gpus):
-    return {"workload": "C2: %d MH chains/GPU x %d steps, 2-D correlated normal "
-                        "(mcmc_prob4a), thin=%d, Philox4x32-10" % (args.chains, args.walk_steps,
-                                                                  args.thin),
-            "chains_per_gpu": args.chains, "walk_steps": args.walk_steps, "thin": args.thin,
-            "accept": args.accept, "parallelism": "chains x%d" % n_gpus,
-            "l2": "outputs per walk (%.0f MB) exceed the 126 MB L2; no explicit flush"
-                  % (args.chains * (args.walk_steps // args.thin) * 24 / 1e6)}
-
-
-# ---------------------------------------------------------------------------
-# clocks: sample nvidia-smi during the timed region
-# ---------------------------------------------------------------------------
 class ClockSampler:
     """SM clock / throttle-reason samples DURING the timed region.  The timed region of
     the headline is a few tens of milliseconds, shorter than one `nvidia-smi` query, so
@@ -191,85 +202,35 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-# ---------------------------------------------------------------------------
-# CPU arm: the oracle port on the host cores (cpu_baseline / --impl reference)
-# ---------------------------------------------------------------------------
-def cpu_walk_rate(chains, steps, accept, seed=1234):
-    """Times the oracle port of the C2 walk on a bounded sample.  Prefers the C
-    restatement (OpenMP, all host cores); falls back to the numpy restatement
-    (1 core).  Returns (chain_steps_per_s, cores, kind_detail, seconds)."""
+def bind_to_gpu_cpus(index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU (same NUMA node /
+    PCIe root), before any pinned host buffer is allocated: with 8 ranks streaming
+    samples device->host at once, remote-node pinned memory halves the aggregate rate.
+    Returns a short description for the bench line."""
     try:
-        from oracle.c import liboracle
-        lib = liboracle.load()
-    except Exception:
-        lib = None
-    if lib is not None:
-        cores = liboracle.use_all_cores()
-        t0 = time.perf_counter()
-        liboracle.mh_mvn_walk(np.tile(INIT, (chains, 1)), MEAN, COV, steps, seed,
-                              accept=accept, record=True)
-        dt = time.perf_counter() - t0
-        return chains * steps / dt, cores, "C restatement (oracle/c, OpenMP)", dt
-    from oracle import np_oracle as o
-    from oracle import philox
-    t0 = time.perf_counter()
-    Z = philox.normals(seed, steps, chains, 2)
-    U = philox.thresholds(seed, steps, chains)
-    o.mh_mvn_walk(np.tile(INIT, (chains, 1)), Z, U, MEAN, COV, accept=accept)
-    dt = time.perf_counter() - t0
-    return chains * steps / dt, 1, "numpy restatement (oracle/np_oracle.py)", dt
-
-
-def auto_cpu_steps(chains, accept):
-    """Sizes the CPU sample for roughly 10-20 s of work from a short probe."""
-    rate, _, _, _ = cpu_walk_rate(chains, 20, accept)
-    return int(max(50, min(10000, rate * 12.0 / chains)))
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    steps = args.cpu_sample_steps or auto_cpu_steps(args.chains, args.accept)
-    rates = []
-    for _ in range(args.warmup):
-        cpu_walk_rate(args.chains, max(10, steps // 10), args.accept)
-    t_all = time.perf_counter()
-    for _ in range(args.steps):
-        r, cores, detail, dt = cpu_walk_rate(args.chains, steps, args.accept)
-        rates.append(r)
-        if time.perf_counter() - t_all > 150:
-            break
-    value = float(np.mean(rates))
-    sample = "%d chains x %d steps per bench step (%s)" % (args.chains, steps, detail)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
-            "n_gpus": args.gpus, "steps": len(rates), "warmup": args.warmup,
-            "ms_per_step": 1e3 * args.chains * steps / value, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config(args, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
-
-
-# ---------------------------------------------------------------------------
-# GPU arm
-# ---------------------------------------------------------------------------
-def measured_peaks():
-    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f), "measured"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(
+                ("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        bind_to_gpu_cpus.original = allowed
+        use = ideal & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return "bound to %d of %d allowed CPUs (GPU-local)" % (len(use), len(allowed))
+        return "no narrower GPU-local CPU set (%d ideal, %d allowed)" % (len(ideal), len(allowed))
+    except Exception as e:                                   # diagnostics only
+        return "unbound (%s)" % type(e).__name__
 
 
 
-# ---------------------------------------------------------------------------
-# secondary measurements: the other configs of BASELINE.json, one short pass each
-# ---------------------------------------------------------------------------
 def secondary(eng, peaks, fp64_peak, quick=False):
     """log-likelihood evals/s (C3 shape), HBM-streaming likelihood roofline, DGEI
     (C4 shape) and Gibbs (C5 shape) kernel timings; kernel-only, CUDA events."""
@@ -449,197 +410,762 @@ def secondary(eng, peaks, fp64_peak, quick=False):
     return out
 
 
-def bind_to_gpu_cpus(index):
-    """Pins this rank to the CPUs NVML reports as local to its GPU (same NUMA node /
-    PCIe root), before any pinned host buffer is allocated: with 8 ranks streaming
-    samples device->host at once, remote-node pinned memory halves the aggregate rate.
-    Returns a short description for the bench line."""
-    try:
-        import pynvml
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def k1_counters():
+    """ncu counters of ONE K1 launch on the default c2 workload, written by
+    scripts/ncu_counters.py from the --set full capture of the same kernel build
+    (profiles/k1_counters.json names the capture)."""
+    path = os.path.join(ROOT, "profiles", "k1_counters.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def liboracle_all_cores():
+    from oracle.c import liboracle
+    liboracle.load()
+    return liboracle, liboracle.use_all_cores()
+
+
+def timed_repeats(fn, budget_s=10.0, max_reps=40):
+    """Median rate over repeated calls of fn() -> (units, seconds) for ~budget_s."""
+    rates, tot, reps = [], 0.0, 0
+    while tot < budget_s and reps < max_reps:
+        units, dt = fn(reps)
+        rates.append(units / dt)
+        tot += dt
+        reps += 1
+    return float(np.median(rates)), reps, tot
+
+
+class Dist:
+    """rank / world / barrier / max-over-ranks, one process per GPU."""
+
+    def __init__(self):
         import torch
-        pynvml.nvmlInit()
-        uuid = str(torch.cuda.get_device_properties(index).uuid)
-        try:
-            h = pynvml.nvmlDeviceGetHandleByUUID(
-                ("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
-        except Exception:
-            h = pynvml.nvmlDeviceGetHandleByIndex(index)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
-        allowed = os.sched_getaffinity(0)
-        bind_to_gpu_cpus.original = allowed
-        use = ideal & allowed
-        if use and use != allowed:
-            os.sched_setaffinity(0, use)
-            return "bound to %d of %d allowed CPUs (GPU-local)" % (len(use), len(allowed))
-        return "no narrower GPU-local CPU set (%d ideal, %d allowed)" % (len(ideal), len(allowed))
-    except Exception as e:                                   # diagnostics only
-        return "unbound (%s)" % type(e).__name__
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.cpu_binding = bind_to_gpu_cpus(self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v):
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    cpu_binding = bind_to_gpu_cpus(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from probayes_b200.engine import get_engine
-    eng = get_engine(local)
-    C, T, thin, D = args.chains, args.walk_steps, args.thin, 2
-    R = T // thin
-    chain0 = rank * C
-    init_host = np.tile(INIT[:, None], (1, C))
-    state = eng.to_device(init_host)
-    init_dev = eng.to_device(init_host)
-    out_bytes = R * (D + 1) * C * 8
+# ---------------------------------------------------------------------------
+# workloads.  Each has:  setup(eng, d) ; step(k, ev=None) -- one bench step on the device,
+# inputs resident; units (whole job, per step); roofline(kernel_ms); e2e_step(k) through the
+# public API with host buffers; cpu_sample() on the host cores; finish() -> quality dict
+# ---------------------------------------------------------------------------
+class C2:
+    name, metric, unit, scaling = "c2", "mh_chain_steps_per_sec", "chain-steps/s", "weak"
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def __init__(self, args, world):
+        self.a = args
+        self.C = args.chains or 4096
+        self.T, self.thin, self.W = args.walk_steps, args.thin, args.walks_per_step
+        self.world = world
+        self.units = world * self.C * self.T * self.W
+        self.D = 2
+        self.R = self.T // self.thin
+        self.out_bytes = self.R * (self.D + 1) * self.C * 8
 
-    bufs = {"x": eng.empty(R, D, C), "prob": eng.empty(R, C)}
+    def config(self):
+        return {"workload": "C2 (BASELINE.json configs[1]): %d MH chains/GPU x %d steps, 2-D "
+                            "correlated normal (mcmc_prob4a), thin=%d, Philox4x32-10; one bench "
+                            "step = %d walks" % (self.C, self.T, self.thin, self.W),
+                "chains_per_gpu": self.C, "walk_steps": self.T, "thin": self.thin,
+                "walks_per_step": self.W, "accept": self.a.accept,
+                "parallelism": "chains x%d (weak: every rank runs its own chains)" % self.world,
+                "l2": "outputs per walk (%.0f MB) exceed the 126 MB L2; no explicit flush"
+                      % (self.out_bytes / 1e6)}
 
-    def walk(seed, events=None):
-        state.copy_(init_dev)
-        return eng.mh_mvn(state, MEAN, COV, T, thin=thin, seed=seed, chain0=chain0,
-                          accept=args.accept, variant=args.variant, out=bufs, events=events)
+    def setup(self, eng, d):
+        self.eng, self.d = eng, d
+        init_host = np.tile(INIT[:, None], (1, self.C))
+        self.state = eng.to_device(init_host)
+        self.init_dev = eng.to_device(init_host)
+        self.bufs = {"x": eng.empty(self.R, self.D, self.C), "prob": eng.empty(self.R, self.C)}
+        self.chain0 = d.rank * self.C
+        self.last = None
 
-    # ---- device-resident timing ------------------------------------------------
-    for w in range(args.warmup):
-        walk(1000 + w)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
+    def walk(self, seed, ev=None):
+        self.state.copy_(self.init_dev)
+        self.last = self.eng.mh_mvn(self.state, MEAN, COV, self.T, thin=self.thin, seed=seed,
+                                    chain0=self.chain0, accept=self.a.accept,
+                                    variant=self.a.variant, out=self.bufs, events=ev)
+        return self.last
+
+    def step(self, k, ev=None):
+        for w in range(self.W):              # CUDA events bracket the first walk's kernel
+            self.walk(1000 + k * self.W + w, ev if w == 0 else None)
+
+    kernel = "mh_mvn_ws_kernel<2>"
+
+    def roofline(self, kernel_ms, peaks, which, fp64_peak, sm_mhz):
+        eng = self.eng
+        sms = int(eng.info.sm_count)
+        clk = (sm_mhz or 1965.0) * 1e6
+        cs = self.C * self.T
+        out = {"bound": "fp64_pipe", "kernel": self.kernel if self.a.variant != 1 else "mh_mvn_kernel<2>",
+               "kernel_ms": kernel_ms, "unit": "G FP64 warp-instr/s",
+               "peak": sms * 4 * 0.5 * clk / 1e9,
+               "peak_source": "%d SMs x 4 sub-partitions x 1 FP64 warp-instruction per 2 cycles x "
+                              "%.0f MHz (the SM clock sampled during the timed region)"
+                              % (sms, clk / 1e6),
+               "output_gbs": self.out_bytes / (kernel_ms * 1e-3) / 1e9,
+               "output_frac_of_hbm": self.out_bytes / (kernel_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+               "hbm_peak_source": which,
+               "algorithmic_bytes_per_launch": self.out_bytes,
+               "note": "K1 is bound by the FP64 pipe / issue slots of the draw (Philox + "
+                       "Box-Muller + log) and record code, not by HBM: it only WRITES (D+1)*8 B "
+                       "per recorded chain-step"}
+        kc = k1_counters()
+        if kc and kc.get("chains") == self.C and kc.get("steps") == self.T and \
+                kc.get("thin") == self.thin and self.a.variant != 1:
+            fp64_per_cs, inst_per_cs = kc["fp64_warp_inst"] / cs, kc["warp_inst"] / cs
+            out["achieved"] = fp64_per_cs * cs / (kernel_ms * 1e-3) / 1e9
+            out["frac"] = out["achieved"] / out["peak"]
+            out["issue"] = {"warp_inst_per_launch": kc["warp_inst"],
+                            "achieved_ginst_s": inst_per_cs * cs / (kernel_ms * 1e-3) / 1e9,
+                            "peak_ginst_s": sms * 4 * clk / 1e9,
+                            "frac": inst_per_cs * cs / (kernel_ms * 1e-3) / (sms * 4 * clk)}
+            out["traffic"] = kc.get("dram_bytes")
+            out["counters_source"] = kc.get("source")
+        else:
+            out["achieved"] = out["frac"] = out["traffic"] = None
+            out["counters_source"] = "no ncu counters for this kernel build / workload shape"
+        return out
+
+    # ---- public API, host buffers ---------------------------------------------------------
+    def e2e_setup(self):
+        import scipy.stats
+        import probayes_b200 as pb
+        xr = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+        yr = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+        self.process = pb.SP(xr & yr)
+        self.process.set_prob(scipy.stats.multivariate_normal, list(MEAN), COV.tolist())
+        self.process.set_tran(lambda **kw: 1.)
+        self.process.set_delta(scipy.stats.norm(0., 1.))
+        self.process.set_scores('hastings')
+        self.process.set_update('metropolis')
+        self.hostbuf = {}
+        self.e2e_units = self.world * self.C * self.T
+        self.h2d = self.D * self.C * 8
+        self.d2h = self.out_bytes + (2 * self.D + 2) * self.C * 8 + self.D * self.C * 8
+        self.e2e_note = ("pb.SP(...).sampler(init, chains=%d, host_stream=True) -> walk -> "
+                         "process(samples): one walk per e2e step, every recorded sample and "
+                         "density streamed D2H into pinned host buffers" % self.C)
+
+    def e2e_step(self, k):
+        smp = self.process.sampler({'x': INIT[0], 'y': INIT[1]}, stop=self.T, chains=self.C,
+                                   thin=self.thin, seed=4000 + k, accept=self.a.accept,
+                                   host_stream=True, host_buffers=self.hostbuf)
+        summary = self.process(self.process.walk(smp))
+        return summary.v['x'][0, -1] + summary.u.count(True)     # touch the result
+
+    # ---- CPU ---------------------------------------------------------------------------------
+    def cpu_sample(self, budget_s=10.0):
+        lo, cores = liboracle_all_cores()
+        C = self.C
+        init = np.tile(INIT, (C, 1))
+
+        def one(steps, seed):
+            t0 = time.perf_counter()
+            lo.mh_mvn_walk(init, MEAN, COV, steps, seed, accept=self.a.accept, record=True)
+            return C * steps, time.perf_counter() - t0
+        steps = self.a.cpu_sample_steps
+        if not steps:
+            u, dt = one(20, 1)
+            steps = int(max(50, min(10000, u / dt * 1.2 / C)))
+        rate, reps, tot = timed_repeats(lambda r: one(steps, 1234 + r), budget_s)
+        return rate, cores, "%d x (%d chains x %d steps), %.1f s in total, median (C restatement " \
+                            "oracle/c, OpenMP)" % (reps, C, steps, tot)
+
+    def finish(self):
+        out, eng, d = self.last, self.eng, self.d
+        st = eng.chain_stats(out["stat_sum"], out["stat_sumsq"], self.T)
+        if d.world > 1:                      # the path's only collective: [D, 4] summaries
+            d.dist.all_reduce(st)
+        from probayes_b200.dist import rhat_from_stats
+        rhat = rhat_from_stats(st, self.T)
+        acc = float(out["accept_count"].sum().item()) / (self.C * self.T)
+        return {"accept_rate": acc, "rhat": [float(v) for v in rhat]}
+
+
+LR_LIMS = np.array([[-6., 6.], [-6., 6.], [0.001, 10.]])
+LR_EX = np.array([[0, 0], [0, 0], [1, 0]])
+LR_LG = np.zeros(3, int)
+
+
+def linreg_data(N, seed=2024):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(0, 1, N)
+    y = -1 + 1.5 * x + rng.normal(0, .5, N)
+    return x, y
+
+
+class C3:
+    name, metric, unit, scaling = "c3", "loglik_evals_per_sec", "evals/s", "strong"
+
+    def __init__(self, args, world, chains=None, n_obs=None, mh_steps=None):
+        self.a = args
+        self.Ctot = chains or args.chains or 16384
+        self.N = n_obs or args.n_obs or 1_000_000
+        self.T = mh_steps or args.mh_steps
+        self.world = world
+        self.units = self.Ctot * self.T
+
+    def config(self):
+        return {"workload": "C3 (BASELINE.json configs[2]): Bayesian linear regression posterior, "
+                            "normal likelihood over N=%d synthetic obs, 3 params, %d MH chains "
+                            "sharded over %d GPU(s); one bench step = %d MH steps of every chain"
+                            % (self.N, self.Ctot, self.world, self.T),
+                "chains_total": self.Ctot, "n_obs": self.N, "mh_steps_per_step": self.T,
+                "parallelism": "chains sharded x%d (strong), observations replicated" % self.world,
+                "l2": "the 16 MB of observations are L2-resident by design (shared by all chains "
+                      "of a CTA through TMA-staged shared-memory tiles); the kernel is FP64-bound",
+                "terms_per_eval": self.N}
+
+    def setup(self, eng, d):
+        from probayes_b200.dist import shard_range
+        self.eng, self.d = eng, d
+        self.chain0, self.C = shard_range(self.Ctot, d.rank, d.world)
+        self.xh, self.yh = linreg_data(self.N)
+        self.x, self.y = eng.to_device(self.xh), eng.to_device(self.yh)
+        self.sd = 0.5 / np.sqrt(self.N)
+        self.state = eng.to_device(np.tile(np.array([[-1.], [1.5], [.5]]), (1, self.C)))
+        burn = eng.mh_normreg(self.state, self.y, self.x, 2, LR_LIMS, LR_EX, LR_LG,
+                              [2.4 * self.sd] * 3, seed=1, chain0=self.chain0, record=False)
+        self.lp = burn["state_lp"]
+        self.step0 = 2
+        self.acc = 0
+        self.nsteps = 0
+
+    def step(self, k, ev=None):
+        if ev is not None:
+            ev[0].record(self.eng.stream)
+        out = self.eng.mh_normreg(self.state, self.y, self.x, self.T, LR_LIMS, LR_EX, LR_LG,
+                                  [2.4 * self.sd] * 3, seed=1, step0=self.step0,
+                                  chain0=self.chain0, state_lp=self.lp, record=True, stats=False)
+        if ev is not None:
+            ev[1].record(self.eng.stream)
+        self.step0 += self.T
+        self.last = out
+
+    kernel = "nr_tiles_kernel<4>"
+
+    def roofline(self, kernel_ms, peaks, which, fp64_peak, sm_mhz):
+        # kernel_ms brackets T launches (one per MH step) of this rank's C chains
+        flops = 5.0 * self.N * self.C * self.T
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "fp64", "kernel": self.kernel, "kernel_ms": kernel_ms / self.T,
+                "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                "peak_source": "pbx_fp64_peak (dependent-free DFMA stream, measured in this run)",
+                "traffic": None,
+                "algorithmic_flops_per_launch": 5.0 * self.N * self.C,
+                "terms_per_s": self.N * self.C * self.T / (kernel_ms * 1e-3),
+                "note": "3 FP64 instr (fma, add, fma = 5 flop) per (chain, observation): the pipe-"
+                        "time ceiling is 5/6 of the FMA-only flop peak; observation tiles are read "
+                        "once per CTA (TMA) and shared by 128 x KC chains"}
+
+    def e2e_setup(self):
+        import scipy.stats
+        import probayes_b200 as pb
+        x = pb.RV('x', vtype=float, vset=[-np.inf, np.inf])
+        y = pb.RV('y', vtype=float, vset=[-np.inf, np.inf])
+        beta_0 = pb.RV('beta_0', vtype=float, vset=[-6., 6.], pscale='log')
+        beta_1 = pb.RV('beta_1', vtype=float, vset=[-6., 6.], pscale='log')
+        y_sigma = pb.RV('y_sigma', vtype=float, vset=[(0.001), 10.], pscale='log')
+
+        def norm_reg(x, y, beta_0, beta_1, y_sigma):
+            return scipy.stats.norm.logpdf(y, loc=beta_0 + beta_1 * x, scale=y_sigma)
+        paras = beta_0 & beta_1 & y_sigma
+        self.process = pb.SP(x & y, paras)
+        self.process.set_prob(norm_reg, pscale='log')
+        paras.set_tran(lambda **k: 0.)
+        paras.set_delta([2.4 * self.sd])
+        self.process.set_tran(paras)
+        self.process.set_delta(paras)
+        self.process.set_scores('metropolis')
+        self.e2e_units = self.Ctot * self.T
+        self.h2d = 16 * self.N + 3 * self.C * 8
+        self.d2h = self.T * 4 * self.C * 8 + self.C * 8
+        self.e2e_note = ("pb.SP(stats, paras).sampler(init, {'x,y': [x_obs, y_obs]}, chains=%d, "
+                         "iid=True, joint=True) -> walk -> process(samples): host observations "
+                         "uploaded and every recorded sample read back each step" % self.C)
+
+    def e2e_step(self, k):
+        smp = self.process.sampler({'beta_0': -1., 'beta_1': 1.5, 'y_sigma': 0.5},
+                                   {'x,y': [self.xh, self.yh]}, stop=self.T, iid=True, joint=True,
+                                   chains=self.C, seed=50 + k, chain0=self.chain0)
+        summary = self.process(self.process.walk(smp))
+        return summary.v['beta_1'][0, -1] + summary.u.count(True)
+
+    def cpu_sample(self, budget_s=10.0):
+        lo, cores = liboracle_all_cores()
+        rng = np.random.default_rng(3)
+        xh, yh = linreg_data(self.N)
+
+        def one(Cs, seed):
+            th = np.stack([rng.normal(-1, .001, Cs), rng.normal(1.5, .001, Cs),
+                           rng.uniform(.49, .51, Cs)], axis=1)
+            t0 = time.perf_counter()
+            lo.normreg_logjoint(th, xh, yh, LR_LIMS, LR_EX, LR_LG)
+            return Cs, time.perf_counter() - t0
+        u, dt = one(max(cores, 8), 0)
+        Cs = int(max(cores, min(4096, u / dt * 1.5)))
+        rate, reps, tot = timed_repeats(lambda r: one(Cs, r), budget_s)
+        return rate, cores, "%d x (%d chains x N=%d log-joint evaluations), %.1f s in total, " \
+                            "median (C restatement oracle/c, OpenMP)" % (reps, Cs, self.N, tot)
+
+    def finish(self):
+        acc = self.d.sum(float(self.last["accept_count"].sum().item()))
+        return {"accept_rate_last_step": acc / (self.Ctot * self.T)}
+
+
+class C4:
+    name, metric, unit, scaling = "c4", "loglik_evals_per_sec", "evals/s", "strong"
+
+    def __init__(self, args, world, grid=None, n_obs=None):
+        self.a = args
+        self.M = self.S = grid or args.grid
+        self.N = n_obs or args.n_obs or 100_000
+        self.world = world
+        self.units = self.M * self.S
+
+    def config(self):
+        return {"workload": "C4 (BASELINE.json configs[3]): discrete grid exact inference of a "
+                            "normal mean/std posterior, %dx%d grid over N=%d synthetic obs, mu-row "
+                            "slabs sharded over %d GPU(s); one bench step = log-joint + normalise "
+                            "+ posterior + both marginals" % (self.M, self.S, self.N, self.world),
+                "grid": [self.M, self.S], "n_obs": self.N,
+                "parallelism": "mu-row slabs x%d (strong); all-reduce(max), all-reduce(sum), "
+                               "all-reduce of the sigma marginal, all-gather of the mu marginal"
+                               % self.world,
+                "l2": "the 134 MB log-joint exceeds the 126 MB L2 at N=1; no explicit flush",
+                "terms_per_eval": self.N}
+
+    def setup(self, eng, d):
+        from probayes_b200.dist import shard_range
+        self.eng, self.d = eng, d
+        rng = np.random.default_rng(7)
+        self.data_h = rng.normal(50., 10., self.N)
+        self.mu_h = np.linspace(40, 60, self.M + 2)[1:-1]
+        self.sg_h = np.exp(np.linspace(np.log(5), np.log(20), self.S + 2)[1:-1])
+        self.lpm_h = np.full(self.M, -np.log(20.))
+        self.lps_h = np.full(self.S, -np.log(np.log(4.)))
+        self.r0, self.rows = shard_range(self.M, d.rank, d.world)
+        sl = slice(self.r0, self.r0 + self.rows)
+        self.data = eng.to_device(self.data_h)
+        self.mu, self.sg = eng.to_device(self.mu_h[sl]), eng.to_device(self.sg_h)
+        self.lpm, self.lps = eng.to_device(self.lpm_h[sl]), eng.to_device(self.lps_h)
+        self.lj = eng.empty(self.rows, self.S)
+        self.counts = [shard_range(self.M, r, d.world)[1] for r in range(d.world)]
+        self.group = None
+        self.ms_a = self.ms_b = None
+
+    def step(self, k, ev=None):
+        from probayes_b200 import dist as pdist
+        eng = self.eng
+        if ev is not None:
+            ev[0].record(eng.stream)
+        eng.grid_norm_logjoint(self.data, self.mu, self.sg, self.lpm, self.lps, out=self.lj)
+        if ev is not None:
+            ev[1].record(eng.stream)
+        if k == -1:
+            return
+        r = eng.grid_conditionalise(self.lj, want_post=True, inplace=True,
+                                    group=self.d.dist.group.WORLD if self.d.world > 1 else None)
+        self.marg_mu = pdist.gather_slabs(r["marg_mu"], self.counts)
+        self.last = r
+
+    kernel = "grid_logjoint_kernel"
+
+    def roofline(self, kernel_ms, peaks, which, fp64_peak, sm_mhz):
+        cellobs = float(self.N) * self.rows * self.S
+        ach = 4.0 * cellobs / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "fp64", "kernel": self.kernel, "kernel_ms": kernel_ms,
+                "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                "peak_source": "pbx_fp64_peak (measured in this run)", "traffic": None,
+                "algorithmic_flops_per_launch": 4.0 * cellobs,
+                "terms_per_s": cellobs / (kernel_ms * 1e-3),
+                "note": "2 FP64 instr (mul, fma) per (cell, observation), counted as 2 FMA slots = "
+                        "4 flop (SURVEY 8d); the normalise/marginal passes are HBM-bound and "
+                        "reported under normalise"}
+
+    def e2e_setup(self):
+        self.e2e_units = self.M * self.S
+        self.h2d = 8 * (self.N + self.rows + self.S) + 8 * (self.rows + self.S)
+        self.d2h = 8 * (self.M + self.S) + 16
+        self.e2e_note = ("probayes_b200.dist.dgei_sharded(engine, data, mu, sigma, priors): host "
+                         "observations / grids uploaded every step; both marginals and the "
+                         "normaliser read back; the posterior slab [M/G, S] stays device-backed "
+                         "(PD.prob copies it on first access)")
+
+    def e2e_step(self, k):
+        from probayes_b200 import dist as pdist
+        r = pdist.dgei_sharded(self.eng, self.data_h, self.mu_h, self.sg_h, self.lpm_h, self.lps_h)
+        mm = r["marg_mu"].cpu().numpy()
+        ms = r["marg_sigma"].cpu().numpy()
+        return float(mm[0] + ms[0] + r["gsum"].item())
+
+    def cpu_sample(self, budget_s=10.0):
+        lo, cores = liboracle_all_cores()
+        rng = np.random.default_rng(7)
+        data = rng.normal(50., 10., self.N)
+
+        def one(m, seed):
+            mu = np.linspace(40, 60, m + 2)[1:-1]
+            sg = np.exp(np.linspace(np.log(5), np.log(20), m + 2)[1:-1])
+            t0 = time.perf_counter()
+            lj = lo.grid_norm_logjoint(data, mu, sg, np.full(m, -np.log(20.)),
+                                       np.full(m, -np.log(np.log(4.))))
+            lo.grid_posterior(lj)
+            return m * m, time.perf_counter() - t0
+        u, dt = one(16, 0)
+        m = int(max(16, min(512, np.sqrt(u / dt * 1.5))))
+        rate, reps, tot = timed_repeats(lambda r: one(m, r), budget_s)
+        return rate, cores, "%d x (%dx%d grid cells x N=%d, log-joint + posterior), %.1f s in " \
+                            "total, median (C restatement oracle/c, OpenMP)" % (reps, m, m, self.N, tot)
+
+    def finish(self):
+        torch = self.d.torch
+        lp = self.last["post"]
+        tot = self.d.sum(float(torch.exp(lp).sum().item()))
+        return {"posterior_sum": tot,
+                "marg_mu_sum": float(torch.exp(self.marg_mu).sum().item())}
+
+
+class C5:
+    name, metric, unit, scaling = "c5", "mh_chain_steps_per_sec", "chain-steps/s", "strong"
+
+    def __init__(self, args, world, chains=None, sweeps=None):
+        self.a = args
+        self.d_ = 64
+        self.Ctot = chains or args.chains or 65536
+        self.sweeps = sweeps or args.sweeps
+        self.world = world
+        self.units = self.Ctot * self.d_ * self.sweeps
+
+    def config(self):
+        return {"workload": "C5 (BASELINE.json configs[4]): multivariate normal-covariance Gibbs "
+                            "(cond_cov) d=64, %d chains sharded over %d GPU(s); one bench step = %d "
+                            "sweeps of 64 coordinate updates, every sweep's state recorded with its "
+                            "target density (FP64 DMMA)" % (self.Ctot, self.world, self.sweeps),
+                "chains_total": self.Ctot, "dims": self.d_, "sweeps_per_step": self.sweeps,
+                "chain_step": "one coordinate update (the reference's step with tsteps=1)",
+                "parallelism": "chains sharded x%d (strong)" % self.world,
+                "l2": "recorded states per step (%.0f MB per rank) exceed the L2; no explicit flush"
+                      % (self.sweeps * self.d_ * (self.Ctot / self.world) * 8 / 1e6)}
+
+    def model(self):
+        rng = np.random.default_rng(0)
+        d = self.d_
+        A = rng.standard_normal((d, d))
+        cov = A @ A.T / d + np.eye(d)
+        mean = rng.standard_normal(d)
+        return mean, cov
+
+    def setup(self, eng, d):
+        from probayes_b200.dist import shard_range
+        from probayes_b200.cond_cov import CondCov
+        self.eng, self.d = eng, d
+        self.chain0, self.C = shard_range(self.Ctot, d.rank, d.world)
+        self.mean, self.cov = self.model()
+        self.cc = CondCov(self.mean, self.cov, np.tile([-10., 10.], (self.d_, 1)))
+        self.state = eng.to_device(np.tile(self.mean[:, None], (1, self.C)))
+        self.step0 = 0
+
+    def step(self, k, ev=None):
+        if ev is not None:
+            ev[0].record(self.eng.stream)
+        self.last = self.eng.gibbs_mvn(self.state, self.cc, self.sweeps * self.d_, thin=self.d_,
+                                       seed=5, step0=self.step0, chain0=self.chain0,
+                                       want_prob=True, stats=False)
+        if ev is not None:
+            ev[1].record(self.eng.stream)
+        self.step0 += self.sweeps * self.d_
+
+    kernel = "gibbs_mvn_kernel + mvn_logpdf_mma64_kernel"
+
+    def roofline(self, kernel_ms, peaks, which, fp64_peak, sm_mhz):
+        d = self.d_
+        flops = (4.0 * d * d + 2 * d) * self.C * self.sweeps
+        ach = flops / (kernel_ms * 1e-3) / 1e12
+        return {"bound": "fp64", "kernel": self.kernel, "kernel_ms": kernel_ms,
+                "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                "peak_source": "pbx_fp64_peak (measured in this run)", "traffic": None,
+                "algorithmic_flops_per_launch": flops,
+                "ms_per_sweep": kernel_ms / self.sweeps,
+                "note": "SURVEY 8d: 2 d^2 flop of conditional means + 2 d^2 + 2 d of density per "
+                        "chain-sweep; each coordinate update also needs one Philox block and one "
+                        "inverse normal cdf, which bound the kernel (serial over coordinates)"}
+
+    def e2e_setup(self):
+        self.e2e_units = self.Ctot * self.d_ * self.e2e_sweeps()
+        self.h2d = self.d_ * self.C * 8
+        self.d2h = self.e2e_sweeps() * (self.d_ + 1) * self.C * 8
+        self.e2e_note = ("pb.SP(x0 & ... & x63) with set_tran(scipy.stats.multivariate_normal, "
+                         "mean, cov, tsteps=1), set_scores('gibbs'): sampler(init, chains=%d, "
+                         "thin=64) -> walk -> process(samples); host initial state in, every kept "
+                         "state and density out" % self.C)
+        import scipy.stats
+        import probayes_b200 as pb
+        import functools
+        rvs = [pb.RV('x%d' % i, vtype=float, vset=(-10., 10.)) for i in range(self.d_)]
+        self.process = pb.SP(functools.reduce(lambda a, b: a & b, rvs))
+        self.process.set_prob(scipy.stats.multivariate_normal, self.mean, self.cov)
+        self.process.set_tran(scipy.stats.multivariate_normal, self.mean, self.cov, tsteps=1)
+        self.process.set_scores('gibbs')
+        self.init = {'x%d' % i: float(self.mean[i]) for i in range(self.d_)}
+
+    def e2e_sweeps(self):
+        return min(self.sweeps, 20)
+
+    def e2e_step(self, k):
+        smp = self.process.sampler(self.init, stop=self.e2e_sweeps() * self.d_, chains=self.C,
+                                   thin=self.d_, seed=70 + k, chain0=self.chain0)
+        summary = self.process(self.process.walk(smp))
+        return summary.v['x0'][0, -1]
+
+    def cpu_sample(self, budget_s=10.0):
+        lo, cores = liboracle_all_cores()
+        from probayes_b200.cond_cov import CondCov
+        mean, cov = self.model()
+        cc = CondCov(mean, cov, np.tile([-10., 10.], (self.d_, 1)))
+        coef = cc.coef_matrix()
+
+        def one(Cs, seed):
+            x = np.tile(mean, (Cs, 1))
+            t0 = time.perf_counter()
+            lo.gibbs_mvn_walk(x, mean, coef, cc.stdv, cc.cdfs, 4 * self.d_, seed=seed)
+            return Cs * 4 * self.d_, time.perf_counter() - t0
+        u, dt = one(256, 0)
+        Cs = int(max(256, min(65536, u / dt * 1.5 / (4 * self.d_))))
+        rate, reps, tot = timed_repeats(lambda r: one(Cs, r), budget_s)
+        return rate, cores, "%d x (%d chains x 4 sweeps of 64 coordinate updates), %.1f s in " \
+                            "total, median (C restatement oracle/c, OpenMP; no density " \
+                            "evaluation)" % (reps, Cs, tot)
+
+    def finish(self):
+        x = self.last["x"][-1]                       # [d, C] last kept sweep
+        m = self.d.sum(float(x[0].sum().item())) / self.Ctot
+        return {"mean_x0": m, "target_mean_x0": float(self.mean[0])}
+
+
+WORKLOADS = {"c2": C2, "c3": C3, "c4": C4, "c5": C5}
+
+
+# ---------------------------------------------------------------------------
+# timing of one workload on the device (used for the headline and for secondary_n)
+# ---------------------------------------------------------------------------
+def time_workload(wl, d, steps, warmup, sampler=None):
+    torch = d.torch
+    eng = wl.eng
+    for w in range(warmup):
+        wl.step(-1000 + w)
+    d.barrier()
+    if sampler is not None:
         sampler.start()
     l0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+          for _ in range(steps)]
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
-    for k in range(args.steps):
-        out = walk(2000 + k, ev[k])          # CUDA events around the kernel on its stream;
-    t_end.record()                           # no host sync inside the timed region
-    barrier()
+    for k in range(steps):
+        wl.step(k, ev[k])                    # no host sync inside the timed region
+    t_end.record()
+    d.barrier()
     launches = eng.launches - l0
-    total_ms = t_start.elapsed_time(t_end)
-    kms = [a_.elapsed_time(b_) for a_, b_ in ev]
-    clocks = sampler.stop() if rank == 0 else None
-    tm = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
-    ms_per_step = total_ms / args.steps
-    value = world * C * T / (ms_per_step * 1e-3)
-    kernel_ms = float(np.mean(kms))
+    clocks = sampler.stop() if sampler is not None else None
+    total_ms = d.max(t_start.elapsed_time(t_end))
+    kms = float(np.mean([a_.elapsed_time(b_) for a_, b_ in ev]))
+    ms_per_step = total_ms / steps
+    return dict(value=wl.units / (ms_per_step * 1e-3), ms_per_step=ms_per_step,
+                kernel_ms=kms, launches=int(launches), clocks=clocks)
 
-    # per-chain summaries -> R-hat inputs, all-reduced once (not in the timed region)
-    st = eng.chain_stats(out["stat_sum"], out["stat_sumsq"], T)
-    if world > 1:
-        dist.all_reduce(st)
-    st = st.cpu().numpy()
-    Cn = st[:, 3]
-    W = st[:, 2] / Cn
-    B = T * (st[:, 1] - st[:, 0] ** 2 / Cn) / (Cn - 1)
-    rhat = np.sqrt(((T - 1) / T * W + B / T) / W)
-    acc_rate = float(out["accept_count"].sum().item()) / (C * T)
 
-    # ---- end-to-end through the PUBLIC API (the call a user makes) ----------------
-    # pb.SP(...).sampler(init, chains=, host_stream=True) -> walk -> process(samples):
-    # host init state -> H2D, chunked kernel launches, every recorded sample and
-    # density streamed D2H into pinned buffers, summary PDs built from them.
-    import scipy.stats
-    import probayes_b200 as pb
-    xr = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
-    yr = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
-    process = pb.SP(xr & yr)
-    process.set_prob(scipy.stats.multivariate_normal, list(MEAN), COV.tolist())
-    process.set_tran(lambda **kw: 1.)
-    process.set_delta(scipy.stats.norm(0., 1.))
-    process.set_scores('hastings')
-    process.set_update('metropolis')
-    hostbuf = {}
-    e2e_steps = max(3, min(args.steps, 10))
-
-    def api_walk(seed):
-        smp = process.sampler({'x': INIT[0], 'y': INIT[1]}, stop=T, chains=C, thin=thin,
-                              seed=seed, accept=args.accept, host_stream=True,
-                              host_buffers=hostbuf)
-        summary = process(process.walk(smp))
-        return summary.v['x'][0, -1] + summary.u.count(True)     # touch the result
-
-    for w in range(2):
-        api_walk(3000 + w)
-    barrier()
+def time_e2e(wl, d, steps, warmup=2):
+    wl.e2e_setup()
+    for w in range(warmup):
+        wl.e2e_step(-100 + w)
+    d.barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        api_walk(4000 + k)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * C * T * e2e_steps / float(te.item())
-    h2d = D * C * 8
-    d2h = out_bytes + (2 * D + 2) * C * 8 + D * C * 8
+    for k in range(steps):
+        wl.e2e_step(k)
+    d.torch.cuda.synchronize()
+    dt = d.max(time.perf_counter() - t0)
+    return {"value": wl.e2e_units * steps / dt, "unit": wl.unit,
+            "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
+            "steps": steps, "ms_per_step": 1e3 * dt / steps, "api": wl.e2e_note}
 
-    if rank == 0:
+
+def reference_numpy_c1():
+    """The REAL reference's NumPy sampler (oracle/_ref, config C1) on this box's cores."""
+    try:
+        from oracle import ref_run
+        if not ref_run.available():
+            return {"unavailable": "oracle/_ref/probayes not shipped (run oracle/ref_run.py in "
+                                   "the development container)"}
+        r1, dt1, nacc = ref_run.c1_rate(4096, seed=0)
+        rn, procs, wall = ref_run.c1_rate_all_cores(2048)
+        return {"value": r1, "unit": "chain-steps/s", "cores": 1, "kind": "oracle/_ref",
+                "sample": "examples/mcmc/mcmc_prob4a.py model, 1 chain x 4096 steps incl. "
+                          "process(samples), np.random.seed(0): %.2f s, %d accepted" % (dt1, nacc),
+                "all_cores": {"value": rn, "cores": procs,
+                              "sample": "%d independent single-chain samplers x 2048 steps in %d "
+                                        "processes, %.2f s wall" % (procs, procs, wall)}}
+    except Exception as e:                                   # diagnostics only
+        return {"unavailable": repr(e)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the SAME workload on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload](args, max(1, args.gpus))
+    for _ in range(min(args.warmup, 1)):
+        wl.cpu_sample(budget_s=1.0)
+    rates, t_all = [], time.perf_counter()
+    for _ in range(args.steps):
+        r, cores, sample = wl.cpu_sample(budget_s=max(2.0, 60.0 / max(1, args.steps)))
+        rates.append(r)
+        if time.perf_counter() - t_all > 150:
+            break
+    value = float(np.mean(rates))
+    line = {"impl": "reference", "metric": wl.metric, "value": value, "unit": wl.unit,
+            "n_gpus": args.gpus, "steps": len(rates), "warmup": args.warmup,
+            "ms_per_step": 1e3 * wl.units / value, "higher_is_better": True,
+            "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": wl.config(),
+            "cpu_baseline": {"value": value, "unit": wl.unit, "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if args.workload == "c2":
+        line["cpu_baseline"]["reference_numpy"] = reference_numpy_c1()
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    d = Dist()
+    torch = d.torch
+    from probayes_b200.engine import get_engine
+    eng = get_engine(d.local)
+    wl = WORKLOADS[args.workload](args, d.world)
+    wl.setup(eng, d)
+    sampler = ClockSampler(d.local) if d.rank == 0 else None
+    res = time_workload(wl, d, args.steps, args.warmup, sampler)
+    quality = wl.finish()
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 10))
+        try:
+            e2e = time_e2e(wl, d, e2e_steps)
+        except Exception as e:                               # never lose the headline line
+            e2e = {"value": None, "error": repr(e)}
+    sec_n = None
+    if args.workload == "c2" and not args.no_secondary:
+        # the other half of the metric at the SAME N: short sharded passes of c3 / c4 / c5
+        sec_n = {}
+        small = args.quick
+        for name, mk in (("c3", lambda: C3(args, d.world, chains=16384,
+                                          n_obs=100_000 if small else 1_000_000, mh_steps=10)),
+                         ("c4", lambda: C4(args, d.world, grid=1024 if small else 4096,
+                                          n_obs=10_000 if small else 100_000)),
+                         ("c5", lambda: C5(args, d.world, chains=65536, sweeps=20))):
+            try:
+                w2 = mk()
+                w2.setup(eng, d)
+                r2 = time_workload(w2, d, 3, 2)
+                sec_n[name] = {"metric": w2.metric, "value": r2["value"], "unit": w2.unit,
+                               "n_gpus": d.world, "scaling": w2.scaling,
+                               "ms_per_step": r2["ms_per_step"],
+                               "workload": w2.config()["workload"]}
+                del w2
+            except Exception as e:
+                sec_n[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+    if d.rank == 0:
         peaks, which = measured_peaks()
-        achieved = out_bytes / (kernel_ms * 1e-3) / 1e9
         fp64_peak = eng.fp64_peak_tflops()
+        clocks = res["clocks"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config(args, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": NCU_K1_DRAM_BYTES if (C, T, thin, args.variant) == (4096, 10000, 1, 0) else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                                           "profiles/r1i_ncu_full_k1.csv",
-                         "peak_source": which, "kernel": "mh_mvn_kernel<2>" if args.variant == 1 else "mh_mvn_ws_kernel<2>",
-                         "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_launch": out_bytes,
-                         "note": "K1 writes (D+1)*8 B per recorded chain-step; it is "
-                                 "FP64-pipe/latency bound, not HBM bound (see fp64)"},
+            "metric": wl.metric, "value": res["value"], "unit": wl.unit, "n_gpus": d.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": wl.config(),
+            "e2e": e2e, "gpu_launches": res["launches"],
+            "roofline": wl.roofline(res["kernel_ms"], peaks, which, fp64_peak,
+                                    (clocks or {}).get("sm_mhz")),
             "fp64": {"peak_tflops_measured": fp64_peak},
-            "clocks": clocks,
-            "cpu_binding": cpu_binding,
-            "quality": {"accept_rate": acc_rate, "rhat": [float(v) for v in rhat]},
+            "clocks": clocks, "cpu_binding": d.cpu_binding, "quality": quality,
         }
-        if not args.no_secondary and world == 1:        # the other configs: N = 1 only
+        if sec_n is not None:
+            line["secondary_n"] = sec_n
+        if args.workload == "c2" and not args.no_secondary and d.world == 1:
             try:
                 line["secondary"] = secondary(eng, peaks, fp64_peak, quick=args.quick)
                 line["roofline_stream"] = line["secondary"].pop("roofline_stream")
-            except Exception as e:                           # never lose the headline line
+            except Exception as e:
                 line["secondary"] = {"error": repr(e)}
-        if not args.no_cpu_baseline and world == 1:     # reported on rank 0 at N = 1 only
-            if getattr(bind_to_gpu_cpus, "original", None):     # the CPU arm gets every core
+        if not args.no_cpu_baseline and d.world == 1:       # rank 0 at N = 1 only
+            if getattr(bind_to_gpu_cpus, "original", None):  # the CPU arm gets every core
                 os.sched_setaffinity(0, bind_to_gpu_cpus.original)
-            steps = args.cpu_sample_steps or auto_cpu_steps(C, args.accept)
-            rs, tot, reps = [], 0.0, 0
-            while tot < 10.0 and reps < 40:            # ~10 s of CPU work, median over repeats
-                r, cores, detail, dt = cpu_walk_rate(C, steps, args.accept, seed=1234 + reps)
-                rs.append(r)
-                tot += dt
-                reps += 1
-            r = float(np.median(rs))
-            line["cpu_baseline"] = {"value": r, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d x (%d chains x %d steps), %.1f s in total, "
-                                              "median (%s)" % (reps, C, steps, tot, detail),
-                                    "reference_python_survey": "1332 chain-steps/s, 1 core "
-                                                               "(BASELINE.md, config C1)"}
+            try:
+                r, cores, sample = wl.cpu_sample()
+                line["cpu_baseline"] = {"value": r, "unit": wl.unit, "cores": cores,
+                                        "kind": "port", "sample": sample}
+                if args.workload == "c2":
+                    line["cpu_baseline"]["reference_numpy"] = reference_numpy_c1()
+            except Exception as e:
+                line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    d.close()
 
 
 def main():
