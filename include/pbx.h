@@ -118,7 +118,9 @@ typedef struct {
   int32_t accept_mode;     /* PBX_ACCEPT_* */
   int32_t prop_kind;       /* PBX_PROP_* */
   int32_t has_prop_mat;    /* delta = prop_mat @ (scaled draw)  (rf.py:346-348) */
-  int32_t kernel_variant;  /* 0 auto; 1 force the one-thread-per-chain kernel; 2 warp-specialised */
+  int32_t kernel_variant;  /* 0 auto; 1 one thread per chain; 2 warp-specialised, exact reference
+                              arithmetic in the decision; 4 warp-specialised, decisions on the
+                              whitened state (the auto choice for the log rule, n_dims <= 4) */
   int32_t reserved0;
   double mean[PBX_MAX_DIMS];
   /* whitening matrix U (row-major [D][D]) of scipy's _PSD with the value

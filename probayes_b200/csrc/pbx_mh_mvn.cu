@@ -31,10 +31,18 @@
 // max(1, |value|), sin/cos <= 4e-16 against an extended-precision reference); inputs
 // are the RNG's uniforms, so no special-case handling is needed.
 // ---------------------------------------------------------------------------
+// Shared-memory bank conflicts: a 128-bit shared load is served a quarter-warp (8 lanes) at
+// a time, each lane touching one of the 8 sixteen-byte bank groups; with per-lane random
+// table indices ~2.7 lanes collide per quarter and a lookup costs ~11 wavefronts instead of
+// 4 (measured: 36 % of the kernel's shared-memory wavefronts were conflicts, and that pipe,
+// not the FP64 pipe, was the busiest unit).  So every table is stored 8 (16 for the 8-byte
+// exp table) times, interleaved, and lane l reads copy l % 8: entry j of copy g sits at
+// index 8 j + g, i.e. always in bank group g -- conflict-free for any index pattern.  To
+// keep the footprint the tables have 128 entries (polynomials two terms longer).
 struct PbxTables {
-  double2 lg[1024];  // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/1024
-  double2 sc[1024];  // (cos, sin) of 2 pi (k + 0.5)/1024
-  double ex[64];     // 2^(j/64)
+  double2 lg[128 * 8];   // (1/c_j, -2 log c_j),         c_j = 1 + (j + 0.5)/128
+  double2 sc[128 * 8];   // (cos, sin) of 2 pi (k + 0.5)/128
+  double ex[64 * 16];    // 2^(j/64)
 };
 static __device__ PbxTables g_tables;
 __constant__ double kSinP[3] = {-1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0};
@@ -44,17 +52,20 @@ __constant__ double kExpP[4] = {0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0};
 // -2 log(x) for positive normal x (what both Box-Muller and the accept threshold need):
 // the same reduction with the factor -2 folded into the table value, the polynomial
 // and the exponent term -- one multiply less than scaling a plain log afterwards
-__constant__ double kN2LogP[3] = {1.0, -2.0 / 3.0, 0.5};
+__constant__ double kN2LogP[5] = {1.0, -2.0 / 3.0, 0.5, -0.4, 1.0 / 3.0};
 __device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
   const int hi = __double2hiint(x), lo = __double2loint(x);
   const int e = (hi >> 20) - 1023;
   const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, lo);   // [1, 2)
-  const double2 t = tb->lg[(hi >> 10) & 1023];
-  const double r = fma(m, t.x, -1.0);                                      // |r| < 2^-11
-  // -2 log1p(r) = -2r + r^2 (1 - 2r/3 + r^2/2 - ...); the next term is < 0.4 * 2^-55
-  double p = fma(r, kN2LogP[2], kN2LogP[1]);
+  const double2 t = tb->lg[((hi >> 10) & 0x3F8) | (threadIdx.x & 7)];
+  const double r = fma(m, t.x, -1.0);                                      // |r| < 2^-8
+  // -2 log1p(r) = -2r + r^2 (1 - 2r/3 + r^2/2 - 2r^3/5 + r^4/3 - ...); the next term is
+  // (2/7) r^7 < 0.3 * 2^-56
+  double p = fma(r, kN2LogP[4], kN2LogP[3]);
+  p = fma(r, p, kN2LogP[2]);
+  p = fma(r, p, kN2LogP[1]);
   p = fma(r, p, kN2LogP[0]);
-  p = fma(r * r, p, t.y);                        // -2 log c + r^2 (1 - 2r/3 + r^2/2)
+  p = fma(r * r, p, t.y);                        // -2 log c + r^2 (1 - 2r/3 + ...)
   p = fma(r, -2.0, p);                           // ... - 2r  = -2 log(c (1 + r))
   const double ed = __hiloint2double(0x43300000, e ^ (int)0x80000000) - 4503601774854144.0;
   return fma(ed, -1.386294361119890618835, p);   // -2 ln 2
@@ -63,16 +74,16 @@ __device__ __forceinline__ double fast_neg2log(double x, const PbxTables* tb) {
 // (sin, cos)(2 pi u), u = (w + 0.5) / 2^32
 __device__ __forceinline__ void fast_sincos2pi(uint32_t w, const PbxTables* tb, double& s,
                                                double& c) {
-  const double2 t = tb->sc[w >> 22];
-  // rho = 2 pi ((w & 0x3fffff) + 0.5 - 2^21) / 2^32,  |rho| < pi/1024.  The 22 bits go
+  const double2 t = tb->sc[((w >> 22) & 0x3F8) | (threadIdx.x & 7)];
+  // rho = 2 pi ((w & 0x1ffffff) + 0.5 - 2^24) / 2^32,  |rho| < pi/128.  The 25 bits go
   // into the mantissa of 2^51 (unit in the last place 1/2) doubled, so that 2^51 + k is
-  // exact and one subtraction of 2^51 + 2^21 - 0.5 (representable) centres it
-  const double v = __hiloint2double(0x43200000, (int)((w & 0x003FFFFFu) << 1));
-  const double rho = (v - 2251799815782399.5) * 1.4629180792671596e-9;    // 2 pi / 2^32
+  // exact and one subtraction of 2^51 + 2^24 - 0.5 (representable) centres it
+  const double v = __hiloint2double(0x43200000, (int)((w & 0x01FFFFFFu) << 1));
+  const double rho = (v - 2251799830462463.5) * 1.4629180792671596e-9;    // 2 pi / 2^32
   const double q = rho * rho;
-  // |rho| < 3.1e-3: the dropped terms are rho^7/5040 < 1e-21 and rho^6/720 < 2e-18
-  const double sr = fma(rho * q, fma(q, kSinP[1], kSinP[0]), rho);         // sin(rho)
-  const double cr = fma(q, fma(q, kCosP[1], kCosP[0]), 1.0);               // cos(rho)
+  // |rho| < 2.46e-2: the dropped terms are rho^9/9! < 1e-20 and rho^8/8! < 4e-18
+  const double sr = fma(rho * q, fma(q, fma(q, kSinP[2], kSinP[1]), kSinP[0]), rho);   // sin(rho)
+  const double cr = fma(q, fma(q, fma(q, kCosP[2], kCosP[1]), kCosP[0]), 1.0);         // cos(rho)
   c = fma(t.x, cr, -(t.y * sr));
   s = fma(t.y, cr, t.x * sr);
 }
@@ -88,7 +99,7 @@ __device__ __forceinline__ double fast_exp(double x, const PbxTables* tb) {
   p = fma(r, p, kExpP[1]);
   p = fma(r, p, kExpP[0]);
   p = fma(r * r, p, r);                                                    // expm1(r)
-  const double tj = tb->ex[n & 63];
+  const double tj = tb->ex[((n & 63) << 4) | (threadIdx.x & 15)];
   const double y = fma(tj, p, tj);
   return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
@@ -119,19 +130,26 @@ static int init_tables(pbx_ctx* ctx) {
   static bool done[64] = {false};
   if (ctx->device < 64 && done[ctx->device]) return PBX_OK;
   static PbxTables h;
-  for (int j = 0; j < 1024; ++j) {
-    const long double c = 1.0L + (j + 0.5L) / 1024.0L;
-    h.lg[j].x = (double)(1.0L / c);
+  for (int j = 0; j < 128; ++j) {
+    const long double c = 1.0L + (j + 0.5L) / 128.0L;
+    const double inv = (double)(1.0L / c);
     // log c_j must pair with the ROUNDED reciprocal: log(1/inv) keeps r = m*inv - 1 exact
-    h.lg[j].y = (double)(2.0L * logl((long double)h.lg[j].x));        // = -2 log c_j
+    const double n2l = (double)(2.0L * logl((long double)inv));        // = -2 log c_j
+    for (int g = 0; g < 8; ++g) {
+      h.lg[8 * j + g].x = inv;
+      h.lg[8 * j + g].y = n2l;
+    }
   }
   const long double two_pi = 6.283185307179586476925286766559L;
-  for (int k = 0; k < 1024; ++k) {
-    const long double th = two_pi * (k + 0.5L) / 1024.0L;
-    h.sc[k].x = (double)cosl(th);
-    h.sc[k].y = (double)sinl(th);
+  for (int k = 0; k < 128; ++k) {
+    const long double th = two_pi * (k + 0.5L) / 128.0L;
+    for (int g = 0; g < 8; ++g) {
+      h.sc[8 * k + g].x = (double)cosl(th);
+      h.sc[8 * k + g].y = (double)sinl(th);
+    }
   }
-  for (int j = 0; j < 64; ++j) h.ex[j] = (double)exp2l(j / 64.0L);
+  for (int j = 0; j < 64; ++j)
+    for (int g = 0; g < 16; ++g) h.ex[16 * j + g] = (double)exp2l(j / 64.0L);
   PBX_CUDA(cudaMemcpyToSymbolAsync(g_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice,
                                    ctx->stream));
   PBX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -698,12 +716,454 @@ __global__ void __launch_bounds__(WsCfg<D>::THREADS, 1)
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// "Whitened-decision" kernel (log accept rule, D <= 4): the default native-RNG path.
+//
+// The accept test of the log rule, maha(x + d) <= maha(x) - 2 log t, is quadratic in the
+// WHITENED state y = W^T (x - mean):  |y + e|^2 <= |y|^2 + th  with e = W^T d, i.e.
+//         y . e  <=  (th - |e|^2) / 2  =: kappa
+// and kappa, like e, does not depend on the chain state.  So the producers (parallel over
+// steps) ship e, kappa and d, and the inherently sequential part shrinks to one D-term dot
+// product, one compare and predicated adds (y += e, x += d): ~13 instructions per step
+// instead of ~39, with a dependent chain of ~23 cycles per step instead of ~100.  Steps are
+// taken in pairs (A, B): both dots use the state before A, and B's threshold is picked
+// between kappa_B (A rejected) and kappa_B - e_A . e_B (A accepted), also state-free.
+// x is still advanced by exactly x + d (the reference's arithmetic, sp.py:231-239 /
+// variable.py:693-697), and the recorded density is recomputed from the recorded x by the
+// writers with the same quadratic form as everywhere else, so trajectories and densities
+// are bit-identical to the exact-arithmetic kernels as long as the decisions agree; a
+// decision can only differ where the margin |y . e - kappa| is below the rounding of the
+// incrementally tracked y (~1e-14 relative): ~1e-14 per step.
+//
+// CTA = `cpc` chains (<= 32, chosen by the host so that the grid fills all SMs: 28 for
+// 4096 chains on 148 SMs), 15 warps:
+//   warp 0        decisions: lane = chain
+//   warps 1..14   producers / writers, parallel over a flat list of 448 (pair, chain)
+//                 items per batch (batch = 448 / cpc pairs of steps); each thread owns one
+//                 item of every batch: drains its previous result (record x, density,
+//                 running sums), then draws the next pair of steps.  No lane is idle
+//                 whatever cpc is.
+// Ring of NSLOT batches in shared memory, [field pair][item] as double2 (128-bit
+// conflict-free accesses on both sides), one mbarrier pair per slot.
+// ---------------------------------------------------------------------------
+#define WD_NPROD 14
+#define WD_ITEMS (WD_NPROD * 32)
+#define WD_THREADS 512                // 16 warps: decisions, 14 producers, one idle (see below)
+#define WD_MAXD 4
+#ifndef WD_IPT
+#define WD_IPT 1                      // measured: 2 (four steps in flight per thread) gains nothing
+#endif
+#ifndef WD_PF
+#define WD_PF 2                       // pairs in flight in the decision warp's registers (D <= 2)
+#endif
+// shared-memory accesses of the decision warp by 32-bit shared-space address (a generic
+// pointer makes the compiler rebuild the shared window base -- S2UR SR_CgaCtaId, ~100 cycles
+// -- in front of every access of the loop); volatile keeps fetches and stores in program order
+__device__ __forceinline__ double2 pbx_lds_v2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void pbx_sts_v2(uint32_t addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
+}
+template <int D> struct WdCfg {
+  static constexpr int NF2 = 2 * D + 2;   // double2 per item: eA[D] eB[D] kA kB0 kB1 pad dA[D] dB[D]
+  // items per producer thread and batch (build-time experiment knob; 2 = four steps in
+  // flight per thread, needs the doubled slots to fit into shared memory)
+  static constexpr int IPT = (D <= 2) ? WD_IPT : 1;
+  static constexpr int ITEMS = WD_ITEMS * IPT;
+  static constexpr int NSLOT = (D <= 2 && IPT == 1) ? 3 : 2;
+  static constexpr size_t SMEM = (size_t)NSLOT * NF2 * ITEMS * sizeof(double2);
+};
+
+template <int D, bool kFast, bool kZeroMean>
+__global__ void __launch_bounds__(WD_THREADS, 1)
+    mh_mvn_wd_kernel(const MhMvnArgs a, const __grid_constant__ MhMvnConst m, const int cpc) {
+  constexpr int NF2 = WdCfg<D>::NF2;
+  constexpr int NS = WdCfg<D>::NSLOT;
+  constexpr int IPT = WdCfg<D>::IPT;
+  constexpr int ITEMS = WdCfg<D>::ITEMS;
+  extern __shared__ __align__(16) double2 ring2[];        // [NS][NF2][ITEMS]
+  __shared__ __align__(8) unsigned long long in_full[NS], out_full[NS];
+  __shared__ __align__(16) PbxTables s_tb;
+  {
+    const double* src = reinterpret_cast<const double*>(&g_tables);
+    double* dst = reinterpret_cast<double*>(&s_tb);
+    for (int i = threadIdx.x; i < (int)(sizeof(PbxTables) / sizeof(double)); i += WD_THREADS)
+      dst[i] = src[i];
+  }
+  const PbxTables* tb = &s_tb;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t C = a.C;
+  const int P0 = WD_ITEMS / cpc;                // pairs of steps per batch and item index
+  const int P = IPT * P0;                       // pairs of steps per batch
+  const int S = 2 * P;                          // steps per batch
+  const int nb = (a.T + S - 1) / S;
+  const int cbase = blockIdx.x * cpc;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) {
+      pbx_mbar_init(&in_full[i], WD_NPROD);
+      pbx_mbar_init(&out_full[i], 1);
+    }
+  }
+  __syncthreads();
+
+  double ssum[D], ssq[D];                       // producers: running sums of their items
+#pragma unroll
+  for (int j = 0; j < D; ++j) ssum[j] = ssq[j] = 0.0;
+  // Warp w runs on SM sub-partition w % 4.  The decision warp (0) is latency-critical:
+  // it shares sub-partition 0 with only TWO producers (warps 4 and 8; warp 12 idles), the
+  // other three sub-partitions run four producers each.  Producer index pi = 0..13.
+  const int pi = (warp & 3) ? (warp - 1 - (warp >> 2)) : (warp == 4 ? 12 : (warp == 8 ? 13 : -1));
+  const int item = (pi >= 0) ? pi * 32 + lane : 0;
+
+  if (pi >= 0) {
+    // ===================== producer / writer: one (pair, chain) item per batch ==========
+    const int pr = item / cpc, ch = item - pr * cpc;
+    const int c = cbase + ch;
+    const bool valid = c < a.C;
+    const uint32_t gchain = (uint32_t)(a.chain0 + (valid ? c : 0));
+    const bool rec_all = a.thin == 1 && a.out_x != nullptr && a.out_prob != nullptr;
+    // My items of a batch: pairs pr + k P0 (k < IPT) of chain ch.  Records of the batch being
+    // drained (thin == 1: record index = step index) through running pointers.
+    double* px = rec_all ? a.out_x + ((int64_t)(2 * pr) * D) * C + c : nullptr;
+    double* pp = rec_all ? a.out_prob + (int64_t)(2 * pr) * C + c : nullptr;
+    const int64_t kx = (int64_t)(2 * P0) * D * C, kp = (int64_t)(2 * P0) * C;
+    for (int b = 0; b < nb + NS; ++b) {
+      const int s = b % NS;
+      double2* slot = ring2 + (size_t)s * NF2 * ITEMS + item;
+      if (b >= NS) {
+        // ---- drain my items of batch b - NS: the states after steps A and B -------------
+        const int bd = b - NS;
+        pbx_mbar_wait(&out_full[s], (uint32_t)(bd / NS) & 1);
+        const bool whole = rec_all && (bd + 1) * S <= a.T;
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+          double r[2 * D];
+#pragma unroll
+          for (int q = 0; q < D; ++q) {
+            const double2 t2 = slot[(D + 2 + q) * ITEMS + k * WD_ITEMS];
+            r[2 * q] = t2.x;
+            r[2 * q + 1] = t2.y;
+          }
+          const int kA = bd * S + 2 * (pr + k * P0);
+          if (valid && whole) {
+            // common case (every step recorded, whole batch live): straight-line code
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              double xs[D];
+#pragma unroll
+              for (int j = 0; j < D; ++j) {
+                xs[j] = r[h * D + j];
+                ssum[j] += xs[j];
+                ssq[j] = fma(xs[j], xs[j], ssq[j]);
+                px[k * kx + (h * D + j) * C] = xs[j];
+              }
+              const double lpv = -0.5 * (m.norm_c + mvn_maha<D, kZeroMean>(xs, m));
+              pp[k * kp + h * C] = a.log_pscale ? lpv : out_exp(lpv, tb);
+            }
+          } else if (valid) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int kk = kA + h;
+              if (kk < a.T) {
+                double xs[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                  xs[j] = r[h * D + j];
+                  ssum[j] += xs[j];
+                  ssq[j] = fma(xs[j], xs[j], ssq[j]);
+                }
+                const bool keep = ((kk + 1) % a.thin) == 0;
+                const int64_t rec = (kk + 1) / a.thin - 1;
+                if (keep) {
+                  if (a.out_x) {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) a.out_x[(rec * D + j) * C + c] = xs[j];
+                  }
+                  if (a.out_prob) {
+                    const double lpv = -0.5 * (m.norm_c + mvn_maha<D, kZeroMean>(xs, m));
+                    a.out_prob[rec * C + c] = a.log_pscale ? lpv : out_exp(lpv, tb);
+                  }
+                }
+              }
+            }
+          }
+        }
+        if (rec_all) {
+          px += (int64_t)S * D * C;
+          pp += (int64_t)S * C;
+        }
+      }
+      if (b >= nb) continue;
+      // ---- draw my pairs of steps of batch b (IPT independent pairs: ILP) ------------------
+#pragma unroll
+      for (int k = 0; k < IPT; ++k) {
+        const int64_t gA = a.step0 + (int64_t)b * S + 2 * (pr + k * P0);
+        double eA[D], eB[D], dA_[D], dB_[D], kA_, kB_;
+        auto gen = [&](int64_t gstep, double (&eta)[D], double (&dv)[D], double& kap) {
+          double dl[D], t;
+          draw_step<D, kFast>(a.seed, (uint64_t)gstep, gchain, a.prop_kind, m, tb, dl, t);
+          colour_delta<D>(kFast ? 0 : a.has_L, m, dl, dv);
+          const double th = fast_neg2log(t, tb);
+          double n2 = 0.0;
+#pragma unroll
+          for (int kk = 0; kk < D; ++kk) {
+            double e = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) e = fma(dv[j], m.W[j * D + kk], e);
+            eta[kk] = e;
+            n2 = fma(e, e, n2);
+          }
+          kap = 0.5 * (th - n2);
+        };
+        gen(gA, eA, dA_, kA_);
+        gen(gA + 1, eB, dB_, kB_);
+        double cross = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < D; ++kk) cross = fma(eA[kk], eB[kk], cross);
+        double v[4 * D + 4];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          v[j] = eA[j];
+          v[D + j] = eB[j];
+          v[2 * D + 4 + j] = dA_[j];
+          v[3 * D + 4 + j] = dB_[j];
+        }
+        v[2 * D] = kA_;
+        v[2 * D + 1] = kB_;
+        v[2 * D + 2] = kB_ - cross;
+        v[2 * D + 3] = 0.0;
+        if (gA == 0) v[2 * D] = INFINITY;        // global step 0 accepts unconditionally (sp.py:253)
+#pragma unroll
+        for (int q = 0; q < NF2; ++q)
+          slot[q * ITEMS + k * WD_ITEMS] = make_double2(v[2 * q], v[2 * q + 1]);
+      }
+      __syncwarp();
+      if (lane == 0) pbx_mbar_arrive(&in_full[s]);
+    }
+  } else if (warp == 0) {
+    // ======================= decisions: lane = chain ======================================
+    const bool active = lane < cpc;
+    const int c = cbase + lane;
+    const bool valid = active && c < a.C;
+    const int li = active ? lane : cpc - 1;      // idle lanes shadow the last chain (no stores)
+    double x[D], y[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) x[j] = valid ? a.state[j * C + c] : 0.0;
+    {
+      double dev[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) dev[j] = kZeroMean ? x[j] : x[j] - m.mean[j];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) e = fma(dev[j], m.W[j * D + k], e);
+        y[k] = e;
+      }
+    }
+    int nacc = 0;
+    // (laundered through an opaque move so that the compiler keeps the base in a register
+    // instead of rematerialising it -- S2UR SR_CgaCtaId and friends -- at every use)
+    uint32_t ring_base = pbx_smem_u32(ring2);
+    asm volatile("mov.u32 %0, %0;" : "+r"(ring_base));
+    // one pair of steps; v = the item's fields (see WdCfg), results overwrite dA / dB
+    auto process = [&](uint32_t it, const double (&v)[4 * D + 4], bool liveB) {
+      double dA = y[0] * v[0], dB = y[0] * v[D];
+#pragma unroll
+      for (int j = 1; j < D; ++j) {
+        dA = fma(y[j], v[j], dA);
+        dB = fma(y[j], v[D + j], dB);
+      }
+      const bool aA = dA <= v[2 * D];
+      const double kB = aA ? v[2 * D + 2] : v[2 * D + 1];
+      const bool aB = liveB && (dB <= kB);
+      // y (on the dependent chain): speculative add + select.  x (off the chain): one
+      // fma with a 0.0 / 1.0 mask per component -- fma(1, d, x) rounds x + d exactly as the
+      // add does, fma(0, d, x) returns x -- instead of an add and two 32-bit selects.
+      const double mA = __hiloint2double(aA ? 0x3FF00000 : 0, 0);
+      const double mB = __hiloint2double(aB ? 0x3FF00000 : 0, 0);
+      double r[2 * D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double ya = y[j] + v[j];
+        y[j] = aA ? ya : y[j];
+        x[j] = fma(mA, v[2 * D + 4 + j], x[j]);
+        r[j] = x[j];
+      }
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double yb = y[j] + v[D + j];
+        y[j] = aB ? yb : y[j];
+        x[j] = fma(mB, v[3 * D + 4 + j], x[j]);
+        r[D + j] = x[j];
+      }
+      nacc += (int)aA + (int)aB;
+      if (active) {
+#pragma unroll
+        for (int q = 0; q < D; ++q)
+          pbx_sts_v2(it + (D + 2 + q) * ITEMS * 16, r[2 * q], r[2 * q + 1]);
+      }
+    };
+    auto fetch = [&](uint32_t it, double (&v)[4 * D + 4]) {
+#pragma unroll
+      for (int q = 0; q < NF2; ++q) {
+        const double2 t2 = pbx_lds_v2(it + q * ITEMS * 16);
+        v[2 * q] = t2.x;
+        v[2 * q + 1] = t2.y;
+      }
+    };
+#pragma unroll 1
+    for (int b = 0; b < nb; ++b) {
+      const int s = b % NS;
+      const uint32_t slot = ring_base + (uint32_t)((s * NF2 * ITEMS + li) * 16);
+      pbx_mbar_wait(&in_full[s], (uint32_t)(b / NS) & 1);
+      const int kb = b * S;
+      const int np = min(P, (a.T - kb + 1) / 2);            // pairs with a live step
+      const bool tail = kb + S > a.T;                       // only the last batch can be short
+      // A pair's fields are fetched three pairs before they are used (register ring of four
+      // pairs), so that the shared-memory latency -- long under the producers' traffic --
+      // stays off the chain; the fetches are volatile, i.e. issued exactly here.  Whole
+      // batches run as straight-line groups of four pairs (one backward branch per group:
+      // every branch costs the single decision warp a predicate + fetch bubble).
+      int p = 0;
+      if (!tail) {
+        const int last = (np - 1) * cpc * 16;
+        const int step16 = cpc * 16;
+        uint32_t it = slot;
+        int off = 0;                                       // byte offset of pair p
+        if constexpr (D <= 2) {
+          const int nfull = np & ~3;
+          double v0[4 * D + 4], v1[4 * D + 4], v2[4 * D + 4], v3[4 * D + 4];
+          fetch(slot, v0);
+          fetch(slot + min(step16, last), v1);
+          fetch(slot + min(2 * step16, last), v2);
+#pragma unroll 1
+          for (; p < nfull; p += 4) {
+            fetch(slot + min(off + 3 * step16, last), v3);
+            process(it, v0, true);
+            fetch(slot + min(off + 4 * step16, last), v0);
+            process(it + step16, v1, true);
+            fetch(slot + min(off + 5 * step16, last), v1);
+            process(it + 2 * step16, v2, true);
+            fetch(slot + min(off + 6 * step16, last), v2);
+            process(it + 3 * step16, v3, true);
+            it += 4 * step16;
+            off += 4 * step16;
+          }
+        } else {                                           // fewer registers to spare: ring of two
+          const int nfull = np & ~1;
+          double v0[4 * D + 4], v1[4 * D + 4];
+          fetch(slot, v0);
+#pragma unroll 1
+          for (; p < nfull; p += 2) {
+            fetch(slot + min(off + step16, last), v1);
+            process(it, v0, true);
+            fetch(slot + min(off + 2 * step16, last), v0);
+            process(it + step16, v1, true);
+            it += 2 * step16;
+            off += 2 * step16;
+          }
+        }
+      }
+#pragma unroll 1
+      for (; p < np; ++p) {                                // tail batch / remainder pairs
+        double v[4 * D + 4];
+        fetch(slot + p * cpc * 16, v);
+        process(slot + p * cpc * 16, v, kb + 2 * p + 1 < a.T);
+      }
+      __syncwarp();
+      if (lane == 0) pbx_mbar_arrive(&out_full[s]);
+    }
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < D; ++j) a.state[j * C + c] = x[j];
+      a.state_lp[c] = -0.5 * (m.norm_c + mvn_maha<D, kZeroMean>(x, m));
+      if (a.accept_count) a.accept_count[c] += (int64_t)nacc;
+    }
+  }
+  // ---- running sums: fixed-order reduction of the per-item partials (deterministic) -------
+  if (a.stat_sum == nullptr && a.stat_sumsq == nullptr) return;
+  __syncthreads();                               // every slot is drained: reuse the ring
+  double* part = reinterpret_cast<double*>(ring2);           // [2 D][WD_ITEMS]
+  if (pi >= 0) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      part[(2 * j) * WD_ITEMS + item] = ssum[j];
+      part[(2 * j + 1) * WD_ITEMS + item] = ssq[j];
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cpc * D; t += WD_THREADS) {
+    const int j = t / cpc, ch = t - j * cpc;
+    const int c = cbase + ch;
+    if (c >= a.C) continue;
+    double s1 = 0.0, s2 = 0.0;
+    for (int p = 0; p < P0; ++p) {
+      s1 += part[(2 * j) * WD_ITEMS + p * cpc + ch];
+      s2 += part[(2 * j + 1) * WD_ITEMS + p * cpc + ch];
+    }
+    if (a.stat_sum) a.stat_sum[j * C + c] += s1;
+    if (a.stat_sumsq) a.stat_sumsq[j * C + c] += s2;
+  }
+}
+
+// chains per CTA of the whitened-decision kernel: 448 / cpc must be an even integer or 14;
+// the grid should fill whole waves of SMs with as few chains per CTA as possible (the CTA's
+// time is proportional to cpc: its producers work on cpc chains)
+static int wd_pick_cpc(int C, int sms) {
+  const int cand[5] = {32, 28, 16, 8, 4};
+  int best = 32;
+  long best_cost = -1;
+  for (int i = 0; i < 5; ++i) {
+    const long ctas = (C + cand[i] - 1) / cand[i];
+    const long cost = ((ctas + sms - 1) / sms) * cand[i];
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = cand[i];
+    }
+  }
+  return best;
+}
+
 template <int D>
 static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, int kernel_variant) {
   const bool injected = a.inj_delta != nullptr;
   const bool per_step = a.out_accept != nullptr || a.out_score != nullptr ||
                         a.out_xprop != nullptr || a.out_pprop != nullptr;
   const bool use_ws = !injected && !per_step && kernel_variant != 1;
+  const bool wd_ok = use_ws && D <= WD_MAXD && a.accept_mode == PBX_ACCEPT_LOG;
+  if (kernel_variant == 4 && !wd_ok) {
+    pbx_set_error("pbx_mh_mvn_run: kernel_variant 4 (whitened-decision kernel) needs the native "
+                  "RNG, the log accept rule, no per-step outputs and n_dims <= %d", WD_MAXD);
+    return PBX_ERR_UNSUPPORTED;
+  }
+  if constexpr (D <= WD_MAXD) {
+    if (wd_ok && kernel_variant != 2) {
+      const int cpc = wd_pick_cpc(a.C, ctx->sm_count);
+      const int grid = (a.C + cpc - 1) / cpc;
+      const size_t smem = WdCfg<D>::SMEM;
+      const bool fast = a.prop_kind == PBX_PROP_NORMAL && !a.has_L;
+      bool zero_mean = true;
+      for (int j = 0; j < D; ++j) zero_mean = zero_mean && m.mean[j] == 0.0;
+#define PBX_WD_LAUNCH(F, Z)                                                                   \
+  do {                                                                                        \
+    PBX_CUDA(cudaFuncSetAttribute(mh_mvn_wd_kernel<D, F, Z>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    mh_mvn_wd_kernel<D, F, Z><<<grid, WD_THREADS, smem, ctx->stream>>>(a, m, cpc);          \
+  } while (0)
+      if (fast && zero_mean) PBX_WD_LAUNCH(true, true);
+      else if (fast) PBX_WD_LAUNCH(true, false);
+      else if (zero_mean) PBX_WD_LAUNCH(false, true);
+      else PBX_WD_LAUNCH(false, false);
+#undef PBX_WD_LAUNCH
+      PBX_LAUNCH_CHECK(ctx);
+      return PBX_OK;
+    }
+  }
   if (use_ws) {
     const int grid = (a.C + 31) / 32;
     const size_t smem = WsCfg<D>::SMEM;

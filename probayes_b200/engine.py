@@ -191,7 +191,10 @@ class Engine:
         x [R, D, C], prob [R, C] (record), accept [T, C] uint8 + score [T, C]
         (per_step), accept_count [C] int64, stat_sum/stat_sumsq [D, C] (stats),
         state_lp [C].  ``out`` may carry preallocated "x"/"prob" buffers to
-        reuse; ``variant`` 1 forces the one-thread-per-chain kernel."""
+        reuse; ``variant`` 0 picks the kernel (native RNG + log rule + D <= 4: the
+        warp-specialised kernel that decides on the whitened state), 1 forces the
+        one-thread-per-chain kernel, 2 the warp-specialised kernel with the reference's
+        arithmetic in the decision, 4 the whitened-decision kernel."""
         torch = _torch()
         D, C_ = state.shape
         T = int(steps)

@@ -112,6 +112,57 @@ def test_warp_specialised_equals_per_thread_kernel(D, C, T, accept, logp, prop, 
     assert np.array_equal(host(s1), host(s2))
 
 
+@pytest.mark.parametrize("D,C,T,logp,prop,chol,thin", [
+    (2, 4096, 333, False, "normal", False, 1), (2, 4096, 1000, True, "normal", False, 1),
+    (2, 100, 257, False, "normal", False, 3), (2, 33, 101, True, "uniform", False, 1),
+    (3, 65, 130, True, "normal", True, 2), (1, 50, 77, False, "normal", False, 1),
+    (4, 48, 95, False, "normal", False, 1), (4, 300, 64, True, "spherical", False, 5),
+    (2, 5000, 129, False, "normal", False, 1), (3, 7, 40, False, "normal", False, 1)])
+def test_whitened_decision_kernel_equals_per_thread_kernel(D, C, T, logp, prop, chol, thin):
+    """The default native-RNG kernel (decisions taken on the incrementally tracked whitened
+    state, kernel_variant 4) against the exact-arithmetic per-thread kernel: same Philox
+    stream, identical decisions, and therefore bit-identical trajectories and densities
+    (x is advanced by the same x + delta, the density recomputed from the recorded x).
+    Covers every chains-per-CTA choice (4 ... 32), odd walk lengths, partial batches."""
+    eng = engine()
+    rng = np.random.default_rng(11 * D + C)
+    A = rng.standard_normal((D, D))
+    cov = A @ A.T / D + np.eye(D)
+    mean = rng.standard_normal(D) if C % 2 else np.zeros(D)
+    init = rng.standard_normal((D, C))
+    L = np.linalg.cholesky(0.3 * cov) if chol else None
+    kw = dict(seed=99173, accept="log", log_pscale=logp, prop=prop, prop_scale=0.7,
+              prop_chol=L, thin=thin, prop_radius=0.9 if prop == "spherical" else 0.0)
+    s1, s2 = dev(eng, init), dev(eng, init)
+    a = eng.mh_mvn(s1, mean, cov, T, variant=1, **kw)
+    b = eng.mh_mvn(s2, mean, cov, T, variant=4, **kw)
+    eng.sync()
+    for key in ("x", "prob", "accept_count", "state_lp"):
+        assert np.array_equal(host(a[key]), host(b[key])), key
+    assert np.array_equal(host(s1), host(s2))
+    # running sums: the same terms in a different (fixed) order
+    assert relerr(host(a["stat_sum"]) + 1e3, host(b["stat_sum"]) + 1e3) <= 1e-12
+    assert relerr(host(a["stat_sumsq"]), host(b["stat_sumsq"])) <= 1e-12
+    # resumed in two launches == one launch (y is re-derived from x at the resume point)
+    s3 = dev(eng, init)
+    h = (T // 2) // thin * thin
+    c1 = eng.mh_mvn(s3, mean, cov, h, variant=4, **kw)
+    c2 = eng.mh_mvn(s3, mean, cov, T - h, variant=4, step0=h, state_lp=c1["state_lp"], **kw)
+    eng.sync()
+    assert np.array_equal(np.concatenate([host(c1["x"]), host(c2["x"])])[:host(b["x"]).shape[0]],
+                          host(b["x"]))
+
+
+def test_whitened_decision_variant_is_refused_where_it_does_not_apply():
+    eng = engine()
+    st = dev(eng, np.zeros((2, 8)))
+    with pytest.raises(Exception):
+        eng.mh_mvn(st, [0., 0.], COV, 10, seed=1, accept="reference", variant=4)
+    st5 = dev(eng, np.zeros((5, 8)))
+    with pytest.raises(Exception):
+        eng.mh_mvn(st5, np.zeros(5), np.eye(5), 10, seed=1, accept="log", variant=4)
+
+
 def test_warp_specialised_philox_replay_general_d():
     """Fast path vs the CPU restatement fed with the CPU-generated Philox stream."""
     eng = engine()
