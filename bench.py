@@ -341,8 +341,9 @@ def secondary(eng, peaks, fp64_peak, quick=False):
     alg = 2.0 * 8 * M * S + 8.0 * (M + S)
     out["c4_normalise_marginals"] = {"ms": ms, "algorithmic_gbs": alg / (ms * 1e-3) / 1e9,
                                      "frac": alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                                     "note": "max + sumexp + posterior/marginal passes "
-                                             "(3 reads + 1 write of the grid)"}
+                                     "note": "two passes: online (max, sum-exp), then posterior + "
+                                             "both marginals (2 reads + 1 write of the grid; "
+                                             "algorithmic = 1 read + 1 write)"}
     del lj, r
     # ---- C5: Gibbs d = 64, 65536 chains, one sweep = 64 coordinate steps ----------------
     from probayes_b200.cond_cov import CondCov
@@ -540,7 +541,7 @@ class C2:
         for w in range(self.W):              # CUDA events bracket the first walk's kernel
             self.walk(1000 + k * self.W + w, ev if w == 0 else None)
 
-    kernel = "mh_mvn_ws_kernel<2>"
+    kernel = "mh_mvn_wd_kernel<2>"
 
     def roofline(self, kernel_ms, peaks, which, fp64_peak, sm_mhz):
         eng = self.eng

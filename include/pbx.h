@@ -144,6 +144,13 @@ typedef struct {
   double* stat_sumsq;      /* [D][C] accumulated sum of squares, or NULL */
   double* out_xprop;       /* [T][D][C] or NULL: the proposal of every step (opqr.p values) */
   double* out_pprop;       /* [T][C] or NULL: the target density at the proposal (opqr.p.prob) */
+  /* set_delta(..., bound=True) (probayes/variable.py:700-739): a proposal beyond a CLOSED
+   * limit is clipped to it, beyond an OPEN limit it bounces back to the current value.  The
+   * proposal then depends on the state, so these walks run the one-thread-per-chain kernel. */
+  int32_t prop_bound;      /* 0 / 1 */
+  int32_t reserved1;
+  double lims[PBX_MAX_DIMS][2];
+  int32_t open_end[PBX_MAX_DIMS][2];
 } pbx_mh_mvn_params;
 
 PBX_API int pbx_mh_mvn_run(pbx_ctx* ctx, const pbx_mh_mvn_params* p);
@@ -247,6 +254,23 @@ PBX_API int pbx_grid_sumexp(pbx_ctx* ctx, const double* logjoint, int64_t n,
 PBX_API int pbx_grid_posterior(pbx_ctx* ctx, const double* logjoint, int32_t n_mu, int32_t n_sigma,
                        const double* gmax, const double* gsum,
                        double* post, double* marg_mu_lin, double* marg_sigma_lin);
+/* The same algebra in TWO passes over the grid (PD.conditionalise + both PD.marginal calls,
+ * pd.py:214-295,136-165), for log-pscale (linear = 0) or linear-pscale (linear = 1) input:
+ * out2[0] = max (0 for linear input), out2[1] = sum exp_logp(v - max) (plain sum for linear
+ * input), from ONE read of v with online rescaling (device scalars) */
+PBX_API int pbx_grid_max_sumexp(pbx_ctx* ctx, const double* v, int64_t n, int32_t linear,
+                                double* out2);
+/* slab-sharded grids: sum_inout[0] *= exp(local_max[0] - global_max[0]) (device scalars), so
+ * that per-rank sums taken against the local maxima can be all-reduced */
+PBX_API int pbx_grid_rescale_sumexp(pbx_ctx* ctx, const double* local_max,
+                                    const double* global_max, double* sum_inout);
+/* pbx_grid_posterior with linear-pscale support (post = p / max(tiny, sum), marginals plain
+ * sums) and the marginals' clamped logs fused: marg_log_flags bit 0 -> marg_mu = log_prob(sum),
+ * bit 1 -> marg_sigma likewise (leave a bit clear where the sum must be all-reduced first) */
+PBX_API int pbx_grid_posterior2(pbx_ctx* ctx, const double* prob, int32_t n_mu, int32_t n_sigma,
+                                const double* gmax, const double* gsum, int32_t linear,
+                                double* post, double* marg_mu, double* marg_sigma,
+                                int32_t marg_log_flags);
 /* v[i] = log_prob(v[i]) in place (clamped log of pscales.py:44-53) */
 PBX_API int pbx_log_prob_inplace(pbx_ctx* ctx, double* v, int64_t n);
 /* v[i] = exp_logp(v[i]) in place (clamped exp of pscales.py:56-65; PD.rescaled) */

@@ -78,6 +78,35 @@ def mh_mvn(seed, T, init, log_pscale=False, cov_tran=None):
     return out
 
 
+def mh_mvn_bound(seed, T):
+    """mcmc_prob4a's 2-D normal target on BOUNDED variables with set_delta([d], bound=True)
+    (probayes/variable.py:700-739): x closed (proposals clip at the limits), y open
+    (proposals beyond a limit bounce back to the current value).  Uniforms injected."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    mean, cov = [0., 0.], [[2.0, 1.2], [1.2, 2.0]]
+    x = pb.RV('x', vtype=float, vset=[-1.5, 1.5])
+    y = pb.RV('y', vtype=float, vset=(-1.5, 1.5))
+    sp = pb.SP(x & y)
+    sp.set_prob(scipy.stats.multivariate_normal, mean, cov)
+    sp.set_tran(lambda **kwds: 1.)
+    step = 0.9
+    sp.set_delta([step], bound=True)
+    sp.set_scores('hastings')
+    sp.set_update('metropolis')
+    R = rng.random((T, 3))               # per step: d_x, d_y, threshold
+    init = (0.5, -1.0)
+    with ref_shim.injected_uniform(R.ravel()):
+        sampler = sp.sampler({'x': init[0], 'y': init[1]}, stop=T)
+        samples = [s for s in sampler]
+    out = _summary_arrays(sp, samples, ['x', 'y'])
+    out.update(delta=-step + (2 * step) * R[:, :2], thresh=R[:, 2], init=np.array(init),
+               mean=np.array(mean), cov=np.array(cov), step=np.array(step),
+               lims=np.array([[-1.5, 1.5], [-1.5, 1.5]]),
+               ex=np.array([[False, False], [True, True]]))
+    return out
+
+
 # ---------------------------------------------------------------------------
 def mh_mvn3d(seed, T):
     """Three variables, non-exchangeable mean / covariance: pins the value
@@ -366,6 +395,38 @@ def pd_algebra(seed, N, M, S):
                                 post.name, mm.name, pc.name]))
 
 
+def pd_cond_array(seed, N, M, S):
+    """PD.conditionalise on ARRAY-valued keys (probayes/pd.py:214-295): p(mu, sigma, x)
+    -> p(mu, x | sigma), p(sigma, x | mu) (axis move), p(mu | sigma, x) (normalise first),
+    in log and linear pscale, with the marginal taken from a conditional."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+    data = rng.normal(50., 10., size=N)
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    model = pb.SD(pb.RF(x), pb.RF(mu, sigma))
+    model.set_prob(scipy.stats.norm.logpdf,
+                   order={'x': 0, 'mu': 'loc', 'sigma': 'scale'}, pscale='log')
+    joint = model({x: data, 'mu': {M}, 'sigma': {S}}, iid=True, joint=True)
+    c_sig = joint.conditionalise('sigma')
+    c_mu = joint.conditionalise('mu')
+    c_sx = joint.conditionalise(['sigma', 'x'])
+    lin = joint.conditionalise('x').rescaled()
+    l_sig = lin.conditionalise('sigma')
+    l_mu = lin.conditionalise('mu')
+    dims = lambda pd: np.array([-1 if pd.dims[k] is None else pd.dims[k] for k in ('mu', 'sigma')])
+    return dict(data=data, mu=np.ravel(joint['mu']), sigma=np.ravel(joint['sigma']),
+                joint=np.asarray(joint.prob),
+                c_sig=np.asarray(c_sig.prob), c_mu=np.asarray(c_mu.prob),
+                c_sx=np.asarray(c_sx.prob), lin=np.asarray(lin.prob),
+                l_sig=np.asarray(l_sig.prob), l_mu=np.asarray(l_mu.prob),
+                dims=np.stack([dims(c_sig), dims(c_mu), dims(c_sx), dims(l_sig), dims(l_mu)]),
+                shapes=np.array([np.shape(c_mu['mu']), np.shape(c_mu['sigma'])]),
+                names=np.array([c_sig.name, c_mu.name, c_sx.name, l_sig.name, l_mu.name]))
+
+
 # ---------------------------------------------------------------------------
 def gibbs2d(seed, T):
     """examples/mcmc/gibbs_norm2d.py:15-22 with the cdf uniforms injected."""
@@ -453,6 +514,7 @@ def main():
         "mh_mvn_c1_b": lambda: mh_mvn(12, 256, (-2.5, 3.0)),
         "mh_mvn_log": lambda: mh_mvn(13, 256, (0., 1.), log_pscale=True),
         "mh_mvn_3d": lambda: mh_mvn3d(15, 256),
+        "mh_mvn_bound": lambda: mh_mvn_bound(16, 400),
         "gibbs3d": lambda: gibbs3d(54, 300),
         "mh_norm1d_hastings": lambda: mh_norm1d(21, 300, 60, 'hastings'),
         "mh_norm1d_metropolis": lambda: mh_norm1d(22, 300, 60, 'metropolis'),
@@ -465,6 +527,7 @@ def main():
         "dgei_peaked": lambda: dgei(42, 2000, 40, 36),
         "gibbs2d": lambda: gibbs2d(51, 400),
         "pd_algebra": lambda: pd_algebra(71, 40, 9, 7),
+        "pd_cond_array": lambda: pd_cond_array(72, 40, 9, 7),
         "omc_rs_norm1d": lambda: omc_rs_norm1d(61, 60, 400),
         "condcov_d8": lambda: condcov_bare(52, 8, 160),
         "condcov_d64": lambda: condcov_bare(53, 64, 256),

@@ -214,7 +214,7 @@ def mh_walk(init, delta, thresh, target, propose, log_pscale,
 # config C1/C2: 2-D (d-D) correlated-normal target, additive proposal
 # ----------------------------------------------------------------------------
 def mh_mvn_walk(init, delta, thresh, mean, cov, tran_chol=None,
-                log_pscale=False, reorder=True, accept="reference"):
+                log_pscale=False, reorder=True, accept="reference", bound=None):
     """MH on scipy.stats.multivariate_normal(mean, cov) as set up in
     examples/mcmc/mcmc_prob4a.py:38-49.
 
@@ -236,6 +236,8 @@ def mh_mvn_walk(init, delta, thresh, mean, cov, tran_chol=None,
     def propose(x, dl):
         if tran_chol is not None:
             dl = dl @ np.asarray(tran_chol, dtype=float).T
+        if bound is not None:            # set_delta(..., bound=True): variable.py:700-727
+            return ufun_propose(x, dl, [False] * d, bound)
         return x + dl
 
     return mh_walk(init, delta, thresh, target, propose, log_pscale, accept)

@@ -45,6 +45,9 @@ class MhMvnParams(C.Structure):
         ("out_accept", C.c_void_p), ("out_score", C.c_void_p),
         ("accept_count", C.c_void_p), ("stat_sum", C.c_void_p), ("stat_sumsq", C.c_void_p),
         ("out_xprop", C.c_void_p), ("out_pprop", C.c_void_p),
+        ("prop_bound", C.c_int32), ("reserved1", C.c_int32),
+        ("lims", (C.c_double * 2) * PBX_MAX_DIMS),
+        ("open_end", (C.c_int32 * 2) * PBX_MAX_DIMS),
     ]
 
 
@@ -112,6 +115,11 @@ SIGNATURES = {
     "pbx_grid_posterior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
+    "pbx_grid_max_sumexp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "pbx_grid_rescale_sumexp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pbx_grid_posterior2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int32]),
     "pbx_log_prob_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "pbx_exp_logp_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "pbx_gibbs_mvn_run": (C.c_int, [C.c_void_p, C.POINTER(GibbsMvnParams)]),

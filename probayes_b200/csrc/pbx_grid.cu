@@ -371,3 +371,338 @@ extern "C" int pbx_grid_posterior(pbx_ctx* ctx, const double* logjoint, int32_t 
   PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   return PBX_OK;
 }
+
+// ---------------------------------------------------------------------------
+// K4 in two passes over the grid (was max, sum-exp, posterior: three reads + a write).
+//
+// Pass A  pbx_grid_max_sumexp: ONE read.  Every thread keeps an online (max, sum-exp)
+//         pair: per chunk of 8 entries held in registers, the running maximum is raised
+//         first (one rescaling exp per chunk, and only when the maximum moves), then the
+//         8 terms exp(v - max) are added.  Pairs are merged (m, s) + (m', s') =
+//         (M = max, s exp(m - M) + s' exp(m' - M)) by shuffles and shared memory in a
+//         fixed order; the last CTA to finish (ticket) merges the per-CTA pairs in index
+//         order.  The result differs from sum exp(v - global max) only by the rounding of
+//         the rescaling factors (~1e-16 relative).  Linear-pscale input: plain sum.
+// Pass B  pbx_grid_posterior2: one read + one write (or in place), both marginals from
+//         the same pass, their clamped logs fused into the finishing kernel.
+// ---------------------------------------------------------------------------
+struct MsPair { double m, s; };
+__device__ __forceinline__ MsPair ms_merge(MsPair a, MsPair b) {
+  const double M = fmax(a.m, b.m);
+  MsPair r;
+  r.m = M;
+  // exp(-inf - -inf) never occurs: a pair with m = -inf has s = 0 and is skipped
+  r.s = (a.s == 0.0 ? 0.0 : a.s * exp(a.m - M)) + (b.s == 0.0 ? 0.0 : b.s * exp(b.m - M));
+  return r;
+}
+
+#define MS_THREADS 256
+#define MS_CHUNK 8
+template <bool kLinear>
+__global__ void __launch_bounds__(MS_THREADS)
+    grid_max_sumexp_kernel(const double* __restrict__ v, int64_t n, MsPair* __restrict__ partial,
+                           unsigned int* __restrict__ ticket, double* __restrict__ out2) {
+  double m = -INFINITY, s = 0.0;
+  const int64_t nchunk = n / MS_CHUNK;
+  const int64_t stride = (int64_t)gridDim.x * MS_THREADS;
+  const bool vec = (((uintptr_t)v) & 15) == 0;
+  for (int64_t ch = (int64_t)blockIdx.x * MS_THREADS + threadIdx.x; ch < nchunk; ch += stride) {
+    double e[MS_CHUNK];
+    if (vec) {
+      const double2* v2 = reinterpret_cast<const double2*>(v + ch * MS_CHUNK);
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK / 2; ++i) {
+        const double2 t = __ldcs(v2 + i);
+        e[2 * i] = t.x;
+        e[2 * i + 1] = t.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK; ++i) e[i] = v[ch * MS_CHUNK + i];
+    }
+    if (kLinear) {
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK; ++i) s += e[i];
+    } else {
+      double cm = e[0];
+#pragma unroll
+      for (int i = 1; i < MS_CHUNK; ++i) cm = fmax(cm, e[i]);
+      if (cm > m) {
+        s = (s == 0.0) ? 0.0 : s * exp(m - cm);
+        m = cm;
+      }
+      double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK; i += 2) {
+        t0 += pbx_exp_logp(e[i] - m);
+        t1 += pbx_exp_logp(e[i + 1] - m);
+      }
+      s += t0 + t1;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {               // the n % 8 tail
+    for (int64_t i = nchunk * MS_CHUNK; i < n; ++i) {
+      if (kLinear) {
+        s += v[i];
+      } else {
+        if (v[i] > m) {
+          s = (s == 0.0) ? 0.0 : s * exp(m - v[i]);
+          m = v[i];
+        }
+        s += pbx_exp_logp(v[i] - m);
+      }
+    }
+  }
+  MsPair p;
+  p.m = kLinear ? 0.0 : m;
+  p.s = s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MsPair q;
+    q.m = __shfl_xor_sync(0xffffffffu, p.m, o);
+    q.s = __shfl_xor_sync(0xffffffffu, p.s, o);
+    if (kLinear) p.s += q.s;
+    else p = ms_merge(p, q);              // symmetric: both lanes of a pair get the same bits
+  }
+  __shared__ MsPair sh[MS_THREADS / 32];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) sh[warp] = p;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    MsPair a = sh[0];
+    for (int w = 1; w < MS_THREADS / 32; ++w) {
+      if (kLinear) a.s += sh[w].s;
+      else a = ms_merge(a, sh[w]);
+    }
+    partial[blockIdx.x] = a;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {                                              // fixed tree: deterministic
+    __threadfence();
+    const volatile MsPair* pv = partial;
+    MsPair a;
+    a.m = kLinear ? 0.0 : -INFINITY;
+    a.s = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += MS_THREADS) {
+      MsPair b;
+      b.m = pv[i].m;
+      b.s = pv[i].s;
+      if (kLinear) a.s += b.s;
+      else a = ms_merge(a, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      MsPair q;
+      q.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+      q.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+      if (kLinear) a.s += q.s;
+      else a = ms_merge(a, q);
+    }
+    __syncthreads();                                       // sh[] is free again
+    if (lane == 0) sh[warp] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      MsPair t = sh[0];
+      for (int w = 1; w < MS_THREADS / 32; ++w) {
+        if (kLinear) t.s += sh[w].s;
+        else t = ms_merge(t, sh[w]);
+      }
+      out2[0] = t.m;
+      out2[1] = t.s;
+      *ticket = 0;                                         // ready for the next call
+    }
+  }
+}
+
+__global__ void grid_rescale_sumexp_kernel(const double* lmax, const double* gmax, double* sum) {
+  sum[0] = (sum[0] == 0.0) ? 0.0 : sum[0] * exp(lmax[0] - gmax[0]);
+}
+
+#define P2_ROWS 32
+#define P2_CPT 4                        // columns per thread (two 128-bit accesses per row)
+#define P2_THREADS 256
+#define P2_COLS (P2_THREADS * P2_CPT)
+#define P2_RU 4                         // rows in flight per thread
+
+// kLinear: the input (and the output) are linear-pscale probabilities: post = p / max(tiny,
+// sum) (pd.py:285-295 without the log/exp round trip), marginals = plain sums.
+template <bool kLinear>
+__global__ void __launch_bounds__(P2_THREADS)
+    grid_posterior2_kernel(const double* lj, int M, int S, const double* __restrict__ gmax,
+                           const double* __restrict__ gsum, double* post,
+                           double* __restrict__ row_partial, double* __restrict__ col_partial,
+                           int n_colblocks) {
+  __shared__ double s_row[P2_ROWS][P2_THREADS / 32];
+  const int s0 = blockIdx.x * P2_COLS + threadIdx.x * P2_CPT;
+  const int m0 = blockIdx.y * P2_ROWS;
+  const double mx = kLinear ? 0.0 : gmax[0];
+  const double den = fmax(PBX_TINY, gsum[0]);
+  const double lden = kLinear ? 0.0 : log(den);
+  const double rden = 1.0 / den;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // 128-bit path: whole 4-column group inside the row, rows 16-byte aligned
+  const bool vec = (S % 2 == 0) && ((((uintptr_t)lj) & 15) == 0) &&
+                   (post == nullptr || (((uintptr_t)post) & 15) == 0) && (s0 + P2_CPT <= S);
+  double col[P2_CPT];
+#pragma unroll
+  for (int k = 0; k < P2_CPT; ++k) col[k] = 0.0;
+  for (int r0 = 0; r0 < P2_ROWS; r0 += P2_RU) {
+    double e[P2_RU][P2_CPT];
+    // all loads of the P2_RU rows first (post may alias lj: the compiler cannot hoist them)
+#pragma unroll
+    for (int u = 0; u < P2_RU; ++u) {
+      const int m = m0 + r0 + u;
+      if (m < M && vec) {
+        const double2* src = reinterpret_cast<const double2*>(lj + (int64_t)m * S + s0);
+        const double2 a = __ldcs(src), b = __ldcs(src + 1);
+        e[u][0] = a.x; e[u][1] = a.y; e[u][2] = b.x; e[u][3] = b.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < P2_CPT; ++k)
+          e[u][k] = (m < M && s0 + k < S) ? lj[(int64_t)m * S + s0 + k] : (kLinear ? 0.0 : -PBX_HUGE);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < P2_RU; ++u) {
+      const int m = m0 + r0 + u;
+      double q[P2_CPT], o[P2_CPT];
+#pragma unroll
+      for (int k = 0; k < P2_CPT; ++k) {
+        if (kLinear) {
+          // reference: div_prob(p, sum) = p / max(tiny, sum)
+          q[k] = e[u][k] / den;
+          o[k] = q[k];
+        } else {
+          // reference: q = exp_logp(lj - max) / max(tiny, sum); post = log_prob(q); the
+          // marginal term is exp_logp(post).  log(q) is evaluated as (lj - max) - log(den)
+          // and exp(log q) as q itself: the same values to ~1e-16 relative for a third of
+          // the transcendental work; the clamp decision (q < tiny -> -1.797e308) is the
+          // reference's, taken on q.
+          const double sh = e[u][k] - mx;
+          const double qq = pbx_exp_logp(sh) * rden;         // q only feeds the marginal sums
+          const bool keep = qq >= PBX_TINY;
+          o[k] = keep ? sh - lden : -PBX_HUGE;
+          q[k] = keep ? qq : 0.0;                           // exp_logp(-1.797e308) = 0
+        }
+        if (!(m < M && s0 + k < S)) q[k] = 0.0;
+        col[k] += q[k];
+      }
+      if (post && m < M) {
+        if (vec) {
+          double2* dst = reinterpret_cast<double2*>(post + (int64_t)m * S + s0);
+          __stcs(dst, make_double2(o[0], o[1]));
+          __stcs(dst + 1, make_double2(o[2], o[3]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < P2_CPT; ++k)
+            if (s0 + k < S) post[(int64_t)m * S + s0 + k] = o[k];
+        }
+      }
+      double w = (q[0] + q[1]) + (q[2] + q[3]);
+#pragma unroll
+      for (int ofs = 16; ofs > 0; ofs >>= 1) w += __shfl_xor_sync(0xffffffffu, w, ofs);
+      if (lane == 0) s_row[r0 + u][warp] = w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < P2_CPT; ++k)
+    if (s0 + k < S) col_partial[(int64_t)blockIdx.y * S + s0 + k] = col[k];
+  __syncthreads();
+  if (threadIdx.x < P2_ROWS) {
+    const int m = m0 + threadIdx.x;
+    if (m < M) {
+      double w = 0.0;
+#pragma unroll
+      for (int k = 0; k < P2_THREADS / 32; ++k) w += s_row[threadIdx.x][k];
+      row_partial[(int64_t)m * n_colblocks + blockIdx.x] = w;
+    }
+  }
+}
+
+// log_flags: bit 0 -> marg_mu through the clamped log, bit 1 -> marg_sigma
+__global__ void __launch_bounds__(256)
+    grid_marginal_finish2(const double* __restrict__ row_partial, int M, int n_colblocks,
+                          const double* __restrict__ col_partial, int n_rowblocks, int S,
+                          double* __restrict__ marg_mu, double* __restrict__ marg_sigma,
+                          int log_flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M && marg_mu) {
+    double w = 0.0;
+    for (int k = 0; k < n_colblocks; ++k) w += row_partial[(int64_t)i * n_colblocks + k];
+    marg_mu[i] = (log_flags & 1) ? pbx_log_prob(w) : w;
+  }
+  if (i < S && marg_sigma) {
+    double w = 0.0;
+    for (int k = 0; k < n_rowblocks; ++k) w += col_partial[(int64_t)k * S + i];
+    marg_sigma[i] = (log_flags & 2) ? pbx_log_prob(w) : w;
+  }
+}
+
+extern "C" int pbx_grid_max_sumexp(pbx_ctx* ctx, const double* v, int64_t n, int32_t linear,
+                                   double* out2) {
+  PBX_REQUIRE(ctx && v && out2 && n >= 1, "pbx_grid_max_sumexp: bad argument");
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  int64_t want = (n + (int64_t)MS_THREADS * MS_CHUNK * 4 - 1) / ((int64_t)MS_THREADS * MS_CHUNK * 4);
+  const int np = (int)(want < 1 ? 1 : (want > ctx->sm_count * 8 ? ctx->sm_count * 8 : want));
+  // workspace: [ticket (256 B, zero between calls)] [np pairs]
+  int rc = pbx_ws_reserve(ctx, 256 + (size_t)np * sizeof(MsPair));
+  if (rc) return rc;
+  unsigned int* ticket = (unsigned int*)ctx->ws;
+  MsPair* partial = (MsPair*)((char*)ctx->ws + 256);
+  PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  // the ticket word lives at the start of the shared workspace, which other entry points
+  // overwrite: zero it every call (a 4-byte memset node, no kernel)
+  PBX_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ctx->stream));
+  if (linear)
+    grid_max_sumexp_kernel<true><<<np, MS_THREADS, 0, ctx->stream>>>(v, n, partial, ticket, out2);
+  else
+    grid_max_sumexp_kernel<false><<<np, MS_THREADS, 0, ctx->stream>>>(v, n, partial, ticket, out2);
+  PBX_LAUNCH_CHECK(ctx);
+  PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  return PBX_OK;
+}
+
+extern "C" int pbx_grid_rescale_sumexp(pbx_ctx* ctx, const double* local_max,
+                                       const double* global_max, double* sum_inout) {
+  PBX_REQUIRE(ctx && local_max && global_max && sum_inout, "pbx_grid_rescale_sumexp: null argument");
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  grid_rescale_sumexp_kernel<<<1, 1, 0, ctx->stream>>>(local_max, global_max, sum_inout);
+  PBX_LAUNCH_CHECK(ctx);
+  return PBX_OK;
+}
+
+extern "C" int pbx_grid_posterior2(pbx_ctx* ctx, const double* prob, int32_t n_mu, int32_t n_sigma,
+                                   const double* gmax, const double* gsum, int32_t linear,
+                                   double* post, double* marg_mu, double* marg_sigma,
+                                   int32_t marg_log_flags) {
+  PBX_REQUIRE(ctx && prob && gsum && (linear || gmax), "pbx_grid_posterior2: null argument");
+  PBX_REQUIRE(n_mu >= 1 && n_sigma >= 1, "pbx_grid_posterior2: sizes must be positive");
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  const int ncb = (n_sigma + P2_COLS - 1) / P2_COLS, nrb = (n_mu + P2_ROWS - 1) / P2_ROWS;
+  PBX_REQUIRE(nrb <= 65535, "pbx_grid_posterior2: too many rows per call (slab it)");
+  const size_t rp = ((size_t)n_mu * ncb * 8 + 255) / 256 * 256;
+  const size_t cp = (size_t)nrb * n_sigma * 8;
+  int rc = pbx_ws_reserve(ctx, rp + cp);
+  if (rc) return rc;
+  double* row_partial = (double*)ctx->ws;
+  double* col_partial = (double*)((char*)ctx->ws + rp);
+  PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (linear)
+    grid_posterior2_kernel<true><<<dim3(ncb, nrb), P2_THREADS, 0, ctx->stream>>>(
+        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb);
+  else
+    grid_posterior2_kernel<false><<<dim3(ncb, nrb), P2_THREADS, 0, ctx->stream>>>(
+        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb);
+  PBX_LAUNCH_CHECK(ctx);
+  if (marg_mu || marg_sigma) {
+    const int n = n_mu > n_sigma ? n_mu : n_sigma;
+    grid_marginal_finish2<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
+        row_partial, n_mu, ncb, col_partial, nrb, n_sigma, marg_mu, marg_sigma, marg_log_flags);
+    PBX_LAUNCH_CHECK(ctx);
+  }
+  PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  return PBX_OK;
+}

@@ -165,6 +165,9 @@ struct MhMvnConst {
   double norm_c;
   double radius;
   pbx_round_keys rk;         // Philox round keys of the walk's seed
+  int bound;                 // set_delta(..., bound=True)
+  double lims[PBX_MAX_DIMS][2];
+  int open_end[PBX_MAX_DIMS][2];
 };
 
 struct MhMvnArgs {
@@ -317,6 +320,21 @@ __global__ void __launch_bounds__(128) mh_mvn_kernel(const MhMvnArgs a,
     colour_delta<D>(a.has_L, m, dl, dv);
 #pragma unroll
     for (int j = 0; j < D; ++j) xp[j] = x[j] + dv[j];
+    if (m.bound) {
+      // Variable.apply_delta(bound=True), scalar branch (variable.py:700-727): closed
+      // ends clip; beyond an open end the proposal bounces back to the current value
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const double lo = m.lims[j][0], hi = m.lims[j][1];
+        const bool olo = m.open_end[j][0] != 0, ohi = m.open_end[j][1] != 0;
+        double v = xp[j];
+        if (!olo && !ohi) v = fmax(lo, fmin(hi, v));
+        else if (olo && ohi) v = (v > lo && v < hi) ? v : x[j];
+        else if (olo) v = (v < lo) ? x[j] : fmin(hi, v);
+        else v = (v > hi) ? x[j] : fmax(lo, v);
+        xp[j] = v;
+      }
+    }
     // ---- evaluate target ----------------------------------------------------
     const double maha = mvn_maha<D>(xp, m);
     const double lpp = -0.5 * (m.norm_c + maha);
@@ -1134,7 +1152,7 @@ static int launch_mh_mvn(pbx_ctx* ctx, const MhMvnArgs& a, const MhMvnConst& m, 
   const bool injected = a.inj_delta != nullptr;
   const bool per_step = a.out_accept != nullptr || a.out_score != nullptr ||
                         a.out_xprop != nullptr || a.out_pprop != nullptr;
-  const bool use_ws = !injected && !per_step && kernel_variant != 1;
+  const bool use_ws = !injected && !per_step && kernel_variant != 1 && !m.bound;
   const bool wd_ok = use_ws && D <= WD_MAXD && a.accept_mode == PBX_ACCEPT_LOG;
   if (kernel_variant == 4 && !wd_ok) {
     pbx_set_error("pbx_mh_mvn_run: kernel_variant 4 (whitened-decision kernel) needs the native "
@@ -1229,6 +1247,12 @@ static void fill_const(const pbx_mh_mvn_params* p, MhMvnConst& m) {
   m.norm_c = p->norm_c;
   m.radius = p->prop_radius;
   pbx_make_round_keys(p->seed, m.rk);
+  m.bound = p->prop_bound ? 1 : 0;
+  for (int j = 0; j < PBX_MAX_DIMS; ++j)
+    for (int e = 0; e < 2; ++e) {
+      m.lims[j][e] = p->lims[j][e];
+      m.open_end[j][e] = p->open_end[j][e];
+    }
 }
 
 static int run_device(pbx_ctx* ctx, const pbx_mh_mvn_params* p) {

@@ -118,14 +118,15 @@ def dgei_sharded(engine, x_obs, mu, sigma, logprior_mu, logprior_sigma, group=No
     lj = engine.grid_norm_logjoint(engine.to_device(x_obs), engine.to_device(mu[sl]),
                                    engine.to_device(sigma), engine.to_device(logprior_mu[sl]),
                                    engine.to_device(logprior_sigma))
-    gmax, gsum = grid_normaliser(engine.grid_max(lj), lambda g: engine.grid_sumexp(lj, g), group)
-    post, mm, ms = engine.grid_posterior(lj, gmax, gsum, inplace=True)
-    if ws > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.SUM, group=group)
-    counts = [shard_range(M, r, ws)[1] for r in range(ws)]
-    mm = gather_slabs(mm, counts, group)
-    return dict(post=post, marg_mu=engine.log_prob_(mm), marg_sigma=engine.log_prob_(ms),
-                rows=(start, count), gmax=gmax, gsum=gsum)
+    import torch.distributed as tdist
+    on = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1
+    if on and group is None:
+        group = tdist.group.WORLD
+    r = engine.grid_conditionalise(lj, want_post=True, inplace=True, group=group if on else None)
+    counts = [shard_range(M, q, ws)[1] for q in range(ws)]
+    mm = gather_slabs(r["marg_mu"], counts, group)
+    return dict(post=r["post"], marg_mu=mm, marg_sigma=r["marg_sigma"], rows=(start, count),
+                gmax=r["gmax"], gsum=r["gsum"])
 
 
 def allreduce_expectation(sums, group=None):

@@ -147,7 +147,7 @@ class Engine:
     # ------------------------------------------------------------ K1: mh mvn
     def _mvn_params(self, D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
                     prop, prop_scale, prop_chol, mean, cov, reorder, variant=0,
-                    prop_radius=0.0):
+                    prop_radius=0.0, bound=None):
         if not 1 <= D <= PBX_MAX_DIMS:
             raise NotImplementedError(
                 "mh_mvn supports 1..%d dimensions (got %d)" % (PBX_MAX_DIMS, D))
@@ -179,18 +179,27 @@ class Engine:
             p.has_prop_mat = 1
             for i, v in enumerate(L.ravel()):
                 p.prop_mat[i] = v
+        if bound is not None:                  # (lims [D, 2], open_end [D, 2])
+            lims = np.asarray(bound[0], dtype=np.float64).reshape(D, 2)
+            ex = np.asarray(bound[1]).reshape(D, 2)
+            p.prop_bound = 1
+            for j in range(D):
+                p.lims[j][0], p.lims[j][1] = lims[j]
+                p.open_end[j][0], p.open_end[j][1] = int(ex[j][0]), int(ex[j][1])
         return p
 
     def mh_mvn(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
                log_pscale=False, accept="reference", prop="normal", prop_scale=1.0,
                prop_chol=None, reorder=True, inj_delta=None, inj_thresh=None,
                state_lp=None, record=True, per_step=False, stats=True, variant=0,
-               out=None, prop_radius=0.0, events=None):
+               out=None, prop_radius=0.0, events=None, bound=None):
         """Runs ``steps`` MH steps for all chains of ``state`` ([D, C] device fp64,
         updated in place).  Returns a dict of device tensors:
         x [R, D, C], prob [R, C] (record), accept [T, C] uint8 + score [T, C]
         (per_step), accept_count [C] int64, stat_sum/stat_sumsq [D, C] (stats),
-        state_lp [C].  ``out`` may carry preallocated "x"/"prob" buffers to
+        state_lp [C].  ``bound`` = (lims [D, 2], open_end [D, 2]) applies
+        set_delta(..., bound=True): closed limits clip the proposal, open ones bounce it
+        back (one-thread-per-chain kernel).  ``out`` may carry preallocated "x"/"prob" buffers to
         reuse; ``variant`` 0 picks the kernel (native RNG + log rule + D <= 4: the
         warp-specialised kernel that decides on the whitened state), 1 forces the
         one-thread-per-chain kernel, 2 the warp-specialised kernel with the reference's
@@ -200,7 +209,7 @@ class Engine:
         T = int(steps)
         p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
                              prop, prop_scale, prop_chol, mean, cov, reorder, variant,
-                             prop_radius)
+                             prop_radius, bound)
         out = dict(out) if out else {}
         if state_lp is None and step0 != 0:
             raise ValueError("state_lp is required when resuming (step0 > 0)")
@@ -252,7 +261,8 @@ class Engine:
     def mh_mvn_walk_host(self, state, mean, cov, steps, thin=1, seed=0, step0=0, chain0=0,
                          log_pscale=False, accept="reference", prop="normal",
                          prop_scale=1.0, prop_chol=None, reorder=True, state_lp=None,
-                         chunk_steps=1000, out_x=None, out_prob=None, prop_radius=0.0):
+                         chunk_steps=1000, out_x=None, out_prob=None, prop_radius=0.0,
+                         bound=None):
         """Whole walk through the host-buffer entry point: ``state`` is a HOST
         ndarray [D, C] (updated in place); samples are streamed back into pinned
         host buffers while the next chunk runs.  Returns dict of ndarrays."""
@@ -262,7 +272,8 @@ class Engine:
         T = int(steps)
         R = T // thin
         p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
-                             prop, prop_scale, prop_chol, mean, cov, reorder, 0, prop_radius)
+                             prop, prop_scale, prop_chol, mean, cov, reorder, 0, prop_radius,
+                             bound)
         if out_x is None:
             out_x = torch.empty((R, D, C_), dtype=torch.float64, pin_memory=True)
         if out_prob is None:
@@ -433,24 +444,54 @@ class Engine:
                    "pbx_exp_logp_inplace")
         return v
 
-    def grid_conditionalise(self, lj, want_post=True, inplace=False, group=None):
-        """PD.conditionalise + both PD.marginal calls on a log-joint slab [M_local, S].
-        With ``group`` (a torch.distributed group over mu-row slabs) the normaliser
+    def grid_max_sumexp(self, v, linear=False):
+        """[2] device tensor (max, sum exp_logp(v - max)) of all entries of ``v`` from ONE
+        read (online rescaling); linear-pscale input: (0, sum v)."""
+        out = self.empty(2)
+        _lib.check(self.lib.pbx_grid_max_sumexp(self.ctx, self._ptr(v), int(v.numel()),
+                                                1 if linear else 0, self._ptr(out)),
+                   "pbx_grid_max_sumexp")
+        return out
+
+    def grid_posterior2(self, prob, gmax, gsum, linear=False, want_post=True, inplace=False,
+                        marg_log=3):
+        """(post [M, S] or None, marg_mu [M], marg_sigma [S]); ``marg_log`` bit 0 / 1: pass
+        marg_mu / marg_sigma through the clamped log (log-pscale results)."""
+        M, S = prob.shape
+        post = (prob if inplace else self.empty(M, S)) if want_post else None
+        mm, ms = self.empty(M), self.empty(S)
+        _lib.check(self.lib.pbx_grid_posterior2(
+            self.ctx, self._ptr(prob), M, S, self._ptr(gmax), self._ptr(gsum),
+            1 if linear else 0, self._ptr(post), self._ptr(mm), self._ptr(ms), int(marg_log)),
+            "pbx_grid_posterior2")
+        return post, mm, ms
+
+    def grid_conditionalise(self, lj, want_post=True, inplace=False, group=None, linear=False):
+        """PD.conditionalise + both PD.marginal calls on a joint slab [M_local, S] in two
+        passes over the grid: (max, sum-exp) with online rescaling, then posterior + both
+        marginals.  ``linear``: the slab holds linear-pscale probabilities (results linear
+        too).  With ``group`` (a torch.distributed group over mu-row slabs) the normaliser
         and the sigma marginal are all-reduced; the mu marginal stays a local slab.
-        Returns dict(post, marg_mu, marg_sigma, gmax, gsum) with log-pscale values."""
-        gmax = self.grid_max(lj)
+        Returns dict(post, marg_mu, marg_sigma, gmax, gsum) in the input's pscale."""
+        ms = self.grid_max_sumexp(lj, linear)
+        gmax, gsum = ms[0:1], ms[1:2]
         dist = None
         if group is not None:
             import torch.distributed as dist
-            dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
-        gsum = self.grid_sumexp(lj, gmax)
-        if dist is not None:
+            if not linear:
+                lmax = gmax.clone()
+                dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+                _lib.check(self.lib.pbx_grid_rescale_sumexp(self.ctx, self._ptr(lmax),
+                                                            self._ptr(gmax), self._ptr(gsum)),
+                           "pbx_grid_rescale_sumexp")
             dist.all_reduce(gsum, op=dist.ReduceOp.SUM, group=group)
-        post, mm, ms = self.grid_posterior(lj, gmax, gsum, want_post, inplace)
+        log_bits = 0 if linear else (1 if dist is not None else 3)
+        post, mm, msig = self.grid_posterior2(lj, gmax, gsum, linear, want_post, inplace, log_bits)
         if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.SUM, group=group)
-        return dict(post=post, marg_mu=self.log_prob_(mm), marg_sigma=self.log_prob_(ms),
-                    gmax=gmax, gsum=gsum)
+            dist.all_reduce(msig, op=dist.ReduceOp.SUM, group=group)
+            if not linear:
+                self.log_prob_(msig)
+        return dict(post=post, marg_mu=mm, marg_sigma=msig, gmax=gmax, gsum=gsum)
 
     # ------------------------------------------------------------ K5: Gibbs
     def mvn_logpdf(self, x, mean, cov, log_pscale=True, reorder=True):

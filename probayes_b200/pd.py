@@ -222,6 +222,17 @@ class PD(collections.OrderedDict):
         return self._new(self._name, collections.OrderedDict(self), self._dims, prob, dst)
 
     # ---- marginal-sum algebra ----------------------------------------------------------
+    def _device_linear(self, what):
+        """True / False for a device-backed PD in linear (1.) / log (0j) pscale; any other
+        pscale has no kernel and raises instead of falling back to the host."""
+        if iscomplex(self._pscale) and self._pscale == 0j:
+            return False
+        if not iscomplex(self._pscale) and self._pscale == 1.:
+            return True
+        raise NotImplementedError("{} of a device-backed PD with pscale {} is outside the "
+                                  "device catalogue (log and linear pscales are): call "
+                                  ".rescaled() first".format(what, self._pscale))
+
     def _split_keys(self, keys):
         if isinstance(keys, str):
             keys = [keys]
@@ -250,25 +261,34 @@ class PD(collections.OrderedDict):
         cached = self._cache.get(("marginalise", frozenset(keys)))
         if cached is not None:
             return self._new(name, vals, dims, cached)
-        if self._prob_dev is not None and len(axes) == self.ndim and self._pscale == 0j:
-            # every array axis goes: log_prob(sum exp_logp(p)) without a max shift, as the
-            # reference evaluates it (underflows like the reference for large |log p|)
+        if self._prob_dev is not None:
+            # device-backed: kernels only (no silent host path).  log (0j) and linear (1.)
+            # pscales, 1-D / 2-D arrays -- everything the device catalogue produces
+            linear = self._device_linear("marginalise")
             eng = self._engine()
             import torch
-            zero = torch.zeros(1, dtype=torch.float64, device=self._prob_dev.device)
-            tot = eng.log_prob_(eng.grid_sumexp(self._prob_dev.reshape(-1), zero))
-            return self._new(name, vals, dims, float(tot.item()))
-        if self._prob_dev is not None and self.ndim == 2 and len(axes) == 1 \
-                and iscomplex(self._pscale) and self._pscale == 0j:
-            eng = self._engine()
-            import torch
-            one = torch.ones(1, dtype=torch.float64, device=self._prob_dev.device)
-            zero = torch.zeros(1, dtype=torch.float64, device=self._prob_dev.device)
-            # sum_axis exp_logp(prob): the posterior kernel with gmax = 0, gsum = 1
-            # recomputes log_prob(exp_logp(p)) = p up to the clamp, then row/col sums
-            _, rows, cols = eng.grid_posterior(self._prob_dev, zero, one, want_post=False)
-            lin = rows if 1 in axes else cols
-            return self._new(name, vals, dims, eng.log_prob_(lin))
+            if len(axes) == self.ndim:
+                # every array axis goes: log_prob(sum exp_logp(p)) without a max shift, as
+                # the reference evaluates it (underflows like the reference for large |log p|)
+                if linear:
+                    tot = eng.grid_max_sumexp(self._prob_dev.reshape(-1), linear=True)[1:2]
+                else:
+                    zero = torch.zeros(1, dtype=torch.float64, device=self._prob_dev.device)
+                    tot = eng.log_prob_(eng.grid_sumexp(self._prob_dev.reshape(-1), zero))
+                return self._new(name, vals, dims, float(tot.item()))
+            if self.ndim == 2 and len(axes) == 1:
+                one = torch.ones(1, dtype=torch.float64, device=self._prob_dev.device)
+                zero = torch.zeros(1, dtype=torch.float64, device=self._prob_dev.device)
+                # sum_axis exp_logp(prob): the posterior pass with max = 0, sum = 1 and no
+                # posterior output; row / column sums, through the clamped log for log pscale
+                _, rows, cols = eng.grid_posterior2(self._prob_dev, zero, one, linear,
+                                                    want_post=False, marg_log=0 if linear else 3)
+                return self._new(name, vals, dims, rows if 1 in axes else cols)
+            if not axes:
+                return self._new(name, vals, dims, self._prob_dev)
+            raise NotImplementedError("marginalise of a device-backed PD with {} array axes "
+                                      "over {} of them is outside the device catalogue"
+                                      .format(self.ndim, len(axes)))
         prob = rescale(self.prob, self._pscale, 1.)
         prob = rescale(np.sum(prob, axis=tuple(axes), keepdims=False), 1., self._pscale)
         return self._new(name, vals, dims, prob)
@@ -295,42 +315,99 @@ class PD(collections.OrderedDict):
         marg = collections.OrderedDict(self._marg)
         cond = collections.OrderedDict(self._cond)
         normalise = False
+        array_keys = []
         for key, single in zip(self.keys(), self._aresingleton):
             if key in keys:
                 cond[key] = marg.pop(key)
                 if single:
                     normalise = True
                 else:
-                    raise NotImplementedError(
-                        "conditionalising on an array-valued key is outside the device "
-                        "catalogue (only the scalar / iid-reduced normalisation is)")
+                    array_keys.append(key)
         name = margcond_str(marg, cond)
+        if array_keys:
+            return self._conditionalise_array(name, array_keys, normalise)
         vals = collections.OrderedDict(self)
         if not normalise:
             return self._new(name, vals, self._dims, self._prob_dev
                              if self._prob_dev is not None else self.prob)
-        if self._prob_dev is not None and self.ndim == 1 and self._pscale == 0j:
-            r = self._engine().grid_conditionalise(self._prob_dev.reshape(1, -1))
-            out = self._new(name, vals, self._dims, r["post"].reshape(-1))
-            out._vals_dev = dict(self._vals_dev)
-            return out
-        if self._prob_dev is not None and self.ndim == 2 and self._pscale == 0j:
+        if self._prob_dev is not None:
+            linear = self._device_linear("conditionalise")
             eng = self._engine()
-            r = eng.grid_conditionalise(self._prob_dev)
-            out = self._new(name, vals, self._dims, r["post"])
-            # the posterior pass already produced both marginal sums
-            akeys = [k for k, s in zip(self.keys(), self._aresingleton) if not s]
-            k0 = [k for k in akeys if self._dims[k] == 0]
-            k1 = [k for k in akeys if self._dims[k] == 1]
-            out._cache[("marginalise", frozenset(k1))] = r["marg_mu"]
-            out._cache[("marginalise", frozenset(k0))] = r["marg_sigma"]
-            return out
+            if self.ndim == 1:
+                r = eng.grid_conditionalise(self._prob_dev.reshape(1, -1), linear=linear)
+                out = self._new(name, vals, self._dims, r["post"].reshape(-1))
+                out._vals_dev = dict(self._vals_dev)
+                return out
+            if self.ndim == 2:
+                r = eng.grid_conditionalise(self._prob_dev, linear=linear)
+                out = self._new(name, vals, self._dims, r["post"])
+                # the posterior pass already produced both marginal sums
+                akeys = [k for k, s in zip(self.keys(), self._aresingleton) if not s]
+                k0 = [k for k in akeys if self._dims[k] == 0]
+                k1 = [k for k in akeys if self._dims[k] == 1]
+                out._cache[("marginalise", frozenset(k1))] = r["marg_mu"]
+                out._cache[("marginalise", frozenset(k0))] = r["marg_sigma"]
+                return out
+            raise NotImplementedError("conditionalise of a device-backed PD with {} array "
+                                      "axes is outside the device catalogue".format(self.ndim))
         prob = np.asarray(self.prob, dtype=float)
         if iscomplex(self._pscale):
             prob = prob - prob.max()
         prob = rescale(prob, self._pscale, 1.)
         prob = div_prob(prob, np.sum(prob))
         return self._new(name, vals, self._dims, rescale(prob, 1., self._pscale))
+
+    def _conditionalise_array(self, name, array_keys, normalise):
+        """p(A, K | B) -> p(A | B, K) for an ARRAY-valued key K (pd.py:214-295): K's axis
+        moves behind the remaining marginal axis and every slice along it is divided by its
+        sum over that axis (pd.py:285-295: to linear, [normalise,] div_prob by the keepdims
+        sum, back to the PD's pscale).  2-D arrays with one conditioned array key."""
+        akeys = [k for k, sg in zip(self.keys(), self._aresingleton) if not sg]
+        if self.ndim != 2 or len(array_keys) != 1 or len(akeys) != 2:
+            raise NotImplementedError("conditionalising on array-valued keys is in the "
+                                      "catalogue for 2-D PDs and one such key")
+        key = array_keys[0]
+        other = [k for k in akeys if k != key][0]
+        assert other in self._marg, \
+            "Key {} must stay marginal when conditionalising on {}".format(other, key)
+        ax = self._dims[key]                              # axis of K in the stored array
+        dims = collections.OrderedDict(self._dims)
+        dims[other], dims[key] = 0, 1
+        vals = collections.OrderedDict()
+        for k, v in self.items():
+            if k in akeys:
+                shp = [1, 1]
+                shp[dims[k]] = int(np.size(v))
+                vals[k] = np.reshape(np.asarray(v), shp)
+            else:
+                vals[k] = v
+        if self._prob_dev is not None:
+            linear = self._device_linear("conditionalise")
+            eng = self._engine()
+            import torch
+            base = self._prob_dev
+            if normalise:
+                base = eng.grid_conditionalise(base, linear=linear)["post"]
+            one = torch.ones(1, dtype=torch.float64, device=base.device)
+            zero = torch.zeros(1, dtype=torch.float64, device=base.device)
+            # linear sums over the remaining marginal axis, one per value of K
+            _, rows, cols = eng.grid_posterior2(base, zero, one, linear, want_post=False,
+                                                marg_log=0)
+            den = cols.reshape(1, -1) if ax == 1 else rows.reshape(-1, 1)
+            out = eng.pd_binary('div', base, not linear, den, False, not linear)
+            if ax == 0:
+                out = out.t().contiguous()                # K's axis goes last (layout only)
+            return self._new(name, vals, dims, out)
+        prob = np.asarray(self.prob, dtype=float)
+        if ax == 0:
+            prob = prob.T
+        if normalise and iscomplex(self._pscale):
+            prob = prob - prob.max()
+        prob = rescale(prob, self._pscale, 1.)
+        if normalise:
+            prob = div_prob(prob, np.sum(prob))
+        prob = div_prob(prob, np.sum(prob, axis=0, keepdims=True))
+        return self._new(name, vals, dims, rescale(prob, 1., self._pscale))
 
     def prod(self, keys):
         """iid product over ``keys``: sum (log pscale) / product (linear) along their

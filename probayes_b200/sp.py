@@ -383,9 +383,11 @@ class SP(SD):
         coef = prop['coef'] if self._scores == 'hastings' else 1.0
         if spec['kind'] == 'mvn':
             assert spec['names'] == keys
+            bound = None
             if prop['bound'] and any(np.isfinite(state_rf[k].vlims).any() for k in keys):
-                raise NotImplementedError("bound=True on a bounded RV is in the device catalogue "
-                                          "for the normal-likelihood targets (K2) only")
+                # set_delta(..., bound=True) on bounded RVs (variable.py:700-739)
+                bound = (np.array([state_rf[k].vlims for k in keys]),
+                         np.array([state_rf[k].open_ends for k in keys], dtype=int))
             if opts['host_stream'] and not injected and not per_step:
                 h = eng.mh_mvn_walk_host(state.cpu().numpy(), spec['mean'], spec['cov'], T,
                                          thin=thin, seed=seed, step0=step0,
@@ -394,7 +396,8 @@ class SP(SD):
                                          prop_radius=prop['radius'], prop_chol=prop['chol'],
                                          state_lp=None if sampler.state_lp is None
                                          else sampler.state_lp.cpu().numpy(),
-                                         chain0=chain0, **self._host_bufs(opts, T // thin, D, C))
+                                         chain0=chain0, bound=bound,
+                                         **self._host_bufs(opts, T // thin, D, C))
                 sampler.state = eng.to_device(h['state'])
                 sampler.state_lp = eng.to_device(h['state_lp'])
                 res.update(x=h['x'], prob=h['prob'], accept_count=h['accept_count'],
@@ -406,7 +409,8 @@ class SP(SD):
                              prop=prop['kind'], prop_scale=prop['scale'],
                              prop_radius=prop['radius'], prop_chol=prop['chol'],
                              inj_delta=inj_d, inj_thresh=inj_t, state_lp=sampler.state_lp,
-                             per_step=per_step, variant=opts['variant'], chain0=chain0)
+                             per_step=per_step, variant=opts['variant'], chain0=chain0,
+                             bound=bound)
         else:
             if not opts['iid']:
                 raise NotImplementedError("the normal-likelihood target needs iid=True")

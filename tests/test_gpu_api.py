@@ -331,3 +331,32 @@ def test_sampler_chain0_shards_the_public_api(host_stream):
     assert np.array_equal(np.concatenate([lo.v['x'], hi.v['x']]), full.v['x'])
     assert np.array_equal(np.concatenate([lo.v.prob, hi.v.prob]), full.v.prob)
     assert lo.u.count(True) + hi.u.count(True) == full.u.count(True)
+
+
+def test_mvn_target_with_bounded_delta_through_api():
+    """SP(x & y) on bounded variables with set_delta([d], bound=True): x closed (clips),
+    y open (bounces) -- golden from the live reference (variable.py:700-739)."""
+    engine()
+    g = load_golden("mh_mvn_bound")
+    T = len(g["thresh"])
+    x = pb.RV('x', vtype=float, vset=[-1.5, 1.5])
+    y = pb.RV('y', vtype=float, vset=(-1.5, 1.5))
+    process = pb.SP(x & y)
+    process.set_prob(scipy.stats.multivariate_normal, list(g["mean"]), g["cov"].tolist())
+    process.set_tran(lambda **kwds: 1.)
+    process.set_delta([float(g["step"])], bound=True)
+    process.set_scores('hastings')
+    process.set_update('metropolis')
+    sampler = process.sampler({'x': g["init"][0], 'y': g["init"][1]}, stop=T,
+                              inj_delta=g["delta"], inj_thresh=g["thresh"])
+    summary = process(process.walk(sampler))
+    assert [u is True for u in summary.u] == list(g["u"])
+    assert np.abs(summary.v['x'] - g["x"][:, 0]).max() <= TOL
+    assert np.abs(summary.v['y'] - g["x"][:, 1]).max() <= TOL
+    assert relerr(summary.v.prob, g["prob"]) <= TOL
+    assert relerr(np.stack([summary.p['x'], summary.p['y']], 1), g["xprop"]) <= TOL
+    # native RNG, many chains: every sample inside the box
+    s2 = process(process.walk(process.sampler({'x': 0.5, 'y': -1.0}, stop=300, chains=512,
+                                              seed=5)))
+    assert np.abs(s2.v['x']).max() <= 1.5 and np.abs(s2.v['y']).max() < 1.5
+    assert 0.5 < s2.u.rate() < 0.98

@@ -32,6 +32,42 @@ def test_golden_injected(name):
     assert int(host(out["accept_count"])[0]) == int(g["u"].sum())
 
 
+def test_bounded_delta_golden_and_native():
+    """K1 with set_delta(..., bound=True) (variable.py:700-739): the live-reference fixture
+    with injected streams (decisions identical, trajectory <= 1e-12), then native RNG on
+    many chains against the Philox replay through the oracle."""
+    eng = engine()
+    g = load_golden("mh_mvn_bound")
+    T = len(g["thresh"])
+    bound = (g["lims"], g["ex"])
+    state = dev(eng, g["init"][:, None])
+    out = eng.mh_mvn(state, g["mean"], g["cov"], T, prop="uniform", prop_scale=float(g["step"]),
+                     inj_delta=dev(eng, tcd_to_tdc(g["delta"][:, None, :])),
+                     inj_thresh=dev(eng, g["thresh"][:, None]), per_step=True, bound=bound)
+    eng.sync()
+    assert np.array_equal(host(out["accept"])[:, 0].astype(bool), g["u"])
+    assert np.abs(host(out["x"])[:, :, 0] - g["x"]).max() <= TOL
+    assert relerr(host(out["prob"])[:, 0], g["prob"]) <= TOL
+    assert np.abs(host(out["xprop"])[:, :, 0] - g["xprop"]).max() <= TOL
+    # native RNG, uniform proposal, 70 chains: Philox replay
+    C, T2, seed = 70, 200, 424242
+    init = np.tile(g["init"], (C, 1))
+    t = np.arange(T2, dtype=np.uint64)[:, None]
+    c = np.arange(C, dtype=np.uint64)[None, :]
+    r0, r1 = philox.uniform_pair(seed, t, c, 0)
+    step = float(g["step"])
+    delta = np.stack([-step + (2 * step) * r0, -step + (2 * step) * r1], axis=-1)
+    ref = o.mh_mvn_walk(init, delta, philox.thresholds(seed, T2, C), g["mean"], g["cov"],
+                        accept="log", bound=bound)
+    out = eng.mh_mvn(dev(eng, init.T), g["mean"], g["cov"], T2, seed=seed, accept="log",
+                     prop="uniform", prop_scale=step, bound=bound)
+    eng.sync()
+    assert np.array_equal(host(out["accept_count"]), ref["u"].sum(axis=0))
+    assert np.abs(host(out["x"]) - tcd_to_tdc(ref["x"])).max() <= 1e-11
+    x = host(out["x"])
+    assert x.min() >= -1.5 and x.max() <= 1.5 and (np.abs(x[:, 0]) == 1.5).any()
+
+
 @pytest.mark.parametrize("D,C,T,log_pscale,chol", [
     (2, 257, 300, False, False), (2, 64, 200, True, False), (3, 33, 150, False, True),
     (5, 100, 120, True, False), (8, 40, 100, False, True), (1, 31, 100, False, False)])

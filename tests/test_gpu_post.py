@@ -408,6 +408,81 @@ def test_api_pd_algebra_golden():
     assert np.abs(pc.prob - g["cond_sigma"]).max() <= 1e-12 * np.abs(g["joint"]).max()
 
 
+def _dgei_model():
+    import probayes_b200 as pb
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    model = pb.SD(pb.RF(x), pb.RF(mu, sigma))
+    model.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'},
+                   pscale='log')
+    return model, x
+
+
+def test_api_conditionalise_on_array_keys_golden():
+    """PD.conditionalise on array-valued keys (pd.py:214-295) with device-backed PDs, log
+    and linear pscale, against the live-reference fixture: values, names, axis moves."""
+    engine()
+    g = load_golden("pd_cond_array")
+    names = [str(n) for n in g["names"]]
+    M, S = len(g["mu"]), len(g["sigma"])
+    model, x = _dgei_model()
+    joint = model({x: g["data"], 'mu': {M}, 'sigma': {S}}, iid=True, joint=True)
+    atol = 1e-12 * np.abs(g["joint"]).max()
+    cases = [('sigma', "c_sig"), ('mu', "c_mu"), (['sigma', 'x'], "c_sx")]
+    for i, (keys, k) in enumerate(cases):
+        c = joint.conditionalise(keys)
+        assert c.prob_device is not None and c.name == names[i]
+        assert [c.dims['mu'], c.dims['sigma']] == list(g["dims"][i])
+        assert np.abs(c.prob - g[k]).max() <= atol
+    c_mu = joint.conditionalise('mu')
+    assert np.shape(c_mu['mu']) == tuple(g["shapes"][0])
+    assert np.shape(c_mu['sigma']) == tuple(g["shapes"][1])
+    lin = joint.conditionalise('x').rescaled()
+    assert lin.prob_device is not None and lin.pscale == 1.
+    assert np.abs(lin.prob - g["lin"]).max() <= atol * g["lin"].max()
+    for i, (keys, k) in enumerate([('sigma', "l_sig"), ('mu', "l_mu")]):
+        c = lin.conditionalise(keys)
+        assert c.prob_device is not None and c.name == names[3 + i]
+        assert [c.dims['mu'], c.dims['sigma']] == list(g["dims"][3 + i])
+        assert np.abs(c.prob - g[k]).max() <= atol * g[k].max()
+
+
+def test_linear_pscale_device_pds_stay_on_the_device():
+    """A device-backed PD in LINEAR pscale (after .rescaled()) is normalised and
+    marginalised by the linear-pscale kernel variants -- no host copy -- with the values
+    numpy gives on the same arrays; other pscales raise instead of falling back."""
+    eng = engine()
+    import probayes_b200 as pb
+    rng = np.random.default_rng(3)
+    data = rng.normal(50., 10., 30)
+    model, x = _dgei_model()
+    joint = model({x: data, 'mu': {37}, 'sigma': {29}}, iid=True, joint=True)
+    lin = joint.rescaled()                               # un-normalised linear joint
+    assert lin.prob_device is not None and lin._prob is None
+    post = lin.conditionalise('x')
+    assert post.prob_device is not None and lin._prob is None and post.pscale == 1.
+    p = np.exp(joint.prob)
+    want = p / p.sum()
+    assert relerr(post.prob, want) <= 1e-12
+    mm = post.marginal('mu')
+    ms = post.marginal('sigma')
+    assert mm.prob_device is not None
+    assert relerr(np.ravel(mm.prob), want.sum(axis=1)) <= 1e-12
+    assert relerr(np.ravel(ms.prob), want.sum(axis=0)) <= 1e-12
+    tot = lin.marginalise(['mu', 'sigma'])
+    assert abs(float(tot.prob) - p.sum()) <= 1e-12 * p.sum()
+    # log-pscale twin: identical normalised values
+    lpost = joint.conditionalise('x')
+    assert np.abs(np.exp(lpost.prob) - want).max() <= 1e-12 * want.max()
+    odd = pb.PD(joint.name, dict(joint), dims=joint.dims, prob=joint.prob_device, pscale=2.0)
+    with pytest.raises(NotImplementedError):
+        odd.conditionalise('x')
+    with pytest.raises(NotImplementedError):
+        odd.marginal('mu')
+
+
 # ---- full-size properties (no CPU oracle at these sizes) --------------------------------------
 def test_argsort_full_size_properties():
     """2^26 keys: the result is sorted, is a permutation, is stable for ties, and sorting

@@ -328,3 +328,22 @@ def test_differential_against_live_reference():
     assert np.array_equal(rps.rescale(vals, 0j, 1.), pb.rescale(vals, 0j, 1.))
     assert np.array_equal(rps.rescale(np.exp(vals), 1., 0j), pb.rescale(np.exp(vals), 1., 0j))
     assert rps.prod_pscale([0j, 2.0]) == pb.prod_pscale([0j, 2.0])
+
+
+def test_conditionalise_on_array_keys_host():
+    """Host-backed PDs: PD.conditionalise on array-valued keys reproduces the live
+    reference bit for bit (pd.py:214-295; pd_cond_array fixture)."""
+    import probayes_b200 as pb
+    g = load_golden("pd_cond_array")
+    M, S = len(g["mu"]), len(g["sigma"])
+    vals = {'mu': g["mu"].reshape(M, 1), 'sigma': g["sigma"].reshape(1, S), 'x': {len(g["data"])}}
+    joint = pb.PD('mu,sigma,x', vals, dims={'mu': 0, 'sigma': 1, 'x': None}, prob=g["joint"],
+                  pscale='log')
+    for i, (keys, k) in enumerate([('sigma', "c_sig"), ('mu', "c_mu"), (['sigma', 'x'], "c_sx")]):
+        c = joint.conditionalise(keys)
+        assert np.array_equal(c.prob, g[k])
+        assert [c.dims['mu'], c.dims['sigma']] == list(g["dims"][i])
+    lin = joint.conditionalise('x').rescaled()
+    assert np.array_equal(lin.prob, g["lin"])
+    assert np.array_equal(lin.conditionalise('sigma').prob, g["l_sig"])
+    assert np.array_equal(lin.conditionalise('mu').prob, g["l_mu"])

@@ -23,6 +23,19 @@ def test_mh_mvn(name):
     assert np.isnan(g["s"][0]) and g["u"][0]          # step 1 accepts with s=None
 
 
+def test_mh_mvn_bounded_delta():
+    """set_delta([d], bound=True) on bounded variables with the mvn target
+    (variable.py:700-739): closed limits clip, open limits bounce back."""
+    g = load_golden("mh_mvn_bound")
+    r = o.mh_mvn_walk(g["init"][None], g["delta"][:, None, :], g["thresh"][:, None],
+                      g["mean"], g["cov"], bound=(g["lims"], g["ex"]))
+    assert np.array_equal(r["u"][:, 0], g["u"])
+    assert np.abs(r["x"][:, 0] - g["x"]).max() <= TOL
+    assert relerr(r["prob"][:, 0], g["prob"]) <= TOL
+    assert relerr(r["xprop"][:, 0], g["xprop"]) <= TOL
+    assert (np.abs(g["xprop"][:, 0]) == 1.5).sum() > 20          # the fixture does clip
+
+
 @pytest.mark.parametrize("name", ["mh_norm1d_hastings", "mh_norm1d_metropolis",
                                   "mh_norm1d_underflow", "mh_norm1d_bound_open",
                                   "mh_norm1d_bound_mixed"])
