@@ -277,6 +277,40 @@ PBX_API int pbx_log_prob_inplace(pbx_ctx* ctx, double* v, int64_t n);
 PBX_API int pbx_exp_logp_inplace(pbx_ctx* ctx, double* v, int64_t n);
 
 /* ---------------------------------------------------------------------------
+ * Ordinary Monte Carlo with rejection sampling: SP.next with a proposal DENSITY
+ * (set_prop) and custom scores / thresh / update (probayes/sp.py:221-258, sd.py:228-250,
+ * rf.py:146-161,584-602), as in examples/omc/omc_rejection_sp_circle.py:26-39.  Catalogue:
+ * target = indicator of a ball; proposal density = product of normal pdfs or the box-uniform
+ * density; score = p or the safe ratio p / q; threshold ~ U(thresh_lo, thresh_hi);
+ * update = (s >= t).  One sample per reference step; samples shard like chains (global
+ * sample id = sample0 + t).
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_params;        /* P variables, 1..8 */
+  int32_t target_kind;     /* 0 = indicator( |x - centre|^2 <= radius^2 ) */
+  int32_t prop_kind;       /* 0 = prod_j norm.pdf(x_j; loc_j, scale_j); 1 = prod_j 1 / length_j */
+  int32_t score_mode;      /* 0 = p; 1 = p / max(tiny, q) */
+  int64_t n_samples;       /* T */
+  int64_t sample0;
+  uint64_t seed;
+  double lims[8][2];       /* box of every variable (finite) */
+  int32_t log_ufun[8];     /* uniform in log space (the (np.log, np.exp) ufun) */
+  double target_centre[8];
+  double target_radius;
+  double prop_loc[8];
+  double prop_scale[8];
+  double thresh_lo, thresh_hi;
+  const double* inj_unif;  /* [T][P + 1] injected uniforms (draws, then threshold) or NULL */
+  double* out_theta;       /* [P][T] the proposals */
+  double* out_p;           /* [T] target at the proposal */
+  double* out_q;           /* [T] proposal density at the proposal */
+  double* out_s;           /* [T] score */
+  double* out_t;           /* [T] threshold */
+  uint8_t* out_u;          /* [T] update flag (1 = kept) */
+} pbx_rejection_params;
+PBX_API int pbx_rejection_sample(pbx_ctx* ctx, const pbx_rejection_params* p);
+
+/* ---------------------------------------------------------------------------
  * K5  batched Gibbs sweep over the conditionals of a multivariate normal.
  * Replaces RF.eval_tfun -> sample_cond_cov -> CondCov.interp
  * (probayes/rf.py:413-462, rf_utils.py:50-65, cond_cov.py:22-65) with the
@@ -286,7 +320,7 @@ PBX_API int pbx_exp_logp_inplace(pbx_ctx* ctx, double* v, int64_t n);
  * ------------------------------------------------------------------------- */
 typedef struct {
   int32_t n_chains;
-  int32_t n_dims;          /* d, 1..64 */
+  int32_t n_dims;          /* d, 1..128 */
   int32_t n_steps;         /* coordinate steps in this call */
   int32_t thin;
   int64_t step0;

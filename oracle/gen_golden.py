@@ -138,9 +138,10 @@ def mh_mvn3d(seed, T):
     return out
 
 
-def gibbs3d(seed, T):
+def gibbs3d(seed, T, tsteps=1):
     """Gibbs on a 3-D mvn (tsteps=1): conditional draws in natural order, recorded
-    density on the permuted point."""
+    density on the permuted point.  tsteps=3 / None: a whole sweep per step
+    (probayes/rf.py:446-452), three uniforms per step."""
     pb = ref_shim.load()
     rng = np.random.default_rng(seed)
     lims = (-8., 8.)
@@ -152,9 +153,12 @@ def gibbs3d(seed, T):
     z = pb.RV('z', vtype=float, vset=lims)
     sp = pb.SP(x & y & z)
     sp.set_prob(scipy.stats.multivariate_normal, means, covar)
-    sp.set_tran(scipy.stats.multivariate_normal, means, covar, tsteps=1)
+    if tsteps is None:
+        sp.set_tran(scipy.stats.multivariate_normal, means, covar)
+    else:
+        sp.set_tran(scipy.stats.multivariate_normal, means, covar, tsteps=tsteps)
     sp.set_scores('gibbs')
-    R = rng.random(T)
+    R = rng.random(T * (3 if tsteps in (None, 3) else tsteps))
     with ref_shim.injected_uniform(R):
         sampler = sp.sampler({'x': 0., 'y': 1., 'z': -1.}, stop=T)
         samples = [s for s in sampler]
@@ -395,6 +399,53 @@ def pd_algebra(seed, N, M, S):
                                 post.name, mm.name, pc.name]))
 
 
+def omc_rejection_circle(seed, T, radius=1.):
+    """examples/omc/omc_rejection_sp_circle.py:26-39: ordinary Monte Carlo with rejection
+    sampling (set_prop + custom scores / thresh / update): per step two box-uniform draws
+    (x, y), the proposal density norm2d there (q), the target indicator (p), one threshold
+    uniform in [0, coef_max); kept iff p >= t.  All uniforms injected, in call order."""
+    pb = ref_shim.load()
+    rng = np.random.default_rng(seed)
+
+    def inside(x, y):
+        return np.array(x**2 + y**2 <= radius**2, dtype=float)
+
+    def norm2d(x, y, loc=0., scale=radius):
+        return scipy.stats.norm.pdf(x, loc=loc, scale=scale) * \
+            scipy.stats.norm.pdf(y, loc=loc, scale=scale)
+
+    xy_range = [-radius, radius]
+    x = pb.RV("x", xy_range)
+    y = pb.RV("y", xy_range)
+    process = pb.SP(x & y)
+    process.set_prob(inside)
+    process.set_prop(norm2d)
+    process.set_scores(lambda opqr: opqr.p.prob)
+    coef_max = float(norm2d(radius, 1.))
+    R = rng.random((T, 3))               # per step: x draw, y draw, threshold
+    with ref_shim.injected_uniform(R.ravel()):
+        process.set_thresh(np.random.uniform, low=0., high=coef_max)   # captures the patch
+        process.set_update(lambda stu: stu.s >= stu.t)
+        sampler = process.sampler({0}, stop=T)
+        samples = [sample for sample in sampler]
+    summary = process(samples)
+    xy = np.array([(float(s.p['x']), float(s.p['y'])) for s in samples])
+    kept = summary.p
+    return dict(runif=R, xy=xy, p=np.array([float(s.p.prob) for s in samples]),
+                q=np.array([float(s.q.prob) for s in samples]),
+                s=np.array([float(s.s) for s in samples]),
+                t=np.array([float(s.t) for s in samples]),
+                u=np.array([bool(s.u) for s in samples]),
+                kept_x=np.asarray(kept['x'], float), kept_y=np.asarray(kept['y'], float),
+                kept_prob=np.asarray(kept.prob, float), kept_size=np.array(kept.size),
+                coef_max=np.array(coef_max), radius=np.array(radius),
+                names=np.array([samples[0].p.name, samples[0].q.name, kept.name,
+                                summary.q.name]),
+                q_keys=np.array(list(samples[0].q.keys())),
+                first_v_is_p=np.array(samples[0].v is samples[0].p),
+                v_none=np.array([s.v is None for s in samples]))
+
+
 def pd_cond_array(seed, N, M, S):
     """PD.conditionalise on ARRAY-valued keys (probayes/pd.py:214-295): p(mu, sigma, x)
     -> p(mu, x | sigma), p(sigma, x | mu) (axis move), p(mu | sigma, x) (normalise first),
@@ -516,6 +567,8 @@ def main():
         "mh_mvn_3d": lambda: mh_mvn3d(15, 256),
         "mh_mvn_bound": lambda: mh_mvn_bound(16, 400),
         "gibbs3d": lambda: gibbs3d(54, 300),
+        "gibbs3d_sweep": lambda: gibbs3d(55, 120, tsteps=3),
+        "gibbs3d_all": lambda: gibbs3d(56, 120, tsteps=None),
         "mh_norm1d_hastings": lambda: mh_norm1d(21, 300, 60, 'hastings'),
         "mh_norm1d_metropolis": lambda: mh_norm1d(22, 300, 60, 'metropolis'),
         "mh_norm1d_underflow": lambda: mh_norm1d(23, 60, 1000, 'metropolis'),
@@ -529,6 +582,7 @@ def main():
         "pd_algebra": lambda: pd_algebra(71, 40, 9, 7),
         "pd_cond_array": lambda: pd_cond_array(72, 40, 9, 7),
         "omc_rs_norm1d": lambda: omc_rs_norm1d(61, 60, 400),
+        "omc_rejection_circle": lambda: omc_rejection_circle(62, 500),
         "condcov_d8": lambda: condcov_bare(52, 8, 160),
         "condcov_d64": lambda: condcov_bare(53, 64, 256),
         "pscales": pscales_table,

@@ -17,7 +17,8 @@ from .sd import SD
 from .sp import SP, MCMC_SAMPLERS, Walk, Sampler, AcceptRecord
 from .pd import PD, product
 from .cond_cov import CondCov
-from .catalogue import NormalRegression
+from . import catalogue
+from .catalogue import NormalRegression, BallIndicator, NormalProduct, BoxUniform
 from ._lib import PbxError
 
 __version__ = "0.1.0"

@@ -51,6 +51,20 @@ class MhMvnParams(C.Structure):
     ]
 
 
+class RejectionParams(C.Structure):
+    _fields_ = [
+        ("n_params", C.c_int32), ("target_kind", C.c_int32), ("prop_kind", C.c_int32),
+        ("score_mode", C.c_int32), ("n_samples", C.c_int64), ("sample0", C.c_int64),
+        ("seed", C.c_uint64), ("lims", (C.c_double * 2) * 8), ("log_ufun", C.c_int32 * 8),
+        ("target_centre", C.c_double * 8), ("target_radius", C.c_double),
+        ("prop_loc", C.c_double * 8), ("prop_scale", C.c_double * 8),
+        ("thresh_lo", C.c_double), ("thresh_hi", C.c_double),
+        ("inj_unif", C.c_void_p), ("out_theta", C.c_void_p), ("out_p", C.c_void_p),
+        ("out_q", C.c_void_p), ("out_s", C.c_void_p), ("out_t", C.c_void_p),
+        ("out_u", C.c_void_p),
+    ]
+
+
 class MhNormregParams(C.Structure):
     _fields_ = [
         ("n_chains", C.c_int32), ("n_params", C.c_int32), ("n_steps", C.c_int32),
@@ -120,6 +134,7 @@ SIGNATURES = {
     "pbx_grid_posterior2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_int32]),
+    "pbx_rejection_sample": (C.c_int, [C.c_void_p, C.POINTER(RejectionParams)]),
     "pbx_log_prob_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "pbx_exp_logp_inplace": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "pbx_gibbs_mvn_run": (C.c_int, [C.c_void_p, C.POINTER(GibbsMvnParams)]),

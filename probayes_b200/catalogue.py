@@ -15,6 +15,11 @@ Targets
            ``norm_reg``), or an explicit ``NormalRegression`` spec
 Proposals (field.py:220-317, variable.py:600-638, rf.py:209-220)
   [d] uniform per RV, (d,) spherical, frozen scipy.stats.norm, covariance-matrix tran
+Rejection sampling (set_prop + custom scores / thresh / update, omc_rejection_sp_circle)
+  target    BallIndicator (1.0 inside a ball, 0.0 outside)
+  proposal  NormalProduct (prod_j norm.pdf(x_j; loc_j, scale_j)) or BoxUniform
+  scores    opqr.p.prob  or  opqr.p.prob / opqr.q.prob ;  thresh np.random.uniform(low, high) ;
+  update    stu.s >= stu.t   -- Python callables are recognised by probing (with a warning)
 """
 import inspect
 import itertools
@@ -98,6 +103,16 @@ def identify_target(holder, stats, paras):
     if callable(prob):
         spec = _probe_normreg(prob, stats, paras, log_pscale)
         if spec is not None:
+            import warnings
+            warnings.warn(
+                "probayes_b200: the Python likelihood {!r} was recognised BY PROBING as the normal "
+                "linear-regression log-density log N({} | {} + {} * {}, {}) and is replaced by "
+                "the device kernel; it is never called during the walk.  Pass "
+                "probayes_b200.catalogue.NormalRegression(...) to state this explicitly (a "
+                "function that only coincides with norm.logpdf on the probed range would be "
+                "evaluated wrongly).".format(getattr(prob, '__name__', prob), spec['obs_y'],
+                                             spec['params'][0], spec['params'][1], spec['obs_x'],
+                                             spec['params'][2]), stacklevel=3)
             return spec
     raise NotImplementedError(
         "target {!r} is outside the device catalogue (multivariate_normal, "
@@ -117,19 +132,41 @@ def _probe_normreg(func, stats, paras, log_pscale):
     if not set(names).issubset(sig.parameters.keys()):
         return None
     rng = np.random.default_rng(12345)
-    obs = {k: rng.normal(0., 1., 7) for k in stats.keylist}
-    pars = {k: float(v) for k, v in zip(paras.keylist, rng.uniform(0.5, 1.5, 3))}
-    try:
-        got = np.asarray(func(**obs, **pars), dtype=float)
-    except Exception:
-        return None
-    if got.shape != (7,):
-        return None
+    n_probe, n_obs = 24, 7
+
+    def par_draw(rv):
+        # across the variable's own range (finite limits), else a wide default
+        lo, hi = (float(v) for v in rv.vlims)
+        lo = lo if np.isfinite(lo) else -50.
+        hi = hi if np.isfinite(hi) else 50.
+        return lo + (hi - lo) * rng.uniform(0.02, 0.98, n_probe)
+
+    obs_sets = [{k: rng.normal(0., 1., n_obs) * sc + off for k in stats.keylist}
+                for sc, off in zip(rng.uniform(0.1, 30., n_probe), rng.normal(0., 20., n_probe))]
+    par_sets = {k: par_draw(paras[k]) for k in paras.keylist}
+    got = []
+    for i in range(n_probe):
+        pars = {k: float(par_sets[k][i]) for k in paras.keylist}
+        try:
+            g = np.asarray(func(**obs_sets[i], **pars), dtype=float)
+        except Exception:
+            return None
+        if g.shape != (n_obs,):
+            return None
+        got.append(g)
     for (xk, yk) in itertools.permutations(stats.keylist, 2):
         for (a, b, s) in itertools.permutations(paras.keylist, 3):
-            want = scipy.stats.norm.logpdf(obs[yk], loc=pars[a] + pars[b] * obs[xk],
-                                           scale=pars[s])
-            if np.allclose(got, want, rtol=1e-12, atol=1e-12):
+            ok = True
+            for i in range(n_probe):
+                sd = par_sets[s][i]
+                if not sd > 0:
+                    continue
+                want = scipy.stats.norm.logpdf(obs_sets[i][yk], loc=par_sets[a][i] +
+                                               par_sets[b][i] * obs_sets[i][xk], scale=sd)
+                if not np.allclose(got[i], want, rtol=1e-12, atol=1e-12, equal_nan=True):
+                    ok = False
+                    break
+            if ok:
                 return dict(kind='normreg', has_slope=True, obs_y=yk, obs_x=xk,
                             params=[a, b, s], log_pscale=True)
     return None
@@ -222,3 +259,161 @@ def _probe_constant(func, rf):
         except Exception:
             return None
     return seen[0] if max(seen) == min(seen) else None
+
+
+# ---------------------------------------------------------------------------
+# rejection sampling (examples/omc/omc_rejection_sp_circle.py:26-39)
+# ---------------------------------------------------------------------------
+class BallIndicator:
+    """Explicit target spec: 1.0 where sum_j (x_j - centre_j)^2 <= radius^2, else 0.0."""
+
+    def __init__(self, radius, centre=0.):
+        self.radius, self.centre = float(radius), centre
+
+
+class NormalProduct:
+    """Explicit proposal-density spec: prod_j scipy.stats.norm.pdf(x_j, loc_j, scale_j)."""
+
+    def __init__(self, loc=0., scale=1.):
+        self.loc, self.scale = loc, scale
+
+
+class BoxUniform:
+    """Explicit proposal-density spec: the box-uniform density prod_j 1 / length_j."""
+
+
+def _warn_probed(what, func, as_what):
+    import warnings
+    warnings.warn("probayes_b200: the Python {} {!r} was recognised BY PROBING as {} and is "
+                  "replaced by the device kernel; it is never called during the walk.  Pass the "
+                  "explicit probayes_b200.catalogue spec to state this."
+                  .format(what, getattr(func, '__name__', func), as_what), stacklevel=4)
+
+
+def _sig(x, digits=12):
+    return float(('%.' + str(digits) + 'g') % x)
+
+
+def identify_rejection_target(prob, args, kwds, rvs):
+    """-> dict(kind='ball', radius, centre [P]) or NotImplementedError."""
+    P = len(rvs)
+    names = [rv.name for rv in rvs]
+    if isinstance(prob, BallIndicator):
+        return dict(kind='ball', radius=prob.radius,
+                    centre=np.broadcast_to(np.asarray(prob.centre, float), (P,)).copy())
+    if callable(prob):
+        lims = np.array([rv.vlims for rv in rvs], dtype=float)
+        if np.isfinite(lims).all():
+            f = lambda pt: float(np.asarray(prob(*args, **dict(zip(names, pt)), **kwds)))
+            try:
+                centre = lims.mean(axis=1)
+                if f(centre) == 1.0:
+                    # radius by bisection along the first axis, then verified on random points
+                    lo, hi = 0.0, float(lims[0, 1] - centre[0]) * 4.0
+                    for _ in range(80):
+                        mid = 0.5 * (lo + hi)
+                        pt = centre.copy()
+                        pt[0] += mid
+                        lo, hi = (mid, hi) if f(pt) == 1.0 else (lo, mid)
+                    radius = _sig(lo)
+                    rng = np.random.default_rng(2468)
+                    pts = lims[:, 0] + (lims[:, 1] - lims[:, 0]) * rng.random((256, P))
+                    want = (((pts - centre) ** 2).sum(axis=1) <= radius ** 2).astype(float)
+                    got = np.array([f(pt) for pt in pts])
+                    if np.array_equal(got, want) and 0 < want.sum() < len(want):
+                        _warn_probed('target', prob, 'the indicator of a ball of radius {} '
+                                     'centred at {}'.format(radius, list(centre)))
+                        return dict(kind='ball', radius=radius, centre=centre)
+            except Exception:
+                pass
+    raise NotImplementedError("rejection-sampling target {!r} is outside the device catalogue "
+                              "(BallIndicator)".format(prob))
+
+
+def identify_rejection_prop(prop, args, kwds, rvs):
+    """-> dict(kind='normal', loc [P], scale [P]) | dict(kind='box')."""
+    P = len(rvs)
+    names = [rv.name for rv in rvs]
+    if isinstance(prop, BoxUniform):
+        return dict(kind='box')
+    if isinstance(prop, NormalProduct):
+        return dict(kind='normal', loc=np.broadcast_to(np.asarray(prop.loc, float), (P,)).copy(),
+                    scale=np.broadcast_to(np.asarray(prop.scale, float), (P,)).copy())
+    if callable(prop):
+        f = lambda pt: float(np.asarray(prop(*args, **dict(zip(names, pt)), **kwds)))
+        try:
+            base = np.zeros(P)
+            g0 = np.log(f(base))
+            loc, scale = np.zeros(P), np.ones(P)
+            for j in range(P):
+                e = np.zeros(P)
+                e[j] = 1.0
+                gp, gm = np.log(f(base + e)), np.log(f(base - e))
+                inv_var = -(gp - 2.0 * g0 + gm)               # second difference = -1 / s^2
+                if not inv_var > 0:
+                    raise ValueError
+                scale[j] = _sig(1.0 / np.sqrt(inv_var))
+                loc[j] = _sig(0.5 * (gp - gm) / inv_var) if abs(gp - gm) > 1e-13 else 0.0
+            rng = np.random.default_rng(1357)
+            pts = loc + scale * rng.standard_normal((64, P)) * 1.5
+            want = np.prod(scipy.stats.norm.pdf(pts, loc=loc, scale=scale), axis=1)
+            got = np.array([f(pt) for pt in pts])
+            if np.allclose(got, want, rtol=1e-12, atol=0.0):
+                _warn_probed('proposal density', prop, 'the product of normal pdfs with loc {} '
+                             'and scale {}'.format(list(loc), list(scale)))
+                return dict(kind='normal', loc=loc, scale=scale)
+        except Exception:
+            pass
+    raise NotImplementedError("proposal density {!r} is outside the device catalogue "
+                              "(NormalProduct, BoxUniform)".format(prop))
+
+
+class _Obj:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def identify_scores(func, args=(), kwds=None):
+    """'p' for opqr -> opqr.p.prob, 'p/q' for opqr -> opqr.p.prob / opqr.q.prob."""
+    kwds = kwds or {}
+    try:
+        a = func(_Obj(o=None, p=_Obj(prob=0.37), q=_Obj(prob=0.11), r=None), *args, **kwds)
+        b = func(_Obj(o=None, p=_Obj(prob=0.05), q=_Obj(prob=0.4), r=None), *args, **kwds)
+        if np.isclose(a, 0.37, rtol=1e-14) and np.isclose(b, 0.05, rtol=1e-14):
+            return 'p'
+        if np.isclose(a, 0.37 / 0.11, rtol=1e-14) and np.isclose(b, 0.05 / 0.4, rtol=1e-14):
+            return 'p/q'
+    except Exception:
+        pass
+    raise NotImplementedError("scores must be 'metropolis' | 'hastings' | 'gibbs', or a function "
+                              "equal to opqr.p.prob or opqr.p.prob / opqr.q.prob (custom Python "
+                              "score functions cannot run in the kernel)")
+
+
+def identify_thresh(func, args=(), kwds=None):
+    """('uniform', low, high) for np.random.uniform(low=, high=)."""
+    kwds = dict(kwds or {})
+    if getattr(func, '__name__', '') == 'uniform' and \
+            'random' in str(getattr(func, '__module__', None) or
+                            type(getattr(func, '__self__', None)).__module__):
+        a = list(args)
+        low = kwds.pop('low', a.pop(0) if a else 0.0)
+        high = kwds.pop('high', a.pop(0) if a else 1.0)
+        if not kwds and not a:
+            return ('uniform', float(low), float(high))
+    raise NotImplementedError("thresh must be one of the MCMC sampler names or "
+                              "np.random.uniform with low / high")
+
+
+def identify_update(func, args=(), kwds=None):
+    """'s>=t' for stu -> stu.s >= stu.t."""
+    kwds = kwds or {}
+    try:
+        probes = [(0.7, 0.2, True), (0.1, 0.2, False), (0.2, 0.2, True), (0.0, 1e-300, False)]
+        if all(bool(func(_Obj(s=s_, t=t_, u=None, v=None), *args, **kwds)) is w
+               for s_, t_, w in probes):
+            return 's>=t'
+    except Exception:
+        pass
+    raise NotImplementedError("update must be one of the MCMC sampler names or a function equal "
+                              "to stu.s >= stu.t")

@@ -82,16 +82,26 @@ int pbx_ctx_create(int device, void* stream, int32_t own_stream, pbx_ctx** out) 
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaSuccess;
   if (own_stream) {
-    PBX_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    c->own_stream = true;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    c->own_stream = (e == cudaSuccess);
   } else {
     c->stream = (cudaStream_t)stream;                  // NULL = the default stream
     c->own_stream = false;
   }
-  PBX_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  PBX_CUDA(cudaEventCreate(&c->ev0));
-  PBX_CUDA(cudaEventCreate(&c->ev1));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+  if (e != cudaSuccess) {                              // no half-built context is leaked
+    pbx_set_error("pbx_ctx_create: %s", cudaGetErrorString(e));
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PBX_ERR_CUDA;
+  }
   *out = c;
   return PBX_OK;
 }
@@ -149,7 +159,11 @@ __global__ void __launch_bounds__(256) pbx_rescale_kernel(double* __restrict__ v
 }
 
 // ---------------------------------------------------------------------------
-// chain summaries: one block per dim, fixed-order tree => deterministic
+// chain summaries: one block per dim, fixed-order tree => deterministic.
+// The within-chain variance is formed from the raw running sums the walk kernels keep,
+// (sum x^2 - sum x * mean) / (T - 1): relative error ~ eps * mean^2 / var, i.e. fine for
+// posteriors whose spread is not many orders below their location (1e-8 relative at
+// |mean| / sd = 1e4); documented limitation.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pbx_chain_stats_kernel(const double* __restrict__ ssum,
                                                               const double* __restrict__ ssq,
@@ -217,6 +231,7 @@ extern "C" {
 
 int pbx_fp64_dep_latency(pbx_ctx* ctx, double* dfma_cycles, double* dadd_cycles) {
   PBX_REQUIRE(ctx && dfma_cycles && dadd_cycles, "pbx_fp64_dep_latency: null argument");
+  PBX_CUDA(cudaSetDevice(ctx->device));
   {
     int rc = pbx_ws_reserve(ctx, 64);
     if (rc) return rc;
@@ -236,6 +251,7 @@ int pbx_fp64_dep_latency(pbx_ctx* ctx, double* dfma_cycles, double* dadd_cycles)
 int pbx_log_prob_inplace(pbx_ctx* ctx, double* v, int64_t n) {
   PBX_REQUIRE(ctx && v && n >= 0, "pbx_log_prob_inplace: bad argument");
   if (n == 0) return PBX_OK;
+  PBX_CUDA(cudaSetDevice(ctx->device));
   int grid = (int)((n + 255) / 256);
   if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
   pbx_rescale_kernel<true><<<grid, 256, 0, ctx->stream>>>(v, n);
@@ -246,6 +262,7 @@ int pbx_log_prob_inplace(pbx_ctx* ctx, double* v, int64_t n) {
 int pbx_exp_logp_inplace(pbx_ctx* ctx, double* v, int64_t n) {
   PBX_REQUIRE(ctx && v && n >= 0, "pbx_exp_logp_inplace: bad argument");
   if (n == 0) return PBX_OK;
+  PBX_CUDA(cudaSetDevice(ctx->device));
   int grid = (int)((n + 255) / 256);
   if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
   pbx_rescale_kernel<false><<<grid, 256, 0, ctx->stream>>>(v, n);
@@ -258,6 +275,7 @@ int pbx_reduce_chain_stats(pbx_ctx* ctx, const double* stat_sum, const double* s
   PBX_REQUIRE(ctx && stat_sum && stat_sumsq && out, "pbx_reduce_chain_stats: null argument");
   PBX_REQUIRE(n_dims >= 1 && n_chains >= 1 && n_steps >= 1,
               "pbx_reduce_chain_stats: sizes must be positive");
+  PBX_CUDA(cudaSetDevice(ctx->device));
   pbx_chain_stats_kernel<<<n_dims, 256, 0, ctx->stream>>>(stat_sum, stat_sumsq, n_chains,
                                                          (double)n_steps, out);
   PBX_LAUNCH_CHECK(ctx);
@@ -266,6 +284,7 @@ int pbx_reduce_chain_stats(pbx_ctx* ctx, const double* stat_sum, const double* s
 
 int pbx_fp64_peak(pbx_ctx* ctx, double* tflops) {
   PBX_REQUIRE(ctx && tflops, "pbx_fp64_peak: null argument");
+  PBX_CUDA(cudaSetDevice(ctx->device));
   {
     int rc = pbx_ws_reserve(ctx, 64);
     if (rc) return rc;

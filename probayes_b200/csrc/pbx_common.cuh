@@ -19,6 +19,7 @@ struct pbx_ctx {
   cudaEvent_t ev0, ev1;      // bracket the kernels of the most recent *_run call
   void* ws;                  // device workspace
   size_t ws_bytes;
+  bool tables_ready;         // K1 math tables uploaded to this context's device
 };
 
 void pbx_set_error(const char* fmt, ...);

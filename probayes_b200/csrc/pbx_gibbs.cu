@@ -294,6 +294,9 @@ static int mvn_logpdf_launch(pbx_ctx* ctx, const double* x, int d, int64_t C, in
   } else {
     const size_t smem = ((size_t)d * d + d) * sizeof(double);
     const int64_t grid = (C * R + 127) / 128;
+    if (smem > 48 * 1024)
+      PBX_CUDA(cudaFuncSetAttribute(mvn_logpdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem));
     mvn_logpdf_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(x, d, C, R, mean, W, norm_c,
                                                                  log_pscale, out);
   }
@@ -305,7 +308,7 @@ extern "C" int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int
                               const double* mean, const double* whiten, double norm_c,
                               int32_t log_pscale, double* out) {
   PBX_REQUIRE(ctx && x && mean && whiten && out, "pbx_mvn_logpdf: null argument");
-  PBX_REQUIRE(n_dims >= 1 && n_dims <= 64, "pbx_mvn_logpdf: n_dims must be in 1..64");
+  PBX_REQUIRE(n_dims >= 1 && n_dims <= 128, "pbx_mvn_logpdf: n_dims must be in 1..128");
   PBX_REQUIRE(n_chains >= 0, "pbx_mvn_logpdf: negative point count");
   PBX_CUDA(cudaSetDevice(ctx->device));
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -338,7 +341,7 @@ static int gibbs_launch(pbx_ctx* ctx, const GibbsArgs& a) {
 extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
   PBX_REQUIRE(ctx != nullptr && p != nullptr, "pbx_gibbs_mvn_run: null argument");
   PBX_REQUIRE(p->n_chains >= 1, "pbx_gibbs_mvn_run: n_chains must be >= 1");
-  PBX_REQUIRE(p->n_dims >= 1 && p->n_dims <= 64, "pbx_gibbs_mvn_run: n_dims must be in 1..64");
+  PBX_REQUIRE(p->n_dims >= 1 && p->n_dims <= 128, "pbx_gibbs_mvn_run: n_dims must be in 1..128");
   PBX_REQUIRE(p->n_steps >= 0 && p->thin >= 1, "pbx_gibbs_mvn_run: n_steps >= 0, thin >= 1");
   PBX_REQUIRE(p->step0 >= 0 && p->chain0 >= 0, "pbx_gibbs_mvn_run: step0/chain0 must be >= 0");
   PBX_REQUIRE(p->mean && p->coef && p->stdv && p->cdf_lo && p->cdf_hi && p->state,
@@ -358,13 +361,14 @@ extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
   a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   if (a.T > 0) {
-    gibbs_c0_kernel<<<1, 64, 0, ctx->stream>>>(p->coef, p->mean, d, c0);
+    gibbs_c0_kernel<<<1, 128, 0, ctx->stream>>>(p->coef, p->mean, d, c0);
     PBX_LAUNCH_CHECK(ctx);
     if (d <= 4) rc = gibbs_launch<1>(ctx, a);
     else if (d <= 8) rc = gibbs_launch<2>(ctx, a);
     else if (d <= 16) rc = gibbs_launch<4>(ctx, a);
     else if (d <= 32) rc = gibbs_launch<8>(ctx, a);
-    else rc = gibbs_launch<16>(ctx, a);
+    else if (d <= 64) rc = gibbs_launch<16>(ctx, a);
+    else rc = gibbs_launch<32>(ctx, a);
     if (rc) return rc;
     if (p->out_prob && p->want_prob) {
       // the target is evaluated and recorded on every kept step (sd.py:286)

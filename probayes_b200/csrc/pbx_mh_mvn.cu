@@ -127,9 +127,11 @@ __device__ __forceinline__ double out_exp(double l, const PbxTables* tb) {
 }
 
 static int init_tables(pbx_ctx* ctx) {
-  static bool done[64] = {false};
-  if (ctx->device < 64 && done[ctx->device]) return PBX_OK;
-  static PbxTables h;
+  // per context (one per device and process; a context is not thread-safe): no process-wide
+  // flags that would go stale after a device reset or race between threads
+  if (ctx->tables_ready) return PBX_OK;
+  PbxTables* hp = new PbxTables();
+  PbxTables& h = *hp;
   for (int j = 0; j < 128; ++j) {
     const long double c = 1.0L + (j + 0.5L) / 128.0L;
     const double inv = (double)(1.0L / c);
@@ -150,10 +152,12 @@ static int init_tables(pbx_ctx* ctx) {
   }
   for (int j = 0; j < 64; ++j)
     for (int g = 0; g < 16; ++g) h.ex[16 * j + g] = (double)exp2l(j / 64.0L);
-  PBX_CUDA(cudaMemcpyToSymbolAsync(g_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice,
-                                   ctx->stream));
-  PBX_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (ctx->device < 64) done[ctx->device] = true;
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_tables, &h, sizeof(h), 0, cudaMemcpyHostToDevice,
+                                          ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  delete hp;
+  PBX_CUDA(e);
+  ctx->tables_ready = true;
   return PBX_OK;
 }
 
@@ -1337,19 +1341,31 @@ extern "C" int pbx_mh_mvn_walk_host(pbx_ctx* ctx, const pbx_mh_mvn_params* p,
   PBX_CUDA(cudaMemsetAsync(ws + o_sum, 0, sbytes, st));
   PBX_CUDA(cudaMemsetAsync(ws + o_sq, 0, sbytes, st));
 
-  cudaEvent_t done[2], copied[2];
+  cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+  // every failure below goes through ONE exit that drains both streams (no D2H copy may
+  // still be writing into the caller's buffers when we return) and destroys the events
+  int status = PBX_OK;
+#define PBX_WH(call)                                                              \
+  do {                                                                            \
+    cudaError_t _e = (call);                                                      \
+    if (_e != cudaSuccess && status == PBX_OK) {                                  \
+      pbx_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call,            \
+                    cudaGetErrorString(_e));                                      \
+      status = PBX_ERR_CUDA;                                                      \
+    }                                                                             \
+  } while (0)
   for (int b = 0; b < 2; ++b) {
-    PBX_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
-    PBX_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    PBX_WH(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+    PBX_WH(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
   }
-  PBX_CUDA(cudaEventRecord(ctx->ev0, st));
+  PBX_WH(cudaEventRecord(ctx->ev0, st));
   int64_t rec_done = 0;
   int chunk = 0;
-  for (int64_t t0 = 0; t0 < T; t0 += chunk_steps, ++chunk) {
+  for (int64_t t0 = 0; t0 < T && status == PBX_OK; t0 += chunk_steps, ++chunk) {
     const int b = chunk & 1;
     const int64_t nt = (T - t0 < chunk_steps) ? (T - t0) : chunk_steps;
     const int64_t nrec = nt / thin;
-    if (chunk >= 2) PBX_CUDA(cudaStreamWaitEvent(st, copied[b], 0));
+    if (chunk >= 2) PBX_WH(cudaStreamWaitEvent(st, copied[b], 0));
     pbx_mh_mvn_params q = *p;
     q.n_steps = (int32_t)nt;
     q.step0 = p->step0 + t0;
@@ -1360,35 +1376,44 @@ extern "C" int pbx_mh_mvn_walk_host(pbx_ctx* ctx, const pbx_mh_mvn_params* p,
     q.accept_count = (int64_t*)(ws + o_acc);
     q.stat_sum = (double*)(ws + o_sum);
     q.stat_sumsq = (double*)(ws + o_sq);
-    rc = run_device(ctx, &q);
-    if (rc) return rc;
-    PBX_CUDA(cudaEventRecord(done[b], st));
-    PBX_CUDA(cudaStreamWaitEvent(cs, done[b], 0));
+    if (status == PBX_OK) status = run_device(ctx, &q);
+    if (status != PBX_OK) break;
+    PBX_WH(cudaEventRecord(done[b], st));
+    PBX_WH(cudaStreamWaitEvent(cs, done[b], 0));
     if (p->out_x && nrec)
-      PBX_CUDA(cudaMemcpyAsync(p->out_x + rec_done * D * C, ws + o_x[b], (size_t)nrec * D * C * 8,
-                               cudaMemcpyDeviceToHost, cs));
+      PBX_WH(cudaMemcpyAsync(p->out_x + rec_done * D * C, ws + o_x[b], (size_t)nrec * D * C * 8,
+                             cudaMemcpyDeviceToHost, cs));
     if (p->out_prob && nrec)
-      PBX_CUDA(cudaMemcpyAsync(p->out_prob + rec_done * C, ws + o_p[b], (size_t)nrec * C * 8,
-                               cudaMemcpyDeviceToHost, cs));
-    PBX_CUDA(cudaEventRecord(copied[b], cs));
+      PBX_WH(cudaMemcpyAsync(p->out_prob + rec_done * C, ws + o_p[b], (size_t)nrec * C * 8,
+                             cudaMemcpyDeviceToHost, cs));
+    PBX_WH(cudaEventRecord(copied[b], cs));
     rec_done += nrec;
   }
-  PBX_CUDA(cudaEventRecord(ctx->ev1, st));
-  PBX_CUDA(cudaMemcpyAsync(p->state, ws + o_state, sbytes, cudaMemcpyDeviceToHost, st));
-  PBX_CUDA(cudaMemcpyAsync(p->state_lp, ws + o_lp, C * 8, cudaMemcpyDeviceToHost, st));
-  if (p->accept_count)
-    PBX_CUDA(cudaMemcpyAsync(p->accept_count, ws + o_acc, C * 8, cudaMemcpyDeviceToHost, st));
-  if (p->stat_sum)
-    PBX_CUDA(cudaMemcpyAsync(p->stat_sum, ws + o_sum, sbytes, cudaMemcpyDeviceToHost, st));
-  if (p->stat_sumsq)
-    PBX_CUDA(cudaMemcpyAsync(p->stat_sumsq, ws + o_sq, sbytes, cudaMemcpyDeviceToHost, st));
-  PBX_CUDA(cudaStreamSynchronize(st));
-  PBX_CUDA(cudaStreamSynchronize(cs));
-  for (int b = 0; b < 2; ++b) {
-    cudaEventDestroy(done[b]);
-    cudaEventDestroy(copied[b]);
+  if (status == PBX_OK) {
+    PBX_WH(cudaEventRecord(ctx->ev1, st));
+    PBX_WH(cudaMemcpyAsync(p->state, ws + o_state, sbytes, cudaMemcpyDeviceToHost, st));
+    PBX_WH(cudaMemcpyAsync(p->state_lp, ws + o_lp, C * 8, cudaMemcpyDeviceToHost, st));
+    if (p->accept_count)
+      PBX_WH(cudaMemcpyAsync(p->accept_count, ws + o_acc, C * 8, cudaMemcpyDeviceToHost, st));
+    if (p->stat_sum)
+      PBX_WH(cudaMemcpyAsync(p->stat_sum, ws + o_sum, sbytes, cudaMemcpyDeviceToHost, st));
+    if (p->stat_sumsq)
+      PBX_WH(cudaMemcpyAsync(p->stat_sumsq, ws + o_sq, sbytes, cudaMemcpyDeviceToHost, st));
   }
-  return PBX_OK;
+  {
+    cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(cs);
+    if (status == PBX_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+      pbx_set_error("pbx_mh_mvn_walk_host: stream synchronisation failed: %s",
+                    cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      status = PBX_ERR_CUDA;
+    }
+  }
+#undef PBX_WH
+  for (int b = 0; b < 2; ++b) {
+    if (done[b]) cudaEventDestroy(done[b]);
+    if (copied[b]) cudaEventDestroy(copied[b]);
+  }
+  return status;
 }
 
 

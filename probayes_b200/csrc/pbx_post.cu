@@ -1003,3 +1003,135 @@ extern "C" int pbx_box_sample(pbx_ctx* ctx, int32_t n_params, int64_t n_samples,
   PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
 }
+
+
+// ===========================================================================
+// Ordinary Monte Carlo with REJECTION sampling (examples/omc/omc_rejection_sp_circle.py:
+// 26-39; SP.next with a proposal density, probayes/sp.py:221-258, sd.py:228-250,
+// rf.py:584-602).  Per sample: every variable afresh from its box (uniform in ufun space,
+// variable.py:558-583), the proposal density q there, the target p, the score s (p or the
+// safe ratio p / q), one threshold uniform t in [t_lo, t_hi) and the update flag s >= t.
+// RNG: the box draws are those of pbx_box_sample (Philox block (seed, sample, 0, slot));
+// the threshold is u52 of block (seed, sample, 1, 0).  Injected: [T][P + 1] per sample
+// (draws in variable order, then the threshold), the reference's call order.
+// ===========================================================================
+struct RejConst {
+  double ulo[8], ulen[8];
+  int lg[8];
+  double centre[8], loc[8], scale[8], radius, t_lo, t_hi;
+  int target_kind, prop_kind, score_mode;
+};
+
+__global__ void __launch_bounds__(256) rejection_kernel(int P, long long T, const RejConst rc,
+                                                        unsigned long long seed, long long t0,
+                                                        const double* __restrict__ inj,
+                                                        double* __restrict__ theta,
+                                                        double* __restrict__ op,
+                                                        double* __restrict__ oq,
+                                                        double* __restrict__ os,
+                                                        double* __restrict__ ot,
+                                                        unsigned char* __restrict__ ou) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  double x[8];
+  for (int s = 0; s < (P + 1) / 2; ++s) {
+    double r0, r1 = 0.0;
+    if (inj) {
+      r0 = inj[t * (P + 1) + 2 * s];
+      if (2 * s + 1 < P) r1 = inj[t * (P + 1) + 2 * s + 1];
+    } else {
+      const pbx_u4 w = pbx_block(seed, (uint64_t)(t0 + t), 0u, (uint32_t)s);
+      r0 = pbx_u52(w.x, w.y);
+      r1 = pbx_u32(w.z);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = 2 * s + h;
+      if (j >= P) break;
+      const double u = __dadd_rn(rc.ulo[j], __dmul_rn(rc.ulen[j], h ? r1 : r0));
+      x[j] = rc.lg[j] ? exp(u) : u;
+      theta[(long long)j * T + t] = x[j];
+    }
+  }
+  // proposal density: product of normal pdfs as scipy evaluates them (exp(-z^2/2) /
+  // sqrt(2 pi) / scale), or of the box-uniform densities 1 / length
+  double q = 1.0;
+  for (int j = 0; j < P; ++j) {
+    if (rc.prop_kind == 0) {
+      const double z = (x[j] - rc.loc[j]) / rc.scale[j];
+      q *= (exp(-(z * z) / 2.0) / 2.50662827463100050242) / rc.scale[j];
+    } else {
+      q *= 1.0 / rc.ulen[j];
+    }
+  }
+  // target: indicator of a ball (1.0 / 0.0)
+  double ss = 0.0;
+  for (int j = 0; j < P; ++j) {
+    const double dlt = x[j] - rc.centre[j];
+    ss += __dmul_rn(dlt, dlt);
+  }
+  const double p = (ss <= rc.radius * rc.radius) ? 1.0 : 0.0;
+  const double sc = rc.score_mode == 0 ? p : p / fmax(PBX_TINY, q);    // div_prob
+  double r;
+  if (inj) {
+    r = inj[t * (P + 1) + P];
+  } else {
+    const pbx_u4 w = pbx_block(seed, (uint64_t)(t0 + t), 1u, 0u);
+    r = pbx_u52(w.x, w.y);
+  }
+  const double th = __dadd_rn(rc.t_lo, __dmul_rn(rc.t_hi - rc.t_lo, r));
+  op[t] = p;
+  oq[t] = q;
+  os[t] = sc;
+  ot[t] = th;
+  ou[t] = (sc >= th) ? 1 : 0;
+}
+
+extern "C" int pbx_rejection_sample(pbx_ctx* ctx, const pbx_rejection_params* p) {
+  PBX_REQUIRE(ctx != nullptr && p != nullptr, "pbx_rejection_sample: null argument");
+  PBX_REQUIRE(p->n_params >= 1 && p->n_params <= 8,
+              "pbx_rejection_sample: n_params must be in 1..8 (got %d)", p->n_params);
+  PBX_REQUIRE(p->n_samples >= 0 && p->sample0 >= 0, "pbx_rejection_sample: negative size");
+  PBX_REQUIRE(p->target_kind == 0, "pbx_rejection_sample: unknown target_kind %d", p->target_kind);
+  PBX_REQUIRE(p->prop_kind == 0 || p->prop_kind == 1,
+              "pbx_rejection_sample: unknown prop_kind %d", p->prop_kind);
+  PBX_REQUIRE(p->score_mode == 0 || p->score_mode == 1,
+              "pbx_rejection_sample: unknown score_mode %d", p->score_mode);
+  if (p->n_samples == 0) return PBX_OK;
+  PBX_REQUIRE(p->out_theta && p->out_p && p->out_q && p->out_s && p->out_t && p->out_u,
+              "pbx_rejection_sample: every output buffer is mandatory");
+  RejConst rc;
+  for (int j = 0; j < 8; ++j) {
+    rc.ulo[j] = rc.ulen[j] = rc.centre[j] = rc.loc[j] = 0.0;
+    rc.scale[j] = 1.0;
+    rc.lg[j] = 0;
+    if (j >= p->n_params) continue;
+    const double lo = p->lims[j][0], hi = p->lims[j][1];
+    rc.lg[j] = p->log_ufun[j] != 0;
+    PBX_REQUIRE(std::isfinite(lo) && std::isfinite(hi) && hi >= lo,
+                "pbx_rejection_sample: variable %d needs finite limits (variable.py:572-574)", j);
+    PBX_REQUIRE(!rc.lg[j] || lo > 0.0, "pbx_rejection_sample: log ufun needs positive limits");
+    const double ulo = rc.lg[j] ? log(lo) : lo, uhi = rc.lg[j] ? log(hi) : hi;
+    rc.ulo[j] = ulo;
+    rc.ulen[j] = uhi - ulo;
+    rc.centre[j] = p->target_centre[j];
+    rc.loc[j] = p->prop_loc[j];
+    rc.scale[j] = p->prop_scale[j];
+    PBX_REQUIRE(p->prop_kind != 0 || rc.scale[j] > 0.0,
+                "pbx_rejection_sample: proposal scale %d must be positive", j);
+  }
+  rc.radius = p->target_radius;
+  rc.t_lo = p->thresh_lo;
+  rc.t_hi = p->thresh_hi;
+  rc.target_kind = p->target_kind;
+  rc.prop_kind = p->prop_kind;
+  rc.score_mode = p->score_mode;
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  const int grid = (int)((p->n_samples + 255) / 256);
+  rejection_kernel<<<grid, 256, 0, ctx->stream>>>(p->n_params, (long long)p->n_samples, rc,
+                                                  p->seed, (long long)p->sample0, p->inj_unif,
+                                                  p->out_theta, p->out_p, p->out_q, p->out_s,
+                                                  p->out_t, p->out_u);
+  PBX_LAUNCH_CHECK(ctx);
+  return PBX_OK;
+}

@@ -11,6 +11,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import (PbxError, MhMvnParams, MhNormregParams, GibbsMvnParams, DevInfo,
+                   RejectionParams,
                    ACCEPT_REFERENCE, ACCEPT_LOG, PROP_NORMAL, PROP_UNIFORM, PROP_SPHERICAL,
                    PBX_MAX_DIMS)
 
@@ -144,6 +145,28 @@ class Engine:
     def _ptr(t):
         return C.c_void_p(0 if t is None else t.data_ptr())
 
+    def _dev(self, t, shape, what, dtype=None):
+        """Checks a tensor whose pointer crosses the C ABI: on this engine's device,
+        contiguous, ``dtype`` (fp64 by default) and exactly ``shape``.  The kernels read
+        raw pointers as contiguous arrays; anything else would be silent garbage or an
+        out-of-bounds write, so it raises."""
+        torch = _torch()
+        if t is None:
+            return None
+        dtype = dtype or torch.float64
+        if not isinstance(t, torch.Tensor):
+            raise TypeError("%s must be a torch tensor on %s" % (what, self.device))
+        if not t.is_cuda or t.device.index != self.device_index:
+            raise ValueError("%s must live on %s (got %s)" % (what, self.device, t.device))
+        if t.dtype != dtype:
+            raise TypeError("%s must be %s (got %s)" % (what, dtype, t.dtype))
+        if not t.is_contiguous():
+            raise ValueError("%s must be contiguous (got strides %s)" % (what, t.stride()))
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s (got %s)" % (what, tuple(shape),
+                                                                 tuple(t.shape)))
+        return t
+
     # ------------------------------------------------------------ K1: mh mvn
     def _mvn_params(self, D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
                     prop, prop_scale, prop_chol, mean, cov, reorder, variant=0,
@@ -207,6 +230,10 @@ class Engine:
         torch = _torch()
         D, C_ = state.shape
         T = int(steps)
+        self._dev(state, (D, C_), "state")
+        self._dev(state_lp, (C_,), "state_lp")
+        self._dev(inj_delta, (T, D, C_), "inj_delta")
+        self._dev(inj_thresh, (T, C_), "inj_thresh")
         p = self._mvn_params(D, C_, T, thin, step0, chain0, seed, log_pscale, accept,
                              prop, prop_scale, prop_chol, mean, cov, reorder, variant,
                              prop_radius, bound)
@@ -224,8 +251,8 @@ class Engine:
                 out["x"] = self.empty(R, D, C_)
             if "prob" not in out:
                 out["prob"] = self.empty(R, C_)
-            if tuple(out["x"].shape) != (R, D, C_) or tuple(out["prob"].shape) != (R, C_):
-                raise ValueError("preallocated outputs must be x[R, D, C], prob[R, C]")
+            self._dev(out["x"], (R, D, C_), "out['x']")
+            self._dev(out["prob"], (R, C_), "out['prob']")
         if per_step:
             out["accept"] = self.empty(T, C_, dtype=torch.uint8)
             out["score"] = self.empty(T, C_)
@@ -278,7 +305,14 @@ class Engine:
             out_x = torch.empty((R, D, C_), dtype=torch.float64, pin_memory=True)
         if out_prob is None:
             out_prob = torch.empty((R, C_), dtype=torch.float64, pin_memory=True)
+        for t, shp, what in ((out_x, (R, D, C_), "out_x"), (out_prob, (R, C_), "out_prob")):
+            if t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() \
+                    or tuple(t.shape) != shp:
+                raise ValueError("%s must be a contiguous host fp64 tensor of shape %s"
+                                 % (what, shp))
         lp = np.zeros(C_) if state_lp is None else np.ascontiguousarray(state_lp, np.float64)
+        if lp.shape != (C_,):
+            raise ValueError("state_lp must have shape (%d,)" % C_)
         acc = np.zeros(C_, dtype=np.int64)
         ssum = np.zeros((D, C_))
         ssq = np.zeros((D, C_))
@@ -339,6 +373,12 @@ class Engine:
         T = int(steps)
         if int(thin) < 1:
             raise ValueError("thin must be >= 1")
+        self._dev(state, (P, C_), "state")
+        self._dev(state_lp, (C_,), "state_lp")
+        self._dev(y_obs, None, "y_obs")
+        self._dev(x_obs, None, "x_obs")
+        self._dev(inj_delta, (T, P, C_), "inj_delta")
+        self._dev(inj_thresh, (T, C_), "inj_thresh")
         p = self._normreg_params(C_, P, x_obs, y_obs, lims, open_end, log_ufun, prop_scale,
                                  accept, accept_coef, prop, variant, prop_radius, prop_bound)
         p.n_steps, p.thin, p.step0, p.chain0 = T, thin, step0, chain0
@@ -382,6 +422,9 @@ class Engine:
     def normreg_logjoint(self, theta, y_obs, x_obs, lims, open_end, log_ufun, variant=0):
         """log-joint (likelihood + box priors) of theta [P, C] -> [C] device."""
         P, C_ = theta.shape
+        self._dev(theta, (P, C_), "theta")
+        self._dev(y_obs, None, "y_obs")
+        self._dev(x_obs, None, "x_obs")
         p = self._normreg_params(C_, P, x_obs, y_obs, lims, open_end, log_ufun, 0.0,
                                  variant=variant)
         out = self.empty(C_)
@@ -515,10 +558,12 @@ class Engine:
         with x [R, d, C] and prob [R, C] (the mvn target evaluated on every kept
         state, as the reference's SP.next does)."""
         d, C_ = state.shape
+        self._dev(state, (d, C_), "state")
+        self._dev(inj_runif, (int(steps), C_), "inj_runif")
         if d != cond_cov.n:
             raise ValueError("state has %d dims, CondCov has %d" % (d, cond_cov.n))
-        if d > 64:
-            raise NotImplementedError("gibbs_mvn supports up to 64 dimensions")
+        if d > 128:
+            raise NotImplementedError("gibbs_mvn supports up to 128 dimensions")
         if int(thin) < 1:
             raise ValueError("thin must be >= 1")
         T = int(steps)
@@ -666,10 +711,46 @@ class Engine:
             0 if inj_unif is None else self._ptr(inj_unif), out.data_ptr()), "pbx_box_sample")
         return out
 
+    def rejection_sample(self, lims, log_ufun, n_samples, target, prop, score_mode, thresh,
+                         seed=0, sample0=0, inj_unif=None):
+        """Ordinary Monte Carlo with rejection sampling (sp.py:221-258 with a proposal
+        density): returns dict(theta [P, T], p, q, s, t [T], u [T] uint8) device tensors.
+        target = dict(kind='ball', radius, centre); prop = dict(kind='normal', loc, scale) |
+        dict(kind='box'); score_mode 'p' | 'p/q'; thresh = (low, high); inj_unif [T, P + 1]."""
+        torch = _torch()
+        lims = np.asarray(lims, dtype=np.float64)
+        P, T = lims.shape[0], int(n_samples)
+        p = RejectionParams()
+        p.n_params, p.n_samples, p.sample0 = P, T, int(sample0)
+        p.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        if target['kind'] != 'ball':
+            raise NotImplementedError("rejection target kind %r" % target['kind'])
+        p.target_kind, p.target_radius = 0, float(target['radius'])
+        p.prop_kind = {'normal': 0, 'box': 1}[prop['kind']]
+        p.score_mode = {'p': 0, 'p/q': 1}[score_mode]
+        p.thresh_lo, p.thresh_hi = float(thresh[0]), float(thresh[1])
+        for j in range(P):
+            p.lims[j][0], p.lims[j][1] = lims[j]
+            p.log_ufun[j] = int(np.asarray(log_ufun)[j])
+            p.target_centre[j] = float(np.asarray(target['centre'])[j])
+            p.prop_loc[j] = float(prop['loc'][j]) if prop['kind'] == 'normal' else 0.0
+            p.prop_scale[j] = float(prop['scale'][j]) if prop['kind'] == 'normal' else 1.0
+        out = dict(theta=self.empty(P, T), p=self.empty(T), q=self.empty(T), s=self.empty(T),
+                   t=self.empty(T), u=self.empty(T, dtype=torch.uint8))
+        self._dev(inj_unif, (T, P + 1), "inj_unif")
+        p.inj_unif = 0 if inj_unif is None else inj_unif.data_ptr()
+        p.out_theta, p.out_p, p.out_q = out['theta'].data_ptr(), out['p'].data_ptr(), \
+            out['q'].data_ptr()
+        p.out_s, p.out_t, p.out_u = out['s'].data_ptr(), out['t'].data_ptr(), out['u'].data_ptr()
+        _lib.check(self.lib.pbx_rejection_sample(self.ctx, C.byref(p)), "pbx_rejection_sample")
+        return out
+
     # ------------------------------------------------------- chain summaries
     def chain_stats(self, stat_sum, stat_sumsq, n_steps):
         """[D, 4] device tensor (sum_c mean, sum_c mean^2, sum_c var, C)."""
         D, C_ = stat_sum.shape
+        self._dev(stat_sum, (D, C_), "stat_sum")
+        self._dev(stat_sumsq, (D, C_), "stat_sumsq")
         out = self.empty(D, 4)
         _lib.check(self.lib.pbx_reduce_chain_stats(self.ctx, self._ptr(stat_sum),
                                                    self._ptr(stat_sumsq), D, C_, int(n_steps),

@@ -25,9 +25,13 @@ class RV:
     ``[(lo,), hi]`` / ``[lo, (hi,)]`` -> mixed; a two-element ``set`` -> closed.
     """
 
-    def __init__(self, name, vtype=float, vset=None, pscale=None):
+    def __init__(self, name, vset=None, vtype=None, prob=None, *args, pscale=None, **kwds):
+        # positional order of the reference (probayes/rv.py:57-62): name, vset, vtype, prob
         assert isinstance(name, str) and name.isidentifier(), \
             "Variable name must be a valid identifier: {}".format(name)
+        if prob is not None or args or kwds:
+            raise NotImplementedError("per-variable probability expressions are outside the "
+                                      "device catalogue (box-uniform priors are)")
         if vtype not in (float, np.float64, None):
             raise NotImplementedError(
                 "only float random variables are in the device catalogue (got {})".format(vtype))

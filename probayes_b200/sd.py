@@ -45,6 +45,7 @@ class SD:
         self._tran_obj = self._own_rf
         self._delta_obj = self._own_rf
         self._prob, self._prob_args, self._prob_kwds, self._order = None, (), {}, None
+        self._prop, self._prop_args, self._prop_kwds = None, (), {}
         self._pscale = self._all.pscale
         self.Delta = self._state_rf.Delta
         self.opqr = collections.namedtuple(self._id, ['o', 'p', 'q', 'r'])
@@ -88,6 +89,20 @@ class SD:
         self._order = kwds.pop('order', None)
         kwds.pop('passdims', None)
         self._prob, self._prob_args, self._prob_kwds = prob, tuple(args), kwds
+
+    @property
+    def prop(self):
+        return self._prop
+
+    def set_prop(self, prop=None, *args, **kwds):
+        """Proposal DENSITY for ordinary Monte Carlo / rejection sampling (rf.py:146-161):
+        a callable of the variables, or a catalogue spec (NormalProduct, BoxUniform)."""
+        if prop is not None:
+            assert self._tran_obj.tran is None, \
+                "Cannot assign both proposition and transition probabilities"
+        kwds = dict(kwds)
+        kwds.pop('deps', None)
+        self._prop, self._prop_args, self._prop_kwds = prop, tuple(args), kwds
 
     def set_tran(self, tran=None, *args, **kwds):
         member = self._member(tran)

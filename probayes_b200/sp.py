@@ -115,33 +115,36 @@ class SP(SD):
     def update(self):
         return self._update
 
-    def _check_spec(self, spec, what):
+    def _check_spec(self, spec, what, args=(), kwds=None):
+        """MCMC sampler names pass through; Python callables are mapped onto the kernel
+        modes the catalogue knows (rejection sampling: scores opqr.p.prob [/ opqr.q.prob],
+        thresh np.random.uniform(low, high), update stu.s >= stu.t) or refused."""
         if spec is None:
             return None
         if isinstance(spec, str) and spec in MCMC_SAMPLERS:
+            assert not args and not kwds, \
+                "Neither args nor kwds permitted with spec '{}'".format(spec)
             return spec
+        if callable(spec):
+            fn = {'scores': catalogue.identify_scores, 'thresh': catalogue.identify_thresh,
+                  'update': catalogue.identify_update}[what]
+            return fn(spec, args, kwds)
         raise NotImplementedError(
-            "{} must be one of {} on the device path (custom Python {} functions cannot "
-            "run in the kernel)".format(what, MCMC_SAMPLERS, what))
+            "{} must be one of {} or a catalogue-recognised function on the device path"
+            .format(what, MCMC_SAMPLERS))
 
     def set_scores(self, scores=None, *args, **kwds):
-        assert not args and not kwds, \
-            "Neither args nor kwds permitted with spec '{}'".format(scores)
-        self._scores = self._check_spec(scores, 'scores')
-        if self._scores is not None:            # the reference chains these (sp.py:61-66)
+        self._scores = self._check_spec(scores, 'scores', args, kwds)
+        if self._scores in MCMC_SAMPLERS:       # the reference chains these (sp.py:61-66)
             self.set_thresh(scores)
 
     def set_thresh(self, thresh=None, *args, **kwds):
-        assert not args and not kwds, \
-            "Neither args nor kwds permitted with spec '{}'".format(thresh)
-        self._thresh = self._check_spec(thresh, 'thresh')
-        if self._thresh is not None:
+        self._thresh = self._check_spec(thresh, 'thresh', args, kwds)
+        if self._thresh in MCMC_SAMPLERS:
             self.set_update(thresh)
 
     def set_update(self, update=None, *args, **kwds):
-        assert not args and not kwds, \
-            "Neither args nor kwds permitted with spec '{}'".format(update)
-        self._update = self._check_spec(update, 'update')
+        self._update = self._check_spec(update, 'update', args, kwds)
 
     # ---- sampler bookkeeping --------------------------------------------------------------------
     def reset(self, sampler_id=None, reset_last=True):
@@ -169,6 +172,16 @@ class SP(SD):
         stop = kwds.pop('stop', None)
         if len(args) == 1 and type(args[0]) is int and stop is None:
             stop, args = args[0], ()
+        if self._prop is not None:
+            # proposal DENSITY set: every step draws afresh ({0}) -- rejection sampling
+            assert not args or (isinstance(args[0], set) and list(args[0]) == [0]), \
+                "a sampler with a proposal density draws {0} per step"
+            opts = dict(rejection=True, omc=False, seed=kwds.pop('seed', None),
+                        inj_unif=kwds.pop('inj_unif', None), sample0=kwds.pop('sample0', None))
+            assert not kwds, "Unknown sampler keywords: {}".format(list(kwds))
+            s = Sampler(self, None, None, stop, opts)
+            self._samplers.append(s)
+            return s
         if not args:
             raise NotImplementedError("random initial states ({0}) are not in the device "
                                       "catalogue: pass an initial-state dictionary")
@@ -219,6 +232,16 @@ class SP(SD):
             raise ValueError("No stop specification set - a device walk needs a finite length")
         if sampler.stop is not None:
             T = min(T, sampler.stop - sampler.counter)
+        if sampler.opts.get('rejection'):
+            arrays = self._run_rejection(sampler, int(T))
+            sampler.counter += int(T)
+            if sampler.stop is not None and sampler.counter >= sampler.stop:
+                sampler.counter = 0
+            out = Walk()
+            out.arrays, out.sampler = arrays, sampler
+            if arrays['T'] <= 200000:
+                out.extend(self._rejection_per_step(arrays))
+            return out
         arrays = self._run_omc(sampler, int(T)) if sampler.opts['omc'] \
             else self._run(sampler, int(T))
         sampler.counter += int(T)
@@ -233,6 +256,84 @@ class SP(SD):
         if arrays['chains'] is None and arrays['R'] <= 200000:
             out.extend(self._per_step(arrays))
         return out
+
+    # ---- ordinary Monte Carlo with rejection sampling -----------------------------------------
+    def _run_rejection(self, sampler, T):
+        """examples/omc/omc_rejection_sp_circle.py:26-39 as ONE kernel launch: T proposals
+        from the variables' boxes, proposal density q, target p, score, threshold, update."""
+        from .engine import get_engine
+        from .dist import world
+        eng = get_engine()
+        opts = sampler.opts
+        rvs = self._state_rf.varlist
+        keys = self._state_rf.keylist
+        for rv in rvs:
+            assert rv.isfinite, "Cannot evaluate {{0}} values for bounds: {}".format(rv.ulims)
+        if not (self._scores in ('p', 'p/q') and isinstance(self._thresh, tuple)
+                and self._update == 's>=t'):
+            raise NotImplementedError(
+                "rejection sampling needs set_scores(opqr.p.prob [/ opqr.q.prob]), "
+                "set_thresh(np.random.uniform, low=, high=) and set_update(stu.s >= stu.t)")
+        target = catalogue.identify_rejection_target(self._prob, self._prob_args,
+                                                     self._prob_kwds, rvs)
+        prop = catalogue.identify_rejection_prop(self._prop, self._prop_args, self._prop_kwds,
+                                                 rvs)
+        lims = np.array([rv.vlims for rv in rvs])
+        lg = np.array([rv.log_ufun for rv in rvs], dtype=int)
+        inj = None
+        if opts['inj_unif'] is not None:
+            u = np.asarray(opts['inj_unif'], dtype=np.float64)[sampler.counter:sampler.counter + T]
+            assert u.shape == (T, len(keys) + 1), "injected uniform stream must be [T, P + 1]"
+            inj = eng.to_device(u)
+        seed = opts['seed']
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        sample0 = opts['sample0']
+        if sample0 is None:                      # sharded run: disjoint global sample ids
+            rank, ws = world()
+            sample0 = rank * (sampler.stop or T)
+        out = eng.rejection_sample(lims, lg, T, target, prop, self._scores, self._thresh[1:],
+                                   seed=seed, sample0=int(sample0) + sampler.counter,
+                                   inj_unif=inj)
+        eng.sync()
+        host = {k: v.detach().cpu().numpy() for k, v in out.items()}
+        return dict(rejection=True, keys=keys, T=T, pscale=self._pscale, chains=None,
+                    dev=out, **host)
+
+    def _rejection_pd(self, arrays, sel, primed=False, prob_key='p'):
+        """PD over the samples ``sel`` (an index -> scalar PD, a mask / slice -> arrays)."""
+        keys = arrays['keys']
+        names = [k + "'" for k in keys] if primed else list(keys)
+        th, pr = arrays['theta'], arrays[prob_key]
+        if np.ndim(sel) == 0 and not isinstance(sel, slice):
+            vals = collections.OrderedDict((n, float(th[j, sel])) for j, n in enumerate(names))
+            name = ','.join("{}={}".format(n, vals[n]) for n in names)
+            return PD(name, vals, dims=collections.OrderedDict((n, None) for n in names),
+                      prob=float(pr[sel]), pscale=arrays['pscale'])
+        vals = collections.OrderedDict((n, th[j][sel]) for j, n in enumerate(names))
+        return PD(','.join(names), vals, dims=collections.OrderedDict((n, 0) for n in names),
+                  prob=pr[sel], pscale=arrays['pscale'])
+
+    def _rejection_per_step(self, arrays):
+        """Reference-shaped tuples (sp.py:244-258): p the target PD at the proposal, q the
+        proposal-density PD (primed names, rf.py:584-602), s, t, u; v = p when kept."""
+        out = []
+        for i in range(arrays['T']):
+            p = self._rejection_pd(arrays, i)
+            q = self._rejection_pd(arrays, i, primed=True, prob_key='q')
+            out.append(self.opqrstuv(None, p, q, None, float(arrays['s'][i]),
+                                     float(arrays['t'][i]), bool(arrays['u'][i]),
+                                     p if (arrays['u'][i] or i == 0) else None))
+        return out
+
+    def _rejection_summary(self, arrays):
+        """process(samples) of a rejection run (sp.py:131-198): samples with u == False are
+        dropped, the rest summated."""
+        keep = arrays['u'].astype(bool)
+        p = self._rejection_pd(arrays, keep)
+        q = self._rejection_pd(arrays, keep, primed=True, prob_key='q')
+        return self.opqrstuv(None, p, q, None, list(arrays['s'][keep]), list(arrays['t'][keep]),
+                             [True] * int(keep.sum()), p)
 
     # ---- ordinary Monte Carlo random sampling ------------------------------------------------
     def _run_omc(self, sampler, T):
@@ -352,7 +453,8 @@ class SP(SD):
         if opts['inj_thresh'] is not None:       # thresholds (MH) / cdf uniforms (Gibbs)
             t = np.asarray(opts['inj_thresh'], dtype=np.float64)
             t = (t[:, None] if t.ndim == 1 else t)[step0:step0 + T]
-            assert t.shape == (T, C), "injected threshold stream shape mismatch"
+            gibbs_k = (self._tran_obj.tsteps or D) if self._scores == 'gibbs' else 1
+            assert t.shape == (T, C) or gibbs_k > 1, "injected threshold stream shape mismatch"
             inj_t = eng.to_device(t)
         if injected:
             assert inj_t is not None, "inj_delta needs inj_thresh"
@@ -371,10 +473,19 @@ class SP(SD):
             if spec['kind'] != 'mvn' or cc is None:
                 raise NotImplementedError("Gibbs needs a scipy.stats.multivariate_normal "
                                           "transition (set_tran(mvn, mean, cov, tsteps=1))")
-            tsteps = self._tran_obj.tsteps or D
-            if tsteps != 1:
-                raise NotImplementedError("tsteps=1 (one coordinate per step) only")
-            out = eng.gibbs_mvn(state, cc, T, thin=thin, seed=seed, step0=step0,
+            # tsteps coordinates are updated per step, cursor wrapping at D (rf.py:446-452);
+            # no tsteps = the whole sweep.  The kernel counts single-coordinate updates.
+            k = self._tran_obj.tsteps or D
+            if D % k != 0:
+                raise NotImplementedError("tsteps must divide the number of variables "
+                                          "({} does not divide {})".format(k, D))
+            if inj_t is not None and k > 1:
+                # k cdf uniforms per step, in update order
+                t = np.asarray(opts['inj_thresh'], dtype=np.float64)
+                t = (t[:, None] if t.ndim == 1 else t)[step0 * k:(step0 + T) * k]
+                assert t.shape == (T * k, C), "injected uniform stream shape mismatch"
+                inj_t = eng.to_device(t)
+            out = eng.gibbs_mvn(state, cc, T * k, thin=thin * k, seed=seed, step0=step0 * k,
                                 chain0=chain0, log_pscale=spec['log_pscale'],
                                 inj_runif=inj_t)
             res.update(x=out['x'], prob=out['prob'], accept_count=None, accept=None, score=None)
@@ -561,6 +672,8 @@ class SP(SD):
 
     def _summary(self, samples, conditionalise=None):
         arrays = samples.arrays if isinstance(samples, Walk) else None
+        if arrays is not None and arrays.get('rejection'):
+            return self._rejection_summary(arrays)
         if arrays is not None and arrays.get('omc'):
             pd = self._omc_summary(arrays)
             return pd.conditionalise(self._leafs.keyset) if conditionalise else pd
@@ -588,10 +701,11 @@ class SP(SD):
             if conditionalise:
                 v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])
             u = [s.u for s in kept]
-            s_ = [s.s for s in samples if s.s is not None]
-            t_ = [s.t for s in samples if s.t is not None]
+            s_ = [s.s for s in kept if s.s is not None]      # sp.py:181-190: dropped samples
+            t_ = [s.t for s in kept if s.t is not None]      # contribute nothing
             return self.opqrstuv(concat([s.o for s in kept]), concat([s.p for s in kept]),
-                                 None, None, s_ or None, t_ or None, u, v)
+                                 concat([s.q for s in kept]), None, s_ or None, t_ or None,
+                                 u, v)
         v = self._value_pd(arrays)
         if conditionalise:                      # sp.py:194-196: condition on the leaf (data) keys
             v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])

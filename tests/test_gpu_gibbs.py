@@ -9,6 +9,9 @@ from oracle import philox
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
+# Gibbs trajectories: device normcdfinv against scipy's ndtri (Cephes); both are accurate to
+# ~1 ulp, and every later coordinate inherits the difference through the conditional means
+GTOL = 1e-12
 
 
 def test_condcov_constants_match_reference():
@@ -35,8 +38,8 @@ def test_gibbs2d_golden(name):
     state = dev(eng, g["init"][:, None])
     out = eng.gibbs_mvn(state, cc, T, inj_runif=dev(eng, g["runif"][:, None]))
     eng.sync()
-    assert np.abs(host(out["x"])[:, :, 0] - g["x"]).max() <= 1e-11
-    assert relerr(host(out["prob"])[:, 0], g["prob"]) <= 1e-11
+    assert np.abs(host(out["x"])[:, :, 0] - g["x"]).max() <= GTOL
+    assert relerr(host(out["prob"])[:, 0], g["prob"]) <= GTOL
 
 
 @pytest.mark.parametrize("name", ["condcov_d8", "condcov_d64"])
@@ -50,11 +53,12 @@ def test_condcov_golden_trajectory(name):
     out = eng.gibbs_mvn(state, cc, T, inj_runif=dev(eng, g["runif"][:, None]),
                         want_prob=False)
     eng.sync()
-    assert np.abs(host(out["x"])[:, :, 0] - g["x"]).max() <= 1e-11
+    assert np.abs(host(out["x"])[:, :, 0] - g["x"]).max() <= GTOL
 
 
 @pytest.mark.parametrize("d,C,T,thin", [(2, 100, 41, 1), (3, 33, 50, 3), (8, 257, 64, 8),
-                                        (20, 64, 70, 5), (64, 130, 150, 64)])
+                                        (20, 64, 70, 5), (64, 130, 150, 64),
+                                        (128, 40, 256, 128), (100, 33, 210, 7)])
 def test_oracle_injected_and_resume(d, C, T, thin):
     from probayes_b200.cond_cov import CondCov
     eng = engine()
@@ -73,10 +77,10 @@ def test_oracle_injected_and_resume(d, C, T, thin):
     eng.sync()
     sel = slice(thin - 1, None, thin)
     X = tcd_to_tdc(ref["x"])[sel]
-    assert np.abs(host(out["x"]) - X).max() <= 1e-11
-    assert relerr(host(out["prob"]), ref["prob"][sel]) <= 1e-11
-    assert np.abs(host(state) - ref["x"][-1].T).max() <= 1e-11
-    assert relerr(host(out["stat_sum"]), X.sum(axis=0)) <= 1e-11
+    assert np.abs(host(out["x"]) - X).max() <= GTOL * max(1.0, np.abs(X).max())
+    assert relerr(host(out["prob"]), ref["prob"][sel]) <= GTOL
+    assert np.abs(host(state) - ref["x"][-1].T).max() <= GTOL * max(1.0, np.abs(X).max())
+    assert np.abs(host(out["stat_sum"]) - X.sum(axis=0)).max() <= 1e-11 * max(1.0, np.abs(X).max())
     # resume mid-sweep: two calls == one call
     h = T // 2
     st2 = dev(eng, init.T)
@@ -104,10 +108,11 @@ def test_philox_replay():
     state = dev(eng, init.T)
     out = eng.gibbs_mvn(state, cc, T, seed=seed)
     eng.sync()
-    assert np.abs(host(out["x"]) - tcd_to_tdc(ref["x"])).max() <= 1e-11
+    assert np.abs(host(out["x"]) - tcd_to_tdc(ref["x"])).max() <= GTOL
 
 
-@pytest.mark.parametrize("d,n", [(2, 1000), (5, 777), (64, 4096), (64, 1003), (64, 7)])
+@pytest.mark.parametrize("d,n", [(2, 1000), (5, 777), (64, 4096), (64, 1003), (64, 7),
+                                 (128, 515), (100, 64)])
 def test_mvn_logpdf_batched(d, n):
     """d = 64 goes through the FP64 tensor-core (DMMA) kernel."""
     eng = engine()

@@ -58,9 +58,9 @@ def test_bounded_delta_golden_and_native():
     step = float(g["step"])
     delta = np.stack([-step + (2 * step) * r0, -step + (2 * step) * r1], axis=-1)
     ref = o.mh_mvn_walk(init, delta, philox.thresholds(seed, T2, C), g["mean"], g["cov"],
-                        accept="log", bound=bound)
+                        accept="log", log_pscale=True, bound=bound)
     out = eng.mh_mvn(dev(eng, init.T), g["mean"], g["cov"], T2, seed=seed, accept="log",
-                     prop="uniform", prop_scale=step, bound=bound)
+                     log_pscale=True, prop="uniform", prop_scale=step, bound=bound)
     eng.sync()
     assert np.array_equal(host(out["accept_count"]), ref["u"].sum(axis=0))
     assert np.abs(host(out["x"]) - tcd_to_tdc(ref["x"])).max() <= 1e-11

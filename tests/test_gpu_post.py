@@ -480,7 +480,7 @@ def test_linear_pscale_device_pds_stay_on_the_device():
     with pytest.raises(NotImplementedError):
         odd.conditionalise('x')
     with pytest.raises(NotImplementedError):
-        odd.marginal('mu')
+        odd.marginalise('mu')
 
 
 # ---- full-size properties (no CPU oracle at these sizes) --------------------------------------

@@ -347,3 +347,37 @@ def test_conditionalise_on_array_keys_host():
     assert np.array_equal(lin.prob, g["lin"])
     assert np.array_equal(lin.conditionalise('sigma').prob, g["l_sig"])
     assert np.array_equal(lin.conditionalise('mu').prob, g["l_mu"])
+
+
+def test_rejection_catalogue_recognition():
+    """The rejection-sampling pieces of omc_rejection_sp_circle.py are mapped onto kernel
+    modes by probing; anything else is refused (no Python runs in the kernel)."""
+    import warnings
+    radius = 1.5
+    inside = lambda x, y: np.array(x**2 + y**2 <= radius**2, dtype=float)
+
+    def norm2d(x, y, loc=0.25, scale=0.75):
+        return scipy.stats.norm.pdf(x, loc=loc, scale=scale) * \
+            scipy.stats.norm.pdf(y, loc=loc, scale=scale)
+    rvs = [pb.RV("x", [-2., 2.]), pb.RV("y", [-2., 2.])]
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        t = catalogue.identify_rejection_target(inside, (), {}, rvs)
+        q = catalogue.identify_rejection_prop(norm2d, (), {}, rvs)
+    assert len(w) == 2
+    assert t['kind'] == 'ball' and t['radius'] == radius and list(t['centre']) == [0., 0.]
+    assert q['kind'] == 'normal' and list(q['loc']) == [0.25, 0.25] and list(q['scale']) == [0.75] * 2
+    assert catalogue.identify_scores(lambda opqr: opqr.p.prob) == 'p'
+    assert catalogue.identify_scores(lambda opqr: opqr.p.prob / opqr.q.prob) == 'p/q'
+    assert catalogue.identify_thresh(np.random.uniform, (), dict(low=0., high=0.3)) == \
+        ('uniform', 0., 0.3)
+    assert catalogue.identify_update(lambda stu: stu.s >= stu.t) == 's>=t'
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_scores(lambda opqr: opqr.p.prob ** 2)
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_update(lambda stu: stu.s > stu.t)
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_rejection_target(lambda x, y: np.array(abs(x) + abs(y) <= 1., float),
+                                            (), {}, rvs)
+    with pytest.raises(NotImplementedError):
+        catalogue.identify_thresh(np.random.normal, (), {})
