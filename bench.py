@@ -605,6 +605,31 @@ class C2:
         summary = self.process(self.process.walk(smp))
         return summary.v['x'][0, -1] + summary.u.count(True)     # touch the result
 
+    def e2e_ceiling(self, d):
+        """What bounds the end-to-end figure: the raw pinned device->host copy rate of the
+        SAME bytes (every rank at once, as in the e2e loop), measured here.  The walk's
+        samples must cross PCIe into ONE host's memory; the kernel is ~30x faster."""
+        torch = d.torch
+        hx, hp = self.hostbuf.get('x'), self.hostbuf.get('prob')
+        if hx is None:
+            return None
+        reps = 5
+        for _ in range(2):
+            hx.copy_(self.bufs['x'], non_blocking=True)
+            hp.copy_(self.bufs['prob'], non_blocking=True)
+        d.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            hx.copy_(self.bufs['x'], non_blocking=True)
+            hp.copy_(self.bufs['prob'], non_blocking=True)
+        torch.cuda.synchronize()
+        dt = d.max(time.perf_counter() - t0)
+        gbs = self.world * self.out_bytes * reps / dt / 1e9
+        return {"d2h_gbs_all_ranks": gbs, "d2h_gbs_per_rank": gbs / self.world,
+                "chain_steps_per_s_at_ceiling": self.world * self.C * self.T * reps / dt,
+                "note": "pinned cudaMemcpyAsync D2H of one walk's samples + densities (%.0f MB "
+                        "per rank), all ranks concurrently" % (self.out_bytes / 1e6)}
+
     # ---- CPU ---------------------------------------------------------------------------------
     def cpu_sample(self, budget_s=10.0):
         lo, cores = liboracle_all_cores()
@@ -1038,9 +1063,15 @@ def time_e2e(wl, d, steps, warmup=2):
         wl.e2e_step(k)
     d.torch.cuda.synchronize()
     dt = d.max(time.perf_counter() - t0)
-    return {"value": wl.e2e_units * steps / dt, "unit": wl.unit,
-            "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
-            "steps": steps, "ms_per_step": 1e3 * dt / steps, "api": wl.e2e_note}
+    out = {"value": wl.e2e_units * steps / dt, "unit": wl.unit,
+           "h2d_bytes_per_step": int(wl.h2d), "d2h_bytes_per_step": int(wl.d2h),
+           "steps": steps, "ms_per_step": 1e3 * dt / steps, "api": wl.e2e_note}
+    if hasattr(wl, "e2e_ceiling"):
+        ceil = wl.e2e_ceiling(d)
+        if ceil:
+            out["ceiling"] = ceil
+            out["frac_of_ceiling"] = out["value"] / ceil["chain_steps_per_s_at_ceiling"]
+    return out
 
 
 def reference_numpy_c1():

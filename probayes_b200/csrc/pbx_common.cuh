@@ -20,6 +20,7 @@ struct pbx_ctx {
   void* ws;                  // device workspace
   size_t ws_bytes;
   bool tables_ready;         // K1 math tables uploaded to this context's device
+  bool exptab_ready;         // K4 exp table uploaded
 };
 
 void pbx_set_error(const char* fmt, ...);

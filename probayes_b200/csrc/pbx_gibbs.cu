@@ -73,8 +73,10 @@ __device__ __noinline__ double gibbs_draw_z(uint64_t seed, uint64_t gk, uint32_t
 // next coordinate, i.e. four coordinates' worth in parallel with no redundancy.
 // kSweepRec: records fall on sweep boundaries only (thin % d == 0, call aligned to
 // sweeps) -> one copy of the record code per sweep instead of one per coordinate.
-template <int DQ, bool kSweepRec>
-__global__ void __launch_bounds__(GB_THREADS)
+// NT threads per CTA (256, or 128 when there are too few chains to give every SM a CTA of
+// 64 chains: strong-scaled shards)
+template <int DQ, bool kSweepRec, int NT = GB_THREADS>
+__global__ void __launch_bounds__(NT)
     gibbs_mvn_kernel(const GibbsArgs a) {
   constexpr int DP = 4 * DQ;
   constexpr int RS = DQ + 2;                // padded row stride: the 4 sub-lane rows of a
@@ -86,12 +88,12 @@ __global__ void __launch_bounds__(GB_THREADS)
   double* s_lo = s_sd + DP;
   double* s_w = s_lo + DP;                  // hi - lo
   const int d = a.d;
-  for (int idx = threadIdx.x; idx < DP * 4 * RS; idx += GB_THREADS) {
+  for (int idx = threadIdx.x; idx < DP * 4 * RS; idx += NT) {
     const int i = idx / (4 * RS), r = idx % (4 * RS), q = r / RS, mm = r % RS;
     const int j = 4 * mm + q;
     s_coef[idx] = (i < d && mm < DQ && j < d) ? a.coef[(int64_t)i * d + j] : 0.0;
   }
-  for (int i = threadIdx.x; i < DP; i += GB_THREADS) {
+  for (int i = threadIdx.x; i < DP; i += NT) {
     const bool v = i < d;
     s_c0[i] = v ? a.c0[i] : 0.0;
     s_sd[i] = v ? a.stdv[i] : 0.0;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(GB_THREADS)
   __syncthreads();
   const int lane = threadIdx.x & 31, q = lane & 3;
   const int64_t C = a.C;
-  const int64_t c_raw = ((int64_t)blockIdx.x * (GB_THREADS / 32) + (threadIdx.x >> 5)) * 8 + (lane >> 2);
+  const int64_t c_raw = ((int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)) * 8 + (lane >> 2);
   const bool valid = c_raw < C;
   const int64_t c = valid ? c_raw : C - 1;          // clamp: idle lanes stay in the shuffles
   const uint32_t gchain = (uint32_t)(a.chain0 + c);
@@ -318,24 +320,32 @@ extern "C" int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int
   return PBX_OK;
 }
 
-template <int DQ>
-static int gibbs_launch(pbx_ctx* ctx, const GibbsArgs& a) {
+template <int DQ, int NT>
+static int gibbs_launch_nt(pbx_ctx* ctx, const GibbsArgs& a) {
   constexpr int DP = 4 * DQ;
   const size_t smem = ((size_t)DP * 4 * (DQ + 2) + 4 * DP) * sizeof(double);
-  const int chains_per_cta = (GB_THREADS / 32) * 8;
+  const int chains_per_cta = (NT / 32) * 8;
   const int grid = (a.C + chains_per_cta - 1) / chains_per_cta;
   const bool sweep_rec = (a.thin % a.d == 0) && (a.step0 % a.d == 0) && (a.T % a.d == 0);
   if (sweep_rec) {
-    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, true>,
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, true, NT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gibbs_mvn_kernel<DQ, true><<<grid, GB_THREADS, smem, ctx->stream>>>(a);
+    gibbs_mvn_kernel<DQ, true, NT><<<grid, NT, smem, ctx->stream>>>(a);
   } else {
-    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, false>,
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, false, NT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gibbs_mvn_kernel<DQ, false><<<grid, GB_THREADS, smem, ctx->stream>>>(a);
+    gibbs_mvn_kernel<DQ, false, NT><<<grid, NT, smem, ctx->stream>>>(a);
   }
   PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
+}
+
+template <int DQ>
+static int gibbs_launch(pbx_ctx* ctx, const GibbsArgs& a) {
+  // fewer than ~3 CTAs of 64 chains per SM: halve the CTA so that the grid covers the chip
+  // (a strong-scaled shard of 8192 chains is 128 CTAs of 64 on 148 SMs)
+  if ((int64_t)a.C < (int64_t)ctx->sm_count * 64 * 3) return gibbs_launch_nt<DQ, 128>(ctx, a);
+  return gibbs_launch_nt<DQ, GB_THREADS>(ctx, a);
 }
 
 extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {

@@ -386,6 +386,66 @@ extern "C" int pbx_grid_posterior(pbx_ctx* ctx, const double* logjoint, int32_t 
 // Pass B  pbx_grid_posterior2: one read + one write (or in place), both marginals from
 //         the same pass, their clamped logs fused into the finishing kernel.
 // ---------------------------------------------------------------------------
+// Table-driven exp for the two passes (libm's exp costs ~70 SASS instructions and made pass
+// A instruction-bound at 2.2 TB/s): exp(x) = 2^(n/64) 2^k e^r, |r| <= ln2/128, one 8-byte
+// table entry + a degree-5 polynomial, <= 2 ulp on [-700, 700] (libm outside: a rare branch).
+// The 64-entry table is stored 16 times interleaved (entry j of copy g at 16 j + g) and lane
+// l reads copy l % 16, so the per-lane lookups never collide in a shared-memory bank; each
+// CTA stages the 8 KB into shared memory.
+static __device__ double g_exptab[64 * 16];
+// (constants live in the constant bank: FP64 instructions take no 64-bit immediates, and a
+// literal costs two MOVs at every use)
+__constant__ double kGE[12] = {92.332482616893656877,     // 0: 64 / ln2
+                               6755399441055744.0,        // 1: 1.5 * 2^52
+                               -0.01083042469326756,      // 2: -ln2/64 hi (32 bits)
+                               -2.9815858269852933e-12,   // 3: -ln2/64 lo
+                               1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,   // 4..7
+                               -600.0, 100.0, -700.0,     // 8..10
+                               3.7200759760208361e-44};   // 11: exp(-100)
+__device__ __forceinline__ double grid_fast_exp(double x, const double* tab) {
+  const double fn = fma(x, kGE[0], kGE[1]);
+  const int n = __double2loint(fn);
+  const double k = fn - kGE[1];
+  double r = fma(k, kGE[2], x);                        // k * hi is exact
+  r = fma(k, kGE[3], r);
+  double p = fma(r, kGE[4], kGE[5]);
+  p = fma(r, p, kGE[6]);
+  p = fma(r, p, kGE[7]);
+  p = fma(r * r, p, r);                                                    // expm1(r)
+  const double tj = tab[((n & 63) << 4) | (threadIdx.x & 15)];
+  const double y = fma(tj, p, tj);
+  return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
+}
+// clamped exp of pscales.py:56-65 over the whole double range, BRANCH-FREE (a branch per
+// element kept the compiler from interleaving the elements of a chunk): below -600 the
+// argument is shifted by +100 and the result multiplied by exp(-100), so that results down to
+// the subnormals come out of one correctly rounded multiply; above log(huge) the reference
+// returns huge.
+__device__ __forceinline__ double grid_exp_logp(double l, const double* tab) {
+  const bool lowx = l < kGE[8];
+  const double xs = lowx ? fmax(l + kGE[9], kGE[10]) : fmin(l, PBX_LOG_HUGE);
+  double y = grid_fast_exp(xs, tab);
+  y = lowx ? y * kGE[11] : y;                              // exp(-100)
+  return (l <= PBX_LOG_HUGE) ? y : PBX_HUGE;               // NaN -> huge, as the reference
+}
+__device__ __forceinline__ void grid_stage_exptab(double* s_tab, int nthreads) {
+  for (int i = threadIdx.x; i < 64 * 16; i += nthreads) s_tab[i] = g_exptab[i];
+  __syncthreads();
+}
+static int grid_init_exptab(pbx_ctx* ctx) {
+  if (ctx->exptab_ready) return PBX_OK;
+  double* h = new double[64 * 16];
+  for (int j = 0; j < 64; ++j)
+    for (int g = 0; g < 16; ++g) h[16 * j + g] = (double)exp2l(j / 64.0L);
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_exptab, h, sizeof(double) * 64 * 16, 0,
+                                          cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  delete[] h;
+  PBX_CUDA(e);
+  ctx->exptab_ready = true;
+  return PBX_OK;
+}
+
 struct MsPair { double m, s; };
 __device__ __forceinline__ MsPair ms_merge(MsPair a, MsPair b) {
   const double M = fmax(a.m, b.m);
@@ -402,31 +462,25 @@ template <bool kLinear>
 __global__ void __launch_bounds__(MS_THREADS)
     grid_max_sumexp_kernel(const double* __restrict__ v, int64_t n, MsPair* __restrict__ partial,
                            unsigned int* __restrict__ ticket, double* __restrict__ out2) {
+  __shared__ double s_tab[64 * 16];
+  if (!kLinear) grid_stage_exptab(s_tab, MS_THREADS);
   double m = -INFINITY, s = 0.0;
-  const int64_t nchunk = n / MS_CHUNK;
-  const int64_t stride = (int64_t)gridDim.x * MS_THREADS;
+  // a warp owns 256 consecutive entries per turn: load i of lane l is the double2 at
+  // 32 i + l of the block, so every 128-bit load instruction is one fully used 512-byte
+  // segment (a per-thread run of 64 bytes leaves half of each sector to the next load)
+  constexpr int WCH = 32 * MS_CHUNK;
+  const int64_t nwch = n / WCH;
+  const int lane_ = threadIdx.x & 31;
+  const int64_t wstride = (int64_t)gridDim.x * (MS_THREADS / 32);
   const bool vec = (((uintptr_t)v) & 15) == 0;
-  for (int64_t ch = (int64_t)blockIdx.x * MS_THREADS + threadIdx.x; ch < nchunk; ch += stride) {
-    double e[MS_CHUNK];
-    if (vec) {
-      const double2* v2 = reinterpret_cast<const double2*>(v + ch * MS_CHUNK);
-#pragma unroll
-      for (int i = 0; i < MS_CHUNK / 2; ++i) {
-        const double2 t = __ldcs(v2 + i);
-        e[2 * i] = t.x;
-        e[2 * i + 1] = t.y;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < MS_CHUNK; ++i) e[i] = v[ch * MS_CHUNK + i];
-    }
+  auto fold = [&](const double (&e)[MS_CHUNK], unsigned mask) {      // bit i: slot i holds an entry
     if (kLinear) {
 #pragma unroll
-      for (int i = 0; i < MS_CHUNK; ++i) s += e[i];
+      for (int i = 0; i < MS_CHUNK; ++i) s += ((mask >> i) & 1u) ? e[i] : 0.0;
     } else {
-      double cm = e[0];
+      double cm = -INFINITY;
 #pragma unroll
-      for (int i = 1; i < MS_CHUNK; ++i) cm = fmax(cm, e[i]);
+      for (int i = 0; i < MS_CHUNK; ++i) cm = fmax(cm, ((mask >> i) & 1u) ? e[i] : -INFINITY);
       if (cm > m) {
         s = (s == 0.0) ? 0.0 : s * exp(m - cm);
         m = cm;
@@ -434,24 +488,42 @@ __global__ void __launch_bounds__(MS_THREADS)
       double t0 = 0.0, t1 = 0.0;
 #pragma unroll
       for (int i = 0; i < MS_CHUNK; i += 2) {
-        t0 += pbx_exp_logp(e[i] - m);
-        t1 += pbx_exp_logp(e[i + 1] - m);
+        // e - m <= 0 here; below -700 a term is < 1e-304 of a sum that is >= 1 (the maximum
+        // contributes exp(0)): clamping the argument changes no bit of the result
+        t0 += ((mask >> i) & 1u) ? grid_fast_exp(fmax(e[i] - m, kGE[10]), s_tab) : 0.0;
+        t1 += ((mask >> (i + 1)) & 1u) ? grid_fast_exp(fmax(e[i + 1] - m, kGE[10]), s_tab) : 0.0;
       }
       s += t0 + t1;
     }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {               // the n % 8 tail
-    for (int64_t i = nchunk * MS_CHUNK; i < n; ++i) {
-      if (kLinear) {
-        s += v[i];
-      } else {
-        if (v[i] > m) {
-          s = (s == 0.0) ? 0.0 : s * exp(m - v[i]);
-          m = v[i];
-        }
-        s += pbx_exp_logp(v[i] - m);
+  };
+  for (int64_t wc = (int64_t)blockIdx.x * (MS_THREADS / 32) + (threadIdx.x >> 5); wc < nwch;
+       wc += wstride) {
+    double e[MS_CHUNK];
+    const double* base = v + wc * WCH;
+    if (vec) {
+      const double2* v2 = reinterpret_cast<const double2*>(base);
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK / 2; ++i) {
+        const double2 t = __ldcs(v2 + 32 * i + lane_);
+        e[2 * i] = t.x;
+        e[2 * i + 1] = t.y;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK; ++i) e[i] = base[32 * i + lane_];
     }
+    fold(e, (1u << MS_CHUNK) - 1u);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {               // the n % 256 tail: one warp
+    double e[MS_CHUNK];
+    unsigned mask = 0;
+#pragma unroll
+    for (int i = 0; i < MS_CHUNK; ++i) {
+      const int64_t idx = nwch * WCH + 32 * i + lane_;
+      e[i] = (idx < n) ? v[idx] : 0.0;
+      mask |= (idx < n) ? (1u << i) : 0u;
+    }
+    if (mask) fold(e, mask);
   }
   MsPair p;
   p.m = kLinear ? 0.0 : m;
@@ -536,16 +608,23 @@ __global__ void __launch_bounds__(P2_THREADS)
                            double* __restrict__ row_partial, double* __restrict__ col_partial,
                            int n_colblocks) {
   __shared__ double s_row[P2_ROWS][P2_THREADS / 32];
-  const int s0 = blockIdx.x * P2_COLS + threadIdx.x * P2_CPT;
+  __shared__ double s_tab[64 * 16];
+  if (!kLinear) grid_stage_exptab(s_tab, P2_THREADS);
+  // Column ownership: a warp covers 128 consecutive columns; thread (warp w, lane l) owns
+  // the two column PAIRS at cb + 2 l and cb + 64 + 2 l, cb = block base + 128 w, so each of
+  // its two 128-bit accesses per row is, warp-wide, one contiguous 512-byte segment.
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cb = blockIdx.x * P2_COLS + warp * 128 + 2 * lane;
   const int m0 = blockIdx.y * P2_ROWS;
   const double mx = kLinear ? 0.0 : gmax[0];
   const double den = fmax(PBX_TINY, gsum[0]);
   const double lden = kLinear ? 0.0 : log(den);
   const double rden = 1.0 / den;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // 128-bit path: whole 4-column group inside the row, rows 16-byte aligned
+  // 128-bit path: even row length, 16-byte aligned bases
   const bool vec = (S % 2 == 0) && ((((uintptr_t)lj) & 15) == 0) &&
-                   (post == nullptr || (((uintptr_t)post) & 15) == 0) && (s0 + P2_CPT <= S);
+                   (post == nullptr || (((uintptr_t)post) & 15) == 0);
+  int colidx[P2_CPT];
+  colidx[0] = cb; colidx[1] = cb + 1; colidx[2] = cb + 64; colidx[3] = cb + 65;
   double col[P2_CPT];
 #pragma unroll
   for (int k = 0; k < P2_CPT; ++k) col[k] = 0.0;
@@ -555,14 +634,19 @@ __global__ void __launch_bounds__(P2_THREADS)
 #pragma unroll
     for (int u = 0; u < P2_RU; ++u) {
       const int m = m0 + r0 + u;
-      if (m < M && vec) {
-        const double2* src = reinterpret_cast<const double2*>(lj + (int64_t)m * S + s0);
-        const double2 a = __ldcs(src), b = __ldcs(src + 1);
-        e[u][0] = a.x; e[u][1] = a.y; e[u][2] = b.x; e[u][3] = b.y;
-      } else {
 #pragma unroll
-        for (int k = 0; k < P2_CPT; ++k)
-          e[u][k] = (m < M && s0 + k < S) ? lj[(int64_t)m * S + s0 + k] : (kLinear ? 0.0 : -PBX_HUGE);
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = colidx[2 * h];
+        if (m < M && vec && c0 + 1 < S) {
+          const double2 a = __ldcs(reinterpret_cast<const double2*>(lj + (int64_t)m * S + c0));
+          e[u][2 * h] = a.x;
+          e[u][2 * h + 1] = a.y;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            e[u][2 * h + k] = (m < M && c0 + k < S) ? lj[(int64_t)m * S + c0 + k]
+                                                    : (kLinear ? 0.0 : -PBX_HUGE);
+        }
       }
     }
 #pragma unroll
@@ -582,23 +666,26 @@ __global__ void __launch_bounds__(P2_THREADS)
           // the transcendental work; the clamp decision (q < tiny -> -1.797e308) is the
           // reference's, taken on q.
           const double sh = e[u][k] - mx;
-          const double qq = pbx_exp_logp(sh) * rden;         // q only feeds the marginal sums
+          const double qq = grid_exp_logp(sh, s_tab) * rden;  // q only feeds the marginal sums
           const bool keep = qq >= PBX_TINY;
           o[k] = keep ? sh - lden : -PBX_HUGE;
           q[k] = keep ? qq : 0.0;                           // exp_logp(-1.797e308) = 0
         }
-        if (!(m < M && s0 + k < S)) q[k] = 0.0;
+        if (!(m < M && colidx[k] < S)) q[k] = 0.0;
         col[k] += q[k];
       }
       if (post && m < M) {
-        if (vec) {
-          double2* dst = reinterpret_cast<double2*>(post + (int64_t)m * S + s0);
-          __stcs(dst, make_double2(o[0], o[1]));
-          __stcs(dst + 1, make_double2(o[2], o[3]));
-        } else {
 #pragma unroll
-          for (int k = 0; k < P2_CPT; ++k)
-            if (s0 + k < S) post[(int64_t)m * S + s0 + k] = o[k];
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = colidx[2 * h];
+          if (vec && c0 + 1 < S) {
+            __stcs(reinterpret_cast<double2*>(post + (int64_t)m * S + c0),
+                   make_double2(o[2 * h], o[2 * h + 1]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              if (c0 + k < S) post[(int64_t)m * S + c0 + k] = o[2 * h + k];
+          }
         }
       }
       double w = (q[0] + q[1]) + (q[2] + q[3]);
@@ -609,7 +696,7 @@ __global__ void __launch_bounds__(P2_THREADS)
   }
 #pragma unroll
   for (int k = 0; k < P2_CPT; ++k)
-    if (s0 + k < S) col_partial[(int64_t)blockIdx.y * S + s0 + k] = col[k];
+    if (colidx[k] < S) col_partial[(int64_t)blockIdx.y * S + colidx[k]] = col[k];
   __syncthreads();
   if (threadIdx.x < P2_ROWS) {
     const int m = m0 + threadIdx.x;
@@ -645,6 +732,10 @@ extern "C" int pbx_grid_max_sumexp(pbx_ctx* ctx, const double* v, int64_t n, int
                                    double* out2) {
   PBX_REQUIRE(ctx && v && out2 && n >= 1, "pbx_grid_max_sumexp: bad argument");
   PBX_CUDA(cudaSetDevice(ctx->device));
+  {
+    int rc0 = grid_init_exptab(ctx);
+    if (rc0) return rc0;
+  }
   int64_t want = (n + (int64_t)MS_THREADS * MS_CHUNK * 4 - 1) / ((int64_t)MS_THREADS * MS_CHUNK * 4);
   const int np = (int)(want < 1 ? 1 : (want > ctx->sm_count * 8 ? ctx->sm_count * 8 : want));
   // workspace: [ticket (256 B, zero between calls)] [np pairs]
@@ -681,6 +772,10 @@ extern "C" int pbx_grid_posterior2(pbx_ctx* ctx, const double* prob, int32_t n_m
   PBX_REQUIRE(ctx && prob && gsum && (linear || gmax), "pbx_grid_posterior2: null argument");
   PBX_REQUIRE(n_mu >= 1 && n_sigma >= 1, "pbx_grid_posterior2: sizes must be positive");
   PBX_CUDA(cudaSetDevice(ctx->device));
+  {
+    int rc0 = grid_init_exptab(ctx);
+    if (rc0) return rc0;
+  }
   const int ncb = (n_sigma + P2_COLS - 1) / P2_COLS, nrb = (n_mu + P2_ROWS - 1) / P2_ROWS;
   PBX_REQUIRE(nrb <= 65535, "pbx_grid_posterior2: too many rows per call (slab it)");
   const size_t rp = ((size_t)n_mu * ncb * 8 + 255) / 256 * 256;

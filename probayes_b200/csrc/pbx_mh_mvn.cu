@@ -773,6 +773,9 @@ __global__ void __launch_bounds__(WsCfg<D>::THREADS, 1)
 #define WD_ITEMS (WD_NPROD * 32)
 #define WD_THREADS 512                // 16 warps: decisions, 14 producers, one idle (see below)
 #define WD_MAXD 4
+#ifndef WD_NSLOT
+#define WD_NSLOT 3                    // ring depth in batches for D <= 2
+#endif
 #ifndef WD_IPT
 #define WD_IPT 1                      // measured: 2 (four steps in flight per thread) gains nothing
 #endif
@@ -796,7 +799,7 @@ template <int D> struct WdCfg {
   // flight per thread, needs the doubled slots to fit into shared memory)
   static constexpr int IPT = (D <= 2) ? WD_IPT : 1;
   static constexpr int ITEMS = WD_ITEMS * IPT;
-  static constexpr int NSLOT = (D <= 2 && IPT == 1) ? 3 : 2;
+  static constexpr int NSLOT = (D <= 2 && IPT == 1) ? WD_NSLOT : 2;
   static constexpr size_t SMEM = (size_t)NSLOT * NF2 * ITEMS * sizeof(double2);
 };
 

@@ -138,3 +138,41 @@ def test_full_size_properties():
     assert relerr(np.exp(ms[ok]), lin.sum(axis=0)[ok]) <= 1e-10
     assert np.unravel_index(np.argmax(ljh), ljh.shape) == \
         np.unravel_index(np.argmax(post), post.shape)
+
+
+def test_clamped_exp_edge_cases_through_the_two_pass_path():
+    """The branch-free table exp of the two K4 passes over its whole range: entries far below
+    the maximum (subnormal / underflowing exp), the reference's clamp decision q < tiny ->
+    -1.797e308, and the marginalise path (no max shift) with arguments up to and beyond
+    log(huge) (pscales.py:44-65)."""
+    import torch
+    eng = engine()
+    tail = np.array([0., -1., -37.25, -600.5, -650., -699., -700.5, -701., -707., -708.3,
+                     -708.39, -708.4, -720., -744.4, -745.2, -760., -1e4, NNI])
+    rng = np.random.default_rng(5)
+    lj = np.concatenate([tail, -rng.uniform(0., 760., 4096 - len(tail))]).reshape(64, 64) - 3e5
+    r = eng.grid_conditionalise(dev(eng, lj))
+    eng.sync()
+    want = o.grid_conditionalise(lj)
+    post = host(r["post"])
+    clamp = want == NNI
+    assert np.array_equal(post == NNI, clamp)
+    assert np.abs(post[~clamp] - want[~clamp]).max() <= 1e-12 * 3e5
+    wm = o.grid_marginal(want, axis=1)
+    ok = wm > -690
+    assert np.abs(host(r["marg_mu"])[ok] - wm[ok]).max() <= 1e-10
+    # marginalise path: exp_logp without a shift, incl. overflow clamp and subnormal results
+    big = np.array([[700., 705.5, 709.7, 709.9, 1e4], [-800., -744., -710., -50., 0.]])
+    zero = torch.zeros(1, dtype=torch.float64, device=eng.device)
+    one = torch.ones(1, dtype=torch.float64, device=eng.device)
+    _, rows, cols = eng.grid_posterior2(dev(eng, big), zero, one, want_post=False, marg_log=0)
+    eng.sync()
+    lin = o.exp_logp(big)
+    assert relerr(host(cols), lin.sum(axis=0)) <= 1e-12       # 1.8e308 clamps included
+    assert host(rows)[0] == np.inf and abs(host(rows)[1] - lin[1].sum()) <= 1e-15
+    # a row of tiny values only: subnormal results survive (one rounded multiply)
+    small = np.array([[-800., -744.5, -720., -710., -705.]])
+    _, r2, c2 = eng.grid_posterior2(dev(eng, small), zero, one, want_post=False, marg_log=0)
+    eng.sync()
+    want = o.exp_logp(small)
+    assert np.abs(host(c2) - want[0]).max() <= 1e-15 * want.max() + 1e-323
