@@ -289,6 +289,19 @@ def secondary(eng, peaks, fp64_peak, quick=False):
                                      "3 passes over the observations per call, then O(1) per "
                                      "evaluation"}
     del theta, st, st2
+    # ---- small problems (the reference-feasible sizes): whole walk in one launch vs one
+    # kernel launch per MH step
+    Nsm, Csm, Tsm = 1000, 64, 2000
+    xs_, ys_ = x[:Nsm].contiguous(), y[:Nsm].contiguous()
+    sd_s = 0.5 / np.sqrt(Nsm)
+    for tag, var in (("resident_obs_one_launch", 0), ("launch_per_step", 1)):
+        st_s = eng.to_device(np.tile(np.array([[-1.], [1.5], [.5]]), (1, Csm)))
+        ms_s = timeit(lambda: eng.mh_normreg(st_s, ys_, xs_, Tsm, lims, ex, lg, [2.4 * sd_s] * 3,
+                                             seed=1, variant=var, record=True), reps=3, warm=1)
+        out["c3_small_" + tag] = {"workload": "MH, %d chains, N=%d obs, %d steps (%s)"
+                                              % (Csm, Nsm, Tsm, tag.replace("_", " ")),
+                                  "ms_per_walk": ms_s, "us_per_mh_step": 1e3 * ms_s / Tsm,
+                                  "chain_steps_per_s": Csm * Tsm / (ms_s * 1e-3)}
     # ---- HBM-streaming regime: <= 8 chains, N = 2^27 (2 GiB of observations > L2) ----
     Ns = (1 << 24) if quick else (1 << 27)
     xs = torch.randn(Ns, dtype=torch.float64, device=eng.device)

@@ -189,7 +189,12 @@ typedef struct {
                               2 obs-per-thread streaming + warp-shuffle reduction;
                               3 (opt-in) centred sufficient statistics: one reduction over
                               the observations, then O(1) per likelihood evaluation and the
-                              whole walk in one launch -- same values to <= 1e-15 */
+                              whole walk in one launch -- same values to <= 1e-15;
+                              4 resident observations: a warp per chain, observations in
+                              shared memory, the whole walk in one launch, term-by-term
+                              arithmetic -- the auto choice for small problems (n_obs <= 8192
+                              and n_chains * n_obs <= 2^24), where a kernel launch per MH step
+                              would be all the time there is */
   int64_t n_obs;
   const double* x_obs;     /* device [N] (unused when !has_slope) */
   const double* y_obs;     /* device [N] */
@@ -266,7 +271,9 @@ PBX_API int pbx_grid_rescale_sumexp(pbx_ctx* ctx, const double* local_max,
                                     const double* global_max, double* sum_inout);
 /* pbx_grid_posterior with linear-pscale support (post = p / max(tiny, sum), marginals plain
  * sums) and the marginals' clamped logs fused: marg_log_flags bit 0 -> marg_mu = log_prob(sum),
- * bit 1 -> marg_sigma likewise (leave a bit clear where the sum must be all-reduced first) */
+ * bit 1 -> marg_sigma likewise (leave a bit clear where the sum must be all-reduced first);
+ * bit 2 -> PD.marginalise semantics (pd.py:162-164): the terms exp_logp(p) are summed as they
+ * are, subnormals included, instead of conditionalise's clamp of q < tiny to zero */
 PBX_API int pbx_grid_posterior2(pbx_ctx* ctx, const double* prob, int32_t n_mu, int32_t n_sigma,
                                 const double* gmax, const double* gsum, int32_t linear,
                                 double* post, double* marg_mu, double* marg_sigma,

@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(P2_THREADS)
     grid_posterior2_kernel(const double* lj, int M, int S, const double* __restrict__ gmax,
                            const double* __restrict__ gsum, double* post,
                            double* __restrict__ row_partial, double* __restrict__ col_partial,
-                           int n_colblocks) {
+                           int n_colblocks, double qmin) {
   __shared__ double s_row[P2_ROWS][P2_THREADS / 32];
   __shared__ double s_tab[64 * 16];
   if (!kLinear) grid_stage_exptab(s_tab, P2_THREADS);
@@ -667,7 +667,8 @@ __global__ void __launch_bounds__(P2_THREADS)
           // reference's, taken on q.
           const double sh = e[u][k] - mx;
           const double qq = grid_exp_logp(sh, s_tab) * rden;  // q only feeds the marginal sums
-          const bool keep = qq >= PBX_TINY;
+          // (qmin = tiny; 0 for PD.marginalise, which sums exp_logp(p) unclamped)
+          const bool keep = qq >= qmin;
           o[k] = keep ? sh - lden : -PBX_HUGE;
           q[k] = keep ? qq : 0.0;                           // exp_logp(-1.797e308) = 0
         }
@@ -785,12 +786,13 @@ extern "C" int pbx_grid_posterior2(pbx_ctx* ctx, const double* prob, int32_t n_m
   double* row_partial = (double*)ctx->ws;
   double* col_partial = (double*)((char*)ctx->ws + rp);
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  const double qmin = (marg_log_flags & 4) ? 0.0 : PBX_TINY;
   if (linear)
     grid_posterior2_kernel<true><<<dim3(ncb, nrb), P2_THREADS, 0, ctx->stream>>>(
-        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb);
+        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb, qmin);
   else
     grid_posterior2_kernel<false><<<dim3(ncb, nrb), P2_THREADS, 0, ctx->stream>>>(
-        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb);
+        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb, qmin);
   PBX_LAUNCH_CHECK(ctx);
   if (marg_mu || marg_sigma) {
     const int n = n_mu > n_sigma ? n_mu : n_sigma;

@@ -831,6 +831,134 @@ __global__ void __launch_bounds__(128) ss_walk_kernel(const NrArgs a, const __gr
   if (a.accept_count) a.accept_count[c] += nacc;
 }
 
+
+// ---------------------------------------------------------------------------
+// variant 4: SMALL problems (N <= RW_MAXN observations, C * N <= 2^24 terms per step) --
+// the whole walk in ONE launch.  The per-step kernels above cost a launch (~3-4 us) per MH
+// step, which is all the time there is at the reference-feasible sizes (N = 60 ... 10^4, a
+// handful of chains).  Here a WARP owns one chain for the whole walk: the observations are
+// staged into shared memory once per CTA, lane l takes observations l, l + 32, ..., the
+// residual sum of squares finishes with a fixed xor-shuffle tree (every lane ends up with the
+// same bits, so all 32 lanes carry the chain state redundantly and no broadcast is needed),
+// then proposal, priors, accept test and records exactly as nr_phase_b.  Term-by-term
+// arithmetic as the other variants (the reference's array density path), not sufficient
+// statistics.
+// ---------------------------------------------------------------------------
+#define RW_WARPS 4
+#define RW_MAXN 8192
+template <bool kSlope>
+__global__ void __launch_bounds__(32 * RW_WARPS)
+    rw_walk_kernel(const NrArgs a, const __grid_constant__ NrModel m) {
+  extern __shared__ __align__(16) double rw_sm[];       // y[N], then x[N] (kSlope)
+  double* sy = rw_sm;
+  double* sx = rw_sm + a.N;
+  for (int64_t i = threadIdx.x; i < a.N; i += 32 * RW_WARPS) {
+    sy[i] = a.y[i];
+    if (kSlope) sx[i] = a.x[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  if (c >= a.C) return;
+  const int64_t C = a.C;
+  const int n = (int)a.N;
+  double th[PBX_MAX_PARAMS], ssum[PBX_MAX_PARAMS], ssq[PBX_MAX_PARAMS];
+  for (int j = 0; j < m.P; ++j) {
+    th[j] = a.state[(int64_t)j * C + c];
+    ssum[j] = ssq[j] = 0.0;
+  }
+  auto rss = [&](const double* t) {
+    const double b0 = t[0], b1 = kSlope ? t[1] : 0.0;
+    double s0 = 0.0, s1 = 0.0;
+    int i = lane;
+    for (; i + 32 < n; i += 64) {
+      const double r0 = kSlope ? (sy[i] - b0) - b1 * sx[i] : sy[i] - b0;
+      const double r1 = kSlope ? (sy[i + 32] - b0) - b1 * sx[i + 32] : sy[i + 32] - b0;
+      s0 = fma(r0, r0, s0);
+      s1 = fma(r1, r1, s1);
+    }
+    if (i < n) {
+      const double r0 = kSlope ? (sy[i] - b0) - b1 * sx[i] : sy[i] - b0;
+      s0 = fma(r0, r0, s0);
+    }
+    double s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+  };
+  double lp = (a.step0 > 0) ? a.state_lp[c] : 0.0;
+  int64_t nacc = 0;
+  for (int k = 0; k < a.T; ++k) {
+    const int64_t gstep = a.step0 + k;
+    double dl[PBX_MAX_PARAMS], thp[PBX_MAX_PARAMS];
+    nr_draw_delta(a, m, gstep, k, c, dl);
+    for (int j = 0; j < m.P; ++j) {
+      double v = m.log_ufun[j] ? exp(log(th[j]) + dl[j]) : th[j] + dl[j];
+      if (m.bound) {                                   // variable.py:700-727
+        const double lo = m.lims[j][0], hi = m.lims[j][1];
+        const bool olo = m.open_end[j][0] != 0, ohi = m.open_end[j][1] != 0;
+        if (!olo && !ohi) v = fmax(lo, fmin(hi, v));
+        else if (olo && ohi) v = (v > lo && v < hi) ? v : th[j];
+        else if (olo) v = (v < lo) ? th[j] : fmin(hi, v);
+        else v = (v > hi) ? th[j] : fmax(lo, v);
+      }
+      thp[j] = v;
+    }
+    const double lpp = nr_logjoint(a, m, thp, rss(thp));
+    const double t = nr_threshold(a, gstep, k, c);
+    bool acc;
+    double s = nan("");
+    if (gstep == 0) {
+      acc = true;
+    } else if (m.accept_mode == PBX_ACCEPT_REFERENCE) {
+      const double num = pbx_exp_logp(lpp * m.coef), den = pbx_exp_logp(lp * m.coef);
+      s = fmin(1.0, num / fmax(PBX_TINY, den));
+      acc = (s >= t);
+    } else {
+      const double d = m.coef * (lpp - lp);
+      acc = (d >= log(t));
+      if (a.out_score) s = fmin(1.0, exp(fmin(d, 0.0)));
+    }
+    if (acc) {
+      for (int j = 0; j < m.P; ++j) th[j] = thp[j];
+      lp = lpp;
+      ++nacc;
+    }
+    for (int j = 0; j < m.P; ++j) {
+      ssum[j] += th[j];
+      ssq[j] = fma(th[j], th[j], ssq[j]);
+    }
+    if (lane == 0) {
+      if (a.out_accept) a.out_accept[(int64_t)k * C + c] = acc ? 1 : 0;
+      if (a.out_score) a.out_score[(int64_t)k * C + c] = s;
+      if (a.out_xprop)
+        for (int j = 0; j < m.P; ++j) a.out_xprop[((int64_t)k * m.P + j) * C + c] = thp[j];
+      if (a.out_pprop) a.out_pprop[(int64_t)k * C + c] = lpp;
+      if ((k + 1) % a.thin == 0) {
+        const int64_t r = (k + 1) / a.thin - 1;
+        if (a.out_x)
+          for (int j = 0; j < m.P; ++j) a.out_x[(r * m.P + j) * C + c] = th[j];
+        if (a.out_prob) a.out_prob[r * C + c] = lp;
+      }
+    }
+  }
+  if (lane == 0) {
+    for (int j = 0; j < m.P; ++j) {
+      a.state[(int64_t)j * C + c] = th[j];
+      if (a.stat_sum) a.stat_sum[(int64_t)j * C + c] += ssum[j];
+      if (a.stat_sumsq) a.stat_sumsq[(int64_t)j * C + c] += ssq[j];
+    }
+    a.state_lp[c] = lp;
+    if (a.accept_count) a.accept_count[c] += nacc;
+  }
+}
+
+static bool rw_applies(const pbx_mh_normreg_params* p) {
+  if (p->variant == 4) return true;
+  return p->variant == 0 && p->n_obs <= RW_MAXN && p->n_steps >= 2 &&
+         (int64_t)p->n_chains * p->n_obs <= ((int64_t)1 << 24);
+}
+
 // computes the statistics into the context workspace; *out points at them
 int pbx_ss_compute(pbx_ctx* ctx, const double* x, const double* y, int64_t n, NrStats** out) {
   const int64_t chunk = 8192;
@@ -903,6 +1031,37 @@ extern "C" int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p) 
       rc = pbx_ss_compute(ctx, m.has_slope ? p->x_obs : nullptr, p->y_obs, p->n_obs, &st);
       if (rc) return rc;
       ss_walk_kernel<<<(a.C + 127) / 128, 128, 0, ctx->stream>>>(a, m, st);
+      PBX_LAUNCH_CHECK(ctx);
+    }
+    PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    return PBX_OK;
+  }
+  if (rw_applies(p)) {                         // small problem: the walk in one launch
+    PBX_REQUIRE(p->n_obs <= RW_MAXN, "pbx_mh_normreg_run: variant 4 needs n_obs <= %d", RW_MAXN);
+    NrArgs a;
+    memset(&a, 0, sizeof(a));
+    a.C = p->n_chains; a.N = p->n_obs; a.x = p->x_obs; a.y = p->y_obs;
+    a.state = p->state; a.state_lp = p->state_lp;
+    a.step0 = p->step0; a.T = p->n_steps; a.thin = p->thin;
+    a.chain0 = p->chain0; a.seed = p->seed;
+    a.inj_delta = p->inj_delta; a.inj_thresh = p->inj_thresh;
+    a.out_x = p->out_x; a.out_prob = p->out_prob;
+    a.out_accept = p->out_accept; a.out_score = p->out_score;
+    a.out_xprop = p->out_xprop; a.out_pprop = p->out_pprop;
+    a.accept_count = p->accept_count; a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
+    PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (a.T > 0) {
+      const size_t smem = (size_t)a.N * 8 * (m.has_slope ? 2 : 1);
+      const int grid = (a.C + RW_WARPS - 1) / RW_WARPS;
+      if (m.has_slope) {
+        PBX_CUDA(cudaFuncSetAttribute(rw_walk_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rw_walk_kernel<true><<<grid, 32 * RW_WARPS, smem, ctx->stream>>>(a, m);
+      } else {
+        PBX_CUDA(cudaFuncSetAttribute(rw_walk_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rw_walk_kernel<false><<<grid, 32 * RW_WARPS, smem, ctx->stream>>>(a, m);
+      }
       PBX_LAUNCH_CHECK(ctx);
     }
     PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));

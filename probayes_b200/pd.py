@@ -282,7 +282,7 @@ class PD(collections.OrderedDict):
                 # sum_axis exp_logp(prob): the posterior pass with max = 0, sum = 1 and no
                 # posterior output; row / column sums, through the clamped log for log pscale
                 _, rows, cols = eng.grid_posterior2(self._prob_dev, zero, one, linear,
-                                                    want_post=False, marg_log=0 if linear else 3)
+                                                    want_post=False, marg_log=4 if linear else 7)
                 return self._new(name, vals, dims, rows if 1 in axes else cols)
             if not axes:
                 return self._new(name, vals, dims, self._prob_dev)

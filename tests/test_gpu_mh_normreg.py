@@ -26,7 +26,7 @@ def _run_golden(eng, g, has_slope, accept, variant):
     return out
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 4])
 @pytest.mark.parametrize("name,has_slope", [
     ("mh_norm1d_hastings", False), ("mh_norm1d_metropolis", False),
     ("mh_norm1d_underflow", False), ("mh_linreg", True),
@@ -59,7 +59,10 @@ def test_underflow_golden_log_rule_accepts():
 
 @pytest.mark.parametrize("P,C,N,T,variant", [
     (3, 300, 5000, 40, 1), (3, 7, 4097, 60, 2), (2, 1100, 2048, 30, 1), (2, 5, 12345, 50, 2),
-    (3, 2200, 777, 25, 1), (3, 4300, 4096 * 3 + 1, 12, 1), (2, 1, 3, 20, 2), (3, 9, 1, 20, 1)])
+    (3, 2200, 777, 25, 1), (3, 4300, 4096 * 3 + 1, 12, 1), (2, 1, 3, 20, 2), (3, 9, 1, 20, 1),
+    # variant 4: the whole walk in one launch, a warp per chain, observations in shared memory
+    (3, 37, 1000, 60, 4), (2, 5, 8192, 30, 4), (3, 130, 8192, 12, 4), (2, 3, 1, 20, 4),
+    (3, 1, 33, 25, 4), (2, 257, 64, 40, 4)])
 def test_oracle_injected(P, C, N, T, variant):
     """Ragged / tiny / multi-tile observation counts, both kernels, KC = 1, 2, 4."""
     eng = engine()
@@ -129,7 +132,7 @@ def test_out_of_box_proposals_are_rejected():
     assert (~ref["u"]).sum() > 100
 
 
-@pytest.mark.parametrize("variant,C", [(1, 200), (2, 6)])
+@pytest.mark.parametrize("variant,C", [(1, 200), (2, 6), (4, 70)])
 def test_philox_replay_and_resume(variant, C):
     eng = engine()
     rng = np.random.default_rng(8)
