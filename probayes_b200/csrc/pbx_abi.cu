@@ -112,6 +112,7 @@ int pbx_ctx_destroy(pbx_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->ticket) cudaFree(ctx->ticket);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->copy_stream);

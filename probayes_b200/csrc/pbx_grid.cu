@@ -377,7 +377,7 @@ extern "C" int pbx_grid_posterior(pbx_ctx* ctx, const double* logjoint, int32_t 
 //
 // Pass A  pbx_grid_max_sumexp: ONE read.  Every thread keeps an online (max, sum-exp)
 //         pair: per chunk of 8 entries held in registers, the running maximum is raised
-//         first (one rescaling exp per chunk, and only when the maximum moves), then the
+//         first (one rescaling table-exp per chunk, branch-free), then the
 //         8 terms exp(v - max) are added.  Pairs are merged (m, s) + (m', s') =
 //         (M = max, s exp(m - M) + s' exp(m' - M)) by shuffles and shared memory in a
 //         fixed order; the last CTA to finish (ticket) merges the per-CTA pairs in index
@@ -402,9 +402,24 @@ __constant__ double kGE[12] = {92.332482616893656877,     // 0: 64 / ln2
                                1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,   // 4..7
                                -600.0, 100.0, -700.0,     // 8..10
                                3.7200759760208361e-44};   // 11: exp(-100)
-__device__ __forceinline__ double grid_fast_exp(double x, const double* tab) {
+// Clamps and range selection are done on the HIGH WORD of the double with integer
+// instructions (there is no double min/max instruction:
+// fmax/fmin compile to DSETP + 2 FSEL each, and a first version whose clamp + select logic was
+// written with them came to more instructions than the exponential itself -- 89 SASS
+// instructions per grid cell in the posterior pass, issue-bound at 1.6 TB/s).
+//   * for a negative double the unsigned high word grows with the magnitude, so
+//     min_u(hi, hi(-L)) clamps x at (just below) -L in ONE instruction and leaves
+//     non-negative x alone;
+//   * the binary exponent k = n >> 6 of the result is known as an integer before the result
+//     is assembled, so the subnormal range is handled by adding 200 to k and multiplying by
+//     2^-200 (folded into the normaliser) -- one correctly rounded multiply, as before.
+__device__ __forceinline__ double grid_clamp_neg(double x, unsigned hi_limit) {
+  return __hiloint2double((int)min((unsigned)__double2hiint(x), hi_limit), __double2loint(x));
+}
+// mantissa part y = 2^((n & 63)/64) e^r in [1, 2) and n = round(64 x / ln2)
+__device__ __forceinline__ double grid_exp_core(double x, const double* tab, int& n) {
   const double fn = fma(x, kGE[0], kGE[1]);
-  const int n = __double2loint(fn);
+  n = __double2loint(fn);
   const double k = fn - kGE[1];
   double r = fma(k, kGE[2], x);                        // k * hi is exact
   r = fma(k, kGE[3], r);
@@ -413,20 +428,27 @@ __device__ __forceinline__ double grid_fast_exp(double x, const double* tab) {
   p = fma(r, p, kGE[7]);
   p = fma(r * r, p, r);                                                    // expm1(r)
   const double tj = tab[((n & 63) << 4) | (threadIdx.x & 15)];
-  const double y = fma(tj, p, tj);
+  return fma(tj, p, tj);
+}
+// exp(x) for x <= 0 (or NaN -> garbage the caller masks), clamped at x = -700: for the
+// sum-exp pass, where a term below 1e-304 of a sum >= 1 changes no bit
+__device__ __forceinline__ double grid_exp_nonpos(double x, const double* tab) {
+  int n;
+  const double y = grid_exp_core(grid_clamp_neg(x, 0xC085E000u), tab, n);   // -700 = 0xC085E000..
   return __hiloint2double(__double2hiint(y) + ((n >> 6) << 20), __double2loint(y));
 }
-// clamped exp of pscales.py:56-65 over the whole double range, BRANCH-FREE (a branch per
-// element kept the compiler from interleaving the elements of a chunk): below -600 the
-// argument is shifted by +100 and the result multiplied by exp(-100), so that results down to
-// the subnormals come out of one correctly rounded multiply; above log(huge) the reference
-// returns huge.
-__device__ __forceinline__ double grid_exp_logp(double l, const double* tab) {
-  const bool lowx = l < kGE[8];
-  const double xs = lowx ? fmax(l + kGE[9], kGE[10]) : fmin(l, PBX_LOG_HUGE);
-  double y = grid_fast_exp(xs, tab);
-  y = lowx ? y * kGE[11] : y;                              // exp(-100)
-  return (l <= PBX_LOG_HUGE) ? y : PBX_HUGE;               // NaN -> huge, as the reference
+// exp_logp(l) * scale over the whole double range, branch-free: scale_lo2 = scale * 2^-200
+// (both finite and normal for any realistic normaliser).  l > log(huge) and NaN -> huge * scale.
+__device__ __forceinline__ double grid_exp_logp_scaled(double l, const double* tab, double scale,
+                                                       double scale_lo2) {
+  int n;
+  const double y = grid_exp_core(grid_clamp_neg(l, 0xC0890000u), tab, n);   // -800
+  int k = n >> 6;
+  const bool low = k < -1000;
+  k = low ? k + 200 : k;
+  const double sc = low ? scale_lo2 : scale;
+  const double v = __hiloint2double(__double2hiint(y) + (k << 20), __double2loint(y)) * sc;
+  return (l <= PBX_LOG_HUGE) ? v : PBX_HUGE * scale;
 }
 __device__ __forceinline__ void grid_stage_exptab(double* s_tab, int nthreads) {
   for (int i = threadIdx.x; i < 64 * 16; i += nthreads) s_tab[i] = g_exptab[i];
@@ -447,144 +469,161 @@ static int grid_init_exptab(pbx_ctx* ctx) {
 }
 
 struct MsPair { double m, s; };
-__device__ __forceinline__ MsPair ms_merge(MsPair a, MsPair b) {
-  const double M = fmax(a.m, b.m);
+// (m, s) + (m', s') = (M = max(m, m'), s exp(m - M) + s' exp(m' - M)); an empty pair is
+// (-1.797e308, 0): its factor is clamped at exp(-700) and multiplies a zero, so no infinities
+// or NaNs arise and the merge is branch-free (table exp, ~45 instructions)
+__device__ __forceinline__ MsPair ms_merge(MsPair a, MsPair b, const double* tab) {
+  const double M = (a.m > b.m) ? a.m : b.m;
   MsPair r;
   r.m = M;
-  // exp(-inf - -inf) never occurs: a pair with m = -inf has s = 0 and is skipped
-  r.s = (a.s == 0.0 ? 0.0 : a.s * exp(a.m - M)) + (b.s == 0.0 ? 0.0 : b.s * exp(b.m - M));
+  r.s = fma(a.s, grid_exp_nonpos(a.m - M, tab), b.s * grid_exp_nonpos(b.m - M, tab));
   return r;
 }
 
 #define MS_THREADS 256
+#define MS_WARPS (MS_THREADS / 32)
 #define MS_CHUNK 8
+// Persistent grid (as many CTAs as are resident at once, each warp takes the 256-entry warp
+// chunks w, w + n_warps, ...), the next chunk's four 128-bit loads issued before the current
+// chunk is folded.  Per chunk a lane raises its running maximum and rescales its sum by
+// exp(m_old - m_new) UNCONDITIONALLY: a lane sees a few dozen entries only, so "rescale only
+// when the maximum moves" was a divergent branch taken by 85 % of the warp-chunks (with a libm
+// exp behind it) -- 58 SASS instructions per entry, issue-bound at 2.6 TB/s.
 template <bool kLinear>
 __global__ void __launch_bounds__(MS_THREADS)
     grid_max_sumexp_kernel(const double* __restrict__ v, int64_t n, MsPair* __restrict__ partial,
                            unsigned int* __restrict__ ticket, double* __restrict__ out2) {
   __shared__ double s_tab[64 * 16];
   if (!kLinear) grid_stage_exptab(s_tab, MS_THREADS);
-  double m = -INFINITY, s = 0.0;
+  double m = -PBX_HUGE, s = 0.0;
   // a warp owns 256 consecutive entries per turn: load i of lane l is the double2 at
   // 32 i + l of the block, so every 128-bit load instruction is one fully used 512-byte
   // segment (a per-thread run of 64 bytes leaves half of each sector to the next load)
   constexpr int WCH = 32 * MS_CHUNK;
   const int64_t nwch = n / WCH;
-  const int lane_ = threadIdx.x & 31;
-  const int64_t wstride = (int64_t)gridDim.x * (MS_THREADS / 32);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * MS_WARPS;
   const bool vec = (((uintptr_t)v) & 15) == 0;
   auto fold = [&](const double (&e)[MS_CHUNK], unsigned mask) {      // bit i: slot i holds an entry
     if (kLinear) {
 #pragma unroll
       for (int i = 0; i < MS_CHUNK; ++i) s += ((mask >> i) & 1u) ? e[i] : 0.0;
     } else {
-      double cm = -INFINITY;
+      double cm = m;
 #pragma unroll
-      for (int i = 0; i < MS_CHUNK; ++i) cm = fmax(cm, ((mask >> i) & 1u) ? e[i] : -INFINITY);
-      if (cm > m) {
-        s = (s == 0.0) ? 0.0 : s * exp(m - cm);
-        m = cm;
+      for (int i = 0; i < MS_CHUNK; ++i) {
+        const double ei = ((mask >> i) & 1u) ? e[i] : -PBX_HUGE;
+        cm = (ei > cm) ? ei : cm;
       }
+      const double f = grid_exp_nonpos(m - cm, s_tab);
+      m = cm;
       double t0 = 0.0, t1 = 0.0;
 #pragma unroll
       for (int i = 0; i < MS_CHUNK; i += 2) {
         // e - m <= 0 here; below -700 a term is < 1e-304 of a sum that is >= 1 (the maximum
-        // contributes exp(0)): clamping the argument changes no bit of the result
-        t0 += ((mask >> i) & 1u) ? grid_fast_exp(fmax(e[i] - m, kGE[10]), s_tab) : 0.0;
-        t1 += ((mask >> (i + 1)) & 1u) ? grid_fast_exp(fmax(e[i + 1] - m, kGE[10]), s_tab) : 0.0;
+        // contributes exp(0)): clamping the argument (one integer min on the high word)
+        // changes no bit of the result
+        t0 += ((mask >> i) & 1u) ? grid_exp_nonpos(e[i] - m, s_tab) : 0.0;
+        t1 += ((mask >> (i + 1)) & 1u) ? grid_exp_nonpos(e[i + 1] - m, s_tab) : 0.0;
       }
-      s += t0 + t1;
+      s = fma(s, f, t0 + t1);
     }
   };
-  for (int64_t wc = (int64_t)blockIdx.x * (MS_THREADS / 32) + (threadIdx.x >> 5); wc < nwch;
-       wc += wstride) {
-    double e[MS_CHUNK];
+  auto load = [&](double (&e)[MS_CHUNK], int64_t wc) {
     const double* base = v + wc * WCH;
     if (vec) {
       const double2* v2 = reinterpret_cast<const double2*>(base);
 #pragma unroll
       for (int i = 0; i < MS_CHUNK / 2; ++i) {
-        const double2 t = __ldcs(v2 + 32 * i + lane_);
+        const double2 t = __ldcs(v2 + 32 * i + lane);
         e[2 * i] = t.x;
         e[2 * i + 1] = t.y;
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < MS_CHUNK; ++i) e[i] = base[32 * i + lane_];
+      for (int i = 0; i < MS_CHUNK; ++i) e[i] = base[32 * i + lane];
     }
-    fold(e, (1u << MS_CHUNK) - 1u);
+  };
+  {
+    int64_t wc = (int64_t)blockIdx.x * MS_WARPS + warp;
+    double e[MS_CHUNK], en[MS_CHUNK];
+    if (wc < nwch) load(en, wc);
+    for (; wc < nwch; wc += wstride) {
+#pragma unroll
+      for (int i = 0; i < MS_CHUNK; ++i) e[i] = en[i];
+      if (wc + wstride < nwch) load(en, wc + wstride);
+      fold(e, (1u << MS_CHUNK) - 1u);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {               // the n % 256 tail: one warp
     double e[MS_CHUNK];
     unsigned mask = 0;
 #pragma unroll
     for (int i = 0; i < MS_CHUNK; ++i) {
-      const int64_t idx = nwch * WCH + 32 * i + lane_;
+      const int64_t idx = nwch * WCH + 32 * i + lane;
       e[i] = (idx < n) ? v[idx] : 0.0;
       mask |= (idx < n) ? (1u << i) : 0u;
     }
     if (mask) fold(e, mask);
   }
+  // fixed merge tree: lanes (butterfly: both lanes of a pair get the same bits), the CTA's
+  // warps (warp 0), then the CTAs' pairs by the last CTA to finish (ticket) -- deterministic
+  // for a given grid size
   MsPair p;
   p.m = kLinear ? 0.0 : m;
   p.s = s;
+  auto warp_merge = [&](MsPair a, int from) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    MsPair q;
-    q.m = __shfl_xor_sync(0xffffffffu, p.m, o);
-    q.s = __shfl_xor_sync(0xffffffffu, p.s, o);
-    if (kLinear) p.s += q.s;
-    else p = ms_merge(p, q);              // symmetric: both lanes of a pair get the same bits
-  }
-  __shared__ MsPair sh[MS_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+      if (o > from) continue;
+      MsPair q;
+      q.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+      q.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+      if (kLinear) a.s += q.s;
+      else a = ms_merge(a, q, s_tab);
+    }
+    return a;
+  };
+  p = warp_merge(p, 16);
+  __shared__ MsPair sh[MS_WARPS];
   __shared__ bool last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) sh[warp] = p;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    MsPair a = sh[0];
-    for (int w = 1; w < MS_THREADS / 32; ++w) {
-      if (kLinear) a.s += sh[w].s;
-      else a = ms_merge(a, sh[w]);
+  if (warp == 0) {
+    MsPair a = sh[lane & (MS_WARPS - 1)];
+    a = warp_merge(a, MS_WARPS / 2);
+    if (lane == 0) {
+      partial[blockIdx.x] = a;
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
-    partial[blockIdx.x] = a;
-    __threadfence();
-    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
   __syncthreads();
-  if (last) {                                              // fixed tree: deterministic
+  if (last) {
     __threadfence();
     const volatile MsPair* pv = partial;
     MsPair a;
-    a.m = kLinear ? 0.0 : -INFINITY;
+    a.m = kLinear ? 0.0 : -PBX_HUGE;
     a.s = 0.0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += MS_THREADS) {
       MsPair b;
       b.m = pv[i].m;
       b.s = pv[i].s;
       if (kLinear) a.s += b.s;
-      else a = ms_merge(a, b);
+      else a = ms_merge(a, b, s_tab);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      MsPair q;
-      q.m = __shfl_xor_sync(0xffffffffu, a.m, o);
-      q.s = __shfl_xor_sync(0xffffffffu, a.s, o);
-      if (kLinear) a.s += q.s;
-      else a = ms_merge(a, q);
-    }
+    a = warp_merge(a, 16);
     __syncthreads();                                       // sh[] is free again
     if (lane == 0) sh[warp] = a;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      MsPair t = sh[0];
-      for (int w = 1; w < MS_THREADS / 32; ++w) {
-        if (kLinear) t.s += sh[w].s;
-        else t = ms_merge(t, sh[w]);
+    if (warp == 0) {
+      MsPair t = sh[lane & (MS_WARPS - 1)];
+      t = warp_merge(t, MS_WARPS / 2);
+      if (lane == 0) {
+        out2[0] = t.m;
+        out2[1] = t.s;
+        *ticket = 0;                                       // ready for the next call
       }
-      out2[0] = t.m;
-      out2[1] = t.s;
-      *ticket = 0;                                         // ready for the next call
     }
   }
 }
@@ -593,51 +632,61 @@ __global__ void grid_rescale_sumexp_kernel(const double* lmax, const double* gma
   sum[0] = (sum[0] == 0.0) ? 0.0 : sum[0] * exp(lmax[0] - gmax[0]);
 }
 
-#define P2_ROWS 32
 #define P2_CPT 4                        // columns per thread (two 128-bit accesses per row)
 #define P2_THREADS 256
+#define P2_WARPS (P2_THREADS / 32)
 #define P2_COLS (P2_THREADS * P2_CPT)
-#define P2_RU 4                         // rows in flight per thread
+#define P2_RU 4                         // rows per tile = rows in flight per thread
 
 // kLinear: the input (and the output) are linear-pscale probabilities: post = p / max(tiny,
 // sum) (pd.py:285-295 without the log/exp round trip), marginals = plain sums.
-template <bool kLinear>
+//
+// Persistent grid: CTA b owns the column block b % n_colblocks (P2_COLS columns: a warp covers
+// 128 consecutive columns; thread (warp w, lane l) owns the two column PAIRS at cb + 2 l and
+// cb + 64 + 2 l, so each of its two 128-bit accesses per row is, warp-wide, one contiguous
+// 512-byte segment) and the 4-row tiles b / n_colblocks, + n_rowctas, + 2 n_rowctas ... of it:
+// with 3 CTAs per SM and 4-row tiles the last round of tiles is a few % of the work whatever M
+// (32-row tiles on a (4, 128) grid left 14 % of the CTA slots idle at 4096 x 4096).  Column
+// sums stay in registers for the whole kernel; each warp writes its own partial row sums
+// (no shared memory, no __syncthreads in the loop).
+// kFull: every tile is interior and 16-byte aligned -- no bounds predicates in the loop.
+template <bool kLinear, bool kFull>
 __global__ void __launch_bounds__(P2_THREADS)
     grid_posterior2_kernel(const double* lj, int M, int S, const double* __restrict__ gmax,
                            const double* __restrict__ gsum, double* post,
                            double* __restrict__ row_partial, double* __restrict__ col_partial,
-                           int n_colblocks, double qmin) {
-  __shared__ double s_row[P2_ROWS][P2_THREADS / 32];
+                           int n_colblocks, int n_rowctas, double qmin) {
   __shared__ double s_tab[64 * 16];
-  if (!kLinear) grid_stage_exptab(s_tab, P2_THREADS);
-  // Column ownership: a warp covers 128 consecutive columns; thread (warp w, lane l) owns
-  // the two column PAIRS at cb + 2 l and cb + 64 + 2 l, cb = block base + 128 w, so each of
-  // its two 128-bit accesses per row is, warp-wide, one contiguous 512-byte segment.
+  if (!kLinear) {
+    grid_stage_exptab(s_tab, P2_THREADS);
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cb = blockIdx.x * P2_COLS + warp * 128 + 2 * lane;
-  const int m0 = blockIdx.y * P2_ROWS;
+  const int cblk = blockIdx.x % n_colblocks, rcta = blockIdx.x / n_colblocks;
+  const int cb = cblk * P2_COLS + warp * 128 + 2 * lane;
   const double mx = kLinear ? 0.0 : gmax[0];
   const double den = fmax(PBX_TINY, gsum[0]);
   const double lden = kLinear ? 0.0 : log(den);
   const double rden = 1.0 / den;
+  const double rden_lo2 = rden * 6.223015277861142e-61;            // 2^-200
   // 128-bit path: even row length, 16-byte aligned bases
-  const bool vec = (S % 2 == 0) && ((((uintptr_t)lj) & 15) == 0) &&
-                   (post == nullptr || (((uintptr_t)post) & 15) == 0);
+  const bool vec = kFull || ((S % 2 == 0) && ((((uintptr_t)lj) & 15) == 0) &&
+                             (post == nullptr || (((uintptr_t)post) & 15) == 0));
   int colidx[P2_CPT];
   colidx[0] = cb; colidx[1] = cb + 1; colidx[2] = cb + 64; colidx[3] = cb + 65;
   double col[P2_CPT];
 #pragma unroll
   for (int k = 0; k < P2_CPT; ++k) col[k] = 0.0;
-  for (int r0 = 0; r0 < P2_ROWS; r0 += P2_RU) {
+  const int rp_stride = n_colblocks * P2_WARPS;
+  for (int m0 = rcta * P2_RU; m0 < M; m0 += n_rowctas * P2_RU) {
     double e[P2_RU][P2_CPT];
-    // all loads of the P2_RU rows first (post may alias lj: the compiler cannot hoist them)
+    // all loads of the tile first (post may alias lj: the compiler cannot hoist them)
 #pragma unroll
     for (int u = 0; u < P2_RU; ++u) {
-      const int m = m0 + r0 + u;
+      const int m = m0 + u;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int c0 = colidx[2 * h];
-        if (m < M && vec && c0 + 1 < S) {
+        if (kFull || (m < M && vec && c0 + 1 < S)) {
           const double2 a = __ldcs(reinterpret_cast<const double2*>(lj + (int64_t)m * S + c0));
           e[u][2 * h] = a.x;
           e[u][2 * h + 1] = a.y;
@@ -649,9 +698,10 @@ __global__ void __launch_bounds__(P2_THREADS)
         }
       }
     }
+    double w[P2_RU];
 #pragma unroll
     for (int u = 0; u < P2_RU; ++u) {
-      const int m = m0 + r0 + u;
+      const int m = m0 + u;
       double q[P2_CPT], o[P2_CPT];
 #pragma unroll
       for (int k = 0; k < P2_CPT; ++k) {
@@ -665,21 +715,21 @@ __global__ void __launch_bounds__(P2_THREADS)
           // and exp(log q) as q itself: the same values to ~1e-16 relative for a third of
           // the transcendental work; the clamp decision (q < tiny -> -1.797e308) is the
           // reference's, taken on q.
-          const double sh = e[u][k] - mx;
-          const double qq = grid_exp_logp(sh, s_tab) * rden;  // q only feeds the marginal sums
           // (qmin = tiny; 0 for PD.marginalise, which sums exp_logp(p) unclamped)
+          const double sh = e[u][k] - mx;
+          const double qq = grid_exp_logp_scaled(sh, s_tab, rden, rden_lo2);
           const bool keep = qq >= qmin;
           o[k] = keep ? sh - lden : -PBX_HUGE;
           q[k] = keep ? qq : 0.0;                           // exp_logp(-1.797e308) = 0
         }
-        if (!(m < M && colidx[k] < S)) q[k] = 0.0;
+        if (!kFull && !(m < M && colidx[k] < S)) q[k] = 0.0;
         col[k] += q[k];
       }
-      if (post && m < M) {
+      if (post && (kFull || m < M)) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = colidx[2 * h];
-          if (vec && c0 + 1 < S) {
+          if (kFull || (vec && c0 + 1 < S)) {
             __stcs(reinterpret_cast<double2*>(post + (int64_t)m * S + c0),
                    make_double2(o[2 * h], o[2 * h + 1]));
           } else {
@@ -689,42 +739,72 @@ __global__ void __launch_bounds__(P2_THREADS)
           }
         }
       }
-      double w = (q[0] + q[1]) + (q[2] + q[3]);
-#pragma unroll
-      for (int ofs = 16; ofs > 0; ofs >>= 1) w += __shfl_xor_sync(0xffffffffu, w, ofs);
-      if (lane == 0) s_row[r0 + u][warp] = w;
+      w[u] = (q[0] + q[1]) + (q[2] + q[3]);
+    }
+    // the four row sums of the warp's 128 columns in 6 exchanges instead of 20: fold the
+    // rows onto lane groups first (lanes 16+ keep rows 2, 3; then bit 3 picks the odd row),
+    // then a 3-step butterfly inside each group of 8 lanes.  Row u ends up in lane 8 u.
+    {
+      const bool up = (lane & 16) != 0;
+      double k0 = up ? w[2] : w[0], k1 = up ? w[3] : w[1];
+      const double a0 = up ? w[0] : w[2], a1 = up ? w[1] : w[3];
+      k0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+      k1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+      const bool up2 = (lane & 8) != 0;
+      double kk = up2 ? k1 : k0;
+      const double ss = up2 ? k0 : k1;
+      kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 2);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 1);
+      const int m = m0 + (lane >> 3);
+      if ((lane & 7) == 0 && (kFull || m < M))
+        row_partial[(int64_t)m * rp_stride + cblk * P2_WARPS + warp] = kk;
     }
   }
 #pragma unroll
   for (int k = 0; k < P2_CPT; ++k)
-    if (colidx[k] < S) col_partial[(int64_t)blockIdx.y * S + colidx[k]] = col[k];
-  __syncthreads();
-  if (threadIdx.x < P2_ROWS) {
-    const int m = m0 + threadIdx.x;
-    if (m < M) {
-      double w = 0.0;
-#pragma unroll
-      for (int k = 0; k < P2_THREADS / 32; ++k) w += s_row[threadIdx.x][k];
-      row_partial[(int64_t)m * n_colblocks + blockIdx.x] = w;
-    }
-  }
+    if (kFull || colidx[k] < S) col_partial[(int64_t)rcta * S + colidx[k]] = col[k];
 }
 
 // log_flags: bit 0 -> marg_mu through the clamped log, bit 1 -> marg_sigma
+// blocks [0, row_blocks): a warp per row, the lanes stride over the row's partial sums
+// (contiguous) and finish with a butterfly; blocks from row_blocks on: 32 columns x 8 partial
+// groups per block (coalesced across the columns), the 8 group sums added in order.  Fixed
+// association -> identical bits from run to run.
 __global__ void __launch_bounds__(256)
-    grid_marginal_finish2(const double* __restrict__ row_partial, int M, int n_colblocks,
-                          const double* __restrict__ col_partial, int n_rowblocks, int S,
+    grid_marginal_finish2(const double* __restrict__ row_partial, int M, int n_per_row,
+                          const double* __restrict__ col_partial, int n_rowctas, int S,
                           double* __restrict__ marg_mu, double* __restrict__ marg_sigma,
-                          int log_flags) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < M && marg_mu) {
+                          int log_flags, int row_blocks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((int)blockIdx.x < row_blocks) {
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= M) return;
     double w = 0.0;
-    for (int k = 0; k < n_colblocks; ++k) w += row_partial[(int64_t)i * n_colblocks + k];
-    marg_mu[i] = (log_flags & 1) ? pbx_log_prob(w) : w;
+    for (int k = lane; k < n_per_row; k += 32) w += row_partial[(int64_t)i * n_per_row + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) marg_mu[i] = (log_flags & 1) ? pbx_log_prob(w) : w;
+    return;
   }
-  if (i < S && marg_sigma) {
-    double w = 0.0;
-    for (int k = 0; k < n_rowblocks; ++k) w += col_partial[(int64_t)k * S + i];
+  __shared__ double s_w[8][33];
+  const int i = (blockIdx.x - row_blocks) * 32 + lane;
+  double w0 = 0.0, w1 = 0.0;
+  if (i < S) {
+    int k = warp;
+    for (; k + 8 < n_rowctas; k += 16) {
+      w0 += col_partial[(int64_t)k * S + i];
+      w1 += col_partial[(int64_t)(k + 8) * S + i];
+    }
+    if (k < n_rowctas) w0 += col_partial[(int64_t)k * S + i];
+  }
+  s_w[warp][lane] = w0 + w1;
+  __syncthreads();
+  if (warp == 0 && i < S) {
+    double w = s_w[0][lane];
+#pragma unroll
+    for (int g = 1; g < 8; ++g) w += s_w[g][lane];
     marg_sigma[i] = (log_flags & 2) ? pbx_log_prob(w) : w;
   }
 }
@@ -737,17 +817,26 @@ extern "C" int pbx_grid_max_sumexp(pbx_ctx* ctx, const double* v, int64_t n, int
     int rc0 = grid_init_exptab(ctx);
     if (rc0) return rc0;
   }
-  int64_t want = (n + (int64_t)MS_THREADS * MS_CHUNK * 4 - 1) / ((int64_t)MS_THREADS * MS_CHUNK * 4);
-  const int np = (int)(want < 1 ? 1 : (want > ctx->sm_count * 8 ? ctx->sm_count * 8 : want));
-  // workspace: [ticket (256 B, zero between calls)] [np pairs]
-  int rc = pbx_ws_reserve(ctx, 256 + (size_t)np * sizeof(MsPair));
+  int per_sm = 0;
+  PBX_CUDA(linear ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &per_sm, grid_max_sumexp_kernel<true>, MS_THREADS, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &per_sm, grid_max_sumexp_kernel<false>, MS_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t cap = (int64_t)ctx->sm_count * per_sm;     // one resident wave
+  int64_t want = (n + (int64_t)MS_THREADS * MS_CHUNK * 2 - 1) / ((int64_t)MS_THREADS * MS_CHUNK * 2);
+  const int np = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  // the ticket word is the context's own (zeroed once; the last CTA of every call resets it),
+  // the per-CTA pairs go to the shared workspace
+  if (!ctx->ticket) {
+    PBX_CUDA(cudaMalloc(&ctx->ticket, 256));
+    PBX_CUDA(cudaMemsetAsync(ctx->ticket, 0, 256, ctx->stream));
+  }
+  int rc = pbx_ws_reserve(ctx, (size_t)np * sizeof(MsPair));
   if (rc) return rc;
-  unsigned int* ticket = (unsigned int*)ctx->ws;
-  MsPair* partial = (MsPair*)((char*)ctx->ws + 256);
+  unsigned int* ticket = ctx->ticket;
+  MsPair* partial = (MsPair*)ctx->ws;
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  // the ticket word lives at the start of the shared workspace, which other entry points
-  // overwrite: zero it every call (a 4-byte memset node, no kernel)
-  PBX_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ctx->stream));
   if (linear)
     grid_max_sumexp_kernel<true><<<np, MS_THREADS, 0, ctx->stream>>>(v, n, partial, ticket, out2);
   else
@@ -777,27 +866,56 @@ extern "C" int pbx_grid_posterior2(pbx_ctx* ctx, const double* prob, int32_t n_m
     int rc0 = grid_init_exptab(ctx);
     if (rc0) return rc0;
   }
-  const int ncb = (n_sigma + P2_COLS - 1) / P2_COLS, nrb = (n_mu + P2_ROWS - 1) / P2_ROWS;
-  PBX_REQUIRE(nrb <= 65535, "pbx_grid_posterior2: too many rows per call (slab it)");
-  const size_t rp = ((size_t)n_mu * ncb * 8 + 255) / 256 * 256;
-  const size_t cp = (size_t)nrb * n_sigma * 8;
+  const int ncb = (n_sigma + P2_COLS - 1) / P2_COLS;
+  const int n_tiles = (n_mu + P2_RU - 1) / P2_RU;
+  const bool full = (n_mu % P2_RU == 0) && (n_sigma % P2_COLS == 0) &&
+                    ((((uintptr_t)prob) & 15) == 0) && (!post || (((uintptr_t)post) & 15) == 0);
+  // persistent grid: as many CTAs as are resident at once (3 per SM for the interior variant
+  // at 78 registers; capping at 64 registers for 4 spills), a whole number of row-CTAs per
+  // column block
+  int per_sm = 0;
+  {
+    cudaError_t oe;
+    if (linear)
+      oe = full ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                      &per_sm, grid_posterior2_kernel<true, true>, P2_THREADS, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                      &per_sm, grid_posterior2_kernel<true, false>, P2_THREADS, 0);
+    else
+      oe = full ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                      &per_sm, grid_posterior2_kernel<false, true>, P2_THREADS, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                      &per_sm, grid_posterior2_kernel<false, false>, P2_THREADS, 0);
+    PBX_CUDA(oe);
+    if (per_sm < 1) per_sm = 1;
+  }
+  int nrc = (per_sm * ctx->sm_count) / ncb;
+  if (nrc < 1) nrc = 1;
+  if (nrc > n_tiles) nrc = n_tiles;
+  const int npr = ncb * P2_WARPS;                       // partial sums per row
+  const size_t rp = ((size_t)n_mu * npr * 8 + 255) / 256 * 256;
+  const size_t cp = (size_t)nrc * n_sigma * 8;
   int rc = pbx_ws_reserve(ctx, rp + cp);
   if (rc) return rc;
   double* row_partial = (double*)ctx->ws;
   double* col_partial = (double*)((char*)ctx->ws + rp);
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   const double qmin = (marg_log_flags & 4) ? 0.0 : PBX_TINY;
-  if (linear)
-    grid_posterior2_kernel<true><<<dim3(ncb, nrb), P2_THREADS, 0, ctx->stream>>>(
-        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb, qmin);
-  else
-    grid_posterior2_kernel<false><<<dim3(ncb, nrb), P2_THREADS, 0, ctx->stream>>>(
-        prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb, qmin);
+#define P2_LAUNCH(L, F)                                                                        \
+  grid_posterior2_kernel<L, F><<<ncb * nrc, P2_THREADS, 0, ctx->stream>>>(                     \
+      prob, n_mu, n_sigma, gmax, gsum, post, row_partial, col_partial, ncb, nrc, qmin)
+  if (linear) {
+    if (full) P2_LAUNCH(true, true); else P2_LAUNCH(true, false);
+  } else {
+    if (full) P2_LAUNCH(false, true); else P2_LAUNCH(false, false);
+  }
+#undef P2_LAUNCH
   PBX_LAUNCH_CHECK(ctx);
   if (marg_mu || marg_sigma) {
-    const int n = n_mu > n_sigma ? n_mu : n_sigma;
-    grid_marginal_finish2<<<(n + 255) / 256, 256, 0, ctx->stream>>>(
-        row_partial, n_mu, ncb, col_partial, nrb, n_sigma, marg_mu, marg_sigma, marg_log_flags);
+    const int rb = marg_mu ? (n_mu + 7) / 8 : 0, cbk = marg_sigma ? (n_sigma + 31) / 32 : 0;
+    grid_marginal_finish2<<<rb + cbk, 256, 0, ctx->stream>>>(
+        row_partial, n_mu, npr, col_partial, nrc, n_sigma, marg_mu, marg_sigma, marg_log_flags,
+        rb);
     PBX_LAUNCH_CHECK(ctx);
   }
   PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
