@@ -267,7 +267,8 @@ static double ndtri_(double p) {
 
 /*
  * CondCov Gibbs (probayes/cond_cov.py:42-65 via rf.py:446-462): one coordinate
- * per step, coordinate = (step0 + k) mod d, native Philox uniforms (slot 0).
+ * per step, coordinate = (step0 + k) mod d, native Philox uniforms (slot 0, two steps per
+ * block).
  * x [C][d] in/out; coef [d][d] with zero diagonal.
  */
 void orc_gibbs_mvn_walk(int C, int d, int T, double* x, const double* mean, const double* coef,
@@ -281,9 +282,12 @@ void orc_gibbs_mvn_walk(int C, int d, int T, double* x, const double* mean, cons
       double r;
       if (inj_runif) r = inj_runif[(size_t)k * C + c];
       else {
+        /* steps g and g + 4 share Philox block (seed, g & ~4, chain, 0): words (0, 1) when
+         * bit 2 of g is clear, (2, 3) when it is set (pbx_gibbs.cu header) */
         uint32_t w[4];
-        block(seed, (uint64_t)(step0 + k), (uint32_t)(chain0 + c), 0u, w);
-        r = u52(w[0], w[1]);
+        const uint64_t g = (uint64_t)(step0 + k);
+        block(seed, g & ~(uint64_t)4, (uint32_t)(chain0 + c), 0u, w);
+        r = (g & 4) ? u52(w[2], w[3]) : u52(w[0], w[1]);
       }
       double u = cdf_lo[i] + (cdf_hi[i] - cdf_lo[i]) * r;
       double cm = mean[i];

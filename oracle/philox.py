@@ -17,6 +17,9 @@ Stream layout (must match probayes_b200/csrc/pbx_philox.cuh):
   threshold : the spare bits of slot 0 -- t44 = (2*k + 1) * 2**-45,
       k = (w3 << 12) | (w1 & 0xfff)       => ONE Philox block per step for D <= 2
   (all three are exact in fp64 and strictly inside (0, 1))
+  Gibbs (pbx_gibbs.cu): one uniform per global step g -- u52 of words (0, 1) (bit 2 of g
+      clear) or (2, 3) (bit 2 set) of block (seed, g & ~4, chain, slot 0), so that steps g
+      and g + 4 share a block
 """
 import numpy as np
 
@@ -138,3 +141,11 @@ def thresholds(seed, steps, chains, step0=0):
         else np.asarray(chains, dtype=np.uint64)[None, :]
     w0, w1, w2, w3 = block(seed, t, c, 0)
     return t44(w3, w1)
+
+
+def gibbs_uniforms(seed, step, chain):
+    """The Gibbs kernel's uniform for global step(s) ``step`` and chain id(s) ``chain``
+    (broadcastable uint64 arrays): steps g and g + 4 share one Philox block."""
+    step = np.asarray(step, dtype=np.uint64)
+    w0, w1, w2, w3 = block(seed, step & ~np.uint64(4), chain, 0)
+    return np.where((step & np.uint64(4)) != 0, u52(w2, w3), u52(w0, w1))

@@ -140,6 +140,8 @@ SIGNATURES = {
     "pbx_gibbs_mvn_run": (C.c_int, [C.c_void_p, C.POINTER(GibbsMvnParams)]),
     "pbx_mvn_logpdf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p,
                                  C.c_void_p, C.c_double, C.c_int32, C.c_void_p]),
+    "pbx_ndtri": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pbx_ndtri_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "pbx_reduce_chain_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_int64, C.c_int64, C.c_void_p]),
     "pbx_argsort_workspace_bytes": (C.c_int, [C.c_int64, C.POINTER(C.c_size_t)]),

@@ -21,6 +21,7 @@ struct pbx_ctx {
   size_t ws_bytes;
   bool tables_ready;         // K1 math tables uploaded to this context's device
   bool exptab_ready;         // K4 exp table uploaded
+  bool ndtab_ready;          // K5 ndtri table uploaded
   unsigned int* ticket;      // K4 last-CTA ticket (device, 256 B, zero between calls)
 };
 

@@ -5,6 +5,10 @@
 // one coordinate i = step mod d per step (tsteps=1):
 //     u   = cdf_lo_i + (cdf_hi_i - cdf_lo_i) * r          r ~ U(0,1)  (vtypes.py:186)
 //     x_i = ndtri(u) * stdv_i + mean_i + coef_i . (x_-i - mean_-i)
+// Native uniforms: global step g takes the 52-bit uniform of words (0, 1) (bit 2 of g clear)
+// or (2, 3) (bit 2 set) of Philox block (seed, g & ~4, chain, slot 0): steps g and g + 4 --
+// consecutive coordinates of the same lane below -- share one block (oracle/philox.py
+// gibbs_uniforms replays it).  ndtri is the table-driven pbx_ndtri.cuh.
 // with the truncation limits fixed at construction (cond_cov.py:38-39).  The dot
 // product is evaluated as c0_i + coef_i . x with c0_i = mean_i - coef_i . mean
 // folded on the host (coef_ii = 0).
@@ -19,6 +23,7 @@
 // MMA row block; smaller d uses a plain FMA kernel.
 #include <math.h>
 #include "pbx_common.cuh"
+#include "pbx_ndtri.cuh"
 
 #ifndef GB_THREADS
 #define GB_THREADS 256                 // measured: 0.137 / 0.116 / 0.108 ms per sweep at 64 / 128 / 256
@@ -48,21 +53,38 @@ __global__ void gibbs_c0_kernel(const double* coef, const double* mean, int d, d
   c0[i] = mean[i] - acc;
 }
 
-// State-independent part of one coordinate update, kept out of line: the coordinate
-// loop is fully unrolled (register-resident state) and inlining ~250 instructions of
-// Philox + normcdfinv at every site made the kernel 60 k instructions long and
-// instruction-fetch bound (ncu: stall_no_inst 34 %).
-__device__ __noinline__ double gibbs_draw_z(uint64_t seed, uint64_t gk, uint32_t gchain,
-                                            const double* inj, double lo, double w, double sd,
-                                            double c0) {
-  double r;
-  if (inj) {
-    r = *inj;
-  } else {
-    pbx_u4 b = pbx_block(seed, gk, gchain, 0u);
-    r = pbx_u52(b.x, b.y);
+static __device__ double g_ndtab[NDT_ROWS * NDT_NCOEF];     // 128 KB, read through L1
+// the rows of the 10 binades nearest 0.5 (p >= 2^-11: all but 0.1 % of the draws),
+// TRANSPOSED [coefficient][row] for the tensor-core kernel's shared-memory copy: a lane's
+// eight 64-bit loads then fall on banks that are uniform in its (random) row index
+#define NDT_HOT_BINADES 10
+#define NDT_HOT_ROWS (NDT_HOT_BINADES * NDT_SEGS)
+#define NDT_HOT0 (NDT_ROWS - NDT_HOT_ROWS)
+static __device__ double g_ndhot[NDT_NCOEF * NDT_HOT_ROWS];  // 20 KB
+
+// outside the table (p < 2^-64, u <= 0, u >= 1, NaN): practically never taken, out of line
+__device__ __noinline__ double gibbs_ndtri_cold(double u) { return normcdfinv(u); }
+
+__device__ __forceinline__ double gibbs_ndtri(double u) {
+  const bool upper = u > 0.5;
+  const double p = upper ? 1.0 - u : u;                  // exact for u > 0.5
+  const unsigned seg = ndt_segment(p);
+  if (seg >= (unsigned)NDT_ROWS) return gibbs_ndtri_cold(u);
+  const double2* row = reinterpret_cast<const double2*>(g_ndtab + (size_t)seg * NDT_NCOEF);
+  double c[NDT_NCOEF];
+#pragma unroll
+  for (int j = 0; j < NDT_NCOEF / 2; ++j) {
+    const double2 t = __ldg(row + j);
+    c[2 * j] = t.x;
+    c[2 * j + 1] = t.y;
   }
-  return normcdfinv(lo + w * r) * sd + c0;
+  const double x = ndt_poly(c, p);
+  return upper ? -x : x;
+}
+
+// the uniform of global step gk from its (shared) Philox block
+__device__ __forceinline__ double gibbs_uniform(const pbx_u4& b, int64_t gk) {
+  return (gk & 4) ? pbx_u52(b.z, b.w) : pbx_u52(b.x, b.y);
 }
 
 // One chain = FOUR lanes (a warp = 8 chains): lane q of a chain keeps coordinates
@@ -73,9 +95,11 @@ __device__ __noinline__ double gibbs_draw_z(uint64_t seed, uint64_t gk, uint32_t
 // next coordinate, i.e. four coordinates' worth in parallel with no redundancy.
 // kSweepRec: records fall on sweep boundaries only (thin % d == 0, call aligned to
 // sweeps) -> one copy of the record code per sweep instead of one per coordinate.
+// kPair (whole sweeps and d % 8 == 0): the Philox block of coordinate 4 l + q also serves
+// 4 (l + 1) + q, so it is computed on even l only.
 // NT threads per CTA (256, or 128 when there are too few chains to give every SM a CTA of
 // 64 chains: strong-scaled shards)
-template <int DQ, bool kSweepRec, int NT = GB_THREADS>
+template <int DQ, bool kSweepRec, bool kPair, int NT = GB_THREADS>
 __global__ void __launch_bounds__(NT)
     gibbs_mvn_kernel(const GibbsArgs a) {
   constexpr int DP = 4 * DQ;
@@ -135,6 +159,8 @@ __global__ void __launch_bounds__(NT)
     }
     ++rec;
   };
+  pbx_u4 blk;
+  blk.x = blk.y = blk.z = blk.w = 0u;
   for (int64_t sweep = k_begin / d; sweep * d < k_end; ++sweep) {
 #pragma unroll
     for (int l = 0; l < DQ; ++l) {
@@ -143,10 +169,17 @@ __global__ void __launch_bounds__(NT)
       {
         const int i = 4 * l + q;
         const int64_t gk = sweep * d + i;
-        if (i < d && gk >= k_begin && gk < k_end)
-          z = gibbs_draw_z(a.seed, (uint64_t)gk, gchain,
-                           a.inj_runif ? a.inj_runif + (gk - k_begin) * C + c : nullptr,
-                           s_lo[i], s_w[i], s_sd[i], s_c0[i]);
+        if (i < d && gk >= k_begin && gk < k_end) {
+          double r;
+          if (a.inj_runif) {
+            r = a.inj_runif[(gk - k_begin) * C + c];
+          } else {
+            if (!kPair || (l & 1) == 0)
+              blk = pbx_block(a.seed, (uint64_t)gk & ~(uint64_t)4, gchain, 0u);
+            r = gibbs_uniform(blk, gk);
+          }
+          z = gibbs_ndtri(s_lo[i] + s_w[i] * r) * s_sd[i] + s_c0[i];
+        }
       }
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
@@ -195,6 +228,233 @@ __global__ void __launch_bounds__(NT)
 }
 
 // ---------------------------------------------------------------------------
+// Whole-sweep Gibbs with the conditional means on the FP64 tensor cores (d >= 5).
+//
+// The per-coordinate kernel above reads 8 x 128-bit of coefficients from shared memory per
+// lane per coordinate; ncu showed it bound by exactly that (50 % of the stall samples on the
+// short scoreboard, 29 % issue utilisation, FP64 pipe 17 %): 4 shared-memory wavefronts per
+// 64 useful FMAs.  Here the coordinates are taken in BLOCKS of 8 (blocked Gauss-Seidel, the
+// same sweep order and the same result up to summation order):
+//   1. S = coef[block rows] . x for the 8 chains of the warp with mma.sync.m8n8k4.f64 --
+//      D[chain][n] += A[chain][k] B[k][n], A = the register-resident state (lane (r, q) holds
+//      x[4 ks + q] of chain r: already the A-fragment layout), B = coef[8b + pi(n)][4 ks + k]
+//      from a pre-swizzled shared-memory copy (one conflict-free 64-bit load per MMA = 256
+//      FMAs).  The column permutation pi(2j) = j, pi(2j + 1) = j + 4 makes the D fragment of
+//      lane (r, q) hold exactly the two block coordinates it owns (8b + q and 8b + 4 + q).
+//   2. The 8 coordinates of the block are then resolved in order: x_t = z_t + S_t with S_t
+//      corrected by coef[t][t'] (x_t' new - x_t' old) for the block's earlier t' -- one
+//      4-lane broadcast of the owner's delta and two FMAs per coordinate.
+// Draws: lane (r, q) draws for its own two coordinates of the block from ONE Philox block
+// (steps g and g + 4), table ndtri.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+#define GM_WSTRIDE 12                      // within-block coefficients per (block, q): 4 + 8
+
+// the model in the kernel's shared-memory layout:
+//   [NB][DQ][32] B fragments | [NB][4][12] within-block coefficients | c0, sd, lo, w [DP] each
+template <int DQ>
+__host__ __device__ constexpr size_t gibbs_mma_model_doubles() {
+  return (size_t)(DQ / 2) * DQ * 32 + (size_t)(DQ / 2) * 4 * GM_WSTRIDE + 4 * (4 * DQ);
+}
+
+// builds that image once per launch in the workspace (the first version gathered it from the
+// row-major inputs in every CTA's prologue: 0.06 ms per launch at 1024 CTAs)
+template <int DQ>
+__global__ void gibbs_mma_prep_kernel(const GibbsArgs a, double* __restrict__ img) {
+  constexpr int DP = 4 * DQ, NB = DQ / 2;
+  constexpr int nB = NB * DQ * 32, nW = NB * 4 * GM_WSTRIDE;
+  const int d = a.d;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nB + nW + 4 * DP;
+       idx += gridDim.x * blockDim.x) {
+    double v = 0.0;
+    if (idx < nB) {
+      const int T = idx & 31, ks = (idx >> 5) % DQ, b = idx / (32 * DQ);
+      const int n = T >> 2;
+      const int row = 8 * b + (n >> 1) + 4 * (n & 1), col = 4 * ks + (T & 3);
+      if (row < d && col < d) v = a.coef[(int64_t)row * d + col];
+    } else if (idx < nB + nW) {
+      const int j = idx - nB;
+      const int e = j % GM_WSTRIDE, qq = (j / GM_WSTRIDE) & 3, b = j / (4 * GM_WSTRIDE);
+      // e < 4: row 8b + qq, earlier coordinate t = e (t < qq); e >= 4: row 8b + 4 + qq, t = e - 4
+      const int row = (e < 4) ? 8 * b + qq : 8 * b + 4 + qq;
+      const int t = (e < 4) ? e : e - 4;
+      const bool earlier = (e < 4) ? (t < qq) : (t < 4 + qq);
+      const int col = 8 * b + t;
+      if (earlier && row < d && col < d) v = a.coef[(int64_t)row * d + col];
+    } else {
+      const int j = idx - nB - nW, which = j / DP, i = j % DP;
+      if (i < d)
+        v = which == 0 ? a.c0[i] : which == 1 ? a.stdv[i] : which == 2 ? a.cdf_lo[i]
+                                                          : a.cdf_hi[i] - a.cdf_lo[i];
+    }
+    img[idx] = v;
+  }
+}
+
+template <int DQ, bool kPair, int NT>
+__global__ void __launch_bounds__(NT)
+    gibbs_mvn_mma_kernel(const GibbsArgs a, const double* __restrict__ img) {
+  constexpr int DP = 4 * DQ, NB = DQ / 2;
+  extern __shared__ __align__(16) double sm[];
+  double* s_B = sm;                          // [NB][DQ][32]   B fragments
+  double* s_W = s_B + NB * DQ * 32;          // [NB][4][12]    within-block coefficients
+  double* s_c0 = s_W + NB * 4 * GM_WSTRIDE;  // [DP]
+  double* s_sd = s_c0 + DP;
+  double* s_lo = s_sd + DP;
+  double* s_w = s_lo + DP;                   // hi - lo
+  double* s_z = s_w + DP;                    // [DQ][NT]  the sweep's draws, z[mm][thread]
+  double* s_nd = s_z + DQ * NT;              // [8][NDT_HOT_ROWS]  hot ndtri rows, transposed
+  {
+    constexpr int n2 = (int)(gibbs_mma_model_doubles<DQ>() / 2);
+    const double2* src = reinterpret_cast<const double2*>(img);
+    double2* dst = reinterpret_cast<double2*>(sm);
+    for (int i = threadIdx.x; i < n2; i += NT) dst[i] = src[i];
+    const double2* hsrc = reinterpret_cast<const double2*>(g_ndhot);
+    double2* hdst = reinterpret_cast<double2*>(s_nd);
+    for (int i = threadIdx.x; i < NDT_NCOEF * NDT_HOT_ROWS / 2; i += NT) hdst[i] = hsrc[i];
+  }
+  __syncthreads();
+  const int d = a.d;
+  const int lane = threadIdx.x & 31, q = lane & 3;
+  const int64_t C = a.C;
+  const int64_t c_raw = ((int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5)) * 8 + (lane >> 2);
+  const bool valid = c_raw < C;
+  const int64_t c = valid ? c_raw : C - 1;          // clamp: idle lanes stay in the MMAs
+  const uint32_t gchain = (uint32_t)(a.chain0 + c);
+  double* my_z = s_z + threadIdx.x;
+
+  double x[DQ];
+#pragma unroll
+  for (int mm = 0; mm < DQ; ++mm) {
+    const int j = 4 * mm + q;
+    x[mm] = (j < d) ? a.state[(int64_t)j * C + c] : 0.0;
+  }
+  const bool stats = a.stat_sum != nullptr;
+  const int64_t k_begin = a.step0, k_end = a.step0 + a.T;
+  int until_rec = a.thin;
+  int64_t rec = 0;
+  for (int64_t sweep = k_begin / d; sweep * d < k_end; ++sweep) {
+    // ---- phase A: the sweep's DQ draws of this lane (coordinates 4 mm + q), state
+    // independent and BRANCH-FREE so that the Philox rounds, table loads and polynomials of
+    // all of them interleave.  The table rows come from the shared-memory copy of the 10
+    // binades nearest 0.5 with a clamped index (a first version gathered the 64-byte rows
+    // from global memory: 27 L1 sectors per request made the L1 the bottleneck); the 0.1 %
+    // of arguments outside them leave u in the slot, are flagged and redone afterwards from
+    // the full table (or, outside it, normcdfinv)
+    unsigned bad = 0u;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const int i0 = 8 * b + q, i1 = i0 + 4;
+      const int64_t g0 = sweep * d + i0, g1 = g0 + 4;
+      double r0, r1;
+      if (a.inj_runif) {
+        r0 = (i0 < d) ? a.inj_runif[(g0 - k_begin) * C + c] : 0.5;
+        r1 = (i1 < d) ? a.inj_runif[(g1 - k_begin) * C + c] : 0.5;
+      } else if (kPair) {
+        const pbx_u4 blk = pbx_block(a.seed, (uint64_t)g0, gchain, 0u);     // bit 2 of g0 clear
+        r0 = pbx_u52(blk.x, blk.y);
+        r1 = pbx_u52(blk.z, blk.w);
+      } else {
+        const pbx_u4 b0 = pbx_block(a.seed, (uint64_t)g0 & ~(uint64_t)4, gchain, 0u);
+        const pbx_u4 b1 = pbx_block(a.seed, (uint64_t)g1 & ~(uint64_t)4, gchain, 0u);
+        r0 = gibbs_uniform(b0, g0);
+        r1 = gibbs_uniform(b1, g1);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = h ? i1 : i0;
+        const double u = s_lo[i] + s_w[i] * (h ? r1 : r0);
+        const bool upper = u > 0.5;
+        const double p = upper ? 1.0 - u : u;                  // exact for u > 0.5
+        const unsigned seg = ndt_segment(p) - (unsigned)NDT_HOT0;   // wraps below the hot rows
+        const bool cold = seg >= (unsigned)NDT_HOT_ROWS;
+        if (cold && i < d) bad |= 1u << (2 * b + h);
+        const double* row = s_nd + min(seg, (unsigned)(NDT_HOT_ROWS - 1));
+        double cf[NDT_NCOEF];
+#pragma unroll
+        for (int j = 0; j < NDT_NCOEF; ++j) cf[j] = row[j * NDT_HOT_ROWS];
+        const double xn = ndt_poly(cf, p);
+        const double z = (upper ? -xn : xn) * s_sd[i] + s_c0[i];
+        my_z[(2 * b + h) * NT] = (i < d) ? (cold ? u : z) : 0.0;
+      }
+    }
+    while (bad) {                                              // arguments outside the hot rows
+      const int mm = __ffs(bad) - 1;
+      bad &= bad - 1u;
+      const int i = 4 * mm + q;
+      my_z[mm * NT] = gibbs_ndtri(my_z[mm * NT]) * s_sd[i] + s_c0[i];
+    }
+    // ---- phase B: the blocks in order.  One basic block: the MMAs of block b + 1 that do
+    // not read the two state registers block b rewrites are free to overlap block b's chain.
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      // S = coef[block] . x on the tensor cores (two accumulator chains)
+      double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+      const double* bf = s_B + (b * DQ) * 32 + lane;
+#pragma unroll
+      for (int kk = 0; kk < DQ; kk += 2) {
+        // the k-steps holding the previous block's coordinates last
+        const int ks = (b == 0) ? kk : (kk + 2 * b) % DQ;
+        dmma_m8n8k4(e0, e1, x[ks], bf[ks * 32]);
+        dmma_m8n8k4(f0, f1, x[ks + 1], bf[(ks + 1) * 32]);
+      }
+      double Sa = (e0 + f0) + my_z[(2 * b) * NT], Sb = (e1 + f1) + my_z[(2 * b + 1) * NT];
+      const double xa_old = x[2 * b], xb_old = x[2 * b + 1];
+      // the block's 8 coordinates in order
+      const double2* wv = reinterpret_cast<const double2*>(s_W + (b * 4 + q) * GM_WSTRIDE);
+      double W[GM_WSTRIDE];
+#pragma unroll
+      for (int j = 0; j < GM_WSTRIDE / 2; ++j) {
+        const double2 t2 = wv[j];
+        W[2 * j] = t2.x;
+        W[2 * j + 1] = t2.y;
+      }
+      const int grp = lane & ~3;
+#pragma unroll
+      for (int t = 0; t < 7; ++t) {
+        const double mine = (t < 4) ? Sa - xa_old : Sb - xb_old;   // the owner's is final
+        const double delta = __shfl_sync(0xffffffffu, mine, grp | (t & 3));
+        if (t < 3) Sa = fma(W[t], delta, Sa);                      // W = 0 unless t precedes mine
+        Sb = fma(W[4 + t], delta, Sb);
+      }
+      x[2 * b] = Sa;
+      x[2 * b + 1] = Sb;
+    }
+    until_rec -= d;
+    if (until_rec == 0) {
+      until_rec = a.thin;
+      if (valid) {
+#pragma unroll
+        for (int mm = 0; mm < DQ; ++mm) {
+          const int j = 4 * mm + q;
+          if (j < d) {
+            if (a.out_x) a.out_x[(rec * d + j) * C + c] = x[mm];
+            if (stats) {                              // running sums over RECORDED states
+              a.stat_sum[(int64_t)j * C + c] += x[mm];
+              a.stat_sumsq[(int64_t)j * C + c] =
+                  fma(x[mm], x[mm], a.stat_sumsq[(int64_t)j * C + c]);
+            }
+          }
+        }
+      }
+      ++rec;
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int mm = 0; mm < DQ; ++mm) {
+      const int j = 4 * mm + q;
+      if (j < d) a.state[(int64_t)j * C + c] = x[mm];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // batched mvn density, plain FMA version: one thread per point, W from smem
 // ---------------------------------------------------------------------------
 // points: R blocks of [d][C]; point (r, c) -> x[(r*d + j)*C + c], out[r*C + c]
@@ -229,12 +489,6 @@ __global__ void __launch_bounds__(128)
 //   B[k][n] = W[k][n]                  (thread T: k = T%4, n = T/4)
 //   D[r][n]: thread T holds (r = T/4, n = 2*(T%4) + {0,1})
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
 __global__ void __launch_bounds__(128)
     mvn_logpdf_mma64_kernel(const double* __restrict__ x, int64_t C, int64_t R,
                             const double* __restrict__ mean, const double* __restrict__ W,
@@ -320,22 +574,77 @@ extern "C" int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int
   return PBX_OK;
 }
 
+static int gibbs_init_ndtab(pbx_ctx* ctx) {
+  if (ctx->ndtab_ready) return PBX_OK;
+  static double* h_tab = nullptr;                      // built once per process (19 ms)
+  if (!h_tab) {
+    double* t = new double[NDT_ROWS * NDT_NCOEF];
+    ndt_build_table(t);
+    h_tab = t;
+  }
+  static double* h_hot = nullptr;
+  if (!h_hot) {
+    double* t = new double[NDT_NCOEF * NDT_HOT_ROWS];
+    for (int r = 0; r < NDT_HOT_ROWS; ++r)
+      for (int j = 0; j < NDT_NCOEF; ++j)
+        t[j * NDT_HOT_ROWS + r] = h_tab[(size_t)(NDT_HOT0 + r) * NDT_NCOEF + j];
+    h_hot = t;
+  }
+  PBX_CUDA(cudaMemcpyToSymbolAsync(g_ndtab, h_tab, sizeof(double) * NDT_ROWS * NDT_NCOEF, 0,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+  PBX_CUDA(cudaMemcpyToSymbolAsync(g_ndhot, h_hot, sizeof(double) * NDT_NCOEF * NDT_HOT_ROWS, 0,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+  PBX_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->ndtab_ready = true;
+  return PBX_OK;
+}
+
 template <int DQ, int NT>
 static int gibbs_launch_nt(pbx_ctx* ctx, const GibbsArgs& a) {
   constexpr int DP = 4 * DQ;
-  const size_t smem = ((size_t)DP * 4 * (DQ + 2) + 4 * DP) * sizeof(double);
   const int chains_per_cta = (NT / 32) * 8;
   const int grid = (a.C + chains_per_cta - 1) / chains_per_cta;
   const bool sweep_rec = (a.thin % a.d == 0) && (a.step0 % a.d == 0) && (a.T % a.d == 0);
-  if (sweep_rec) {
-    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, true, NT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gibbs_mvn_kernel<DQ, true, NT><<<grid, NT, smem, ctx->stream>>>(a);
-  } else {
-    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, false, NT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gibbs_mvn_kernel<DQ, false, NT><<<grid, NT, smem, ctx->stream>>>(a);
+  if constexpr (DQ >= 2) {
+    if (sweep_rec) {                       // whole sweeps: conditional means on the tensor cores
+      const size_t model = gibbs_mma_model_doubles<DQ>();
+      const size_t smem = (model + (size_t)DQ * NT + NDT_NCOEF * NDT_HOT_ROWS) * sizeof(double);
+      // workspace: [c0 (d doubles, padded to 256 B)] [model image]
+      const size_t off = ((size_t)a.d * 8 + 255) / 256 * 256;
+      int rc = pbx_ws_reserve(ctx, off + model * sizeof(double));
+      if (rc) return rc;
+      GibbsArgs a2 = a;
+      a2.c0 = (const double*)ctx->ws;                   // (the reserve above may have moved it)
+      double* img = (double*)((char*)ctx->ws + off);
+      gibbs_mma_prep_kernel<DQ><<<(int)((model + 255) / 256), 256, 0, ctx->stream>>>(a2, img);
+      PBX_LAUNCH_CHECK(ctx);
+#define GM_LAUNCH(PR)                                                                          \
+  do {                                                                                         \
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_mma_kernel<DQ, PR, NT>,                            \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    gibbs_mvn_mma_kernel<DQ, PR, NT><<<grid, NT, smem, ctx->stream>>>(a2, img);                \
+  } while (0)
+      if (a.d % 8 == 0) GM_LAUNCH(true);
+      else GM_LAUNCH(false);
+#undef GM_LAUNCH
+      PBX_LAUNCH_CHECK(ctx);
+      return PBX_OK;
+    }
   }
+  const size_t smem = ((size_t)DP * 4 * (DQ + 2) + 4 * DP) * sizeof(double);
+#define GB_LAUNCH(SR)                                                                          \
+  do {                                                                                         \
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_kernel<DQ, SR, false, NT>,                         \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    gibbs_mvn_kernel<DQ, SR, false, NT><<<grid, NT, smem, ctx->stream>>>(a);                   \
+  } while (0)
+  if constexpr (DQ == 1) {
+    if (sweep_rec) GB_LAUNCH(true);
+    else GB_LAUNCH(false);
+  } else {
+    GB_LAUNCH(false);
+  }
+#undef GB_LAUNCH
   PBX_LAUNCH_CHECK(ctx);
   return PBX_OK;
 }
@@ -360,7 +669,11 @@ extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
               "pbx_gibbs_mvn_run: out_prob needs out_x and the whitening matrix");
   PBX_CUDA(cudaSetDevice(ctx->device));
   const int d = p->n_dims;
-  int rc = pbx_ws_reserve(ctx, (size_t)d * 8);
+  int rc = gibbs_init_ndtab(ctx);
+  if (rc) return rc;
+  // c0 [d] + the tensor-core kernel's model image (largest: d = 128), reserved in one go so
+  // that the launcher's own reserve never moves the workspace under the c0 kernel
+  rc = pbx_ws_reserve(ctx, 4096 + gibbs_mma_model_doubles<32>() * sizeof(double));
   if (rc) return rc;
   double* c0 = (double*)ctx->ws;
   GibbsArgs a;
@@ -389,5 +702,43 @@ extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
     }
   }
   PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  return PBX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the table-driven ndtri on its own: device evaluation over an array (accuracy tests) and the
+// host mirror of the same arithmetic (usable without a GPU)
+// ---------------------------------------------------------------------------
+__global__ void ndtri_array_kernel(const double* __restrict__ u, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = gibbs_ndtri(u[i]);
+}
+
+extern "C" int pbx_ndtri(pbx_ctx* ctx, const double* u, int64_t n, double* out) {
+  PBX_REQUIRE(ctx && u && out && n >= 0, "pbx_ndtri: bad argument");
+  PBX_CUDA(cudaSetDevice(ctx->device));
+  int rc = gibbs_init_ndtab(ctx);
+  if (rc) return rc;
+  PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  if (n > 0) {
+    ndtri_array_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(u, n, out);
+    PBX_LAUNCH_CHECK(ctx);
+  }
+  PBX_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  return PBX_OK;
+}
+
+extern "C" int pbx_ndtri_host(const double* u, int64_t n, double* out) {
+  if (!u || !out || n < 0) {
+    pbx_set_error("pbx_ndtri_host: bad argument");
+    return PBX_ERR_INVALID;
+  }
+  static double* h_tab = nullptr;
+  if (!h_tab) {
+    double* t = new double[NDT_ROWS * NDT_NCOEF];
+    ndt_build_table(t);
+    h_tab = t;
+  }
+  for (int64_t i = 0; i < n; ++i) out[i] = ndt_eval_host(h_tab, u[i]);
   return PBX_OK;
 }

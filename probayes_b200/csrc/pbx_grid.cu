@@ -636,7 +636,9 @@ __global__ void grid_rescale_sumexp_kernel(const double* lmax, const double* gma
 #define P2_THREADS 256
 #define P2_WARPS (P2_THREADS / 32)
 #define P2_COLS (P2_THREADS * P2_CPT)
+#ifndef P2_RU
 #define P2_RU 4                         // rows per tile = rows in flight per thread
+#endif
 
 // kLinear: the input (and the output) are linear-pscale probabilities: post = p / max(tiny,
 // sum) (pd.py:285-295 without the log/exp round trip), marginals = plain sums.
@@ -741,11 +743,12 @@ __global__ void __launch_bounds__(P2_THREADS)
       }
       w[u] = (q[0] + q[1]) + (q[2] + q[3]);
     }
-    // the four row sums of the warp's 128 columns in 6 exchanges instead of 20: fold the
-    // rows onto lane groups first (lanes 16+ keep rows 2, 3; then bit 3 picks the odd row),
-    // then a 3-step butterfly inside each group of 8 lanes.  Row u ends up in lane 8 u.
+    // the row sums of the warp's 128 columns: fold the rows onto lane groups first (4 rows:
+    // lanes 16+ keep rows 2, 3; then bit 3 picks the odd row -- 6 exchanges instead of 20),
+    // then a butterfly inside each group.  Row u ends up in lane (32 / P2_RU) u.
     {
       const bool up = (lane & 16) != 0;
+#if P2_RU == 4
       double k0 = up ? w[2] : w[0], k1 = up ? w[3] : w[1];
       const double a0 = up ? w[0] : w[2], a1 = up ? w[1] : w[3];
       k0 += __shfl_xor_sync(0xffffffffu, a0, 16);
@@ -754,11 +757,19 @@ __global__ void __launch_bounds__(P2_THREADS)
       double kk = up2 ? k1 : k0;
       const double ss = up2 ? k0 : k1;
       kk += __shfl_xor_sync(0xffffffffu, ss, 8);
+#elif P2_RU == 2
+      double kk = up ? w[1] : w[0];
+      const double ss = up ? w[0] : w[1];
+      kk += __shfl_xor_sync(0xffffffffu, ss, 16);
+      kk += __shfl_xor_sync(0xffffffffu, kk, 8);
+#else
+#error "P2_RU must be 2 or 4"
+#endif
       kk += __shfl_xor_sync(0xffffffffu, kk, 4);
       kk += __shfl_xor_sync(0xffffffffu, kk, 2);
       kk += __shfl_xor_sync(0xffffffffu, kk, 1);
-      const int m = m0 + (lane >> 3);
-      if ((lane & 7) == 0 && (kFull || m < M))
+      const int m = m0 + lane / (32 / P2_RU);
+      if ((lane & (32 / P2_RU - 1)) == 0 && (kFull || m < M))
         row_partial[(int64_t)m * rp_stride + cblk * P2_WARPS + warp] = kk;
     }
   }

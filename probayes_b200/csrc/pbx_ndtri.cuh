@@ -77,7 +77,6 @@ NDT_HD inline double ndt_poly(const double* c, double p) {
 }
 
 // ---- host: table generation --------------------------------------------------------------
-#ifndef __CUDA_ARCH__
 static inline long double ndt_ndtri_l(long double p) {            // 0 < p < 1
   if (p > 0.5L) return -ndt_ndtri_l(1.0L - p);
   // Acklam's rational approximation (relative error 1.15e-9), lower half
@@ -162,4 +161,3 @@ static inline double ndt_eval_host(const double* tab, double u) {
   const double x = ndt_poly(tab + (size_t)seg * NDT_NCOEF, p);
   return upper ? -x : x;
 }
-#endif

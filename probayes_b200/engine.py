@@ -549,6 +549,15 @@ class Engine:
                                            self._ptr(out)), "pbx_mvn_logpdf")
         return out
 
+    def ndtri(self, u):
+        """ndtri(u) of a device array as the Gibbs kernel evaluates it (pbx_ndtri.cuh)."""
+        u = u.contiguous()
+        self._dev(u, tuple(u.shape), "u")
+        out = self.empty(*u.shape)
+        _lib.check(self.lib.pbx_ndtri(self.ctx, self._ptr(u), u.numel(), self._ptr(out)),
+                   "pbx_ndtri")
+        return out
+
     def gibbs_mvn(self, state, cond_cov, steps, thin=1, seed=0, step0=0, chain0=0,
                   log_pscale=False, reorder=True, inj_runif=None, record=True, want_prob=True,
                   stats=False):

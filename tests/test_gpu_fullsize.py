@@ -109,7 +109,7 @@ def test_c5_full_size_sampled_chain_replay():
     X = host(out["x"])                                        # [sweeps, d, C]
     sel = np.sort(rng.choice(C, 128, replace=False))
     t = np.arange(T, dtype=np.uint64)[:, None]
-    R, _ = philox.uniform_pair(seed, t, sel.astype(np.uint64)[None, :], 0)
+    R = philox.gibbs_uniforms(seed, t, sel.astype(np.uint64)[None, :])
     ref = o.gibbs_mvn_walk(np.tile(mean, (128, 1)), R, mean, cov, lims, log_pscale=True)
     want = np.transpose(ref["x"], (0, 2, 1))[d - 1::d]        # [sweeps, d, 128]
     err = float(np.abs(X[:, :, sel] - want).max())

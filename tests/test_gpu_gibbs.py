@@ -103,7 +103,7 @@ def test_philox_replay():
     init = np.tile(mean, (C, 1))
     t = np.arange(T, dtype=np.uint64)[:, None]
     c = np.arange(C, dtype=np.uint64)[None, :]
-    R, _ = philox.uniform_pair(seed, t, c, 0)
+    R = philox.gibbs_uniforms(seed, t, c)
     ref = o.gibbs_mvn_walk(init, R, mean, cov, lims)
     state = dev(eng, init.T)
     out = eng.gibbs_mvn(state, cc, T, seed=seed)
@@ -150,3 +150,29 @@ def test_gibbs_d64_moments():
     X = host(out["x"]).transpose(1, 0, 2).reshape(d, -1)
     assert np.abs(X.mean(axis=1) - mean).max() < 0.03
     assert np.abs(np.cov(X) - cov).max() < 0.06
+
+
+def test_table_ndtri_device():
+    """pbx_ndtri on the device: the table path against scipy's ndtri and, bit for bit, against
+    the library's host mirror; the out-of-table inputs through normcdfinv (limits kept)."""
+    import ctypes as C
+    import torch
+    from scipy.special import ndtri
+    from probayes_b200 import _lib
+    eng = engine()
+    rng = np.random.default_rng(3)
+    u = np.concatenate([rng.random(1 << 20), 2.0 ** -rng.uniform(1, 63, 1 << 18),
+                        1 - 2.0 ** -rng.uniform(1, 52, 1 << 16),
+                        [0.5, 2.0 ** -53, 1 - 2.0 ** -53]])
+    got = host(eng.ndtri(dev(eng, u)))
+    ref = ndtri(u)
+    err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)
+    assert err.max() <= 3e-15, err.max()
+    hm = np.empty_like(u)
+    assert _lib.load().pbx_ndtri_host(u.ctypes.data_as(C.c_void_p), C.c_int64(len(u)),
+                                      hm.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(got, hm)
+    edge = np.array([0.0, 1.0, 2.0 ** -70, 1e-300])
+    ge = host(eng.ndtri(dev(eng, edge)))
+    assert ge[0] == -np.inf and ge[1] == np.inf
+    assert abs(ge[2] / ndtri(edge[2]) - 1) <= 1e-14 and abs(ge[3] / ndtri(edge[3]) - 1) <= 1e-14

@@ -65,3 +65,29 @@ def test_c_normreg_grid_gibbs_match_golden(lo):
     x = lo.gibbs_mvn_walk(g["init"][None], g["mean"], g["coef"], g["stdv"], g["cdfs"],
                           len(g["runif"]), runif=g["runif"][:, None])
     assert np.abs(x[0] - g["x"][-1]).max() <= 1e-11
+
+
+def test_gibbs_native_stream_c_vs_numpy():
+    """The C restatement's native Gibbs stream (two steps per Philox block: g and g + 4) is
+    the one oracle/philox.py replays: both oracles give the same trajectory."""
+    from oracle import np_oracle as o
+    from oracle import philox
+    from probayes_b200.cond_cov import CondCov
+    d, Cn, T, seed, step0, chain0 = 8, 5, 43, 77, 16, 3
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + np.eye(d)
+    mean = rng.standard_normal(d)
+    lims = np.tile([-10., 10.], (d, 1))
+    cc = CondCov(mean, cov, lims)
+    init = np.tile(mean, (Cn, 1))
+    x = lo.gibbs_mvn_walk(init, mean, cc.coef, cc.stdv, cc.cdfs, T, seed=seed, step0=step0,
+                          chain0=chain0)
+    t = (np.arange(T, dtype=np.uint64) + np.uint64(step0))[:, None]
+    c = (np.arange(Cn, dtype=np.uint64) + np.uint64(chain0))[None, :]
+    R = philox.gibbs_uniforms(seed, t, c)
+    assert R.shape == (T, Cn) and (R > 0).all() and (R < 1).all()
+    # steps g and g + 4 come from one block, different words
+    assert not np.array_equal(R[0], R[4])
+    ref = o.gibbs_mvn_walk(init, R, mean, cov, lims, start=step0)
+    assert np.abs(x - ref["x"][-1]).max() <= 1e-11
