@@ -233,19 +233,27 @@ __global__ void __launch_bounds__(NT)
 // The per-coordinate kernel above reads 8 x 128-bit of coefficients from shared memory per
 // lane per coordinate; ncu showed it bound by exactly that (50 % of the stall samples on the
 // short scoreboard, 29 % issue utilisation, FP64 pipe 17 %): 4 shared-memory wavefronts per
-// 64 useful FMAs.  Here the coordinates are taken in BLOCKS of 8 (blocked Gauss-Seidel, the
-// same sweep order and the same result up to summation order):
-//   1. S = coef[block rows] . x for the 8 chains of the warp with mma.sync.m8n8k4.f64 --
-//      D[chain][n] += A[chain][k] B[k][n], A = the register-resident state (lane (r, q) holds
-//      x[4 ks + q] of chain r: already the A-fragment layout), B = coef[8b + pi(n)][4 ks + k]
-//      from a pre-swizzled shared-memory copy (one conflict-free 64-bit load per MMA = 256
-//      FMAs).  The column permutation pi(2j) = j, pi(2j + 1) = j + 4 makes the D fragment of
-//      lane (r, q) hold exactly the two block coordinates it owns (8b + q and 8b + 4 + q).
-//   2. The 8 coordinates of the block are then resolved in order: x_t = z_t + S_t with S_t
-//      corrected by coef[t][t'] (x_t' new - x_t' old) for the block's earlier t' -- one
-//      4-lane broadcast of the owner's delta and two FMAs per coordinate.
+// 64 useful FMAs.  Here the coordinates are taken in BLOCKS of 8 and a block's eight
+// sequential updates are solved in closed form.  With C_b the block's 8 rows of the
+// coefficient matrix, split into E (columns outside the block), L / U (strictly lower /
+// upper part of its 8 x 8 diagonal block; the diagonal is 0), the Gauss-Seidel updates
+//     x_t' = z_t + E_t x_out + sum_{s < t} L_ts x_s' + sum_{s > t} U_ts x_s     t = 0..7
+// read (I - L) x' = z + E x_out + U x_blk, i.e. with M = (I - L)^-1 (unit lower triangular)
+//     x' = (M [E | U]) x + M z  =  B'_b x + M_b z
+// -- the same sweep order and the same result as the coordinate-by-coordinate recursion, up
+// to rounding.  B'_b (8 x d) and M_b (8 x 8) are built once per launch (gibbs_mma_prep_kernel),
+// so a block costs DQ + 2 tensor-core MMAs (mma.sync.m8n8k4.f64: D[chain][n] += A[chain][k]
+// B[k][n]) and nothing sequential:
+//   * A = the register-resident state: lane (r, q) holds x[4 ks + q] of chain r, which IS the
+//     A-fragment layout, and z in the same ownership for the two M_b steps;
+//   * B = B'_b / M_b pre-swizzled in shared memory, one conflict-free 64-bit load per MMA
+//     (256 FMAs).  The column permutation pi(2j) = j, pi(2j + 1) = j + 4 makes the D
+//     fragment of lane (r, q) hold exactly the two block coordinates it owns (8b + q and
+//     8b + 4 + q), so the result is written straight back into the state registers;
+//   * only the two k-steps holding the previous block's coordinates depend on it; they are
+//     issued last, so consecutive blocks overlap.
 // Draws: lane (r, q) draws for its own two coordinates of the block from ONE Philox block
-// (steps g and g + 4), table ndtri.
+// (steps g and g + 4), table ndtri from shared memory, one block ahead of the MMAs.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -253,62 +261,77 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
                : "d"(a), "d"(b));
 }
 
-#define GM_WSTRIDE 12                      // within-block coefficients per (block, q): 4 + 8
-
 // the model in the kernel's shared-memory layout:
-//   [NB][DQ][32] B fragments | [NB][4][12] within-block coefficients | c0, sd, lo, w [DP] each
+//   [NB][DQ][32] B'_b fragments | [NB][2][32] M_b fragments | c0, sd, lo, w [DP] each
 template <int DQ>
 __host__ __device__ constexpr size_t gibbs_mma_model_doubles() {
-  return (size_t)(DQ / 2) * DQ * 32 + (size_t)(DQ / 2) * 4 * GM_WSTRIDE + 4 * (4 * DQ);
+  return (size_t)(DQ / 2) * DQ * 32 + (size_t)(DQ / 2) * 64 + 4 * (4 * DQ);
 }
 
-// builds that image once per launch in the workspace (the first version gathered it from the
-// row-major inputs in every CTA's prologue: 0.06 ms per launch at 1024 CTAs)
+// builds that image once per launch in the workspace: one CTA per block of 8 coordinates
 template <int DQ>
-__global__ void gibbs_mma_prep_kernel(const GibbsArgs a, double* __restrict__ img) {
+__global__ void __launch_bounds__(256) gibbs_mma_prep_kernel(const GibbsArgs a,
+                                                             double* __restrict__ img) {
   constexpr int DP = 4 * DQ, NB = DQ / 2;
-  constexpr int nB = NB * DQ * 32, nW = NB * 4 * GM_WSTRIDE;
-  const int d = a.d;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nB + nW + 4 * DP;
-       idx += gridDim.x * blockDim.x) {
+  const int d = a.d, b = blockIdx.x, tid = threadIdx.x;
+  __shared__ double sM[8][8];
+  auto coef = [&](int row, int col) -> double {
+    return (row < d && col < d) ? a.coef[(int64_t)row * d + col] : 0.0;
+  };
+  if (tid < 8) {                       // column tid of M = (I - L)^-1 by forward substitution
+    for (int i = 0; i < 8; ++i) {
+      double v = (i == tid) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) v = fma(coef(8 * b + i, 8 * b + k), sM[k][tid], v);
+      sM[i][tid] = v;
+    }
+  }
+  __syncthreads();
+  double* imgB = img + (size_t)b * DQ * 32;
+  for (int idx = tid; idx < DQ * 32; idx += 256) {
+    const int T = idx & 31, ks = idx >> 5, n = T >> 2;
+    const int i = (n >> 1) + 4 * (n & 1), col = 4 * ks + (T & 3);
+    const int jb = col - 8 * b;                           // position inside the block, if any
     double v = 0.0;
-    if (idx < nB) {
-      const int T = idx & 31, ks = (idx >> 5) % DQ, b = idx / (32 * DQ);
-      const int n = T >> 2;
-      const int row = 8 * b + (n >> 1) + 4 * (n & 1), col = 4 * ks + (T & 3);
-      if (row < d && col < d) v = a.coef[(int64_t)row * d + col];
-    } else if (idx < nB + nW) {
-      const int j = idx - nB;
-      const int e = j % GM_WSTRIDE, qq = (j / GM_WSTRIDE) & 3, b = j / (4 * GM_WSTRIDE);
-      // e < 4: row 8b + qq, earlier coordinate t = e (t < qq); e >= 4: row 8b + 4 + qq, t = e - 4
-      const int row = (e < 4) ? 8 * b + qq : 8 * b + 4 + qq;
-      const int t = (e < 4) ? e : e - 4;
-      const bool earlier = (e < 4) ? (t < qq) : (t < 4 + qq);
-      const int col = 8 * b + t;
-      if (earlier && row < d && col < d) v = a.coef[(int64_t)row * d + col];
-    } else {
-      const int j = idx - nB - nW, which = j / DP, i = j % DP;
+    for (int k = 0; k < 8; ++k) {
+      const bool lower_or_diag = jb >= 0 && jb < 8 && jb <= k;    // L and the diagonal: dropped
+      if (!lower_or_diag) v = fma(sM[i][k], coef(8 * b + k, col), v);
+    }
+    imgB[idx] = v;
+  }
+  double* imgM = img + (size_t)NB * DQ * 32 + (size_t)b * 64;
+  for (int idx = tid; idx < 64; idx += 256) {
+    const int T = idx & 31, ks = idx >> 5, n = T >> 2;
+    const int i = (n >> 1) + 4 * (n & 1), k = 4 * ks + (T & 3);
+    imgM[idx] = sM[i][k];
+  }
+  if (b == 0) {
+    double* par = img + (size_t)NB * DQ * 32 + (size_t)NB * 64;
+    for (int j = tid; j < 4 * DP; j += 256) {
+      const int which = j / DP, i = j % DP;
+      double v = 0.0;
       if (i < d)
         v = which == 0 ? a.c0[i] : which == 1 ? a.stdv[i] : which == 2 ? a.cdf_lo[i]
                                                           : a.cdf_hi[i] - a.cdf_lo[i];
+      par[j] = v;
     }
-    img[idx] = v;
   }
 }
 
+#ifndef GM_MINB
+#define GM_MINB 2
+#endif
 template <int DQ, bool kPair, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, (DQ <= 16 ? GM_MINB * (256 / NT) : 1))
     gibbs_mvn_mma_kernel(const GibbsArgs a, const double* __restrict__ img) {
   constexpr int DP = 4 * DQ, NB = DQ / 2;
   extern __shared__ __align__(16) double sm[];
-  double* s_B = sm;                          // [NB][DQ][32]   B fragments
-  double* s_W = s_B + NB * DQ * 32;          // [NB][4][12]    within-block coefficients
-  double* s_c0 = s_W + NB * 4 * GM_WSTRIDE;  // [DP]
+  double* s_B = sm;                          // [NB][DQ][32]   B'_b fragments
+  double* s_M = s_B + NB * DQ * 32;          // [NB][2][32]    M_b fragments
+  double* s_c0 = s_M + NB * 64;              // [DP]
   double* s_sd = s_c0 + DP;
   double* s_lo = s_sd + DP;
   double* s_w = s_lo + DP;                   // hi - lo
-  double* s_z = s_w + DP;                    // [DQ][NT]  the sweep's draws, z[mm][thread]
-  double* s_nd = s_z + DQ * NT;              // [8][NDT_HOT_ROWS]  hot ndtri rows, transposed
+  double* s_nd = s_w + DP;                   // [8][NDT_HOT_ROWS]  hot ndtri rows, transposed
   {
     constexpr int n2 = (int)(gibbs_mma_model_doubles<DQ>() / 2);
     const double2* src = reinterpret_cast<const double2*>(img);
@@ -326,7 +349,6 @@ __global__ void __launch_bounds__(NT)
   const bool valid = c_raw < C;
   const int64_t c = valid ? c_raw : C - 1;          // clamp: idle lanes stay in the MMAs
   const uint32_t gchain = (uint32_t)(a.chain0 + c);
-  double* my_z = s_z + threadIdx.x;
 
   double x[DQ];
 #pragma unroll
@@ -338,92 +360,86 @@ __global__ void __launch_bounds__(NT)
   const int64_t k_begin = a.step0, k_end = a.step0 + a.T;
   int until_rec = a.thin;
   int64_t rec = 0;
-  for (int64_t sweep = k_begin / d; sweep * d < k_end; ++sweep) {
-    // ---- phase A: the sweep's DQ draws of this lane (coordinates 4 mm + q), state
-    // independent and BRANCH-FREE so that the Philox rounds, table loads and polynomials of
-    // all of them interleave.  The table rows come from the shared-memory copy of the 10
-    // binades nearest 0.5 with a clamped index (a first version gathered the 64-byte rows
-    // from global memory: 27 L1 sectors per request made the L1 the bottleneck); the 0.1 %
-    // of arguments outside them leave u in the slot, are flagged and redone afterwards from
-    // the full table (or, outside it, normcdfinv)
+
+  // The two draws of this lane for block b of sweep sw (coordinates 8b + q and 8b + 4 + q):
+  // state independent and BRANCH-FREE.  The table rows come from the shared-memory copy of
+  // the 10 binades nearest 0.5 with a clamped index (a first version gathered the 64-byte
+  // rows from global memory: 27 L1 sectors per request made the L1 the bottleneck); for the
+  // 0.1 % of arguments outside them the draw returns u itself and a flag bit, and the caller
+  // finishes it with draw_fix (full table or, outside it, normcdfinv).
+  auto draw_pair = [&](int64_t sw, int b, double& z0, double& z1) -> unsigned {
+    const int i0 = 8 * b + q, i1 = i0 + 4;
+    const int64_t g0 = sw * d + i0, g1 = g0 + 4;
+    double r0, r1;
+    if (a.inj_runif) {
+      r0 = (i0 < d && g0 < k_end) ? a.inj_runif[(g0 - k_begin) * C + c] : 0.5;
+      r1 = (i1 < d && g1 < k_end) ? a.inj_runif[(g1 - k_begin) * C + c] : 0.5;
+    } else if (kPair) {
+      const pbx_u4 blk = pbx_block(a.seed, (uint64_t)g0, gchain, 0u);       // bit 2 of g0 clear
+      r0 = pbx_u52(blk.x, blk.y);
+      r1 = pbx_u52(blk.z, blk.w);
+    } else {
+      const pbx_u4 b0 = pbx_block(a.seed, (uint64_t)g0 & ~(uint64_t)4, gchain, 0u);
+      const pbx_u4 b1 = pbx_block(a.seed, (uint64_t)g1 & ~(uint64_t)4, gchain, 0u);
+      r0 = gibbs_uniform(b0, g0);
+      r1 = gibbs_uniform(b1, g1);
+    }
     unsigned bad = 0u;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const int i0 = 8 * b + q, i1 = i0 + 4;
-      const int64_t g0 = sweep * d + i0, g1 = g0 + 4;
-      double r0, r1;
-      if (a.inj_runif) {
-        r0 = (i0 < d) ? a.inj_runif[(g0 - k_begin) * C + c] : 0.5;
-        r1 = (i1 < d) ? a.inj_runif[(g1 - k_begin) * C + c] : 0.5;
-      } else if (kPair) {
-        const pbx_u4 blk = pbx_block(a.seed, (uint64_t)g0, gchain, 0u);     // bit 2 of g0 clear
-        r0 = pbx_u52(blk.x, blk.y);
-        r1 = pbx_u52(blk.z, blk.w);
-      } else {
-        const pbx_u4 b0 = pbx_block(a.seed, (uint64_t)g0 & ~(uint64_t)4, gchain, 0u);
-        const pbx_u4 b1 = pbx_block(a.seed, (uint64_t)g1 & ~(uint64_t)4, gchain, 0u);
-        r0 = gibbs_uniform(b0, g0);
-        r1 = gibbs_uniform(b1, g1);
-      }
+    for (int h = 0; h < 2; ++h) {
+      const int i = h ? i1 : i0;
+      const double u = s_lo[i] + s_w[i] * (h ? r1 : r0);
+      const bool upper = u > 0.5;
+      const double p = upper ? 1.0 - u : u;                    // exact for u > 0.5
+      const unsigned seg = ndt_segment(p) - (unsigned)NDT_HOT0;     // wraps below the hot rows
+      const bool cold = seg >= (unsigned)NDT_HOT_ROWS;
+      if (cold && i < d) bad |= 1u << h;
+      const double* row = s_nd + min(seg, (unsigned)(NDT_HOT_ROWS - 1));
+      double cf[NDT_NCOEF];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int i = h ? i1 : i0;
-        const double u = s_lo[i] + s_w[i] * (h ? r1 : r0);
-        const bool upper = u > 0.5;
-        const double p = upper ? 1.0 - u : u;                  // exact for u > 0.5
-        const unsigned seg = ndt_segment(p) - (unsigned)NDT_HOT0;   // wraps below the hot rows
-        const bool cold = seg >= (unsigned)NDT_HOT_ROWS;
-        if (cold && i < d) bad |= 1u << (2 * b + h);
-        const double* row = s_nd + min(seg, (unsigned)(NDT_HOT_ROWS - 1));
-        double cf[NDT_NCOEF];
-#pragma unroll
-        for (int j = 0; j < NDT_NCOEF; ++j) cf[j] = row[j * NDT_HOT_ROWS];
-        const double xn = ndt_poly(cf, p);
-        const double z = (upper ? -xn : xn) * s_sd[i] + s_c0[i];
-        my_z[(2 * b + h) * NT] = (i < d) ? (cold ? u : z) : 0.0;
-      }
+      for (int j = 0; j < NDT_NCOEF; ++j) cf[j] = row[j * NDT_HOT_ROWS];
+      const double xn = ndt_poly(cf, p);
+      const double z = (upper ? -xn : xn) * s_sd[i] + s_c0[i];
+      (h ? z1 : z0) = (i < d) ? (cold ? u : z) : 0.0;
     }
-    while (bad) {                                              // arguments outside the hot rows
-      const int mm = __ffs(bad) - 1;
-      bad &= bad - 1u;
-      const int i = 4 * mm + q;
-      my_z[mm * NT] = gibbs_ndtri(my_z[mm * NT]) * s_sd[i] + s_c0[i];
-    }
-    // ---- phase B: the blocks in order.  One basic block: the MMAs of block b + 1 that do
-    // not read the two state registers block b rewrites are free to overlap block b's chain.
+    return bad;
+  };
+  auto draw_fix = [&](unsigned bad, int b, double& z0, double& z1) {
+    const int i0 = 8 * b + q, i1 = i0 + 4;
+    if (bad & 1u) z0 = gibbs_ndtri(z0) * s_sd[i0] + s_c0[i0];
+    if (bad & 2u) z1 = gibbs_ndtri(z1) * s_sd[i1] + s_c0[i1];
+  };
+
+  // Software pipeline: the draws of the NEXT block (of the next sweep after the last block)
+  // are computed in the same basic block as the current block's MMAs and 8-step chain, whose
+  // dependency stalls they fill -- 4 warps per scheduler do not hide them otherwise.
+  double z0, z1;
+  unsigned bad = draw_pair(k_begin / d, 0, z0, z1);
+  for (int64_t sweep = k_begin / d; sweep * d < k_end; ++sweep) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      // S = coef[block] . x on the tensor cores (two accumulator chains)
-      double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+      if (bad) draw_fix(bad, b, z0, z1);                         // practically never
+      double zn0, zn1;
+      const unsigned badn = (b + 1 < NB) ? draw_pair(sweep, b + 1, zn0, zn1)
+                                         : draw_pair(sweep + 1, 0, zn0, zn1);
+      // x'_blk = B'_b x + M_b z on the tensor cores: M_b z first (state independent), then two
+      // accumulator chains over the state, the k-steps of the previous block's coordinates last
+      double m0 = 0.0, m1 = 0.0, e0 = 0.0, e1 = 0.0;
+      const double* mf = s_M + b * 64 + lane;
+      dmma_m8n8k4(m0, m1, z0, mf[0]);
+      dmma_m8n8k4(m0, m1, z1, mf[32]);
       const double* bf = s_B + (b * DQ) * 32 + lane;
 #pragma unroll
       for (int kk = 0; kk < DQ; kk += 2) {
-        // the k-steps holding the previous block's coordinates last
         const int ks = (b == 0) ? kk : (kk + 2 * b) % DQ;
-        dmma_m8n8k4(e0, e1, x[ks], bf[ks * 32]);
-        dmma_m8n8k4(f0, f1, x[ks + 1], bf[(ks + 1) * 32]);
+        dmma_m8n8k4(m0, m1, x[ks], bf[ks * 32]);
+        dmma_m8n8k4(e0, e1, x[ks + 1], bf[(ks + 1) * 32]);
       }
-      double Sa = (e0 + f0) + my_z[(2 * b) * NT], Sb = (e1 + f1) + my_z[(2 * b + 1) * NT];
-      const double xa_old = x[2 * b], xb_old = x[2 * b + 1];
-      // the block's 8 coordinates in order
-      const double2* wv = reinterpret_cast<const double2*>(s_W + (b * 4 + q) * GM_WSTRIDE);
-      double W[GM_WSTRIDE];
-#pragma unroll
-      for (int j = 0; j < GM_WSTRIDE / 2; ++j) {
-        const double2 t2 = wv[j];
-        W[2 * j] = t2.x;
-        W[2 * j + 1] = t2.y;
-      }
-      const int grp = lane & ~3;
-#pragma unroll
-      for (int t = 0; t < 7; ++t) {
-        const double mine = (t < 4) ? Sa - xa_old : Sb - xb_old;   // the owner's is final
-        const double delta = __shfl_sync(0xffffffffu, mine, grp | (t & 3));
-        if (t < 3) Sa = fma(W[t], delta, Sa);                      // W = 0 unless t precedes mine
-        Sb = fma(W[4 + t], delta, Sb);
-      }
-      x[2 * b] = Sa;
-      x[2 * b + 1] = Sb;
+      x[2 * b] = m0 + e0;
+      x[2 * b + 1] = m1 + e1;
+      z0 = zn0;
+      z1 = zn1;
+      bad = badn;
     }
     until_rec -= d;
     if (until_rec == 0) {
@@ -608,7 +624,7 @@ static int gibbs_launch_nt(pbx_ctx* ctx, const GibbsArgs& a) {
   if constexpr (DQ >= 2) {
     if (sweep_rec) {                       // whole sweeps: conditional means on the tensor cores
       const size_t model = gibbs_mma_model_doubles<DQ>();
-      const size_t smem = (model + (size_t)DQ * NT + NDT_NCOEF * NDT_HOT_ROWS) * sizeof(double);
+      const size_t smem = (model + NDT_NCOEF * NDT_HOT_ROWS) * sizeof(double);
       // workspace: [c0 (d doubles, padded to 256 B)] [model image]
       const size_t off = ((size_t)a.d * 8 + 255) / 256 * 256;
       int rc = pbx_ws_reserve(ctx, off + model * sizeof(double));
@@ -616,7 +632,7 @@ static int gibbs_launch_nt(pbx_ctx* ctx, const GibbsArgs& a) {
       GibbsArgs a2 = a;
       a2.c0 = (const double*)ctx->ws;                   // (the reserve above may have moved it)
       double* img = (double*)((char*)ctx->ws + off);
-      gibbs_mma_prep_kernel<DQ><<<(int)((model + 255) / 256), 256, 0, ctx->stream>>>(a2, img);
+      gibbs_mma_prep_kernel<DQ><<<DQ / 2, 256, 0, ctx->stream>>>(a2, img);
       PBX_LAUNCH_CHECK(ctx);
 #define GM_LAUNCH(PR)                                                                          \
   do {                                                                                         \
