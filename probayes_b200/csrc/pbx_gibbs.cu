@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) gibbs_mma_prep_kernel(const GibbsArgs a,
 #define GM_MINB 2
 #endif
 template <int DQ, bool kPair, int NT>
-__global__ void __launch_bounds__(NT, (DQ <= 16 ? GM_MINB * (256 / NT) : 1))
+__global__ void __launch_bounds__(NT, (DQ <= 16 ? (NT <= 128 ? 2 * GM_MINB : GM_MINB) : 1))
     gibbs_mvn_mma_kernel(const GibbsArgs a, const double* __restrict__ img) {
   constexpr int DP = 4 * DQ, NB = DQ / 2;
   extern __shared__ __align__(16) double sm[];

@@ -20,9 +20,10 @@ New keyword arguments of ``sampler`` (everything else keeps its meaning):
   inj_delta=, inj_thresh=   injected proposal / threshold streams ([T, D] or
                 [T, C, D] and [T] or [T, C]) for bit-parity runs
   host_stream=True   stream samples straight into pinned host buffers (K1)
-  host_buffers=dict  (with host_stream) a dict the sampler fills with its pinned
-                buffers and reuses on later walks / other samplers of the same shape;
-                the returned arrays are then views into them
+  host_buffers=dict  a dict the sampler fills with its pinned host buffers and reuses on
+                later walks / other samplers of the same shape (the streamed K1 outputs
+                with host_stream, the final device-to-host copy of samples and densities
+                otherwise); the returned arrays are then views into them
   inj_unif=     injected prior draws [T, P] for ordinary Monte Carlo random sampling
   suffstat=True (opt-in, normal-likelihood targets) evaluate the likelihood from centred
                 sufficient statistics of the observations: one reduction over the data,
@@ -489,7 +490,7 @@ class SP(SD):
                                 chain0=chain0, log_pscale=spec['log_pscale'],
                                 inj_runif=inj_t)
             res.update(x=out['x'], prob=out['prob'], accept_count=None, accept=None, score=None)
-            return self._finish(res, eng)
+            return self._finish(res, eng, opts.get('host_buffers'))
         prop = catalogue.identify_proposal(self._proposal_rf(), self._pscale, injected)
         coef = prop['coef'] if self._scores == 'hastings' else 1.0
         if spec['kind'] == 'mvn':
@@ -557,7 +558,7 @@ class SP(SD):
                    accept=out.get('accept'), score=out.get('score'),
                    xprop=out.get('xprop'), pprop=out.get('pprop'),
                    stat_sum=out.get('stat_sum'), stat_sumsq=out.get('stat_sumsq'))
-        return self._finish(res, eng)
+        return self._finish(res, eng, opts.get('host_buffers'))
 
     @staticmethod
     def _host_bufs(opts, R, D, C):
@@ -574,16 +575,36 @@ class SP(SD):
         return dict(out_x=cache['x'], out_prob=cache['prob'])
 
     @staticmethod
-    def _finish(res, eng):
-        """Device results -> host arrays ([R, D, C] / [R, C])."""
-        def host(a):
+    def _finish(res, eng, cache=None):
+        """Device results -> host arrays ([R, D, C] / [R, C]).  With the user-supplied
+        ``host_buffers`` dict the two large arrays (samples, densities) go through pinned
+        buffers kept in it (asynchronous copies at PCIe rate instead of a pageable staging
+        copy into freshly faulted memory); the arrays returned then alias those buffers
+        until the next walk that uses the same dict."""
+        import torch
+        pinned = {}
+
+        def host(k, a):
             if a is None or isinstance(a, np.ndarray):
                 return a
+            if cache is not None and k in ('x', 'prob') and a.numel() > 0:
+                key = ('finish', k, tuple(a.shape), str(a.dtype))
+                buf = cache.get(key)
+                if buf is None:
+                    buf = cache[key] = torch.empty(tuple(a.shape), dtype=a.dtype, pin_memory=True)
+                with torch.cuda.stream(eng.stream):
+                    buf.copy_(a.detach(), non_blocking=True)
+                pinned[k] = buf
+                return buf
             return a.detach().cpu().numpy()
         eng.sync()
         for k in ('x', 'prob', 'accept_count', 'accept', 'score', 'stat_sum', 'stat_sumsq',
                   'xprop', 'pprop'):
-            res[k] = host(res.get(k))
+            res[k] = host(k, res.get(k))
+        if pinned:
+            eng.sync()
+            for k, buf in pinned.items():
+                res[k] = buf.numpy()
         return res
 
     # ---- result marshalling --------------------------------------------------------------------------

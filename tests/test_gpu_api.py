@@ -454,3 +454,36 @@ def test_omc_rejection_sp_circle(explicit):
     area = 4. * radius**2 * big.p.size / 2_000_000
     assert abs(area - np.pi * radius**2) < 6e-3               # ~ 5 sigma of the MC error
     assert (big.p['x']**2 + big.p['y']**2 <= radius**2).all()
+
+
+def test_host_buffers_on_the_gibbs_and_likelihood_paths():
+    """host_buffers=dict without host_stream: the final device-to-host copy of samples and
+    densities goes through pinned buffers kept in the dict; same values as the plain path,
+    the buffers are reused by the next walk of the same shape."""
+    engine()
+    d = 16
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((d, d))
+    cov = A @ A.T / d + np.eye(d)
+    mean = rng.standard_normal(d)
+    rvs = [pb.RV('x%d' % i, vtype=float, vset=(-10., 10.)) for i in range(d)]
+    import functools
+    process = pb.SP(functools.reduce(lambda a, b: a & b, rvs))
+    process.set_prob(scipy.stats.multivariate_normal, mean, cov)
+    process.set_tran(scipy.stats.multivariate_normal, mean, cov, tsteps=1)
+    process.set_scores('gibbs')
+    init = {'x%d' % i: float(mean[i]) for i in range(d)}
+    kw = dict(stop=5 * d, chains=200, thin=d, seed=3)
+    plain = process(process.walk(process.sampler(init, **kw)))
+    bufs = {}
+    a = process(process.walk(process.sampler(init, host_buffers=bufs, **kw)))
+    assert len(bufs) == 2 and all(t.is_pinned() for t in bufs.values())
+    for k in init:
+        assert np.array_equal(a.v[k], plain.v[k])
+    assert np.array_equal(a.v.prob, plain.v.prob)
+    ptrs = sorted(t.data_ptr() for t in bufs.values())
+    keep = {k: a.v[k].copy() for k in init}
+    b = process(process.walk(process.sampler(init, host_buffers=bufs, stop=5 * d, chains=200,
+                                             thin=d, seed=4)))
+    assert sorted(t.data_ptr() for t in bufs.values()) == ptrs          # reused, not regrown
+    assert not np.array_equal(b.v['x0'], keep['x0'])                      # a different walk

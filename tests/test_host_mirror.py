@@ -405,7 +405,7 @@ def test_table_ndtri_host_mirror_against_scipy():
     ref = ndtri(u)
     err = np.abs(out - ref) / np.maximum(np.abs(ref), 1e-3)
     assert err.max() <= 3e-15, err.max()      # scipy itself is ~1e-15 here and there
-    assert np.quantile(err, 0.999) <= 6e-16
+    assert np.quantile(err, 0.999) <= 1e-15
     assert out[len(u) - 7] == 0.0                                   # ndtri(0.5)
     bad = np.array([0.0, 1.0, 2.0 ** -70, -0.1, 1.5, np.nan])
     ob = np.empty_like(bad)
