@@ -318,6 +318,60 @@ def dgei(seed, N, M, S):
 
 
 # ---------------------------------------------------------------------------
+def pd_serialise(seed, N, M, S):
+    """probayes/pd_utils.py:433-553: the dict form (serialise / deserialise) of a DGEI joint
+    (two array keys + the set-valued iid key), its posterior and a marginal, and what the
+    reference's own write_serialised stores -- driven through tests/fake_h5py.py (h5py is
+    not installed; the reference imports whatever module is called h5py).  The stored
+    structure is recorded as JSON."""
+    import json
+    pb = ref_shim.load()
+    sys.path.insert(0, os.path.join(os.path.dirname(OUT)))
+    import fake_h5py
+    import probayes.pd_utils as rpu
+    rng = np.random.default_rng(seed)
+    data = rng.normal(50., 10., size=N)
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    model = pb.SD(pb.RF(x), pb.RF(mu, sigma))
+    model.set_prob(scipy.stats.norm.logpdf,
+                   order={'x': 0, 'mu': 'loc', 'sigma': 'scale'}, pscale='log')
+    joint = model({x: data, 'mu': {M}, 'sigma': {S}}, iid=True, joint=True)
+    posterior = joint.conditionalise('x')
+    post_mu = posterior.marginal('mu').rescaled()
+    old = rpu.h5py
+    rpu.h5py = fake_h5py
+    try:
+        out = {}
+        for tag, pd in (("joint", joint), ("posterior", posterior), ("post_mu", post_mu)):
+            ser = rpu.serialise(pd)
+            (name, d), = ser.items()
+            path = "ref_" + tag
+            aux = {"aux data": {"obs": data}} if tag == "joint" else {}
+            out[tag + "_name"] = np.array(name)
+            out[tag + "_keys"] = np.array(json.dumps([k for k in d.keys()]))
+            out[tag + "_dims"] = np.array(json.dumps({k: None if v is None else int(v)
+                                                      for k, v in pd.dims.items()}))
+            # (the reference's writer rewrites None dims to 'None' IN the PD's own dims dict,
+            # pd_utils.py:480-483: write a deep copy)
+            import copy
+            rpu.write_serialised(path, copy.deepcopy(ser), aux)
+            back, = rpu.read_dist(path)
+            out[tag + "_pscale_is_log"] = np.array(bool(np.iscomplexobj(pd.pscale)))
+            out[tag + "_prob"] = np.asarray(pd.prob)
+            out[tag + "_file"] = np.array(json.dumps(
+                fake_h5py.dump(path), default=lambda o: o.item() if hasattr(o, "item") else str(o)))
+            out[tag + "_back_name"] = np.array(back.name)
+            out[tag + "_back_prob"] = np.asarray(back.prob)
+    finally:
+        rpu.h5py = old
+    out.update(data=data, mu=np.ravel(joint['mu']), sigma=np.ravel(joint['sigma']))
+    return out
+
+
+# ---------------------------------------------------------------------------
 def omc_rs_norm1d(seed, N, T):
     """examples/omc/omc_rs_sp_norm1d.py:17-52 with the prior draws injected:
     random sampling of (mu, sigma) through SP.sampler without a proposal, the
@@ -586,6 +640,7 @@ def main():
         "condcov_d8": lambda: condcov_bare(52, 8, 160),
         "condcov_d64": lambda: condcov_bare(53, 64, 256),
         "pscales": pscales_table,
+        "pd_serialise": lambda: pd_serialise(73, 30, 7, 5),
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

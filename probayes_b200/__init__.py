@@ -17,6 +17,8 @@ from .sd import SD
 from .sp import SP, MCMC_SAMPLERS, Walk, Sampler, AcceptRecord
 from .pd import PD, product
 from .cond_cov import CondCov
+from .serial import (serialise, deserialise, write_serialised, read_serialised, write_dist,
+                     read_dist)
 from . import catalogue
 from .catalogue import NormalRegression, BallIndicator, NormalProduct, BoxUniform
 from ._lib import PbxError

@@ -638,6 +638,17 @@ class PD(collections.OrderedDict):
         prob = div_prob(self.prob, divp, self._pscale, other.pscale)
         return self._new(name, vals, dims, prob)
 
+    def serialise(self):
+        """{short name: {key: value, ..., 'attrs': dims, 'prob': prob, 'pscale':
+        pscale}} (distribution.py:286-290, pd.py:698-703); a device-backed ``prob`` is copied
+        to the host."""
+        name = self.short_name
+        d = {key: val for key, val in self.items()}
+        d['attrs'] = self.dims
+        d['prob'] = self.prob
+        d['pscale'] = self.pscale
+        return {name: d}
+
     def __repr__(self):
         return "PD({!r}, shape={}, pscale={})".format(self._name, self._shape, self._pscale)
 

@@ -487,3 +487,46 @@ def test_host_buffers_on_the_gibbs_and_likelihood_paths():
                                              thin=d, seed=4)))
     assert sorted(t.data_ptr() for t in bufs.values()) == ptrs          # reused, not regrown
     assert not np.array_equal(b.v['x0'], keep['x0'])                      # a different walk
+
+
+def test_device_backed_pds_serialise(monkeypatch):
+    """Row f4: the DGEI results (device-backed PDs) through serialise / the HDF5 writer
+    (h5py stand-in, tests/fake_h5py.py): names, keys and the stored structure as the live
+    reference's for the same model (tests/golden/pd_serialise.npz)."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fake_h5py
+    monkeypatch.setitem(sys.modules, 'h5py', fake_h5py)
+    engine()
+    g = load_golden("pd_serialise")
+    mu = pb.RV('mu', vtype=float, vset=(40, 60))
+    sigma = pb.RV('sigma', vtype=float, vset=(5, 20.))
+    x = pb.RV('x', vtype=float, vset={-np.inf, np.inf})
+    sigma.set_ufun((np.log, np.exp))
+    model = pb.SD(pb.RF(x), pb.RF(mu, sigma))
+    model.set_prob(scipy.stats.norm.logpdf, order={'x': 0, 'mu': 'loc', 'sigma': 'scale'},
+                   pscale='log')
+    joint = model({x: g["data"], 'mu': {len(g["mu"])}, 'sigma': {len(g["sigma"])}}, iid=True,
+                  joint=True)
+    posterior = joint.conditionalise('x')
+    post_mu = posterior.marginal('mu').rescaled()
+    assert joint.prob_device is not None
+    for tag, pd in (("joint", joint), ("posterior", posterior), ("post_mu", post_mu)):
+        (name, d), = pb.serialise(pd).items()
+        assert name == str(g[tag + "_name"])
+        assert list(d.keys()) == json.loads(str(g[tag + "_keys"]))
+        assert {k: v for k, v in d['attrs'].items()} == json.loads(str(g[tag + "_dims"]))
+        pb.write_dist("gpu_" + tag, pd)
+        want = json.loads(str(g[tag + "_file"]))
+        got = fake_h5py.dump("gpu_" + tag)
+        assert list(got.keys()) == [k for k in want if ' ' not in k]
+        for key, (kind, shape, vals, attrs) in got[name].items():
+            wk, ws, wv, wa = want[name][key]
+            assert kind == wk and list(shape) == ws and attrs == wa
+            if vals is not None and key != 'pscale':
+                tol = 1e-12 * max(1.0, np.abs(g["joint_prob"]).max())
+                assert np.abs(np.asarray(vals, dtype=float) - np.asarray(wv, dtype=float)).max() <= tol
+        back, = pb.read_dist("gpu_" + tag)
+        assert back.name == str(g[tag + "_back_name"])

@@ -67,11 +67,9 @@ def test_c_normreg_grid_gibbs_match_golden(lo):
     assert np.abs(x[0] - g["x"][-1]).max() <= 1e-11
 
 
-def test_gibbs_native_stream_c_vs_numpy():
+def test_gibbs_native_stream_c_vs_numpy(lo):
     """The C restatement's native Gibbs stream (two steps per Philox block: g and g + 4) is
     the one oracle/philox.py replays: both oracles give the same trajectory."""
-    from oracle import np_oracle as o
-    from oracle import philox
     from probayes_b200.cond_cov import CondCov
     d, Cn, T, seed, step0, chain0 = 8, 5, 43, 77, 16, 3
     rng = np.random.default_rng(4)
@@ -81,7 +79,7 @@ def test_gibbs_native_stream_c_vs_numpy():
     lims = np.tile([-10., 10.], (d, 1))
     cc = CondCov(mean, cov, lims)
     init = np.tile(mean, (Cn, 1))
-    x = lo.gibbs_mvn_walk(init, mean, cc.coef, cc.stdv, cc.cdfs, T, seed=seed, step0=step0,
+    x = lo.gibbs_mvn_walk(init, mean, cc.coef_matrix(), cc.stdv, cc.cdfs, T, seed=seed, step0=step0,
                           chain0=chain0)
     t = (np.arange(T, dtype=np.uint64) + np.uint64(step0))[:, None]
     c = (np.arange(Cn, dtype=np.uint64) + np.uint64(chain0))[None, :]
