@@ -313,12 +313,27 @@ def secondary(eng, peaks, fp64_peak, quick=False):
         out["stream_c%d" % Cs] = {"ms": ms, "hbm_gbs": gbs, "frac": gbs / peaks["hbm_gbs"],
                                   "loglik_evals_per_s": Cs / (ms * 1e-3),
                                   "terms_per_s": Cs * Ns / (ms * 1e-3)}
-    out["roofline_stream"] = {"bound": "hbm", "kernel": "nr_stream_kernel<8,true>",
-                              "achieved": out["stream_c4"]["hbm_gbs"], "peak": peaks["hbm_gbs"],
-                              "unit": "GB/s", "frac": out["stream_c4"]["frac"],
+    # the streaming MH STEP (north_star's roofline target): 4 chains, every step streams all
+    # observations once, proposal + priors + accept test + record fused into the same launch
+    Tst = 6
+    sd_st = 0.5 / np.sqrt(Ns)
+    st4 = eng.to_device(np.tile(np.array([[-1.], [1.5], [.5]]), (1, 4)))
+    ms_mh = timeit(lambda: eng.mh_normreg(st4, ys, xs, Tst, lims, ex, lg, [2.4 * sd_st] * 3,
+                                          seed=2, variant=2, record=True), reps=3, warm=1) / Tst
+    gbs_mh = 16.0 * Ns / (ms_mh * 1e-3) / 1e9
+    out["stream_mh_c4"] = {"ms_per_mh_step": ms_mh, "hbm_gbs": gbs_mh,
+                           "frac": gbs_mh / peaks["hbm_gbs"],
+                           "chain_steps_per_s": 4 / (ms_mh * 1e-3),
+                           "terms_per_s": 4 * Ns / (ms_mh * 1e-3)}
+    out["roofline_stream"] = {"bound": "hbm", "kernel": "nr_stream_kernel<8,true> (one launch "
+                                                        "per MH step, accept fused)",
+                              "achieved": gbs_mh, "peak": peaks["hbm_gbs"],
+                              "unit": "GB/s", "frac": gbs_mh / peaks["hbm_gbs"],
                               "algorithmic_bytes_per_launch": 16.0 * Ns,
-                              "workload": "streaming normal log-likelihood, 4 chains, N=%d "
-                                          "(16 B per observation per step)" % Ns}
+                              "workload": "streaming MH likelihood step, 4 chains, N=%d (16 B "
+                                          "per observation per step), %d steps per call; the "
+                                          "evaluate-only figure is secondary.stream_c4" % (Ns, Tst)}
+    del st4
     del xs, ys
     # ---- C4: DGEI 4096 x 4096 grid, N = 1e5 ---------------------------------------------
     Ng, M, S = (10_000 if quick else 100_000), 4096, 4096
@@ -1110,6 +1125,42 @@ def reference_numpy_c1():
         return {"unavailable": repr(e)}
 
 
+def reference_numpy(workload):
+    """The REAL reference (oracle/_ref) on this box's cores for the workload's config, at the
+    largest size it evaluates sensibly."""
+    if workload == "c2":
+        return reference_numpy_c1()
+    try:
+        from oracle import ref_run
+        if not ref_run.available():
+            return {"unavailable": "oracle/_ref/probayes not shipped (run oracle/ref_run.py in "
+                                   "the development container)"}
+        if workload == "c3":
+            r, dt = ref_run.c3_rate(100000, 40)
+            return {"value": r, "unit": "evals/s", "cores": 1, "kind": "oracle/_ref",
+                    "terms_per_s": r * 1e5,
+                    "sample": "gibbs_linreg model as an MH sampler through SP.sampler, 1 chain x "
+                              "40 steps, N = 100000 obs per log-likelihood evaluation (the full "
+                              "config has N = 1000000): %.2f s" % dt}
+        if workload == "c4":
+            r, tps, dt = ref_run.c4_rate(1000, 256, 256)
+            return {"value": r, "unit": "evals/s", "cores": 1, "kind": "oracle/_ref",
+                    "terms_per_s": tps,
+                    "sample": "dgei_norm1d_improved model: joint + conditionalise + both "
+                              "marginals on a 256 x 256 grid over N = 1000 obs (one eval = one "
+                              "cell = N terms; the full config has 4096 x 4096 x 100000, whose "
+                              "[N, M, S] temporary the reference cannot hold): %.2f s" % dt}
+        if workload == "c5":
+            r, dt = ref_run.c5_rate(64, 4096)
+            return {"value": r, "unit": "chain-steps/s", "cores": 1, "kind": "oracle/_ref",
+                    "sample": "CondCov.interp at d = 64, 1 chain x 4096 coordinate updates "
+                              "(cond_cov.py:42-65 as RF.eval_tfun calls it; through SP the "
+                              "reference needs one numpy axis per RV and stops at 32): %.2f s" % dt}
+    except Exception as e:                                   # diagnostics only
+        return {"unavailable": repr(e)}
+    return {"unavailable": "no reference leg for " + workload}
+
+
 def run_reference(args):
     """--impl reference: the CPU implementation of the SAME workload on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -1135,8 +1186,7 @@ def run_reference(args):
             "e2e": {"value": value, "unit": wl.unit, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    if args.workload == "c2":
-        line["cpu_baseline"]["reference_numpy"] = reference_numpy_c1()
+    line["cpu_baseline"]["reference_numpy"] = reference_numpy(args.workload)
     print(json.dumps(line), flush=True)
 
 
@@ -1209,8 +1259,7 @@ def run_ours(args):
                 r, cores, sample = wl.cpu_sample()
                 line["cpu_baseline"] = {"value": r, "unit": wl.unit, "cores": cores,
                                         "kind": "port", "sample": sample}
-                if args.workload == "c2":
-                    line["cpu_baseline"]["reference_numpy"] = reference_numpy_c1()
+                line["cpu_baseline"]["reference_numpy"] = reference_numpy(args.workload)
             except Exception as e:
                 line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)

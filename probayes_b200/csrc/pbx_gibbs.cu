@@ -22,6 +22,7 @@
 // FP64 tensor cores (mma.sync.m8n8k4.f64 -- tcgen05 has no FP64 kind), 8 chains per
 // MMA row block; smaller d uses a plain FMA kernel.
 #include <math.h>
+#include <vector>
 #include "pbx_common.cuh"
 #include "pbx_ndtri.cuh"
 
@@ -590,22 +591,32 @@ extern "C" int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int
   return PBX_OK;
 }
 
-static int gibbs_init_ndtab(pbx_ctx* ctx) {
-  if (ctx->ndtab_ready) return PBX_OK;
-  static double* h_tab = nullptr;                      // built once per process (19 ms)
-  if (!h_tab) {
-    double* t = new double[NDT_ROWS * NDT_NCOEF];
-    ndt_build_table(t);
-    h_tab = t;
-  }
-  static double* h_hot = nullptr;
-  if (!h_hot) {
-    double* t = new double[NDT_NCOEF * NDT_HOT_ROWS];
+// the host copies of the table, built once per process (19 ms; function-local statics:
+// thread-safe initialisation)
+static const double* ndt_host_table() {
+  static const std::vector<double> tab = [] {
+    std::vector<double> t((size_t)NDT_ROWS * NDT_NCOEF);
+    ndt_build_table(t.data());
+    return t;
+  }();
+  return tab.data();
+}
+static const double* ndt_host_hot_table() {
+  static const std::vector<double> hot = [] {
+    const double* h_tab = ndt_host_table();
+    std::vector<double> t((size_t)NDT_NCOEF * NDT_HOT_ROWS);
     for (int r = 0; r < NDT_HOT_ROWS; ++r)
       for (int j = 0; j < NDT_NCOEF; ++j)
-        t[j * NDT_HOT_ROWS + r] = h_tab[(size_t)(NDT_HOT0 + r) * NDT_NCOEF + j];
-    h_hot = t;
-  }
+        t[(size_t)j * NDT_HOT_ROWS + r] = h_tab[(size_t)(NDT_HOT0 + r) * NDT_NCOEF + j];
+    return t;
+  }();
+  return hot.data();
+}
+
+static int gibbs_init_ndtab(pbx_ctx* ctx) {
+  if (ctx->ndtab_ready) return PBX_OK;
+  const double* h_tab = ndt_host_table();
+  const double* h_hot = ndt_host_hot_table();
   PBX_CUDA(cudaMemcpyToSymbolAsync(g_ndtab, h_tab, sizeof(double) * NDT_ROWS * NDT_NCOEF, 0,
                                    cudaMemcpyHostToDevice, ctx->stream));
   PBX_CUDA(cudaMemcpyToSymbolAsync(g_ndhot, h_hot, sizeof(double) * NDT_NCOEF * NDT_HOT_ROWS, 0,
@@ -749,12 +760,7 @@ extern "C" int pbx_ndtri_host(const double* u, int64_t n, double* out) {
     pbx_set_error("pbx_ndtri_host: bad argument");
     return PBX_ERR_INVALID;
   }
-  static double* h_tab = nullptr;
-  if (!h_tab) {
-    double* t = new double[NDT_ROWS * NDT_NCOEF];
-    ndt_build_table(t);
-    h_tab = t;
-  }
+  const double* h_tab = ndt_host_table();
   for (int64_t i = 0; i < n; ++i) out[i] = ndt_eval_host(h_tab, u[i]);
   return PBX_OK;
 }

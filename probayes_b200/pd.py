@@ -643,7 +643,15 @@ class PD(collections.OrderedDict):
         pscale}} (distribution.py:286-290, pd.py:698-703); a device-backed ``prob`` is copied
         to the host."""
         name = self.short_name
-        d = {key: val for key, val in self.items()}
+        d = {}
+        for key, val in self.items():
+            dim = self._dims.get(key)
+            if dim is not None and self.ndim > 1 and np.ndim(val) == 1:
+                # the reference keeps grid values in their broadcast shape ([M, 1], [1, S])
+                shape = [1] * self.ndim
+                shape[dim] = -1
+                val = np.reshape(val, shape)
+            d[key] = val
         d['attrs'] = self.dims
         d['prob'] = self.prob
         d['pscale'] = self.pscale
