@@ -361,8 +361,8 @@ PBX_API int pbx_mvn_logpdf(pbx_ctx* ctx, const double* x, int32_t n_dims, int64_
                    int32_t log_pscale, double* out);
 
 /* Inverse normal CDF as the Gibbs draws evaluate it (the reference: scipy.stats.norm.ppf ==
- * ndtri, vtypes.py:186 / cond_cov.py:58-65): out[i] = ndtri(u[i]), table-driven degree-7
- * polynomials on 32 segments per binade of min(u, 1 - u) (pbx_ndtri.cuh; <= 3e-16 relative to
+ * ndtri, vtypes.py:186 / cond_cov.py:58-65): out[i] = ndtri(u[i]), table-driven degree-5
+ * polynomials on 64 segments per binade of min(u, 1 - u) (pbx_ndtri.cuh; <= 7e-16 relative to
  * max(|x|, 1e-3)), CUDA's normcdfinv outside the table (p < 2^-64, u <= 0, u >= 1).
  * pbx_ndtri: device arrays.  pbx_ndtri_host: host arrays, the same table and arithmetic on
  * the CPU without touching a GPU (NaN outside the table) -- a self-test hook, not a compute

@@ -54,14 +54,14 @@ __global__ void gibbs_c0_kernel(const double* coef, const double* mean, int d, d
   c0[i] = mean[i] - acc;
 }
 
-static __device__ double g_ndtab[NDT_ROWS * NDT_NCOEF];     // 128 KB, read through L1
+static __device__ __align__(16) double g_ndtab[NDT_ROWS * NDT_NCOEF];   // 192 KB, read through L1
 // the rows of the 10 binades nearest 0.5 (p >= 2^-11: all but 0.1 % of the draws),
 // TRANSPOSED [coefficient][row] for the tensor-core kernel's shared-memory copy: a lane's
-// eight 64-bit loads then fall on banks that are uniform in its (random) row index
+// six 64-bit loads then fall on banks that are uniform in its (random) row index
 #define NDT_HOT_BINADES 10
 #define NDT_HOT_ROWS (NDT_HOT_BINADES * NDT_SEGS)
 #define NDT_HOT0 (NDT_ROWS - NDT_HOT_ROWS)
-static __device__ double g_ndhot[NDT_NCOEF * NDT_HOT_ROWS];  // 20 KB
+static __device__ __align__(16) double g_ndhot[NDT_NCOEF * NDT_HOT_ROWS];   // 30 KB
 
 // outside the table (p < 2^-64, u <= 0, u >= 1, NaN): practically never taken, out of line
 __device__ __noinline__ double gibbs_ndtri_cold(double u) { return normcdfinv(u); }
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(NT, (DQ <= 16 ? (NT <= 128 ? 2 * GM_MINB : GM_
   double* s_sd = s_c0 + DP;
   double* s_lo = s_sd + DP;
   double* s_w = s_lo + DP;                   // hi - lo
-  double* s_nd = s_w + DP;                   // [8][NDT_HOT_ROWS]  hot ndtri rows, transposed
+  double* s_nd = s_w + DP;                   // [NDT_NCOEF][NDT_HOT_ROWS]  hot ndtri rows, transposed
   {
     constexpr int n2 = (int)(gibbs_mma_model_doubles<DQ>() / 2);
     const double2* src = reinterpret_cast<const double2*>(img);

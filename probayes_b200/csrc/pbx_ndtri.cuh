@@ -4,15 +4,16 @@
 // scipy.stats.norm.ppf == ndtri): x = ndtri(cdf_lo + (cdf_hi - cdf_lo) r) * stdv + mean.
 // CUDA's normcdfinv is ~500 static SASS instructions with a central / tail split on which a
 // warp always diverges (P(all 32 lanes central) < 1 %): with Philox it was 60 % of the Gibbs
-// kernel's instructions.  Here ndtri(p), p = min(u, 1 - u), is a degree-7 polynomial in the
-// mantissa offset of p on 32 segments per binade, 64 binades (p >= 2^-64; u52 uniforms are
-// >= 2^-53): the segment index is bits 62..47 of p, the local variable v = mantissa - segment
-// centre is exact (|v| <= 2^-6), eight coefficients = one 64-byte row.  ndtri is analytic in p
-// away from 0 with radius of convergence p, so the segment-relative width 1/32 gives the
-// interpolant at Chebyshev nodes an error ~ (1/128)^8: measured <= 2.3e-16 relative to
-// max(|x|, 1e-3) against 40-digit values over all binades.  The 128 KB table lives in global
-// memory and is read through L1 (binade k is touched with probability 2^-k: the hot set is
-// ~10 KB).  Outside the table (p < 2^-64, u <= 0, u >= 1, NaN) a cold out-of-line call to
+// kernel's instructions.  Here ndtri(p), p = min(u, 1 - u), is a degree-5 polynomial in the
+// mantissa offset of p on 64 segments per binade, 64 binades (p >= 2^-64; u52 uniforms are
+// >= 2^-53): the segment index is bits 62..46 of p, the local variable v = mantissa - segment
+// centre is exact (|v| <= 2^-7), six coefficients = one 48-byte row.  ndtri is analytic in p
+// away from 0 with radius of convergence p, so the segment-relative width 1/64 gives the
+// interpolant at Chebyshev nodes an error ~ (1/256)^6: measured <= 7e-16 relative to
+// max(|x|, 1e-3) against 40-digit values over all binades (<= 3.4e-16 below 1/8).  (A
+// degree-7 table on 32 segments measures 2.3e-16; its eight loads per draw instead of six
+// cost more shared-memory bandwidth than the Gibbs kernel has.)  The 192 KB table lives in
+// global memory and is read through L1.  Outside the table (p < 2^-64, u <= 0, u >= 1, NaN) a cold out-of-line call to
 // normcdfinv keeps the reference's limits (ndtri(0) = -inf, ndtri(1) = +inf).
 //
 // The table is generated on the host at context initialisation in long double (x87 64-bit
@@ -25,9 +26,11 @@
 
 #define NDT_EMIN 959                 // smallest tabulated biased exponent: p >= 2^-64
 #define NDT_BINADES 64               // biased exponents 959 .. 1022
-#define NDT_SEGS 32
-#define NDT_NCOEF 8
+#define NDT_SEG_BITS 6               // leading mantissa bits that select the segment
+#define NDT_SEGS (1 << NDT_SEG_BITS)
+#define NDT_NCOEF 6                  // degree 5
 #define NDT_ROWS (NDT_BINADES * NDT_SEGS)
+#define NDT_SHIFT (20 - NDT_SEG_BITS) // segment index = high word >> NDT_SHIFT
 
 #ifdef __CUDACC__
 #define NDT_HD __host__ __device__
@@ -59,17 +62,15 @@ NDT_HD inline uint32_t ndt_lo(double x) {
 }
 // segment of p (row of the table), or >= NDT_ROWS when p is outside the table
 NDT_HD inline unsigned ndt_segment(double p) {
-  return (unsigned)(ndt_hi(p) >> 15) - ((unsigned)NDT_EMIN << 5);
+  return (unsigned)(ndt_hi(p) >> NDT_SHIFT) - ((unsigned)NDT_EMIN << NDT_SEG_BITS);
 }
-// polynomial of row c[0..7] at p (p inside the row's segment)
+// polynomial of row c[0..5] at p (p inside the row's segment)
 NDT_HD inline double ndt_poly(const double* c, double p) {
   const int hm = (ndt_hi(p) & 0x000FFFFF) | 0x3FF00000;            // mantissa m in [1, 2)
   const double m = ndt_make(hm, ndt_lo(p));
-  const double cen = ndt_make((hm & (int)0xFFFF8000) | 0x4000, 0u); // segment centre
-  const double v = m - cen;                                        // exact, |v| <= 2^-6
-  double x = fma(c[7], v, c[6]);
-  x = fma(x, v, c[5]);
-  x = fma(x, v, c[4]);
+  const double cen = ndt_make((hm & ~((1 << NDT_SHIFT) - 1)) | (1 << (NDT_SHIFT - 1)), 0u);
+  const double v = m - cen;                 // exact, |v| <= 2^-(NDT_SEG_BITS + 1); cen = centre
+  double x = fma(c[5], v, c[4]);
   x = fma(x, v, c[3]);
   x = fma(x, v, c[2]);
   x = fma(x, v, c[1]);
@@ -111,13 +112,13 @@ static inline long double ndt_ndtri_l(long double p) {            // 0 < p < 1
   return x;
 }
 
-// fills tab[NDT_ROWS][8]
+// fills tab[NDT_ROWS][NDT_NCOEF]
 static inline void ndt_build_table(double* tab) {
   const int n = NDT_NCOEF;
   const long double pi = 3.14159265358979323846264338327950288L;
   long double t[NDT_NCOEF];
   for (int i = 0; i < n; ++i) t[i] = cosl(pi * (2 * i + 1) / (2.0L * n));
-  const long double h = 1.0L / (2 * NDT_SEGS);                      // 2^-6
+  const long double h = 1.0L / (2 * NDT_SEGS);                      // half a segment
   for (int be = 0; be < NDT_BINADES; ++be) {
     const long double scale = ldexpl(1.0L, NDT_EMIN + be - 1023);
     for (int k = 0; k < NDT_SEGS; ++k) {
