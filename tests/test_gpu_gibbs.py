@@ -58,7 +58,11 @@ def test_condcov_golden_trajectory(name):
 
 @pytest.mark.parametrize("d,C,T,thin", [(2, 100, 41, 1), (3, 33, 50, 3), (8, 257, 64, 8),
                                         (20, 64, 70, 5), (64, 130, 150, 64),
-                                        (128, 40, 256, 128), (100, 33, 210, 7)])
+                                        (128, 40, 256, 128), (100, 33, 210, 7),
+                                        # whole sweeps -> the tensor-core kernel, incl. d off
+                                        # the 8-coordinate block (zero padding) and ragged C
+                                        (5, 9, 10, 5), (13, 50, 39, 13), (33, 20, 66, 33),
+                                        (64, 70, 128, 64), (100, 11, 200, 100)])
 def test_oracle_injected_and_resume(d, C, T, thin):
     from probayes_b200.cond_cov import CondCov
     eng = engine()

@@ -55,10 +55,14 @@ def test_golden(name):
     assert np.abs(lin - g["post_linear"]).max() <= atol * g["post_linear"].max()
 
 
-@pytest.mark.parametrize("N,M,S", [(1, 3, 5), (1023, 7, 1030), (4097, 33, 257), (20000, 64, 96)])
+@pytest.mark.parametrize("N,M,S", [(1, 3, 5), (1023, 7, 1030), (4097, 33, 257), (20000, 64, 96),
+                                   (5, 1, 1), (50, 5, 1024), (50, 6, 2050), (10, 1027, 8),
+                                   (20, 600, 1024)])
 def test_oracle_ragged(N, M, S):
     """Ragged observation counts (below / across the 1024-obs tile) and grid edges
-    that do not fill a CTA tile."""
+    that do not fill a CTA tile: single cells, row counts off the 4-row tile, column counts on
+    and off the 1024-column block (interior and edge variants of the posterior pass), more
+    4-row tiles than resident CTAs."""
     from oracle.c import liboracle as lo
     eng = engine()
     rng = np.random.default_rng(N + M + S)
