@@ -82,37 +82,50 @@ struct NrArgs {
 // ----------------------------------------------------------------------------
 // proposal: theta' = ufun^-1(ufun(theta) + delta)  (variable.py:693-697)
 // ----------------------------------------------------------------------------
+// kP: the parameter count at compile time (0 = read m.P): with it every index below is a
+// constant and the arrays stay in registers (runtime bounds put them into local memory, which
+// only the one-launch walk kernel -- a latency-bound chain per warp -- cares about)
+template <int kP = 0>
 __device__ __forceinline__ void nr_draw_delta(const NrArgs& a, const NrModel& m, int64_t gstep,
                                               int kk, int c, double (&dl)[PBX_MAX_PARAMS]) {
   const int64_t C = a.C;
+  const int P = kP ? kP : m.P;
   if (a.inj_delta) {
-    for (int j = 0; j < m.P; ++j) dl[j] = a.inj_delta[((int64_t)kk * m.P + j) * C + c];
+#pragma unroll
+    for (int j = 0; j < PBX_MAX_PARAMS; ++j)
+      if (j < P) dl[j] = a.inj_delta[((int64_t)kk * P + j) * C + c];
     return;
   }
   const uint32_t gchain = (uint32_t)(a.chain0 + c);
-  for (int s = 0; s < (m.P + 1) / 2; ++s) {
+#pragma unroll
+  for (int s = 0; s < (PBX_MAX_PARAMS + 1) / 2; ++s) {
+    if (s >= (P + 1) / 2) break;
     pbx_u4 w = pbx_block(a.seed, (uint64_t)gstep, gchain, (uint32_t)s);
     double d0, d1;
     if (m.prop_kind == PBX_PROP_NORMAL) {
       pbx_normal_pair(w, d0, d1);
       d0 *= m.scale[2 * s];
-      if (2 * s + 1 < m.P) d1 *= m.scale[2 * s + 1];
+      if (2 * s + 1 < P) d1 *= m.scale[2 * s + 1];
     } else if (m.prop_kind == PBX_PROP_UNIFORM) {
       d0 = -m.scale[2 * s] + (2.0 * m.scale[2 * s]) * pbx_u52(w.x, w.y);
-      d1 = (2 * s + 1 < m.P) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * pbx_u32(w.z)
+      d1 = (2 * s + 1 < P) ? -m.scale[2 * s + 1] + (2.0 * m.scale[2 * s + 1]) * pbx_u32(w.z)
                              : 0.0;
     } else {                       // spherical: cube sample, rescaled below
       d0 = -m.radius + (2.0 * m.radius) * pbx_u52(w.x, w.y);
-      d1 = (2 * s + 1 < m.P) ? -m.radius + (2.0 * m.radius) * pbx_u32(w.z) : 0.0;
+      d1 = (2 * s + 1 < P) ? -m.radius + (2.0 * m.radius) * pbx_u32(w.z) : 0.0;
     }
     dl[2 * s] = d0;
-    if (2 * s + 1 < m.P) dl[2 * s + 1] = d1;
+    if (2 * s + 1 < P) dl[2 * s + 1] = d1;
   }
   if (m.prop_kind == PBX_PROP_SPHERICAL) {   // field.py:509-531
     double ss = 0.0;
-    for (int j = 0; j < m.P; ++j) ss += dl[j] * dl[j];
+#pragma unroll
+    for (int j = 0; j < PBX_MAX_PARAMS; ++j)
+      if (j < P) ss += dl[j] * dl[j];
     const double nrm = (ss >= PBX_TINY) ? sqrt(ss) : 0.0;
-    for (int j = 0; j < m.P; ++j) dl[j] = ((dl[j] * m.radius) / nrm) * m.scale[j];
+#pragma unroll
+    for (int j = 0; j < PBX_MAX_PARAMS; ++j)
+      if (j < P) dl[j] = ((dl[j] * m.radius) / nrm) * m.scale[j];
   }
 }
 
@@ -147,13 +160,17 @@ __device__ __forceinline__ void nr_propose(const NrArgs& a, const NrModel& m, in
 }
 
 // log-joint from the residual sum of squares S (see file header)
+template <int kP = 0>
 __device__ __forceinline__ double nr_logjoint(const NrArgs& a, const NrModel& m, const double* th,
                                               double S) {
-  const double sg = th[m.P - 1];
+  const int P = kP ? kP : m.P;
+  const double sg = th[P - 1];
   const double n = (double)a.N;
   double ll = -(S / (sg * sg)) * 0.5 - n * (PBX_LOG_SQRT_2PI + log(sg));
   double prior = 0.0;
-  for (int j = 0; j < m.P; ++j) {
+#pragma unroll
+  for (int j = 0; j < PBX_MAX_PARAMS; ++j) {
+    if (j >= P) break;
     const double v = th[j];
     const bool in_lo = m.open_end[j][0] ? (v > m.lims[j][0]) : (v >= m.lims[j][0]);
     const bool in_hi = m.open_end[j][1] ? (v < m.lims[j][1]) : (v <= m.lims[j][1]);
@@ -852,47 +869,69 @@ __global__ void __launch_bounds__(32 * RW_WARPS)
   extern __shared__ __align__(16) double rw_sm[];       // y[N], then x[N] (kSlope)
   double* sy = rw_sm;
   double* sx = rw_sm + a.N;
-  for (int64_t i = threadIdx.x; i < a.N; i += 32 * RW_WARPS) {
+  for (int64_t i = threadIdx.x; i < a.N; i += blockDim.x) {
     sy[i] = a.y[i];
     if (kSlope) sx[i] = a.x[i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= a.C) return;
   const int64_t C = a.C;
   const int n = (int)a.N;
+  constexpr int P = kSlope ? 3 : 2;           // has_slope <=> (b0, b1, sigma), validated by the host
   double th[PBX_MAX_PARAMS], ssum[PBX_MAX_PARAMS], ssq[PBX_MAX_PARAMS];
-  for (int j = 0; j < m.P; ++j) {
+  _Pragma("unroll") for (int j = 0; j < P; ++j) {
     th[j] = a.state[(int64_t)j * C + c];
     ssum[j] = ssq[j] = 0.0;
   }
   auto rss = [&](const double* t) {
     const double b0 = t[0], b1 = kSlope ? t[1] : 0.0;
-    double s0 = 0.0, s1 = 0.0;
+    // four independent partial sums per lane (a fixed association: the result depends on n
+    // only), so that the dependent-FMA latency is hidden at large n
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    auto term = [&](int i) {
+      const double r = kSlope ? (sy[i] - b0) - b1 * sx[i] : sy[i] - b0;
+      return r * r;
+    };
     int i = lane;
-    for (; i + 32 < n; i += 64) {
-      const double r0 = kSlope ? (sy[i] - b0) - b1 * sx[i] : sy[i] - b0;
-      const double r1 = kSlope ? (sy[i + 32] - b0) - b1 * sx[i + 32] : sy[i + 32] - b0;
-      s0 = fma(r0, r0, s0);
-      s1 = fma(r1, r1, s1);
+    for (; i + 96 < n; i += 128) {
+      s0 += term(i);
+      s1 += term(i + 32);
+      s2 += term(i + 64);
+      s3 += term(i + 96);
     }
-    if (i < n) {
-      const double r0 = kSlope ? (sy[i] - b0) - b1 * sx[i] : sy[i] - b0;
-      s0 = fma(r0, r0, s0);
-    }
-    double s = s0 + s1;
+    if (i < n) s0 += term(i);
+    if (i + 32 < n) s1 += term(i + 32);
+    if (i + 64 < n) s2 += term(i + 64);
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
   };
   double lp = (a.step0 > 0) ? a.state_lp[c] : 0.0;
   int64_t nacc = 0;
+  // the state-independent part of a step -- Philox, the proposal delta, the threshold and its
+  // log -- is produced for 32 steps at a time, one step per lane, and handed out by shuffles:
+  // all lanes carry the chain redundantly, so doing it per step would put ~150 dependent
+  // instructions on every step's critical path
+  double dlv[PBX_MAX_PARAMS], tv = 0.5, ltv = 0.0;
+  _Pragma("unroll") for (int j = 0; j < PBX_MAX_PARAMS; ++j) dlv[j] = 0.0;
   for (int k = 0; k < a.T; ++k) {
     const int64_t gstep = a.step0 + k;
+    if ((k & 31) == 0) {
+      const int mine = k + lane;
+      if (mine < a.T) {
+        nr_draw_delta<P>(a, m, a.step0 + mine, mine, c, dlv);
+        tv = nr_threshold(a, a.step0 + mine, mine, c);
+        ltv = log(tv);
+      }
+    }
     double dl[PBX_MAX_PARAMS], thp[PBX_MAX_PARAMS];
-    nr_draw_delta(a, m, gstep, k, c, dl);
-    for (int j = 0; j < m.P; ++j) {
+    _Pragma("unroll") for (int j = 0; j < P; ++j) dl[j] = __shfl_sync(0xffffffffu, dlv[j], k & 31);
+    const double t = __shfl_sync(0xffffffffu, tv, k & 31);
+    const double logt = __shfl_sync(0xffffffffu, ltv, k & 31);
+    _Pragma("unroll") for (int j = 0; j < P; ++j) {
       double v = m.log_ufun[j] ? exp(log(th[j]) + dl[j]) : th[j] + dl[j];
       if (m.bound) {                                   // variable.py:700-727
         const double lo = m.lims[j][0], hi = m.lims[j][1];
@@ -904,8 +943,7 @@ __global__ void __launch_bounds__(32 * RW_WARPS)
       }
       thp[j] = v;
     }
-    const double lpp = nr_logjoint(a, m, thp, rss(thp));
-    const double t = nr_threshold(a, gstep, k, c);
+    const double lpp = nr_logjoint<P>(a, m, thp, rss(thp));
     bool acc;
     double s = nan("");
     if (gstep == 0) {
@@ -916,15 +954,15 @@ __global__ void __launch_bounds__(32 * RW_WARPS)
       acc = (s >= t);
     } else {
       const double d = m.coef * (lpp - lp);
-      acc = (d >= log(t));
+      acc = (d >= logt);
       if (a.out_score) s = fmin(1.0, exp(fmin(d, 0.0)));
     }
     if (acc) {
-      for (int j = 0; j < m.P; ++j) th[j] = thp[j];
+      _Pragma("unroll") for (int j = 0; j < P; ++j) th[j] = thp[j];
       lp = lpp;
       ++nacc;
     }
-    for (int j = 0; j < m.P; ++j) {
+    _Pragma("unroll") for (int j = 0; j < P; ++j) {
       ssum[j] += th[j];
       ssq[j] = fma(th[j], th[j], ssq[j]);
     }
@@ -932,18 +970,18 @@ __global__ void __launch_bounds__(32 * RW_WARPS)
       if (a.out_accept) a.out_accept[(int64_t)k * C + c] = acc ? 1 : 0;
       if (a.out_score) a.out_score[(int64_t)k * C + c] = s;
       if (a.out_xprop)
-        for (int j = 0; j < m.P; ++j) a.out_xprop[((int64_t)k * m.P + j) * C + c] = thp[j];
+        _Pragma("unroll") for (int j = 0; j < P; ++j) a.out_xprop[((int64_t)k * P + j) * C + c] = thp[j];
       if (a.out_pprop) a.out_pprop[(int64_t)k * C + c] = lpp;
       if ((k + 1) % a.thin == 0) {
         const int64_t r = (k + 1) / a.thin - 1;
         if (a.out_x)
-          for (int j = 0; j < m.P; ++j) a.out_x[(r * m.P + j) * C + c] = th[j];
+          _Pragma("unroll") for (int j = 0; j < P; ++j) a.out_x[(r * P + j) * C + c] = th[j];
         if (a.out_prob) a.out_prob[r * C + c] = lp;
       }
     }
   }
   if (lane == 0) {
-    for (int j = 0; j < m.P; ++j) {
+    _Pragma("unroll") for (int j = 0; j < P; ++j) {
       a.state[(int64_t)j * C + c] = th[j];
       if (a.stat_sum) a.stat_sum[(int64_t)j * C + c] += ssum[j];
       if (a.stat_sumsq) a.stat_sumsq[(int64_t)j * C + c] += ssq[j];
@@ -1052,15 +1090,20 @@ extern "C" int pbx_mh_normreg_run(pbx_ctx* ctx, const pbx_mh_normreg_params* p) 
     PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     if (a.T > 0) {
       const size_t smem = (size_t)a.N * 8 * (m.has_slope ? 2 : 1);
-      const int grid = (a.C + RW_WARPS - 1) / RW_WARPS;
+      // warps (chains) per CTA: up to RW_WARPS, fewer when there are few chains, so that they
+      // spread over the SMs (every warp re-reads the resident observations each step: four
+      // warps on one SM share its 128 B/clk of shared-memory bandwidth)
+      int wpc = (a.C + 2 * ctx->sm_count - 1) / (2 * ctx->sm_count);
+      wpc = wpc < 1 ? 1 : (wpc > RW_WARPS ? RW_WARPS : wpc);
+      const int grid = (a.C + wpc - 1) / wpc;
       if (m.has_slope) {
         PBX_CUDA(cudaFuncSetAttribute(rw_walk_kernel<true>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rw_walk_kernel<true><<<grid, 32 * RW_WARPS, smem, ctx->stream>>>(a, m);
+        rw_walk_kernel<true><<<grid, 32 * wpc, smem, ctx->stream>>>(a, m);
       } else {
         PBX_CUDA(cudaFuncSetAttribute(rw_walk_kernel<false>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        rw_walk_kernel<false><<<grid, 32 * RW_WARPS, smem, ctx->stream>>>(a, m);
+        rw_walk_kernel<false><<<grid, 32 * wpc, smem, ctx->stream>>>(a, m);
       }
       PBX_LAUNCH_CHECK(ctx);
     }
