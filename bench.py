@@ -437,6 +437,35 @@ def secondary(eng, peaks, fp64_peak, quick=False):
                                          "over %d log-pscale samples" % n6,
                              "ms": ms, "algorithmic_gbs": 24.0 * n6 / (ms * 1e-3) / 1e9,
                              "frac": 24.0 * n6 / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    del lp, vals
+    # ---- C1: the reference's own example (mcmc_prob4a: ONE chain, 12288 steps) through the
+    # public API, wall clock incl. process(samples) -- what a user of the reference sees
+    try:
+        import scipy.stats
+        import probayes_b200 as pb
+        xr = pb.RV('x', vtype=float, vset=(-np.inf, np.inf))
+        yr = pb.RV('y', vtype=float, vset=(-np.inf, np.inf))
+        proc = pb.SP(xr & yr)
+        proc.set_prob(scipy.stats.multivariate_normal, list(MEAN), COV.tolist())
+        proc.set_tran(lambda **kw: 1.)
+        proc.set_delta(scipy.stats.norm(0., 1.))
+        proc.set_scores('hastings')
+        proc.set_update('metropolis')
+        T1 = 12288
+        walls = []
+        for rep in range(4):
+            t0 = time.perf_counter()
+            summ = proc(proc.walk(proc.sampler({'x': INIT[0], 'y': INIT[1]}, stop=T1, seed=rep)))
+            n_acc = summ.u.count(True)
+            walls.append(time.perf_counter() - t0)
+        w = float(np.median(walls[1:]))
+        out["c1_api_single_chain"] = {"workload": "C1 (BASELINE.json configs[0]): mcmc_prob4a, 1 chain "
+                                                  "x %d steps through SP.sampler -> walk -> "
+                                                  "process(samples), wall clock" % T1,
+                                      "seconds": w, "chain_steps_per_s": T1 / w,
+                                      "accepted": int(n_acc)}
+    except Exception as e:                                   # diagnostics only
+        out["c1_api_single_chain"] = {"error": repr(e)}
     return out
 
 

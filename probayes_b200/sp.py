@@ -75,9 +75,37 @@ class AcceptRecord:
 
 class Walk(list):
     """Result of ``SP.walk``: a list of per-step ``opqrstuv`` tuples for
-    reference-shaped single-chain runs, plus the raw arrays (``.arrays``)."""
+    reference-shaped single-chain runs, plus the raw arrays (``.arrays``).  The per-step
+    tuples (three scalar PDs each) are built on first use of the list -- iteration, indexing,
+    ``len`` -- because ``process(walk)`` works from the arrays and never looks at them:
+    building 12288 of them eagerly was 95 % of the wall clock of the reference's own
+    single-chain example."""
     arrays = None
     sampler = None
+    _builder = None
+
+    def _fill(self):
+        builder, self._builder = self._builder, None
+        if builder is not None:
+            list.extend(self, builder())
+
+
+def _lazy(name):
+    base = getattr(list, name)
+
+    def method(self, *args, **kwds):
+        self._fill()
+        return base(self, *args, **kwds)
+    method.__name__ = name
+    return method
+
+
+for _name in ('__iter__', '__len__', '__getitem__', '__contains__', '__reversed__', '__eq__',
+              '__ne__', '__repr__', '__add__', '__mul__', 'count', 'index', 'copy', 'pop',
+              'append', 'extend', 'insert', 'remove', 'reverse', 'sort', '__setitem__',
+              '__delitem__', '__iadd__'):
+    setattr(Walk, _name, _lazy(_name))
+Walk.__hash__ = None
 
 
 class Sampler:
@@ -241,7 +269,7 @@ class SP(SD):
             out = Walk()
             out.arrays, out.sampler = arrays, sampler
             if arrays['T'] <= 200000:
-                out.extend(self._rejection_per_step(arrays))
+                out._builder = lambda: self._rejection_per_step(arrays)
             return out
         arrays = self._run_omc(sampler, int(T)) if sampler.opts['omc'] \
             else self._run(sampler, int(T))
@@ -252,10 +280,10 @@ class SP(SD):
         out.arrays, out.sampler = arrays, sampler
         if arrays.get('omc'):
             if arrays['T'] <= 200000:
-                out.extend(self._omc_per_step(arrays))
+                out._builder = lambda: self._omc_per_step(arrays)
             return out
         if arrays['chains'] is None and arrays['R'] <= 200000:
-            out.extend(self._per_step(arrays))
+            out._builder = lambda: self._per_step(arrays)
         return out
 
     # ---- ordinary Monte Carlo with rejection sampling -----------------------------------------
@@ -643,25 +671,36 @@ class SP(SD):
     def _has_proposals(arrays):
         return arrays.get('xprop') is not None and arrays['thin'] == 1
 
+    @staticmethod
+    def _stu_lists(arrays):
+        """Per-step ``s / t / u`` of a single-chain run as three lists (sp.py:244-258):
+        Gibbs keeps every step with nan scores; MH has them where the records align with the
+        steps (thin == 1)."""
+        R = arrays['R']
+        acc, score, thr = arrays.get('accept'), arrays.get('score'), arrays.get('inj_thresh')
+        if arrays['gibbs']:
+            return [np.nan] * R, [np.nan] * R, [True] * R
+        if arrays['thin'] == 1 and acc is not None:
+            us = [True if a else None for a in np.asarray(acc)[:R, 0].tolist()]
+            ss = [None] * R if score is None else \
+                [None if v != v else v for v in np.asarray(score, dtype=float)[:R, 0].tolist()]
+            ts = [None] * R if thr is None else [float(v) for v in np.ravel(thr)[:R].tolist()]
+            return ss, ts, us
+        return [None] * R, [None] * R, [None] * R
+
     def _per_step(self, arrays):
         """Reference-shaped per-step tuples for a single chain: ``v`` the retained state,
         and (thin == 1) ``p`` the proposal with its target density, ``o`` the predecessor
         (None on the first step of a fresh sampler), ``s / t / u`` (sp.py:244-258)."""
         out = []
         R = arrays['R']
-        acc, score, thr = arrays.get('accept'), arrays.get('score'), arrays.get('inj_thresh')
         aligned = arrays['thin'] == 1
         props = self._has_proposals(arrays)
+        ss, ts, us = self._stu_lists(arrays)
         prev = None
         for i in range(R):
             v = self._value_pd(arrays, sel=i)
-            s = t = u = p = None
-            if arrays['gibbs']:
-                s, t, u = np.nan, np.nan, True
-            elif aligned and acc is not None:
-                u = True if acc[i, 0] else None
-                s = None if np.isnan(score[i, 0]) else float(score[i, 0])
-                t = None if thr is None else float(np.ravel(thr)[i])
+            s, t, u, p = ss[i], ts[i], us[i], None
             if props:
                 p = self._value_pd(arrays, sel=i, x=arrays['xprop'], prob=arrays['pprop'])
             out.append(self.opqrstuv(prev if aligned else None, p, None, None, s, t, u, v))
@@ -737,10 +776,12 @@ class SP(SD):
             p = self._value_pd(arrays, x=arrays['xprop'], prob=arrays['pprop'])
             if arrays['R'] > 1:
                 o = self._value_pd(arrays, x=arrays['x'][:-1], prob=arrays['prob'][:-1])
-        if arrays['chains'] is None and len(samples):
-            u = [s.u for s in samples]
-            s_ = [s.s for s in samples if s.s is not None]
-            t_ = [s.t for s in samples if s.t is not None]
+        if arrays['chains'] is None and arrays['R'] <= 200000 and arrays['R'] > 0:
+            # reference-shaped single chain: s / t / u straight from the arrays (the per-step
+            # tuples of the Walk are not built for this)
+            ss, ts, u = self._stu_lists(arrays)
+            s_ = [x for x in ss if x is not None]
+            t_ = [x for x in ts if x is not None]
             return self.opqrstuv(o, p, None, None, s_ or None, t_ or None, u, v)
         if arrays['gibbs']:
             C = 1 if arrays['chains'] is None else arrays['chains']
