@@ -324,6 +324,12 @@ PBX_API int pbx_rejection_sample(pbx_ctx* ctx, const pbx_rejection_params* p);
  * per-step evaluation of the mvn target (sd.py:286), as in
  * examples/mcmc/gibbs_norm2d.py:15-22.  One step = one coordinate update
  * (tsteps=1); coordinate = (step0 + k) mod d.
+ * Calls covering whole sweeps (step0, n_steps and thin multiples of d; d >= 5) run the
+ * conditional means on the FP64 tensor cores, 8 coordinates per block in closed form; any
+ * other step range runs coordinate by coordinate.  Same results up to summation order.
+ * Native uniforms: global step g uses the 52-bit uniform of words (0, 1) (bit 2 of g clear)
+ * or (2, 3) (bit 2 set) of Philox block (seed, g & ~4, chain0 + c, slot 0); the inverse
+ * normal cdf is the table-driven pbx_ndtri below.
  * ------------------------------------------------------------------------- */
 typedef struct {
   int32_t n_chains;
@@ -345,7 +351,8 @@ typedef struct {
                               permutation folded in (NULL = mean); see prob.py:349-358 */
   double norm_c;           /* d log 2pi + log_pdet */
   double* state;           /* [d][C] in/out */
-  const double* inj_runif; /* [T][C] injected U(0,1) draws or NULL = Philox */
+  const double* inj_runif; /* [T][C] injected U(0,1) draws (row k = step step0 + k) or
+                              NULL = Philox */
   double* out_x;           /* [T/thin][d][C] or NULL */
   double* out_prob;        /* [T/thin][C] or NULL */
   double* stat_sum;        /* [d][C] accumulated over the RECORDED states, or NULL */

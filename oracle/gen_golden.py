@@ -29,8 +29,18 @@ def _summary_arrays(sp, samples, keys):
     t = np.array([float(v) for v in summary.t])
     u = np.array([v is True for v in summary.u])
     xp = np.stack([np.asarray(summary.p[k], dtype=float) for k in keys], axis=-1)
-    return dict(x=x, prob=np.asarray(summary.v.prob, dtype=float), s=s, t=t, u=u,
-                xprop=xp, pprop=np.asarray(summary.p.prob, dtype=float))
+    out = dict(x=x, prob=np.asarray(summary.v.prob, dtype=float), s=s, t=t, u=u,
+               xprop=xp, pprop=np.asarray(summary.p.prob, dtype=float))
+    if summary.q is not None:
+        # the proposal-density PDs (sp.py:170-198): "x',y'|x,y" with the proposals, their
+        # predecessors (the initial state first) and q's value per step
+        q = summary.q
+        out.update(q_name=np.array(q.name), q_keys=np.array(list(q.keys())),
+                   q_prob=np.asarray(q.prob, dtype=float),
+                   q_pred=np.stack([np.asarray(q[k], dtype=float) for k in keys], axis=-1),
+                   q_prop=np.stack([np.asarray(q[k + "'"], dtype=float) for k in keys], axis=-1),
+                   q_step3_name=np.array(samples[3].q.name))
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -497,6 +497,9 @@ class SP(SD):
         res = dict(keys=keys, chains=Cn, T=T, thin=thin, R=T // thin, spec=spec,
                    inj_thresh=None if inj_t is None else np.asarray(opts['inj_thresh']),
                    gibbs=gibbs, pscale=self._pscale)
+        if per_step and not gibbs:
+            # the state this call starts from: the first predecessor of summary.q
+            res['init'] = state.detach().cpu().numpy()[:, 0].copy()
         if gibbs:
             cc = self._cond_cov
             if spec['kind'] != 'mvn' or cc is None:
@@ -671,6 +674,54 @@ class SP(SD):
     def _has_proposals(arrays):
         return arrays.get('xprop') is not None and arrays['thin'] == 1
 
+    def _q_pd(self, arrays, sel=None):
+        """The proposal-density PD of the reference's ``opqr.q`` / ``summary.q`` (sd.py:253-288,
+        sp.py:170-198) for a reference-shaped single-chain run: named ``x',y'|x,y``, the
+        proposals under the primed keys, their predecessors (the state the call started from,
+        then the retained states) under the plain keys, and the user's transition callable
+        evaluated on them -- on the host, vectorised, after the walk: with a single callable
+        the Hastings score does not use q (sp_utils.py:40-64), it is only recorded.  None for
+        transitions that are not a single callable."""
+        tran = self._proposal_rf()._tran
+        if not callable(tran) or arrays.get('xprop') is None or arrays.get('init') is None \
+                or arrays['thin'] != 1:
+            return None
+        keys = arrays['keys']
+        prop = np.asarray(arrays['xprop'])[:, :, 0]                     # [T, D]
+        pred = np.concatenate([arrays['init'][None, :], np.asarray(arrays['x'])[:-1, :, 0]])
+        cache = arrays.get('_q_prob')
+        if cache is None:
+            kw = {}
+            for j, k in enumerate(keys):
+                kw[k] = pred[:, j]
+                kw[k + "'"] = prop[:, j]
+            try:
+                cache = np.asarray(tran(**kw), dtype=float)
+                if cache.ndim == 0:
+                    cache = np.full(prop.shape[0], float(cache))
+                assert cache.shape == (prop.shape[0],)
+            except Exception:                       # a callable that only takes scalars
+                cache = np.array([float(tran(**{n: float(v[i]) for n, v in kw.items()}))
+                                  for i in range(prop.shape[0])])
+            arrays['_q_prob'] = cache
+        vals = collections.OrderedDict()
+        if sel is None:
+            for j, k in enumerate(keys):
+                vals[k + "'"] = prop[:, j]
+            for j, k in enumerate(keys):
+                vals[k] = pred[:, j]
+            name = ','.join(k + "'" for k in keys) + '|' + ','.join(keys)
+            dims = collections.OrderedDict((k, 0) for k in vals)
+            return PD(name, vals, dims=dims, prob=cache, pscale=self._proposal_rf().pscale)
+        for j, k in enumerate(keys):
+            vals[k] = pred[sel, j]
+        for j, k in enumerate(keys):
+            vals[k + "'"] = prop[sel, j]
+        name = ','.join("{}'={}".format(k, vals[k + "'"]) for k in keys) + '|' + \
+            ','.join("{}={}".format(k, vals[k]) for k in keys)
+        return PD(name, vals, dims=collections.OrderedDict((k, None) for k in vals),
+                  prob=float(cache[sel]), pscale=self._proposal_rf().pscale)
+
     @staticmethod
     def _stu_lists(arrays):
         """Per-step ``s / t / u`` of a single-chain run as three lists (sp.py:244-258):
@@ -701,9 +752,11 @@ class SP(SD):
         for i in range(R):
             v = self._value_pd(arrays, sel=i)
             s, t, u, p = ss[i], ts[i], us[i], None
+            q = None
             if props:
                 p = self._value_pd(arrays, sel=i, x=arrays['xprop'], prob=arrays['pprop'])
-            out.append(self.opqrstuv(prev if aligned else None, p, None, None, s, t, u, v))
+                q = self._q_pd(arrays, sel=i)
+            out.append(self.opqrstuv(prev if aligned else None, p, q, None, s, t, u, v))
             prev = v
         return out
 
@@ -744,6 +797,9 @@ class SP(SD):
                 if not pds:
                     return None
                 keys = list(pds[0].keys())
+                cond = list(pds[0].cond.keys())
+                if cond:                         # a proposal density x',y'|x,y: primed keys first
+                    keys = [k for k in keys if k not in cond] + [k for k in keys if k in cond]
                 vals = collections.OrderedDict()
                 for k in keys:
                     if isinstance(pds[0][k], set):
@@ -754,7 +810,11 @@ class SP(SD):
                                                for k in keys)
                 names = [k if not isinstance(vals[k], set) else "{}={}".format(k, vals[k])
                          for k in keys]
-                return PD(','.join(names), vals, dims=dims,
+                name = ','.join(names)
+                if cond:
+                    name = ','.join(n for n, k in zip(names, keys) if k not in cond) + '|' + \
+                        ','.join(n for n, k in zip(names, keys) if k in cond)
+                return PD(name, vals, dims=dims,
                           prob=np.array([d.prob for d in pds]), pscale=pds[0].pscale)
             kept = [s for s in samples if s.u is not False]
             v = concat([s.v for s in kept])
@@ -769,8 +829,9 @@ class SP(SD):
         v = self._value_pd(arrays)
         if conditionalise:                      # sp.py:194-196: condition on the leaf (data) keys
             v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])
-        o = p = None
+        o = p = q = None
         if self._has_proposals(arrays) and not conditionalise:
+            q = self._q_pd(arrays)
             # summate() of the per-step p / o PDs (sp.py:170-198): every proposal, and the
             # predecessor of every step but the first
             p = self._value_pd(arrays, x=arrays['xprop'], prob=arrays['pprop'])
@@ -782,7 +843,7 @@ class SP(SD):
             ss, ts, u = self._stu_lists(arrays)
             s_ = [x for x in ss if x is not None]
             t_ = [x for x in ts if x is not None]
-            return self.opqrstuv(o, p, None, None, s_ or None, t_ or None, u, v)
+            return self.opqrstuv(o, p, q, None, s_ or None, t_ or None, u, v)
         if arrays['gibbs']:
             C = 1 if arrays['chains'] is None else arrays['chains']
             u = AcceptRecord(np.full(C, arrays['T']), arrays['T'])

@@ -27,7 +27,12 @@ def test_mcmc_prob4a(name):
                          pscale='log')
     else:
         process.set_prob(scipy.stats.multivariate_normal, [0., 0.], [[2.0, 1.2], [1.2, 2.0]])
-    process.set_tran(lambda **kwds: 1.)
+    def q(**kwds):                                       # mcmc_prob4a.py:25-30
+        x_, xprime = kwds['x'], kwds["x'"]
+        y_, yprime = kwds['y'], kwds["y'"]
+        return scipy.stats.norm.pdf(yprime, loc=y_, scale=1.) * \
+            scipy.stats.norm.pdf(xprime, loc=x_, scale=1.)
+    process.set_tran(q)
     process.set_delta(lambda: None)                      # draws are injected below
     process.set_scores('hastings')
     process.set_update('metropolis')
@@ -59,6 +64,16 @@ def test_mcmc_prob4a(name):
                                         inj_delta=g["delta"], inj_thresh=g["thresh"]))
     s2 = process(walk)                       # the Walk path builds the same PDs from arrays
     assert np.array_equal(s2.p['y'], summary.p['y']) and np.array_equal(s2.o.prob, summary.o.prob)
+    # the proposal-density PD (opqr.q, summated sp.py:170-198): x',y'|x,y with the proposals,
+    # their predecessors (initial state first) and the user's q evaluated on them
+    for sq in (summary.q, s2.q):
+        assert sq.name == str(g["q_name"]) and list(sq.keys()) == list(g["q_keys"])
+        assert relerr(sq.prob, g["q_prob"]) <= TOL
+        assert relerr(np.stack([sq["x'"], sq["y'"]], 1), g["q_prop"]) <= TOL
+        assert np.abs(np.stack([sq['x'], sq['y']], 1) - g["q_pred"]).max() <= TOL
+    assert samples[3].q.name.startswith("x'=") and "|x=" in samples[3].q.name
+    assert abs(samples[3].q.prob - g["q_prob"][3]) <= TOL * g["q_prob"][3]
+    assert summary.r is None
 
 
 @pytest.mark.parametrize("name,scores,delta", [
