@@ -24,6 +24,7 @@
 //          128-bit coalesced loads, updates all chains' sums, warp-shuffle + block
 //          reduce.  This is the HBM-roofline regime (16 B per observation per step).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "pbx_common.cuh"
@@ -530,6 +531,10 @@ static NrPlan nr_plan(pbx_ctx* ctx, const pbx_mh_normreg_params* p) {
   pl.smem = 0;
   if (variant == 1) {
     pl.kc = (C >= 4 * NR_THREADS * 8) ? 4 : ((C >= 2 * NR_THREADS * 8) ? 2 : 1);
+    if (const char* e = getenv("PBX_NR_KC")) {           // tuning experiments only
+      const int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4) pl.kc = v;
+    }
     pl.n_groups = (C + NR_THREADS * pl.kc - 1) / (NR_THREADS * pl.kc);
     pl.smem = (size_t)NR_STAGES * 2 * NR_TILE * sizeof(double);     // 48 KB -> 4 CTAs / SM
     const int64_t n_full = p->n_obs / NR_TILE;
