@@ -44,6 +44,12 @@ struct GibbsArgs {
   double* out_x;
   double* stat_sum;
   double* stat_sumsq;
+  // fused target density of the recorded states (whole-sweep kernel, d = 64 only; else null)
+  double* out_prob;
+  const double* whiten;   // [64][64]
+  const double* dens_mean;
+  double norm_c;
+  int log_pscale;
 };
 
 __global__ void gibbs_c0_kernel(const double* coef, const double* mean, int d, double* c0) {
@@ -321,9 +327,14 @@ __global__ void __launch_bounds__(256) gibbs_mma_prep_kernel(const GibbsArgs a,
 #ifndef GM_MINB
 #define GM_MINB 2
 #endif
-template <int DQ, bool kPair, int NT>
+// kDens (d = 64): the target density of every recorded state -- |(x - mean) W|^2 on the tensor
+// cores, straight from the state registers (they are the A fragment of that product too) --
+// instead of a second kernel re-reading the recorded states
+#define GM_WDS 68                          // row stride of the whitening matrix in shared memory
+template <int DQ, bool kPair, int NT, bool kDens = false>
 __global__ void __launch_bounds__(NT, (DQ <= 16 ? (NT <= 128 ? 2 * GM_MINB : GM_MINB) : 1))
     gibbs_mvn_mma_kernel(const GibbsArgs a, const double* __restrict__ img) {
+  static_assert(!kDens || DQ == 16, "the fused density is the d = 64 case");
   constexpr int DP = 4 * DQ, NB = DQ / 2;
   extern __shared__ __align__(16) double sm[];
   double* s_B = sm;                          // [NB][DQ][32]   B'_b fragments
@@ -341,6 +352,12 @@ __global__ void __launch_bounds__(NT, (DQ <= 16 ? (NT <= 128 ? 2 * GM_MINB : GM_
     const double2* hsrc = reinterpret_cast<const double2*>(g_ndhot);
     double2* hdst = reinterpret_cast<double2*>(s_nd);
     for (int i = threadIdx.x; i < NDT_NCOEF * NDT_HOT_ROWS / 2; i += NT) hdst[i] = hsrc[i];
+  }
+  double* s_Wd = s_nd + NDT_NCOEF * NDT_HOT_ROWS;   // [64][GM_WDS]  whitening matrix (kDens)
+  double* s_md = s_Wd + 64 * GM_WDS;                // [64]          density mean
+  if (kDens) {
+    for (int i = threadIdx.x; i < 64 * 64; i += NT) s_Wd[(i >> 6) * GM_WDS + (i & 63)] = a.whiten[i];
+    for (int i = threadIdx.x; i < 64; i += NT) s_md[i] = a.dens_mean[i];
   }
   __syncthreads();
   const int d = a.d;
@@ -457,6 +474,29 @@ __global__ void __launch_bounds__(NT, (DQ <= 16 ? (NT <= 128 ? 2 * GM_MINB : GM_
                   fma(x[mm], x[mm], a.stat_sumsq[(int64_t)j * C + c]);
             }
           }
+        }
+      }
+      if (kDens) {
+        // same fragments and accumulation order as mvn_logpdf_mma64_kernel: bit-identical
+        const int r8 = lane >> 2;
+        double av[DQ];
+#pragma unroll
+        for (int ks = 0; ks < DQ; ++ks) av[ks] = x[ks] - s_md[4 * ks + q];
+        double maha = 0.0;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < DQ; ++ks)
+            dmma_m8n8k4(d0, d1, av[ks], s_Wd[(4 * ks + q) * GM_WDS + nb * 8 + r8]);
+          maha = fma(d0, d0, maha);
+          maha = fma(d1, d1, maha);
+        }
+        maha += __shfl_xor_sync(0xffffffffu, maha, 1);
+        maha += __shfl_xor_sync(0xffffffffu, maha, 2);
+        if (q == 0 && valid) {
+          const double lp = -0.5 * (a.norm_c + maha);
+          a.out_prob[rec * C + c] = a.log_pscale ? lp : exp(lp);
         }
       }
       ++rec;
@@ -635,7 +675,9 @@ static int gibbs_launch_nt(pbx_ctx* ctx, const GibbsArgs& a) {
   if constexpr (DQ >= 2) {
     if (sweep_rec) {                       // whole sweeps: conditional means on the tensor cores
       const size_t model = gibbs_mma_model_doubles<DQ>();
-      const size_t smem = (model + NDT_NCOEF * NDT_HOT_ROWS) * sizeof(double);
+      const bool dens = DQ == 16 && a.d == 64 && a.out_prob != nullptr;
+      const size_t smem = (model + NDT_NCOEF * NDT_HOT_ROWS + (dens ? 64 * GM_WDS + 64 : 0)) *
+                          sizeof(double);
       // workspace: [c0 (d doubles, padded to 256 B)] [model image]
       const size_t off = ((size_t)a.d * 8 + 255) / 256 * 256;
       int rc = pbx_ws_reserve(ctx, off + model * sizeof(double));
@@ -645,14 +687,22 @@ static int gibbs_launch_nt(pbx_ctx* ctx, const GibbsArgs& a) {
       double* img = (double*)((char*)ctx->ws + off);
       gibbs_mma_prep_kernel<DQ><<<DQ / 2, 256, 0, ctx->stream>>>(a2, img);
       PBX_LAUNCH_CHECK(ctx);
-#define GM_LAUNCH(PR)                                                                          \
+#define GM_LAUNCH(PR, DN)                                                                      \
   do {                                                                                         \
-    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_mma_kernel<DQ, PR, NT>,                            \
+    PBX_CUDA(cudaFuncSetAttribute(gibbs_mvn_mma_kernel<DQ, PR, NT, DN>,                        \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    gibbs_mvn_mma_kernel<DQ, PR, NT><<<grid, NT, smem, ctx->stream>>>(a2, img);                \
+    gibbs_mvn_mma_kernel<DQ, PR, NT, DN><<<grid, NT, smem, ctx->stream>>>(a2, img);            \
   } while (0)
-      if (a.d % 8 == 0) GM_LAUNCH(true);
-      else GM_LAUNCH(false);
+      if constexpr (DQ == 16) {
+        if (dens) {
+          if (a.d % 8 == 0) GM_LAUNCH(true, true);
+          else GM_LAUNCH(false, true);
+          PBX_LAUNCH_CHECK(ctx);
+          return PBX_OK;
+        }
+      }
+      if (a.d % 8 == 0) GM_LAUNCH(true, false);
+      else GM_LAUNCH(false, false);
 #undef GM_LAUNCH
       PBX_LAUNCH_CHECK(ctx);
       return PBX_OK;
@@ -709,6 +759,16 @@ extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
   a.coef = p->coef; a.c0 = c0; a.stdv = p->stdv; a.cdf_lo = p->cdf_lo; a.cdf_hi = p->cdf_hi;
   a.state = p->state; a.inj_runif = p->inj_runif; a.out_x = p->out_x;
   a.stat_sum = p->stat_sum; a.stat_sumsq = p->stat_sumsq;
+  // whole sweeps at d = 64: the density of the recorded states is evaluated inside the Gibbs
+  // kernel; otherwise by a second launch over the recorded states (below)
+  const bool want_dens = p->out_prob && p->want_prob;
+  const bool fused_dens = want_dens && d == 64 && (p->thin % d == 0) && (p->step0 % d == 0) &&
+                          (p->n_steps % d == 0);
+  a.out_prob = fused_dens ? p->out_prob : nullptr;
+  a.whiten = p->whiten;
+  a.dens_mean = p->dens_mean ? p->dens_mean : p->mean;
+  a.norm_c = p->norm_c;
+  a.log_pscale = p->log_pscale;
   PBX_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   if (a.T > 0) {
     gibbs_c0_kernel<<<1, 128, 0, ctx->stream>>>(p->coef, p->mean, d, c0);
@@ -720,7 +780,7 @@ extern "C" int pbx_gibbs_mvn_run(pbx_ctx* ctx, const pbx_gibbs_mvn_params* p) {
     else if (d <= 64) rc = gibbs_launch<16>(ctx, a);
     else rc = gibbs_launch<32>(ctx, a);
     if (rc) return rc;
-    if (p->out_prob && p->want_prob) {
+    if (want_dens && !fused_dens) {
       // the target is evaluated and recorded on every kept step (sd.py:286)
       rc = mvn_logpdf_launch(ctx, p->out_x, d, p->n_chains, p->n_steps / p->thin,
                              p->dens_mean ? p->dens_mean : p->mean, p->whiten, p->norm_c,
