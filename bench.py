@@ -1011,7 +1011,7 @@ class C5:
             ev[1].record(self.eng.stream)
         self.step0 += self.sweeps * self.d_
 
-    kernel = "gibbs_mvn_mma_kernel + mvn_logpdf_mma64_kernel"
+    kernel = "gibbs_mvn_mma_kernel (conditional means and the recorded states' density, both DMMA)"
 
     def roofline(self, kernel_ms, peaks, which, fp64_peak, sm_mhz):
         d = self.d_
