@@ -415,3 +415,42 @@ def test_table_ndtri_host_mirror_against_scipy():
     lib.pbx_ndtri_host(bad.ctypes.data_as(C.c_void_p), C.c_int64(len(bad)),
                        ob.ctypes.data_as(C.c_void_p))
     assert np.isnan(ob).all()
+
+
+def test_blocked_gibbs_closed_form_equals_the_recursion():
+    """The algebra behind the tensor-core Gibbs kernel (pbx_gibbs.cu, gibbs_mma_prep_kernel),
+    restated in numpy: with C_b the block's 8 rows of the CondCov coefficient matrix split into
+    E (columns outside the block) and the strictly lower / upper parts L, U of its diagonal
+    block, the eight sequential coordinate updates of cond_cov.py:42-65 equal
+    x' = (M [E | U]) x + M z with M = (I - L)^-1 -- the same sweep, up to rounding."""
+    from probayes_b200.cond_cov import CondCov
+    rng = np.random.default_rng(12)
+    for d in (8, 13, 64):
+        A = rng.standard_normal((d, d))
+        cov = A @ A.T / d + np.eye(d)
+        mean = rng.standard_normal(d)
+        cc = CondCov(mean, cov, np.tile([-10., 10.], (d, 1)))
+        coef = cc.coef_matrix()                                  # zero diagonal
+        assert np.abs(np.diag(coef)).max() == 0.0
+        x0 = rng.standard_normal(d)
+        z = rng.standard_normal(d)            # stands for ndtri(u) * stdv + (mean_i - coef_i . mean)
+        # coordinate by coordinate (Gauss-Seidel order)
+        xs = x0.copy()
+        for i in range(d):
+            xs[i] = z[i] + coef[i] @ xs
+        # blocks of 8 in closed form, zero padding to a multiple of 8
+        dp = (d + 7) // 8 * 8
+        Cp = np.zeros((dp, dp)); Cp[:d, :d] = coef
+        xb = np.zeros(dp); xb[:d] = x0
+        zp = np.zeros(dp); zp[:d] = z
+        for b in range(dp // 8):
+            sl = slice(8 * b, 8 * b + 8)
+            blk = Cp[sl, sl]
+            L, U = np.tril(blk, -1), np.triu(blk, 1)
+            M = np.linalg.inv(np.eye(8) - L)
+            assert np.allclose(np.triu(M, 1), 0.0) and np.allclose(np.diag(M), 1.0)
+            EU = Cp[sl].copy()
+            EU[:, sl] = U                                        # lower part and diagonal dropped
+            xb[sl] = (M @ EU) @ xb + M @ zp[sl]
+        assert np.abs(xb[:d] - xs).max() <= 1e-13 * max(1.0, np.abs(xs).max())
+        assert not np.any(xb[d:])                                # padding coordinates stay 0
