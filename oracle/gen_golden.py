@@ -40,6 +40,12 @@ def _summary_arrays(sp, samples, keys):
                    q_pred=np.stack([np.asarray(q[k], dtype=float) for k in keys], axis=-1),
                    q_prop=np.stack([np.asarray(q[k + "'"], dtype=float) for k in keys], axis=-1),
                    q_step3_name=np.array(samples[3].q.name))
+    if summary.r is not None:               # (q, r) pairs: the reverse density, keys swapped
+        r = summary.r
+        out.update(r_name=np.array(r.name), r_keys=np.array(list(r.keys())),
+                   r_prob=np.asarray(r.prob, dtype=float),
+                   r_pred=np.stack([np.asarray(r[k], dtype=float) for k in keys], axis=-1),
+                   r_prop=np.stack([np.asarray(r[k + "'"], dtype=float) for k in keys], axis=-1))
     return out
 
 

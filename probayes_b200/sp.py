@@ -674,22 +674,29 @@ class SP(SD):
     def _has_proposals(arrays):
         return arrays.get('xprop') is not None and arrays['thin'] == 1
 
-    def _q_pd(self, arrays, sel=None):
+    def _q_pd(self, arrays, sel=None, reverse=False):
         """The proposal-density PD of the reference's ``opqr.q`` / ``summary.q`` (sd.py:253-288,
         sp.py:170-198) for a reference-shaped single-chain run: named ``x',y'|x,y``, the
         proposals under the primed keys, their predecessors (the state the call started from,
         then the retained states) under the plain keys, and the user's transition callable
         evaluated on them -- on the host, vectorised, after the walk: with a single callable
         the Hastings score does not use q (sp_utils.py:40-64), it is only recorded.  None for
-        transitions that are not a single callable."""
+        transitions that are not callables.  A ``(q, r)`` pair (constants in the device
+        catalogue) also yields ``r`` (``reverse=True``): the same values under
+        ``x,y|x',y'`` with ``r`` evaluated on them."""
         tran = self._proposal_rf()._tran
+        if isinstance(tran, tuple) and len(tran) == 2:
+            tran = tran[1] if reverse else tran[0]
+        elif reverse:
+            return None
         if not callable(tran) or arrays.get('xprop') is None or arrays.get('init') is None \
                 or arrays['thin'] != 1:
             return None
         keys = arrays['keys']
         prop = np.asarray(arrays['xprop'])[:, :, 0]                     # [T, D]
         pred = np.concatenate([arrays['init'][None, :], np.asarray(arrays['x'])[:-1, :, 0]])
-        cache = arrays.get('_q_prob')
+        ckey = '_r_prob' if reverse else '_q_prob'
+        cache = arrays.get(ckey)
         if cache is None:
             kw = {}
             for j, k in enumerate(keys):
@@ -703,22 +710,23 @@ class SP(SD):
             except Exception:                       # a callable that only takes scalars
                 cache = np.array([float(tran(**{n: float(v[i]) for n, v in kw.items()}))
                                   for i in range(prop.shape[0])])
-            arrays['_q_prob'] = cache
+            arrays[ckey] = cache
         vals = collections.OrderedDict()
+        primed, plain = [k + "'" for k in keys], list(keys)
+        marg, cond = (plain, primed) if reverse else (primed, plain)
         if sel is None:
-            for j, k in enumerate(keys):
-                vals[k + "'"] = prop[:, j]
-            for j, k in enumerate(keys):
-                vals[k] = pred[:, j]
-            name = ','.join(k + "'" for k in keys) + '|' + ','.join(keys)
+            for k in marg + cond:
+                j = keys.index(k.rstrip("'"))
+                vals[k] = prop[:, j] if k.endswith("'") else pred[:, j]
+            name = ','.join(marg) + '|' + ','.join(cond)
             dims = collections.OrderedDict((k, 0) for k in vals)
             return PD(name, vals, dims=dims, prob=cache, pscale=self._proposal_rf().pscale)
         for j, k in enumerate(keys):
             vals[k] = pred[sel, j]
         for j, k in enumerate(keys):
             vals[k + "'"] = prop[sel, j]
-        name = ','.join("{}'={}".format(k, vals[k + "'"]) for k in keys) + '|' + \
-            ','.join("{}={}".format(k, vals[k]) for k in keys)
+        name = ','.join("{}={}".format(k, vals[k]) for k in marg) + '|' + \
+            ','.join("{}={}".format(k, vals[k]) for k in cond)
         return PD(name, vals, dims=collections.OrderedDict((k, None) for k in vals),
                   prob=float(cache[sel]), pscale=self._proposal_rf().pscale)
 
@@ -752,11 +760,12 @@ class SP(SD):
         for i in range(R):
             v = self._value_pd(arrays, sel=i)
             s, t, u, p = ss[i], ts[i], us[i], None
-            q = None
+            q = r = None
             if props:
                 p = self._value_pd(arrays, sel=i, x=arrays['xprop'], prob=arrays['pprop'])
                 q = self._q_pd(arrays, sel=i)
-            out.append(self.opqrstuv(prev if aligned else None, p, q, None, s, t, u, v))
+                r = self._q_pd(arrays, sel=i, reverse=True)
+            out.append(self.opqrstuv(prev if aligned else None, p, q, r, s, t, u, v))
             prev = v
         return out
 
@@ -824,14 +833,15 @@ class SP(SD):
             s_ = [s.s for s in kept if s.s is not None]      # sp.py:181-190: dropped samples
             t_ = [s.t for s in kept if s.t is not None]      # contribute nothing
             return self.opqrstuv(concat([s.o for s in kept]), concat([s.p for s in kept]),
-                                 concat([s.q for s in kept]), None, s_ or None, t_ or None,
-                                 u, v)
+                                 concat([s.q for s in kept]), concat([s.r for s in kept]),
+                                 s_ or None, t_ or None, u, v)
         v = self._value_pd(arrays)
         if conditionalise:                      # sp.py:194-196: condition on the leaf (data) keys
             v = v.conditionalise([k for k in self._leafs.keylist if k in v.marg])
-        o = p = q = None
+        o = p = q = r = None
         if self._has_proposals(arrays) and not conditionalise:
             q = self._q_pd(arrays)
+            r = self._q_pd(arrays, reverse=True)
             # summate() of the per-step p / o PDs (sp.py:170-198): every proposal, and the
             # predecessor of every step but the first
             p = self._value_pd(arrays, x=arrays['xprop'], prob=arrays['pprop'])
@@ -843,7 +853,7 @@ class SP(SD):
             ss, ts, u = self._stu_lists(arrays)
             s_ = [x for x in ss if x is not None]
             t_ = [x for x in ts if x is not None]
-            return self.opqrstuv(o, p, q, None, s_ or None, t_ or None, u, v)
+            return self.opqrstuv(o, p, q, r, s_ or None, t_ or None, u, v)
         if arrays['gibbs']:
             C = 1 if arrays['chains'] is None else arrays['chains']
             u = AcceptRecord(np.full(C, arrays['T']), arrays['T'])

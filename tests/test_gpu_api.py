@@ -124,6 +124,15 @@ def test_metrohast_norm1d(name, scores, delta):
     assert relerr(summary.p.prob, g["pprop"]) <= TOL
     assert summary.p.name == summary.v.name
     assert summary.o.name == 'mu,sigma,x={{{}}}'.format(len(g["x_obs"]) * (n_steps - 1))
+    if "r_name" in g.files:              # a (q, r) pair: both proposal-density PDs, keys swapped
+        for pd_, tag in ((summary.q, "q"), (summary.r, "r")):
+            assert pd_.name == str(g[tag + "_name"]) and list(pd_.keys()) == list(g[tag + "_keys"])
+            assert np.array_equal(pd_.prob, g[tag + "_prob"])
+            assert relerr(np.stack([pd_["mu'"], pd_["sigma'"]], 1), g[tag + "_prop"]) <= TOL
+            assert relerr(np.stack([pd_['mu'], pd_['sigma']], 1), g[tag + "_pred"]) <= TOL
+        assert samples[2].r.name.startswith("mu=") and "|mu'=" in samples[2].r.name
+    elif scores == 'metropolis':
+        assert summary.r is None and summary.q is not None
     # process(samples, conditionalise=True): normalised over the samples (sp.py:194-196)
     cond = process(samples, conditionalise=True).v
     assert cond.name == 'mu,sigma|x={{{}}}'.format(len(g["x_obs"]) * n_steps)
