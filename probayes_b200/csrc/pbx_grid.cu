@@ -482,7 +482,9 @@ __device__ __forceinline__ MsPair ms_merge(MsPair a, MsPair b, const double* tab
 
 #define MS_THREADS 256
 #define MS_WARPS (MS_THREADS / 32)
+#ifndef MS_CHUNK
 #define MS_CHUNK 8
+#endif
 // Persistent grid (as many CTAs as are resident at once, each warp takes the 256-entry warp
 // chunks w, w + n_warps, ...), the next chunk's four 128-bit loads issued before the current
 // chunk is folded.  Per chunk a lane raises its running maximum and rescales its sum by
