@@ -485,10 +485,12 @@ def k1_counters():
     """ncu counters of ONE K1 launch on the default c2 workload, written by
     scripts/ncu_counters.py from the --set full capture of the same kernel build
     (profiles/k1_counters.json names the capture)."""
-    path = os.path.join(ROOT, "profiles", "k1_counters.json")
-    if os.path.exists(path):
-        with open(path) as f:
-            return json.load(f)
+    # (a copy sits next to the package: profiles/ is listed in .gpurunignore and may not travel)
+    for path in (os.path.join(ROOT, "profiles", "k1_counters.json"),
+                 os.path.join(ROOT, "probayes_b200", "k1_counters.json")):
+        if os.path.exists(path):
+            with open(path) as f:
+                return json.load(f)
     return None
 
 
